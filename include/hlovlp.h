@@ -1,0 +1,191 @@
+/*
+ * hlovlp.h — C ABI of libhlovlp, the B200-native short-read overlap stage for HyLight.
+ *
+ * The reference has no FFI for this path: it is a chain of processes glued by files
+ * (minimap2 | cut | filter_ovlp_inline.py > overlaps.paf ; minimap22sfo.py ; sfo2overlaps.py),
+ * called from /root/reference/script/polyte.tune_params.py:488-529 (preprocessing_denovo) and
+ * :534-579 (run_sfo).  This header is the boundary a maintainer would bind instead of that chain
+ * (see INTEGRATION.md for the ctypes stub that replaces the os.system() calls at
+ * polyte.tune_params.py:510-517 and :549-557).
+ *
+ * Conventions: every function returns 0 or a negative hlo_status; nothing throws or exits.
+ * Inputs are caller-owned plain host pointers, only read during the call.  Outputs are
+ * ctx-owned host buffers valid until the next call on the same ctx (or hlo_ctx_destroy).
+ * A ctx is bound to one CUDA device and is single-threaded; distinct ctxs are independent.
+ * There is no CPU fallback: without a CUDA device hlo_ctx_create fails with HLO_ENODEV.
+ */
+#ifndef HLOVLP_H
+#define HLOVLP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HLO_ABI_VERSION 1
+
+typedef enum hlo_status {
+    HLO_OK = 0,
+    HLO_EINVAL = -1,       /* bad argument */
+    HLO_ENODEV = -2,       /* no usable CUDA device */
+    HLO_ECUDA = -3,        /* CUDA runtime error (hlo_last_error has the text) */
+    HLO_ENOMEM = -4,       /* host or device allocation failed */
+    HLO_EUNSUPPORTED = -5, /* parameter combination outside the supported domain */
+    HLO_ERANGE = -6,       /* a size exceeds a documented limit */
+    HLO_EIO = -7           /* file error (text emitters) */
+} hlo_status;
+
+/*
+ * Parameters of the chain.  Defaults (hlo_params_default) are the literal values of the
+ * reference call site, polyte.tune_params.py:500-510:
+ *   minimap2 --sr -X -c -k 21 -w 11 -s 60 -m 30 -n 2 -r 0 -A 4 -B 2 --end-bonus 100
+ *   filter_ovlp_inline.py <min_overlap_len=60> 0.98 1 0.8
+ */
+typedef struct hlo_params {
+    int32_t k;               /* -k 21 */
+    int32_t w;               /* -w 11 */
+    int32_t min_seeds;       /* -n 2   (1 or 2 supported) */
+    int32_t min_chain_score; /* -m 30  (must be <= 2k) */
+    int32_t mid_occ;         /* 1000: --sr preset; minimizers occurring more often seed nothing */
+    int32_t match_score;     /* -A 4 */
+    int32_t mismatch_pen;    /* -B 2 */
+    int32_t ambi_pen;        /* --score-N default 1 */
+    int32_t end_bonus;       /* --end-bonus 100 (domain check only) */
+    int32_t min_dp_score;    /* -s 60 (domain check only) */
+    int32_t min_ovlp_len;    /* filter_ovlp_inline.py argv[1]; 60 first pass, 50 later passes */
+    int32_t max_overhang;    /* filter_ovlp_inline.py argv[3] = 1 (0..15) */
+    double min_identity;     /* filter_ovlp_inline.py argv[2] = 0.98 */
+    double overhang_ratio;   /* filter_ovlp_inline.py argv[4] = 0.8 */
+} hlo_params;
+
+/*
+ * One chain of minimap2 = one candidate: query read q (the lexicographically smaller decimal
+ * name, minimap2 -X), target read t, relative strand, diagonal and the span of the chained
+ * anchors.  q and t are read indices inside the hlo_reads object (batch-global).
+ *   diag : t_pos - q'_pos, q' = the query as aligned (reverse-complemented when strand = 1),
+ *          i.e. q'[j] is compared with t[j + diag].
+ *   strand_anchor : bit 0 = strand (0 '+', 1 '-'); bits 1..15 = start of the first anchor
+ *          k-mer in q' coordinates; bits 16..31 = end (exclusive) of the last anchor k-mer.
+ *          Bits 16..31 == 0 means "no anchor information": the end rule then scans the whole
+ *          overlap (identical results inside the supported domain).
+ */
+typedef struct hlo_cand {
+    uint32_t q, t;
+    int32_t diag;
+    uint32_t strand_anchor;
+} hlo_cand; /* 16 bytes */
+
+#define HLO_CAND_PACK(strand, a_start, a_end) \
+    ((uint32_t)((strand) & 1u) | ((uint32_t)(a_start) << 1) | ((uint32_t)(a_end) << 16))
+
+/*
+ * One verified overlap = the content of one line of sfo2overlaps.py's sorted 10-field
+ * temporary file (sfo2overlaps.py:37-50): ids numerically ordered (idA < idB), SFO fields
+ * after flip_N / flip_I.  ori: 0 = 'N' (same strand), 1 = 'I'.
+ * idA/idB are read ids local to their cluster (the decimal names written by rename_fas.py).
+ */
+typedef struct hlo_rec {
+    uint32_t idA, idB;
+    int32_t OHA, OHB;
+    uint32_t OLA, OLB;
+    uint32_t K;
+    uint32_t ori;
+} hlo_rec; /* 32 bytes */
+
+/* Extra per-record facts the reference computes on the way (PAF columns 10/11) */
+typedef struct hlo_rec_aux {
+    uint32_t cluster; /* cluster index inside the batch */
+    uint32_t blocklen; /* PAF col 11 */
+} hlo_rec_aux;
+
+typedef struct hlo_recs {
+    const hlo_rec *rec;         /* n records, sorted by (cluster, idA, idB, ...) */
+    const hlo_rec_aux *aux;     /* n entries, parallel to rec */
+    uint64_t n;
+    const uint64_t *cluster_off; /* n_clusters + 1 offsets into rec (NULL for hlo_verify) */
+    uint32_t n_clusters;
+} hlo_recs;
+
+/* minimizer tuple, same two words as minimap2's mm128_t: x = hash<<8 | span, y = rid<<32 | pos<<1 | strand */
+typedef struct hlo_mz {
+    uint64_t x, y;
+} hlo_mz;
+
+/* per-stage device timings of the last hlo_overlap_batch / hlo_verify call, milliseconds (CUDA events) */
+typedef struct hlo_timing {
+    float h2d_ms, pack_ms, sketch_ms, sort_ms, index_ms, pairgen_ms, verify_ms, dedup_ms, d2h_ms, total_ms;
+    uint64_t n_reads, n_bases, n_minimizers, n_seed_hits, n_candidates, n_accepted, n_records;
+    uint64_t n_deferred;     /* candidates that took the exact slow verify path */
+    uint64_t n_overflow_reads; /* query reads whose seed table overflowed shared memory */
+    uint64_t verify_launches, total_launches;
+} hlo_timing;
+
+typedef struct hlo_ctx hlo_ctx;
+typedef struct hlo_reads hlo_reads;
+
+void hlo_params_default(hlo_params *p);
+int hlo_abi_version(void);
+const char *hlo_strerror(int status);
+const char *hlo_last_error(const hlo_ctx *ctx);
+
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int hlo_device_count(void);
+
+int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out);
+void hlo_ctx_destroy(hlo_ctx *ctx);
+
+/*
+ * Upload and 2-bit-pack a batch of clusters.  Replaces rename_fas.py:48-75 + fastq2fasta.py:32-40
+ * + minimap2's own sequence encoding: reads of cluster c are seq[cluster_off[c] .. cluster_off[c+1]),
+ * read i of a cluster gets the decimal name i (rename_fas.py) unless ids != NULL gives it.
+ *   bases      : all sequences concatenated, ASCII (ACGTUN, any case; other letters are ambiguous)
+ *   base_off   : n_reads + 1 offsets into bases
+ *   cluster_off: n_clusters + 1 offsets into the read list (NULL = one cluster)
+ *   ids        : n_reads decimal names (NULL = position inside the cluster)
+ */
+int hlo_pack_reads(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, uint32_t n_reads,
+                   const uint32_t *cluster_off, uint32_t n_clusters, const uint32_t *ids, hlo_reads **out);
+void hlo_reads_free(hlo_reads *reads);
+
+/* Parity entry points ----------------------------------------------------------------------- */
+
+/* (w,k) minimizers of every read, in read order, exactly as minimap2's mm_sketch emits them. */
+int hlo_sketch(hlo_ctx *ctx, const hlo_reads *reads, const hlo_mz **mz, const uint64_t **read_off, uint64_t *n);
+
+/* Chains (candidates) of every query read; sorted by (q, t, strand, diag). */
+int hlo_candidates(hlo_ctx *ctx, const hlo_reads *reads, const hlo_cand **cands, uint64_t *n);
+
+/*
+ * Verify a caller-supplied candidate list (the reference's own candidate list in the parity tests):
+ * base-level ungapped extension with minimap2's end rule, filter_ovlp_inline.py:58,80-87 thresholds,
+ * minimap22sfo.py:47-74 geometry and sfo2overlaps.py:41-49 canonicalisation.  One record per accepted
+ * candidate, no per-pair dedup, sorted by (q, t, strand, diag) of the candidate.
+ */
+int hlo_verify(hlo_ctx *ctx, const hlo_reads *reads, const hlo_cand *cands, uint64_t n, hlo_recs *out);
+
+/* Full path --------------------------------------------------------------------------------- */
+
+/* sketch -> sort -> seed/chain -> verify -> per-pair keep-longest -> sorted records, per cluster. */
+int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *reads, hlo_recs *out);
+
+/* pack + overlap in one call from host buffers (the e2e entry the bench times). */
+int hlo_overlap_host(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, uint32_t n_reads,
+                     const uint32_t *cluster_off, uint32_t n_clusters, hlo_recs *out);
+
+int hlo_get_timing(const hlo_ctx *ctx, hlo_timing *t);
+
+/* Text emitters (host): byte-identical formatting to the reference scripts ------------------- */
+
+/* 8-field SFO lines (minimap22sfo.py:73) in the string-ordered form of quirk D8. */
+int hlo_write_sfo(const hlo_rec *rec, uint64_t n, const char *path);
+/* 13-field SAVAGE .overlaps lines (sfo2overlaps.py:150-200), written to a temp file then renamed. */
+int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path);
+/* Format one 13-field line into buf (>= 128 bytes); returns its length. */
+int hlo_format_overlap_line(const hlo_rec *rec, char *buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLOVLP_H */
