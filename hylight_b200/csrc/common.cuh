@@ -1,0 +1,110 @@
+// common.cuh — shared device/host definitions of libhlovlp (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hlovlp.h"
+
+namespace hlo {
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident batch of packed reads.
+//
+// Layout in HBM: every read has one row of `stride_w` 32-bit words per strand,
+// 16 bases per word, base i at bits [2(i%16), 2(i%16)+2) of word i/16 (little-endian in the word);
+// A=0 C=1 G=2 T=3, ambiguous bases are stored as 0 and flagged in the parallel `amb` plane with the
+// same geometry (01 = ambiguous).  Plane 0 holds the read as given, plane 1 its reverse complement,
+// so the verify kernel always compares two forward-packed rows.  stride_w is a multiple of 16 words
+// (64 B): a row never straddles a 128 B line more than its length requires, and a 4-lane group reads
+// one row of <= 256 bases with one LDG.128 per lane.
+struct DevReads {
+    uint32_t n_reads = 0, n_clusters = 0;
+    uint32_t stride_w = 0;  // words per row
+    uint32_t max_len = 0;
+    uint64_t n_bases = 0;
+    int has_amb = 0;        // any ambiguous base in the batch
+    uint32_t *len = nullptr;    // [n] read length | (has ambiguous base ? 0x80000000 : 0)
+    uint32_t *cbase = nullptr;  // [n] index of the first read of the read's cluster
+    uint32_t *cidx = nullptr;   // [n] cluster index
+    uint32_t *ids = nullptr;    // [n] decimal name
+    uint32_t *nrank = nullptr;  // [n] cbase + numeric rank of the name inside the cluster
+    uint32_t *bases = nullptr;  // [2][n][stride_w]
+    uint32_t *amb = nullptr;    // [2][n][stride_w]
+};
+
+#define HLO_MAX_W_PUBLIC 32  // window sizes the sketch kernel keeps in its per-thread ring
+#define HLO_LEN_MASK 0x7fffffffu
+#define HLO_AMB_FLAG 0x80000000u
+
+// internal compact verified record (16 B): what the verify kernels emit
+struct Rec16 {
+    uint32_t q, t;
+    uint32_t ds;  // (diag + 2^30) << 1 | strand
+    uint32_t kb;  // K | blocklen << 16
+};
+#define HLO_DIAG_BIAS (1 << 30)
+
+// device tables for the python-double threshold tests (filter_ovlp_inline.py:58,83)
+struct VerifyTables {
+    const uint16_t *min_matches;  // [max_len+1] smallest matches with !(matches/blocklen < min_identity)
+    const uint16_t *max_clip;     // [max_len+1] largest overhang with !(overhang > min(o, maplen*r))
+    const uint16_t *max_k_upto;   // [max_len+1] running max of b - min_matches[b]
+    int32_t max_len;
+};
+
+struct VerifyParams {
+    int32_t k, a, b, n;  // k-mer, match, mismatch, ambiguous scores
+    int32_t min_len, max_overhang;
+    int32_t bad_limit;  // fast verify kernel: largest number of bad columns for which a 32-base end window is exact
+};
+
+// ---------------------------------------------------------------------------------------------
+// decimal-string order of two unsigned integers == strcmp(str(a), str(b)) < 0  (minimap2 -X skips a
+// seed when strcmp(qname, tname) > 0; names are the integers written by rename_fas.py:48-57)
+__host__ __device__ __forceinline__ int dec_digits(uint32_t v) {
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+         : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+__host__ __device__ __forceinline__ uint64_t pow10_u64(int e) {
+    uint64_t r = 1;
+    for (int i = 0; i < e; ++i) r *= 10;
+    return r;
+}
+__host__ __device__ __forceinline__ bool name_less(uint32_t a, uint32_t b) {
+    const int da = dec_digits(a), db = dec_digits(b);
+    if (da == db) return a < b;
+    if (da < db) {  // a is the shorter string: pad it, a prefix sorts first
+        const uint64_t as = (uint64_t)a * pow10_u64(db - da);
+        return as <= (uint64_t)b;
+    }
+    const uint64_t bs = (uint64_t)b * pow10_u64(da - db);
+    return (uint64_t)a < bs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Record expansion: minimap22sfo.py:47-74 + sfo2overlaps.py:37-50 from (ql, tl, diag, strand, K).
+// With PAF coordinates qs/qe/ts/te of ANY block on the diagonal:
+//   '+': OHA = qstart - sstart = -diag            OHB = slen - sstart - (qlen - qstart) = tl - ql - diag
+//   '-': OHA = qstart - (slen - send) = ql-tl+diag OHB = send - (qlen - qstart) = diag
+__host__ __device__ __forceinline__ void expand_record(uint32_t qid, uint32_t tid, int ql, int tl, int diag, int strand,
+                                                       uint32_t K, hlo_rec *o) {
+    int OHA, OHB;
+    if (!strand) OHA = -diag, OHB = tl - ql - diag;
+    else OHA = ql - tl + diag, OHB = diag;
+    const int OLA = OHA >= 0 ? ((ql - OHA) < tl ? (ql - OHA) : tl) : ((tl + OHA) < ql ? (tl + OHA) : ql);
+    uint32_t idA = qid, idB = tid;
+    if (name_less(idB, idA)) {  // minimap22sfo.py:62 (string compare); never fires for -X candidates
+        uint32_t t = idA; idA = idB; idB = t;
+        if (!strand) OHA = -OHA, OHB = -OHB;
+        else { int x = OHA; OHA = OHB; OHB = x; }
+    }
+    if (idA > idB) {  // sfo2overlaps.py:41-47 flip_N / flip_I
+        uint32_t t = idA; idA = idB; idB = t;
+        if (!strand) OHA = -OHA, OHB = -OHB;
+        else { int x = OHA; OHA = OHB; OHB = x; }
+    }
+    o->idA = idA, o->idB = idB, o->OHA = OHA, o->OHB = OHB;
+    o->OLA = (uint32_t)OLA, o->OLB = (uint32_t)OLA, o->K = K, o->ori = (uint32_t)strand;
+}
+
+}  // namespace hlo

@@ -1,0 +1,827 @@
+// ctx.cu — C ABI of libhlovlp (include/hlovlp.h): context, packing, stage orchestration, timing.
+//
+// One ctx = one CUDA device + one stream.  All device work of a call is enqueued on the ctx stream;
+// stage boundaries are marked with CUDA events so that hlo_get_timing reports device time per stage.
+// There is deliberately no CPU code path for any stage: every entry point fails with HLO_ENODEV /
+// HLO_ECUDA when the device is missing.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace hlo;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr, cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        else p = nullptr;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr, cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr, cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        else p = nullptr;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr, cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum Stage { ST_BEGIN = 0, ST_H2D, ST_PACK, ST_SKETCH, ST_SORT, ST_INDEX, ST_PAIRGEN, ST_VERIFY, ST_DEDUP, ST_D2H, ST_COUNT };
+
+}  // namespace
+
+struct hlo_reads {
+    hlo_ctx *ctx = nullptr;
+    DevReads d;
+    DevBuf b_ascii, b_off, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_bases, b_amb, b_ambcount;
+    std::vector<uint32_t> h_len, h_ids, h_cidx, h_cluster_off;
+    float h2d_ms = 0.f, pack_ms = 0.f;
+    void release() {
+        b_ascii.release(), b_off.release(), b_len.release(), b_cbase.release(), b_cidx.release(), b_ids.release();
+        b_nrank.release(), b_bases.release(), b_amb.release(), b_ambcount.release();
+    }
+};
+
+struct hlo_ctx {
+    int device = 0;
+    hlo_params P;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    std::string err;
+    LaunchCounter lc;
+    hlo_timing tm;
+    int pairgen_slots_log2 = 10;
+    // verify tables
+    DevBuf b_tab;
+    int tab_len = -1;
+    VerifyTables tab{};
+    // workspaces
+    DevBuf b_cnt, b_mzoff, b_mzx, b_mzrp, b_mzrid, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
+    DevBuf b_cands, b_counters, b_ovf, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
+    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz;
+    PinBuf h_out, h_aux, h_coff, h_mz, h_roff, h_cands, h_rec16, h_small;
+    std::vector<uint64_t> v_coff;
+    hlo_reads scratch_reads;
+    // sketch state of the last run (device)
+    uint64_t n_mz = 0;
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            char buf__[512];                                                                          \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = buf__;                                                                         \
+            cudaGetLastError();                                                                       \
+            return e__ == cudaErrorMemoryAllocation ? HLO_ENOMEM : HLO_ECUDA;                         \
+        }                                                                                             \
+    } while (0)
+
+#define FAIL(code, ...)                              \
+    do {                                             \
+        char buf__[512];                             \
+        snprintf(buf__, sizeof buf__, __VA_ARGS__);  \
+        ctx->err = buf__;                            \
+        return (code);                               \
+    } while (0)
+
+extern "C" {
+
+void hlo_params_default(hlo_params *p) {
+    if (!p) return;
+    p->k = 21, p->w = 11, p->min_seeds = 2, p->min_chain_score = 30, p->mid_occ = 1000;
+    p->match_score = 4, p->mismatch_pen = 2, p->ambi_pen = 1, p->end_bonus = 100, p->min_dp_score = 60;
+    p->min_ovlp_len = 60, p->max_overhang = 1, p->min_identity = 0.98, p->overhang_ratio = 0.8;
+}
+
+int hlo_abi_version(void) { return HLO_ABI_VERSION; }
+
+const char *hlo_strerror(int s) {
+    switch (s) {
+        case HLO_OK: return "ok";
+        case HLO_EINVAL: return "invalid argument";
+        case HLO_ENODEV: return "no usable CUDA device (libhlovlp has no CPU fallback)";
+        case HLO_ECUDA: return "CUDA runtime error";
+        case HLO_ENOMEM: return "out of memory";
+        case HLO_EUNSUPPORTED: return "parameter combination outside the supported domain";
+        case HLO_ERANGE: return "size exceeds a documented limit";
+        case HLO_EIO: return "I/O error";
+        default: return "unknown status";
+    }
+}
+
+const char *hlo_last_error(const hlo_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int hlo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void *hlo_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void hlo_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+static int check_params(const hlo_params &P, std::string &why) {
+    char b[256];
+#define BAD(...)                         \
+    do {                                 \
+        snprintf(b, sizeof b, __VA_ARGS__); \
+        why = b;                         \
+        return HLO_EUNSUPPORTED;         \
+    } while (0)
+    if (P.k < 1 || P.k > 28) BAD("k=%d outside [1,28]", P.k);
+    if (P.w < 1 || P.w > HLO_MAX_W_PUBLIC) BAD("w=%d outside [1,%d]", P.w, HLO_MAX_W_PUBLIC);
+    if (P.min_seeds < 1 || P.min_seeds > 2) BAD("min_seeds=%d: only 1 or 2 reduce to the min/max anchor test", P.min_seeds);
+    if (P.min_chain_score > 2 * P.k) BAD("min_chain_score=%d > 2k: chain score no longer equals the anchor span", P.min_chain_score);
+    if (P.mid_occ < 1) BAD("mid_occ must be >= 1");
+    if (P.match_score < 1 || P.mismatch_pen < 0 || P.ambi_pen < 0) BAD("scores must be A>=1, B>=0, N>=0");
+    if (P.min_ovlp_len < 1 || P.min_ovlp_len > 32767) BAD("min_ovlp_len=%d outside [1,32767]", P.min_ovlp_len);
+    if (P.max_overhang < 0 || P.max_overhang > 15) BAD("max_overhang=%d outside [0,15]", P.max_overhang);
+    if (!(P.min_identity > 0.0 && P.min_identity <= 1.0)) BAD("min_identity must be in (0,1]");
+    if (!(P.overhang_ratio >= 0.0)) BAD("overhang_ratio must be >= 0");
+    // minimap2's own post-alignment filters (-s min_dp_max, mlen >= -m) must never bind on an accepted overlap
+    const double worst = (double)P.min_ovlp_len * ((double)P.match_score - (double)(P.match_score + P.mismatch_pen) * (1.0 - P.min_identity));
+    if (worst < (double)P.min_dp_score) BAD("-s %d could drop overlaps the filter accepts (min dp score %.1f)", P.min_dp_score, worst);
+    if ((double)P.min_ovlp_len * P.min_identity < (double)P.min_chain_score) BAD("-m %d could drop accepted overlaps", P.min_chain_score);
+#undef BAD
+    return HLO_OK;
+}
+
+int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out) {
+    if (!out) return HLO_EINVAL;
+    *out = nullptr;
+    int n = hlo_device_count();
+    if (n <= 0 || device < 0 || device >= n) return HLO_ENODEV;
+    hlo_ctx *ctx = new (std::nothrow) hlo_ctx();
+    if (!ctx) return HLO_ENOMEM;
+    if (params) ctx->P = *params;
+    else hlo_params_default(&ctx->P);
+    std::string why;
+    int rc = check_params(ctx->P, why);
+    if (rc) {
+        fprintf(stderr, "hlo_ctx_create: %s\n", why.c_str());
+        delete ctx;
+        return rc;
+    }
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return HLO_ENODEV;
+    }
+    for (int i = 0; i <= ST_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+    memset(&ctx->tm, 0, sizeof ctx->tm);
+    if (const char *e = getenv("HLO_PAIRGEN_SLOTS_LOG2")) {
+        int v = atoi(e);
+        if (v >= 6 && v <= 13) ctx->pairgen_slots_log2 = v;
+    }
+    ctx->scratch_reads.ctx = ctx;
+    *out = ctx;
+    return HLO_OK;
+}
+
+void hlo_ctx_destroy(hlo_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->b_tab, &ctx->b_cnt, &ctx->b_mzoff, &ctx->b_mzx, &ctx->b_mzrp, &ctx->b_mzrid, &ctx->b_keys[0],
+                      &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_bstart,
+                      &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovfcnt, &ctx->b_gkeys,
+                      &ctx->b_gmn, &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos,
+                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz};
+    for (DevBuf *b : bufs) b->release();
+    PinBuf *pins[] = {&ctx->h_out, &ctx->h_aux, &ctx->h_coff, &ctx->h_mz, &ctx->h_roff, &ctx->h_cands, &ctx->h_rec16, &ctx->h_small};
+    for (PinBuf *b : pins) b->release();
+    ctx->scratch_reads.release();
+    for (int i = 0; i <= ST_COUNT; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// verify tables: the reference's double-precision threshold tests as integer tables
+// (filter_ovlp_inline.py:58 "float(a[9]) / float(a[10]) < min_identity", :83 "overhang > min(o, maplen * r)")
+
+static int build_tables(hlo_ctx *ctx, int max_len) {
+    if (max_len <= ctx->tab_len) return HLO_OK;
+    const int L = std::max(max_len, 256);
+    std::vector<uint16_t> h((size_t)3 * (L + 1));
+    uint16_t *mm = h.data(), *mc = mm + (L + 1), *mk = mc + (L + 1);
+    const double id = ctx->P.min_identity, r = ctx->P.overhang_ratio;
+    const int o = ctx->P.max_overhang;
+    int run = 0;
+    for (int b = 0; b <= L; ++b) {
+        int m;
+        if (b == 0) m = 1;
+        else {
+            m = (int)std::ceil(id * (double)b);
+            if (m < 0) m = 0;
+            while (m > 0 && !((double)(m - 1) / (double)b < id)) --m;
+            while (m <= b && ((double)m / (double)b < id)) ++m;
+        }
+        mm[b] = (uint16_t)m;
+        const double x = (double)b * r;
+        int c;
+        if (x < (double)o) c = (int)std::floor(x);  // python: min(o, x) == x -> keep iff !(overhang > x)
+        else c = o;
+        mc[b] = (uint16_t)std::max(c, 0);
+        if (b >= 1 && b - m > run) run = b - m;
+        mk[b] = (uint16_t)run;
+    }
+    CK(ctx->b_tab.ensure(h.size() * sizeof(uint16_t)));
+    CK(cudaMemcpyAsync(ctx->b_tab.p, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tab.min_matches = ctx->b_tab.as<uint16_t>();
+    ctx->tab.max_clip = ctx->tab.min_matches + (L + 1);
+    ctx->tab.max_k_upto = ctx->tab.max_clip + (L + 1);
+    ctx->tab.max_len = L;
+    ctx->tab_len = L;
+    return HLO_OK;
+}
+
+static VerifyParams verify_params(const hlo_ctx *ctx) {
+    VerifyParams v;
+    v.k = ctx->P.k, v.a = ctx->P.match_score, v.b = ctx->P.mismatch_pen, v.n = ctx->P.ambi_pen;
+    v.min_len = ctx->P.min_ovlp_len, v.max_overhang = ctx->P.max_overhang;
+    const int wmax = ctx->P.match_score + std::max(ctx->P.mismatch_pen, ctx->P.ambi_pen);
+    v.bad_limit = (33 * ctx->P.match_score + wmax - 1) / wmax - 1;  // A*33 - wmax*m > 0
+    if (v.bad_limit < 0) v.bad_limit = 0;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing
+
+static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64_t *base_off, uint32_t n_reads,
+                     const uint32_t *cluster_off, uint32_t n_clusters, const uint32_t *ids) {
+    if (!bases || !base_off) FAIL(HLO_EINVAL, "hlo_pack_reads: null input");
+    uint32_t one[2] = {0, n_reads};
+    if (!cluster_off) cluster_off = one, n_clusters = 1;
+    if (cluster_off[0] != 0 || cluster_off[n_clusters] != n_reads) FAIL(HLO_EINVAL, "cluster_off must span [0, n_reads]");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    R->ctx = ctx;
+    R->h_len.resize(n_reads), R->h_ids.resize(n_reads), R->h_cidx.resize(n_reads);
+    R->h_cluster_off.assign(cluster_off, cluster_off + n_clusters + 1);
+    std::vector<uint32_t> cbase(n_reads), nrank(n_reads);
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < n_reads; ++i) {
+        if (base_off[i + 1] < base_off[i]) FAIL(HLO_EINVAL, "base_off not monotone at read %u", i);
+        const uint64_t l = base_off[i + 1] - base_off[i];
+        if (l > 32767) FAIL(HLO_ERANGE, "read %u is %llu bp; limit is 32767 (anchor fields of hlo_cand)", i, (unsigned long long)l);
+        R->h_len[i] = (uint32_t)l;
+        max_len = std::max(max_len, (uint32_t)l);
+    }
+    for (uint32_t c = 0; c < n_clusters; ++c) {
+        if (cluster_off[c + 1] < cluster_off[c]) FAIL(HLO_EINVAL, "cluster_off not monotone");
+        const uint32_t r0 = cluster_off[c], r1 = cluster_off[c + 1];
+        for (uint32_t i = r0; i < r1; ++i) cbase[i] = r0, R->h_cidx[i] = c, R->h_ids[i] = ids ? ids[i] : i - r0;
+        if (!ids) {
+            for (uint32_t i = r0; i < r1; ++i) nrank[i] = i;
+        } else {
+            std::vector<uint32_t> ord(r1 - r0);
+            for (uint32_t i = 0; i < r1 - r0; ++i) ord[i] = r0 + i;
+            std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b] || (ids[a] == ids[b] && a < b); });
+            for (uint32_t i = 0; i + 1 < r1 - r0; ++i)
+                if (ids[ord[i]] == ids[ord[i + 1]]) FAIL(HLO_EINVAL, "duplicate id %u in cluster %u", ids[ord[i]], c);
+            for (uint32_t i = 0; i < r1 - r0; ++i) nrank[ord[i]] = r0 + i;
+        }
+    }
+    // the ungapped model equals minimap2's banded extension only while an accepted overlap cannot hold a
+    // stretch that triggers z-drop / loses the end bonus
+    {
+        const int lim = std::min(ctx->P.end_bonus, 100);
+        if ((1.0 - ctx->P.min_identity) * (double)max_len * (double)std::max(ctx->P.mismatch_pen, 1) >= (double)lim && max_len > 0)
+            FAIL(HLO_EUNSUPPORTED, "reads of %u bp at min_identity %.3f leave the domain where the ungapped end rule is exact", max_len,
+                 ctx->P.min_identity);
+    }
+    const uint64_t n_bases = base_off[n_reads];
+    uint32_t words = (max_len + 15) / 16;
+    uint32_t stride_w = std::max(16u, (words + 15u) & ~15u);
+    DevReads &d = R->d;
+    d.n_reads = n_reads, d.n_clusters = n_clusters, d.stride_w = stride_w, d.max_len = max_len, d.n_bases = n_bases;
+    const size_t plane_words = (size_t)n_reads * stride_w;
+    CK(R->b_ascii.ensure(n_bases + 16));
+    CK(R->b_off.ensure(((size_t)n_reads + 1) * 8));
+    CK(R->b_len.ensure((size_t)n_reads * 4 + 4));
+    CK(R->b_cbase.ensure((size_t)n_reads * 4 + 4));
+    CK(R->b_cidx.ensure((size_t)n_reads * 4 + 4));
+    CK(R->b_ids.ensure((size_t)n_reads * 4 + 4));
+    CK(R->b_nrank.ensure((size_t)n_reads * 4 + 4));
+    CK(R->b_bases.ensure(plane_words * 2 * 4 + 256));
+    CK(R->b_amb.ensure(plane_words * 2 * 4 + 256));
+    CK(R->b_ambcount.ensure(16));
+    d.len = R->b_len.as<uint32_t>(), d.cbase = R->b_cbase.as<uint32_t>(), d.cidx = R->b_cidx.as<uint32_t>();
+    d.ids = R->b_ids.as<uint32_t>(), d.nrank = R->b_nrank.as<uint32_t>();
+    d.bases = R->b_bases.as<uint32_t>(), d.amb = R->b_amb.as<uint32_t>();
+    CK(cudaEventRecord(ctx->ev[ST_BEGIN], s));
+    if (n_reads) {
+        CK(cudaMemcpyAsync(R->b_ascii.p, bases, n_bases, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(R->b_off.p, base_off, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.len, R->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.cbase, cbase.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.cidx, R->h_cidx.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.ids, R->h_ids.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.nrank, nrank.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));
+    CK(cudaEventRecord(ctx->ev[ST_H2D], s));
+    launch_pack(R->b_ascii.as<uint8_t>(), R->b_off.as<uint64_t>(), d, R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[ST_PACK], s));
+    uint32_t amb = 0;
+    CK(cudaMemcpyAsync(&amb, R->b_ambcount.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));  // also keeps the caller's host buffers alive until the copies are done
+    d.has_amb = amb != 0;
+    CK(cudaEventElapsedTime(&R->h2d_ms, ctx->ev[ST_BEGIN], ctx->ev[ST_H2D]));
+    CK(cudaEventElapsedTime(&R->pack_ms, ctx->ev[ST_H2D], ctx->ev[ST_PACK]));
+    int rc = build_tables(ctx, (int)max_len);
+    if (rc) return rc;
+    return HLO_OK;
+}
+
+extern "C" int hlo_pack_reads(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, uint32_t n_reads,
+                              const uint32_t *cluster_off, uint32_t n_clusters, const uint32_t *ids, hlo_reads **out) {
+    if (!ctx || !out) return HLO_EINVAL;
+    *out = nullptr;
+    hlo_reads *R = new (std::nothrow) hlo_reads();
+    if (!R) return HLO_ENOMEM;
+    int rc = pack_into(ctx, R, bases, base_off, n_reads, cluster_off, n_clusters, ids);
+    if (rc) {
+        R->release();
+        delete R;
+        return rc;
+    }
+    *out = R;
+    return HLO_OK;
+}
+
+extern "C" void hlo_reads_free(hlo_reads *R) {
+    if (!R) return;
+    if (R->ctx) cudaSetDevice(R->ctx->device);
+    R->release();
+    delete R;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stages
+
+static int read_u32(hlo_ctx *ctx, const uint32_t *dptr, uint32_t *out) {
+    CK(cudaMemcpyAsync(out, dptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HLO_OK;
+}
+
+// sketch: count -> scan -> write.  Leaves mz_off (n_reads+1), mz_x, mz_rp, mz_rid on the device.
+static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
+    const DevReads &d = R->d;
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = d.n_reads;
+    CK(ctx->b_cnt.ensure(((size_t)n + 1) * 4));
+    CK(ctx->b_mzoff.ensure(((size_t)n + 2) * 4));
+    CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)n + 1) * 4));
+    CK(cudaMemsetAsync(ctx->b_cnt.p, 0, ((size_t)n + 1) * 4, s));
+    launch_sketch_count(d, ctx->P.w, ctx->P.k, ctx->b_cnt.as<uint32_t>(), s, &ctx->lc);
+    // scanning n+1 counts (the last is 0) puts the total at mz_off[n]
+    launch_exclusive_scan(ctx->b_cnt.as<uint32_t>(), ctx->b_mzoff.as<uint32_t>(), (uint64_t)n + 1, ctx->b_tmp.as<uint32_t>(), nullptr,
+                          s, &ctx->lc);
+    CK(cudaGetLastError());
+    uint32_t total = 0;
+    int rc = read_u32(ctx, ctx->b_mzoff.as<uint32_t>() + n, &total);
+    if (rc) return rc;
+    // guard against u32 wrap of the scan
+    if ((uint64_t)d.n_bases > 0xffffffffull) FAIL(HLO_ERANGE, "batch of %llu bases exceeds the 2^32 minimizer index range", (unsigned long long)d.n_bases);
+    ctx->n_mz = total;
+    CK(ctx->b_mzx.ensure((size_t)total * 8 + 8));
+    CK(ctx->b_mzrp.ensure((size_t)total * 4 + 4));
+    CK(ctx->b_mzrid.ensure((size_t)total * 4 + 4));
+    launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
+                        ctx->b_mzrid.as<uint32_t>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    return HLO_OK;
+}
+
+// hash sort + bucket index.  Leaves range[] (per minimizer, read order) and hits[] (hash order).
+static int run_index(hlo_ctx *ctx, const hlo_reads *R) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t n = ctx->n_mz;
+    for (int i = 0; i < 2; ++i) {
+        CK(ctx->b_keys[i].ensure(n * 8 + 8));
+        CK(ctx->b_vals[i].ensure(n * 4 + 4));
+    }
+    CK(ctx->b_tmp.ensure(std::max(sort_tmp_words(n), scan_tmp_words(n + 1)) * 4));
+    CK(ctx->b_flags.ensure(n * 4 + 4));
+    CK(ctx->b_bid.ensure(n * 4 + 4));
+    CK(ctx->b_bstart.ensure((n + 2) * 4));
+    CK(ctx->b_range.ensure(n * 8 + 8));
+    CK(ctx->b_hits.ensure(n * 8 + 8));
+    launch_hash_keys(ctx->b_mzx.as<uint64_t>(), n, ctx->b_keys[0].as<uint64_t>(), s, &ctx->lc);
+    launch_iota(ctx->b_vals[0].as<uint32_t>(), n, s, &ctx->lc);
+    uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
+    uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
+    const int cur = launch_radix_sort(keys, vals, n, 0, 2 * ctx->P.k, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[ST_SORT], s));
+    launch_mark_buckets(keys[cur], vals[cur], ctx->b_mzrid.as<uint32_t>(), ctx->b_mzrp.as<uint32_t>(), R->d.cbase, n,
+                        ctx->b_flags.as<uint32_t>(), ctx->b_hits.as<uint2>(), s, &ctx->lc);
+    launch_exclusive_scan(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
+    launch_bucket_starts(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_bstart.as<uint32_t>(), s, &ctx->lc);
+    launch_bucket_ranges(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), vals[cur], ctx->b_bstart.as<uint32_t>(), n,
+                         ctx->b_range.as<uint2>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[ST_INDEX], s));
+    return HLO_OK;
+}
+
+static uint32_t next_pow2_u32(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// candidates into b_cands; *n_out = their number
+static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, uint64_t *n_out) {
+    cudaStream_t s = ctx->stream;
+    const DevReads &d = R->d;
+    CK(ctx->b_counters.ensure(8 * 8));
+    CK(ctx->b_ovf.ensure((size_t)d.n_reads * 4 + 4));
+    uint64_t cap = std::max<uint64_t>(ctx->b_cands.cap / sizeof(hlo_cand), std::max<uint64_t>(ctx->n_mz * 3, 1 << 16));
+    PairgenArgs a;
+    a.reads = d;
+    a.mz_off = ctx->b_mzoff.as<uint32_t>(), a.mz_rp = ctx->b_mzrp.as<uint32_t>();
+    a.range = ctx->b_range.as<uint2>(), a.hits = ctx->b_hits.as<uint2>();
+    a.k = ctx->P.k, a.mid_occ = ctx->P.mid_occ;
+    a.gap_min = std::max(std::max(ctx->P.min_chain_score - ctx->P.k, ctx->P.min_seeds - 1), 0);
+    a.counters = ctx->b_counters.as<unsigned long long>();
+    a.overflow_reads = ctx->b_ovf.as<uint32_t>(), a.overflow_cap = d.n_reads;
+    unsigned long long hc[4];
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CK(ctx->b_cands.ensure(cap * sizeof(hlo_cand)));
+        a.cands = ctx->b_cands.as<hlo_cand>(), a.cand_cap = cap;
+        CK(cudaMemsetAsync(ctx->b_counters.p, 0, 64, s));
+        launch_pairgen(a, ctx->pairgen_slots_log2, s, &ctx->lc);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const uint32_t n_ovf = (uint32_t)hc[2];
+        if (n_ovf) {  // exact redo of the overflowed reads with tables in HBM
+            CK(ctx->b_ovfcnt.ensure((size_t)n_ovf * 4 + 4));
+            launch_overflow_hit_counts(a, n_ovf, ctx->b_ovfcnt.as<uint32_t>(), s, &ctx->lc);
+            std::vector<uint32_t> cnt(n_ovf), off(n_ovf + 1);
+            CK(cudaMemcpyAsync(cnt.data(), ctx->b_ovfcnt.p, (size_t)n_ovf * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            uint64_t tot = 0;
+            for (uint32_t i = 0; i < n_ovf; ++i) {
+                off[i] = (uint32_t)tot;
+                tot += next_pow2_u32(std::max(2u * cnt[i], 64u));
+                if (tot > 0xf0000000ull) FAIL(HLO_ERANGE, "overflow seed tables exceed 2^32 slots");
+            }
+            off[n_ovf] = (uint32_t)tot;
+            CK(ctx->b_gkeys.ensure(tot * 8 + 8));
+            CK(ctx->b_gmn.ensure(tot * 4 + 4));
+            CK(ctx->b_gmx.ensure(tot * 4 + 4));
+            CK(ctx->b_goff.ensure(((size_t)n_ovf + 1) * 4));
+            CK(cudaMemcpyAsync(ctx->b_goff.p, off.data(), ((size_t)n_ovf + 1) * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemsetAsync(ctx->b_gkeys.p, 0xff, tot * 8, s));
+            CK(cudaMemsetAsync(ctx->b_gmn.p, 0xff, tot * 4, s));
+            CK(cudaMemsetAsync(ctx->b_gmx.p, 0, tot * 4, s));
+            launch_pairgen_overflow(a, n_ovf, ctx->b_gkeys.as<unsigned long long>(), ctx->b_gmn.as<uint32_t>(),
+                                    ctx->b_gmx.as<uint32_t>(), ctx->b_goff.as<uint32_t>(), s, &ctx->lc);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        ctx->tm.n_overflow_reads = n_ovf;
+        ctx->tm.n_seed_hits = hc[1];
+        if (hc[0] <= cap) {
+            *n_out = hc[0];
+            return HLO_OK;
+        }
+        cap = hc[0] + hc[0] / 16 + 1024;  // buffer was too small: the kernels only counted past the end; redo
+    }
+    FAIL(HLO_ECUDA, "candidate buffer sizing did not converge");
+}
+
+// verify candidates (device) -> Rec16 in b_rec16; *n_acc = accepted
+static int run_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *d_cands, uint64_t n, uint64_t *n_acc) {
+    cudaStream_t s = ctx->stream;
+    *n_acc = 0;
+    CK(ctx->b_counters.ensure(8 * 8));
+    CK(ctx->b_rec16.ensure(n * sizeof(Rec16) + 16));
+    CK(ctx->b_deferred.ensure(n * 4 + 4));
+    CK(cudaMemsetAsync(ctx->b_counters.p, 0, 64, s));
+    VerifyArgs a;
+    a.reads = R->d, a.tab = ctx->tab, a.prm = verify_params(ctx);
+    a.cands = d_cands, a.n = n;
+    a.out = ctx->b_rec16.as<Rec16>();
+    a.counters = ctx->b_counters.as<unsigned long long>();
+    a.deferred = ctx->b_deferred.as<uint32_t>();
+    const bool force_exact = getenv("HLO_VERIFY_EXACT") != nullptr;
+    unsigned long long hc[2] = {0, 0};
+    if (force_exact) {
+        launch_verify_exact(a, nullptr, n, s, &ctx->lc);
+    } else {
+        launch_verify_fast(a, s, &ctx->lc);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (hc[1]) launch_verify_exact(a, a.deferred, hc[1], s, &ctx->lc);
+    }
+    CK(cudaGetLastError());
+    const unsigned long long n_def = hc[1];
+    CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->tm.n_deferred = force_exact ? n : n_def;
+    *n_acc = hc[0];
+    return HLO_OK;
+}
+
+static int bits_for(uint64_t v) {
+    int b = 1;
+    while (b < 63 && (1ull << b) < v) ++b;
+    return b;
+}
+
+static void finish_timing(hlo_ctx *ctx, const hlo_reads *R, int last_stage) {
+    float ms[ST_COUNT + 1] = {0};
+    auto el = [&](int a, int b) {
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, ctx->ev[a], ctx->ev[b]) != cudaSuccess) {
+            cudaGetLastError();
+            v = 0.f;
+        }
+        return v;
+    };
+    hlo_timing &t = ctx->tm;
+    t.h2d_ms = R->h2d_ms, t.pack_ms = R->pack_ms;
+    (void)ms;
+    if (last_stage >= ST_SKETCH) t.sketch_ms = el(ST_PACK, ST_SKETCH);
+    if (last_stage >= ST_SORT) t.sort_ms = el(ST_SKETCH, ST_SORT);
+    if (last_stage >= ST_INDEX) t.index_ms = el(ST_SORT, ST_INDEX);
+    if (last_stage >= ST_PAIRGEN) t.pairgen_ms = el(ST_INDEX, ST_PAIRGEN);
+    if (last_stage >= ST_VERIFY) t.verify_ms = el(ST_PAIRGEN, ST_VERIFY);
+    if (last_stage >= ST_DEDUP) t.dedup_ms = el(ST_VERIFY, ST_DEDUP);
+    if (last_stage >= ST_D2H) t.d2h_ms = el(ST_DEDUP, ST_D2H);
+    t.total_ms = t.h2d_ms + t.pack_ms + t.sketch_ms + t.sort_ms + t.index_ms + t.pairgen_ms + t.verify_ms + t.dedup_ms + t.d2h_ms;
+    t.n_reads = R->d.n_reads, t.n_bases = R->d.n_bases, t.n_minimizers = ctx->n_mz;
+    t.total_launches = ctx->lc.total, t.verify_launches = ctx->lc.verify;
+}
+
+static void reset_timing(hlo_ctx *ctx) {
+    memset(&ctx->tm, 0, sizeof ctx->tm);
+    ctx->lc = LaunchCounter();
+}
+
+extern "C" {
+
+int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64_t **read_off, uint64_t *n) {
+    if (!ctx || !R || !mz || !read_off || !n) return HLO_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    reset_timing(ctx);
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[ST_PACK], s));
+    int rc = run_sketch(ctx, R);
+    if (rc) return rc;
+    const uint64_t tot = ctx->n_mz;
+    CK(ctx->b_mz.ensure(tot * sizeof(hlo_mz) + 16));
+    launch_mz_assemble(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(), ctx->b_mzrid.as<uint32_t>(), tot, ctx->b_mz.as<hlo_mz>(), s,
+                       &ctx->lc);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
+    CK(ctx->h_mz.ensure(tot * sizeof(hlo_mz) + 16));
+    CK(ctx->h_roff.ensure(((size_t)R->d.n_reads + 1) * 8));
+    std::vector<uint32_t> off32((size_t)R->d.n_reads + 1);
+    CK(cudaMemcpyAsync(ctx->h_mz.p, ctx->b_mz.p, tot * sizeof(hlo_mz), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(off32.data(), ctx->b_mzoff.p, off32.size() * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint64_t *ro = ctx->h_roff.as<uint64_t>();
+    for (size_t i = 0; i < off32.size(); ++i) ro[i] = off32[i];
+    *mz = ctx->h_mz.as<hlo_mz>(), *read_off = ro, *n = tot;
+    finish_timing(ctx, R, ST_SKETCH);
+    return HLO_OK;
+}
+
+static int stages_to_candidates(hlo_ctx *ctx, const hlo_reads *R, uint64_t *n_c) {
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[ST_PACK], s));
+    int rc = run_sketch(ctx, R);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
+    rc = run_index(ctx, R);
+    if (rc) return rc;
+    rc = run_pairgen(ctx, R, n_c);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
+    ctx->tm.n_candidates = *n_c;
+    return HLO_OK;
+}
+
+int hlo_candidates(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand **cands, uint64_t *n) {
+    if (!ctx || !R || !cands || !n) return HLO_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    reset_timing(ctx);
+    uint64_t n_c = 0;
+    int rc = stages_to_candidates(ctx, R, &n_c);
+    if (rc) return rc;
+    CK(ctx->h_cands.ensure(n_c * sizeof(hlo_cand) + 16));
+    CK(cudaMemcpyAsync(ctx->h_cands.p, ctx->b_cands.p, n_c * sizeof(hlo_cand), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    hlo_cand *h = ctx->h_cands.as<hlo_cand>();
+    std::sort(h, h + n_c, [](const hlo_cand &x, const hlo_cand &y) {
+        if (x.q != y.q) return x.q < y.q;
+        if (x.t != y.t) return x.t < y.t;
+        const uint32_t sx = x.strand_anchor & 1u, sy = y.strand_anchor & 1u;
+        if (sx != sy) return sx < sy;
+        return x.diag < y.diag;
+    });
+    *cands = h, *n = n_c;
+    finish_timing(ctx, R, ST_PAIRGEN);
+    return HLO_OK;
+}
+
+int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t n, hlo_recs *out) {
+    if (!ctx || !R || (!cands && n) || !out) return HLO_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    reset_timing(ctx);
+    cudaStream_t s = ctx->stream;
+    for (uint64_t i = 0; i < n; ++i)
+        if (cands[i].q >= R->d.n_reads || cands[i].t >= R->d.n_reads) FAIL(HLO_EINVAL, "candidate %llu names a read outside the batch", (unsigned long long)i);
+    CK(ctx->b_cands.ensure(n * sizeof(hlo_cand) + 16));
+    CK(cudaMemcpyAsync(ctx->b_cands.p, cands, n * sizeof(hlo_cand), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
+    uint64_t n_acc = 0;
+    int rc = run_verify(ctx, R, ctx->b_cands.as<hlo_cand>(), n, &n_acc);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
+    CK(ctx->h_rec16.ensure(n_acc * sizeof(Rec16) + 16));
+    CK(cudaMemcpyAsync(ctx->h_rec16.p, ctx->b_rec16.p, n_acc * sizeof(Rec16), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    Rec16 *h = ctx->h_rec16.as<Rec16>();
+    std::sort(h, h + n_acc, [](const Rec16 &x, const Rec16 &y) {
+        if (x.q != y.q) return x.q < y.q;
+        if (x.t != y.t) return x.t < y.t;
+        if ((x.ds & 1u) != (y.ds & 1u)) return (x.ds & 1u) < (y.ds & 1u);
+        if (x.ds != y.ds) return x.ds < y.ds;
+        return x.kb < y.kb;
+    });
+    CK(ctx->h_out.ensure(n_acc * sizeof(hlo_rec) + 16));
+    CK(ctx->h_aux.ensure(n_acc * sizeof(hlo_rec_aux) + 16));
+    hlo_rec *ro = ctx->h_out.as<hlo_rec>();
+    hlo_rec_aux *ao = ctx->h_aux.as<hlo_rec_aux>();
+    for (uint64_t i = 0; i < n_acc; ++i) {
+        const Rec16 &x = h[i];
+        expand_record(R->h_ids[x.q], R->h_ids[x.t], (int)R->h_len[x.q], (int)R->h_len[x.t], (int)(x.ds >> 1) - HLO_DIAG_BIAS,
+                      (int)(x.ds & 1u), x.kb & 0xffffu, &ro[i]);
+        ao[i].cluster = R->h_cidx[x.q], ao[i].blocklen = x.kb >> 16;
+    }
+    out->rec = ro, out->aux = ao, out->n = n_acc, out->cluster_off = nullptr, out->n_clusters = R->d.n_clusters;
+    ctx->tm.n_candidates = n, ctx->tm.n_accepted = n_acc, ctx->tm.n_records = n_acc;
+    {
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, ctx->ev[ST_PAIRGEN], ctx->ev[ST_VERIFY]) == cudaSuccess) ctx->tm.verify_ms = v;
+        else cudaGetLastError();
+        ctx->tm.total_ms = ctx->tm.verify_ms;
+        ctx->tm.n_reads = R->d.n_reads, ctx->tm.n_bases = R->d.n_bases;
+        ctx->tm.total_launches = ctx->lc.total, ctx->tm.verify_launches = ctx->lc.verify;
+    }
+    return HLO_OK;
+}
+
+int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
+    if (!ctx || !R || !out) return HLO_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    reset_timing(ctx);
+    cudaStream_t s = ctx->stream;
+    const DevReads &d = R->d;
+    uint64_t n_c = 0, n_acc = 0;
+    int rc = stages_to_candidates(ctx, R, &n_c);
+    if (rc) return rc;
+    rc = run_verify(ctx, R, ctx->b_cands.as<hlo_cand>(), n_c, &n_acc);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
+    ctx->tm.n_accepted = n_acc;
+    if (n_acc > 0xfffffff0ull) FAIL(HLO_ERANGE, "more than 2^32 accepted overlaps in one batch");
+    // per-pair keep-longest + (idA, idB) order + expansion
+    for (int i = 0; i < 2; ++i) {
+        CK(ctx->b_keys[i].ensure(n_acc * 8 + 8));
+        CK(ctx->b_vals[i].ensure(n_acc * 4 + 4));
+    }
+    CK(ctx->b_tmp.ensure(std::max(sort_tmp_words(n_acc), scan_tmp_words(n_acc + 1)) * 4));
+    CK(ctx->b_flags.ensure(n_acc * 4 + 4));
+    CK(ctx->b_best.ensure(n_acc * 4 + 4));
+    CK(ctx->b_pos.ensure(n_acc * 4 + 8));
+    CK(ctx->b_out.ensure(n_acc * sizeof(hlo_rec) + 32));
+    CK(ctx->b_aux.ensure(n_acc * sizeof(hlo_rec_aux) + 32));
+    CK(ctx->b_coff.ensure(((size_t)d.n_clusters + 2) * 8));
+    uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
+    uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
+    launch_record_keys(ctx->b_rec16.as<Rec16>(), n_acc, d, keys[0], vals[0], s, &ctx->lc);
+    const int nb = bits_for(std::max<uint64_t>(d.n_reads, 2));
+    int cur = launch_radix_sort(keys, vals, n_acc, 0, nb, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+    {
+        uint64_t *k2[2] = {keys[cur], keys[cur ^ 1]};
+        uint32_t *v2[2] = {vals[cur], vals[cur ^ 1]};
+        const int c2 = launch_radix_sort(k2, v2, n_acc, 32, 32 + nb, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+        cur = c2 ? cur ^ 1 : cur;
+    }
+    launch_dedup_flags(keys[cur], vals[cur], ctx->b_rec16.as<Rec16>(), n_acc, 1, ctx->b_flags.as<uint32_t>(), ctx->b_best.as<uint32_t>(),
+                       s, &ctx->lc);
+    uint32_t n_out32 = 0;
+    CK(ctx->h_small.ensure(64));
+    launch_exclusive_scan(ctx->b_flags.as<uint32_t>(), ctx->b_pos.as<uint32_t>(), n_acc, ctx->b_tmp.as<uint32_t>(),
+                          ctx->b_counters.as<uint32_t>() + 8, s, &ctx->lc);
+    launch_expand_records(ctx->b_flags.as<uint32_t>(), ctx->b_pos.as<uint32_t>(), ctx->b_best.as<uint32_t>(), ctx->b_rec16.as<Rec16>(),
+                          n_acc, d, ctx->b_out.as<hlo_rec>(), ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t n_out = n_out32;
+    launch_cluster_offsets(ctx->b_aux.as<hlo_rec_aux>(), n_out, d.n_clusters, ctx->b_coff.as<unsigned long long>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[ST_DEDUP], s));
+    CK(ctx->h_out.ensure(n_out * sizeof(hlo_rec) + 32));
+    CK(ctx->h_aux.ensure(n_out * sizeof(hlo_rec_aux) + 32));
+    CK(ctx->h_coff.ensure(((size_t)d.n_clusters + 2) * 8));
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, n_out * sizeof(hlo_rec), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_aux.p, ctx->b_aux.p, n_out * sizeof(hlo_rec_aux), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_coff.p, ctx->b_coff.p, ((size_t)d.n_clusters + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[ST_D2H], s));
+    CK(cudaStreamSynchronize(s));
+    out->rec = ctx->h_out.as<hlo_rec>(), out->aux = ctx->h_aux.as<hlo_rec_aux>(), out->n = n_out;
+    out->cluster_off = ctx->h_coff.as<uint64_t>(), out->n_clusters = d.n_clusters;
+    ctx->tm.n_records = n_out;
+    finish_timing(ctx, R, ST_D2H);
+    return HLO_OK;
+}
+
+int hlo_overlap_host(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, uint32_t n_reads, const uint32_t *cluster_off,
+                     uint32_t n_clusters, hlo_recs *out) {
+    if (!ctx || !out) return HLO_EINVAL;
+    int rc = pack_into(ctx, &ctx->scratch_reads, bases, base_off, n_reads, cluster_off, n_clusters, nullptr);
+    if (rc) return rc;
+    return hlo_overlap_batch(ctx, &ctx->scratch_reads, out);
+}
+
+int hlo_get_timing(const hlo_ctx *ctx, hlo_timing *t) {
+    if (!ctx || !t) return HLO_EINVAL;
+    *t = ctx->tm;
+    return HLO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// kernels.cuh — host-callable launchers of the sm_100a kernels (one .cu per stage).
+#pragma once
+#include "common.cuh"
+
+namespace hlo {
+
+struct LaunchCounter {
+    uint64_t total = 0, verify = 0;
+};
+
+// ---- pack.cu --------------------------------------------------------------------------------
+// ASCII -> 2-bit rows (both strands) + ambiguity planes.  amb_count (device u32) receives the number
+// of ambiguous bases.  len[] must hold plain lengths on entry; the kernel ORs in HLO_AMB_FLAG.
+void launch_pack(const uint8_t *ascii, const uint64_t *base_off, DevReads r, uint32_t *amb_count, cudaStream_t s,
+                 LaunchCounter *lc);
+
+// ---- sketch.cu ------------------------------------------------------------------------------
+// pass 0: count[r] = number of minimizers of read r;  pass 1: write them at off[r].
+void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc);
+void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp,
+                         uint32_t *mz_rid, cudaStream_t s, LaunchCounter *lc);
+void launch_mz_assemble(const uint64_t *mz_x, const uint32_t *mz_rp, const uint32_t *mz_rid, uint64_t n, hlo_mz *out,
+                        cudaStream_t s, LaunchCounter *lc);
+
+// ---- scan_sort.cu ---------------------------------------------------------------------------
+// Exclusive prefix sum of n u32 values (in may alias out).  `tmp` must hold scan_tmp_words(n) u32.
+// If total != nullptr, *total (device u32) receives the sum of all inputs.
+size_t scan_tmp_words(uint64_t n);
+void launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *tmp, uint32_t *total, cudaStream_t s,
+                           LaunchCounter *lc);
+
+// Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [begin_bit, end_bit).
+// keys/vals are double buffers of n elements each; returns which buffer (0/1) holds the result.
+// `tmp` must hold sort_tmp_words(n) u32.
+size_t sort_tmp_words(uint64_t n);
+int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begin_bit, int end_bit, uint32_t *tmp,
+                      cudaStream_t s, LaunchCounter *lc);
+
+void launch_iota(uint32_t *v, uint64_t n, cudaStream_t s, LaunchCounter *lc);
+void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, LaunchCounter *lc);
+
+// ---- pairgen.cu -----------------------------------------------------------------------------
+// index build on the hash-sorted minimizers
+void launch_hash_keys(const uint64_t *mz_x, uint64_t n, uint64_t *keys, cudaStream_t s, LaunchCounter *lc);
+void launch_mark_buckets(const uint64_t *skeys, const uint32_t *svals, const uint32_t *mz_rid, const uint32_t *mz_rp,
+                         const uint32_t *cbase, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s, LaunchCounter *lc);
+void launch_bucket_starts(const uint32_t *flags, const uint32_t *bid, uint64_t n, uint32_t *bstart, cudaStream_t s,
+                          LaunchCounter *lc);
+void launch_bucket_ranges(const uint32_t *flags, const uint32_t *bid, const uint32_t *svals, const uint32_t *bstart,
+                          uint64_t n, uint2 *range, cudaStream_t s, LaunchCounter *lc);
+
+struct PairgenArgs {
+    DevReads reads;
+    const uint32_t *mz_off;  // [n_reads+1]
+    const uint32_t *mz_rp;   // [n_mz] pos<<1|strand
+    const uint2 *range;      // [n_mz] bucket [s,e) in hits
+    const uint2 *hits;       // [n_mz] (rid, pos<<1|strand) in hash order
+    int k, mid_occ, gap_min;
+    hlo_cand *cands;         // output
+    uint64_t cand_cap;
+    unsigned long long *counters;  // [0] candidates, [1] seed hits, [2] overflow reads, [3] work counter
+    uint32_t *overflow_reads;      // list of reads whose shared-memory table overflowed
+    uint32_t overflow_cap;
+};
+// fast path: one warp per query read, seed table in shared memory (slots_log2 slots per warp)
+void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc);
+// exact fallback for overflowed reads: one block per read, table in global memory
+void launch_pairgen_overflow(const PairgenArgs &a, uint32_t n_overflow, unsigned long long *gtable_keys, uint32_t *gtable_mn,
+                             uint32_t *gtable_mx, const uint32_t *gtable_off, cudaStream_t s, LaunchCounter *lc);
+void launch_overflow_hit_counts(const PairgenArgs &a, uint32_t n_overflow, uint32_t *counts, cudaStream_t s, LaunchCounter *lc);
+
+// ---- verify.cu ------------------------------------------------------------------------------
+struct VerifyArgs {
+    DevReads reads;
+    VerifyTables tab;
+    VerifyParams prm;
+    const hlo_cand *cands;
+    uint64_t n;
+    Rec16 *out;                    // accepted records (unordered)
+    unsigned long long *counters;  // [0] accepted, [1] deferred
+    uint32_t *deferred;            // candidate indices for the exact path
+};
+void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc);
+// exact per-candidate path: idx == nullptr -> candidates [0,n); else the n listed candidates
+void launch_verify_exact(const VerifyArgs &a, const uint32_t *idx, uint64_t n, cudaStream_t s, LaunchCounter *lc);
+
+// ---- records.cu -----------------------------------------------------------------------------
+void launch_record_keys(const Rec16 *rec, uint64_t n, DevReads r, uint64_t *keys, uint32_t *vals, cudaStream_t s,
+                        LaunchCounter *lc);
+// per run of equal keys choose the best record; flags[i] = 1 at the run start, best[i] = chosen index
+void launch_dedup_flags(const uint64_t *skeys, const uint32_t *svals, const Rec16 *rec, uint64_t n, int dedup, uint32_t *flags,
+                        uint32_t *best, cudaStream_t s, LaunchCounter *lc);
+void launch_expand_records(const uint32_t *flags, const uint32_t *pos, const uint32_t *best, const Rec16 *rec, uint64_t n,
+                           DevReads r, hlo_rec *out, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc);
+void launch_cluster_offsets(const hlo_rec_aux *aux, uint64_t n, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,
+                            LaunchCounter *lc);
+
+}  // namespace hlo

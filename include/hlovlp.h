@@ -136,6 +136,11 @@ int hlo_device_count(void);
 int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out);
 void hlo_ctx_destroy(hlo_ctx *ctx);
 
+/* Page-locked host memory for the input buffers (plain malloc'd memory works too, but the
+ * host->device copy of pageable memory is staged and slower). */
+void *hlo_host_alloc(size_t bytes);
+void hlo_host_free(void *p);
+
 /*
  * Upload and 2-bit-pack a batch of clusters.  Replaces rename_fas.py:48-75 + fastq2fasta.py:32-40
  * + minimap2's own sequence encoding: reads of cluster c are seq[cluster_off[c] .. cluster_off[c+1]),
