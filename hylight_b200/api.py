@@ -1,0 +1,277 @@
+"""ctypes binding of libhlovlp (include/hlovlp.h) — the only way Python reaches the CUDA path.
+
+There is no CPU fallback: importing works without a GPU (so the symbol table can be checked), but
+every compute entry point raises `HloError` when the library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhlovlp.so")
+
+CAND_DT = np.dtype([("q", "<u4"), ("t", "<u4"), ("diag", "<i4"), ("strand_anchor", "<u4")])
+REC_DT = np.dtype([("idA", "<u4"), ("idB", "<u4"), ("OHA", "<i4"), ("OHB", "<i4"), ("OLA", "<u4"), ("OLB", "<u4"),
+                   ("K", "<u4"), ("ori", "<u4")])
+AUX_DT = np.dtype([("cluster", "<u4"), ("blocklen", "<u4")])
+MZ_DT = np.dtype([("x", "<u8"), ("y", "<u8")])
+
+# every symbol include/hlovlp.h declares (tests/test_abi.py checks the header against this list too)
+ABI_SYMBOLS = [
+    "hlo_params_default", "hlo_abi_version", "hlo_strerror", "hlo_last_error", "hlo_device_count",
+    "hlo_ctx_create", "hlo_ctx_destroy", "hlo_host_alloc", "hlo_host_free", "hlo_pack_reads", "hlo_reads_free",
+    "hlo_sketch", "hlo_candidates", "hlo_verify", "hlo_overlap_batch", "hlo_overlap_host", "hlo_get_timing",
+    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream",
+]
+
+
+class HloError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("libhlovlp: %s (status %d)" % (msg, status))
+        self.status = status
+
+
+class Params(C.Structure):
+    _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("min_seeds", C.c_int32), ("min_chain_score", C.c_int32),
+                ("mid_occ", C.c_int32), ("match_score", C.c_int32), ("mismatch_pen", C.c_int32),
+                ("ambi_pen", C.c_int32), ("end_bonus", C.c_int32), ("min_dp_score", C.c_int32),
+                ("min_ovlp_len", C.c_int32), ("max_overhang", C.c_int32), ("min_identity", C.c_double),
+                ("overhang_ratio", C.c_double)]
+
+
+class Recs(C.Structure):
+    _fields_ = [("rec", C.c_void_p), ("aux", C.c_void_p), ("n", C.c_uint64), ("cluster_off", C.c_void_p),
+                ("n_clusters", C.c_uint32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "pack_ms", "sketch_ms", "sort_ms", "index_ms", "pairgen_ms",
+                                         "verify_ms", "dedup_ms", "d2h_ms", "total_ms", "verify_fast_ms", "reserved0")] + \
+               [(n, C.c_uint64) for n in ("n_reads", "n_bases", "n_minimizers", "n_seed_hits", "n_candidates",
+                                          "n_accepted", "n_records", "n_deferred", "n_overflow_reads",
+                                          "verify_launches", "total_launches")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load libhlovlp.so (built in-tree by `make -C hylight_b200/csrc`); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HloError(-2, "%s not found: build it with `make -C hylight_b200/csrc` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.hlo_strerror.restype = C.c_char_p
+        L.hlo_last_error.restype = C.c_char_p
+        L.hlo_last_error.argtypes = [C.c_void_p]
+        L.hlo_host_alloc.restype = C.c_void_p
+        L.hlo_host_alloc.argtypes = [C.c_size_t]
+        L.hlo_host_free.argtypes = [C.c_void_p]
+        L.hlo_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.hlo_ctx_destroy.argtypes = [C.c_void_p]
+        L.hlo_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                     C.c_void_p, C.POINTER(C.c_void_p)]
+        L.hlo_reads_free.argtypes = [C.c_void_p]
+        L.hlo_sketch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_uint64)]
+        L.hlo_candidates.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.hlo_verify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Recs)]
+        L.hlo_overlap_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Recs)]
+        L.hlo_overlap_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                       C.POINTER(Recs)]
+        L.hlo_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+        L.hlo_write_sfo.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p]
+        L.hlo_write_overlaps.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p]
+        L.hlo_format_overlap_line.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.hlo_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.hlo_stream.restype = C.c_void_p
+        L.hlo_stream.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def default_params(**kw):
+    p = Params()
+    lib().hlo_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def device_count():
+    return int(lib().hlo_device_count())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _copy_out(ptr, n, dt):
+    if not n:
+        return np.zeros(0, dtype=dt)
+    buf = (C.c_uint8 * (n * dt.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=n).copy()
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory from hlo_host_alloc (fast H2D for the e2e path)."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().hlo_host_alloc(max(int(nbytes), 1))
+        if not self.ptr:
+            raise HloError(-4, "hlo_host_alloc(%d) failed" % nbytes)
+        self.nbytes = int(nbytes)
+        self.array = np.frombuffer((C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr), dtype=np.uint8,
+                                   count=self.nbytes)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().hlo_host_free(self.ptr)
+            self.ptr = None
+
+
+class Reads:
+    def __init__(self, ctx, handle, n_reads, n_clusters):
+        self.ctx, self.handle, self.n_reads, self.n_clusters = ctx, handle, n_reads, n_clusters
+
+    def free(self):
+        if self.handle:
+            lib().hlo_reads_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One CUDA device + stream.  Single-threaded; create one per device/thread."""
+
+    def __init__(self, device=0, params=None, **kw):
+        self.params = params if params is not None else default_params(**kw)
+        h = C.c_void_p()
+        rc = lib().hlo_ctx_create(int(device), C.byref(self.params), C.byref(h))
+        if rc:
+            raise HloError(rc, lib().hlo_strerror(rc).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().hlo_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise HloError(rc, "%s: %s" % (lib().hlo_strerror(rc).decode(), lib().hlo_last_error(self.h).decode()))
+
+    def set_option(self, name, value):
+        self._check(lib().hlo_set_option(self.h, name.encode(), int(value)))
+
+    def pack(self, batch, ids=None):
+        """batch: anything with .bases (u8), .base_off (u64), .cluster_off (u32)."""
+        bases = np.ascontiguousarray(batch.bases, dtype=np.uint8)
+        off = np.ascontiguousarray(batch.base_off, dtype=np.uint64)
+        coff = np.ascontiguousarray(batch.cluster_off, dtype=np.uint32)
+        if ids is None:
+            ids = getattr(batch, "ids", None)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        h = C.c_void_p()
+        self._check(lib().hlo_pack_reads(self.h, _ptr(bases), _ptr(off), len(off) - 1, _ptr(coff), len(coff) - 1,
+                                         _ptr(ids), C.byref(h)))
+        return Reads(self, h, len(off) - 1, len(coff) - 1)
+
+    def sketch(self, reads):
+        mz, ro, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(lib().hlo_sketch(self.h, reads.handle, C.byref(mz), C.byref(ro), C.byref(n)))
+        return _copy_out(mz.value, n.value, MZ_DT), _copy_out(ro.value, reads.n_reads + 1, np.dtype("<u8"))
+
+    def candidates(self, reads):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(lib().hlo_candidates(self.h, reads.handle, C.byref(p), C.byref(n)))
+        return _copy_out(p.value, n.value, CAND_DT)
+
+    def _recs(self, r, copy=True):
+        rec = _copy_out(r.rec, r.n, REC_DT)
+        aux = _copy_out(r.aux, r.n, AUX_DT)
+        coff = _copy_out(r.cluster_off, r.n_clusters + 1, np.dtype("<u8")) if r.cluster_off else None
+        return rec, aux, coff
+
+    def verify(self, reads, cands):
+        cands = np.ascontiguousarray(cands, dtype=CAND_DT)
+        r = Recs()
+        self._check(lib().hlo_verify(self.h, reads.handle, _ptr(cands), len(cands), C.byref(r)))
+        return self._recs(r)[:2]
+
+    def overlap_batch(self, reads):
+        r = Recs()
+        self._check(lib().hlo_overlap_batch(self.h, reads.handle, C.byref(r)))
+        return self._recs(r)
+
+    def overlap_host_raw(self, bases_ptr, off_ptr, n_reads, coff_ptr, n_clusters):
+        """e2e entry with raw host pointers; returns the ctx-owned Recs struct without copying."""
+        r = Recs()
+        self._check(lib().hlo_overlap_host(self.h, bases_ptr, off_ptr, n_reads, coff_ptr, n_clusters, C.byref(r)))
+        return r
+
+    def overlap_host(self, batch):
+        bases = np.ascontiguousarray(batch.bases, dtype=np.uint8)
+        off = np.ascontiguousarray(batch.base_off, dtype=np.uint64)
+        coff = np.ascontiguousarray(batch.cluster_off, dtype=np.uint32)
+        r = self.overlap_host_raw(_ptr(bases), _ptr(off), len(off) - 1, _ptr(coff), len(coff) - 1)
+        return self._recs(r)
+
+    def stream_handle(self):
+        """cudaStream_t of the ctx as an integer (wrap with torch.cuda.ExternalStream to record events on it)."""
+        return int(lib().hlo_stream(self.h) or 0)
+
+    def timing(self):
+        t = Timing()
+        self._check(lib().hlo_get_timing(self.h, C.byref(t)))
+        return t.as_dict()
+
+
+def write_sfo(rec, path):
+    rec = np.ascontiguousarray(rec, dtype=REC_DT)
+    rc = lib().hlo_write_sfo(_ptr(rec), len(rec), os.fsencode(path))
+    if rc:
+        raise HloError(rc, lib().hlo_strerror(rc).decode())
+
+
+def write_overlaps(rec, path):
+    rec = np.ascontiguousarray(rec, dtype=REC_DT)
+    rc = lib().hlo_write_overlaps(_ptr(rec), len(rec), os.fsencode(path))
+    if rc:
+        raise HloError(rc, lib().hlo_strerror(rc).decode())
+
+
+def format_overlap_line(rec_row):
+    r = np.ascontiguousarray(np.asarray(rec_row, dtype=REC_DT).reshape(1))
+    buf = C.create_string_buffer(160)
+    n = lib().hlo_format_overlap_line(_ptr(r), buf, 160)
+    if n < 0:
+        raise HloError(n, "hlo_format_overlap_line")
+    return buf.value.decode()

