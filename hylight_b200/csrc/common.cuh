@@ -10,17 +10,21 @@ namespace hlo {
 // ---------------------------------------------------------------------------------------------
 // Device-resident batch of packed reads.
 //
-// Layout in HBM: every read has one row of `stride_w` 32-bit words per strand,
-// 16 bases per word, base i at bits [2(i%16), 2(i%16)+2) of word i/16 (little-endian in the word);
-// A=0 C=1 G=2 T=3, ambiguous bases are stored as 0 and flagged in the parallel `amb` plane with the
-// same geometry (01 = ambiguous).  Plane 0 holds the read as given, plane 1 its reverse complement,
-// so the verify kernel always compares two forward-packed rows.  stride_w is a multiple of 16 words
-// (64 B): a row never straddles a 128 B line more than its length requires, and a 4-lane group reads
-// one row of <= 256 bases with one LDG.128 per lane.
+// Layout in HBM: every read has one row of `stride_w` = 4*nv 32-bit words per
+// strand (nv 16-byte vectors; 150 bp -> 48 B, 250 bp -> 64 B), 16 bases per word, base i at bits
+// [2(i%16), 2(i%16)+2) of word i/16 (little-endian in the word); A=0 C=1 G=2 T=3, ambiguous bases are
+// stored as 0 and flagged in the parallel `amb` plane with the same geometry (01 = ambiguous).
+// Plane 0 holds the read as given, plane 1 its reverse complement, so the verify kernel always
+// compares two forward-packed rows (and can move a target-limited overlap end to position 0 by
+// switching both reads to the other plane).  Rows are 16-byte aligned: a thread reads a row with nv
+// LDG.128.  The allocation is padded by PAD_WORDS words on both sides (shifted vector loads may run
+// past a row; what they fetch there is masked out).
 struct DevReads {
     uint32_t n_reads = 0, n_clusters = 0;
-    uint32_t stride_w = 0;  // words per row
+    uint32_t stride_w = 0;  // words per row = 4 * nv
+    uint32_t nv = 0;        // 16-byte vectors per row
     uint32_t max_len = 0;
+    uint32_t max_cluster = 0;  // reads in the largest cluster
     uint64_t n_bases = 0;
     int has_amb = 0;        // any ambiguous base in the batch
     uint32_t *len = nullptr;    // [n] read length | (has ambiguous base ? 0x80000000 : 0)
@@ -28,9 +32,11 @@ struct DevReads {
     uint32_t *cidx = nullptr;   // [n] cluster index
     uint32_t *ids = nullptr;    // [n] decimal name
     uint32_t *nrank = nullptr;  // [n] cbase + numeric rank of the name inside the cluster
+    uint32_t *perm = nullptr;   // [n] x -> read: reads of a cluster in strcmp order of their decimal names
     uint32_t *bases = nullptr;  // [2][n][stride_w]
     uint32_t *amb = nullptr;    // [2][n][stride_w]
 };
+#define HLO_PAD_WORDS 64
 
 #define HLO_MAX_W_PUBLIC 32  // window sizes the sketch kernel keeps in its per-thread ring
 #define HLO_LEN_MASK 0x7fffffffu
@@ -43,6 +49,34 @@ struct Rec16 {
     uint32_t kb;  // K | blocklen << 16
 };
 #define HLO_DIAG_BIAS (1 << 30)
+
+// Internal candidate (16 B) = hlo_cand + both read lengths, so that the verify kernel knows the overlap
+// geometry before it touches a row:
+//   z = (diag + 32768) | ql << 16 | strand << 31
+//   w = tl | EL << 15 | ER << 22 | amb << 29
+// EL / ER = number of bases between the overlap's left / right end and the outermost anchor k-mer,
+// capped at 127 (the end rule never looks further inside the supported domain);
+// amb = either read holds an ambiguous base.
+struct CandI {
+    uint32_t q, t, z, w;
+};
+#define HLO_REGION_CAP 127
+__host__ __device__ __forceinline__ CandI make_candi(uint32_t q, uint32_t t, int diag, uint32_t strand, uint32_t ql, uint32_t tl,
+                                                     int a_start, int a_end, uint32_t amb) {
+    const int js = diag < 0 ? -diag : 0;
+    const int je = (int)ql < (int)tl - diag ? (int)ql : (int)tl - diag;
+    if (a_end == 0) a_start = je, a_end = js;  // no anchor information: each end region is the whole overlap
+    if (a_start < js) a_start = js;
+    if (a_end > je) a_end = je;
+    int el = a_start - js, er = je - a_end;
+    el = el < 0 ? 0 : (el > HLO_REGION_CAP ? HLO_REGION_CAP : el);
+    er = er < 0 ? 0 : (er > HLO_REGION_CAP ? HLO_REGION_CAP : er);
+    CandI c;
+    c.q = q, c.t = t;
+    c.z = (uint32_t)(diag + 32768) | ql << 16 | strand << 31;
+    c.w = tl | (uint32_t)el << 15 | (uint32_t)er << 22 | (amb & 1u) << 29;
+    return c;
+}
 
 // device tables for the python-double threshold tests (filter_ovlp_inline.py:58,83)
 struct VerifyTables {

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -74,12 +75,12 @@ struct hlo_reads {
     hlo_ctx *ctx = nullptr;
     int device = -1;
     DevReads d;
-    DevBuf b_ascii, b_off, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_bases, b_amb, b_ambcount;
-    std::vector<uint32_t> h_len, h_ids, h_cidx, h_cluster_off;
+    DevBuf b_ascii, b_off, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_bases, b_amb, b_ambcount;
+    std::vector<uint32_t> h_len, h_ids, h_cidx, h_cluster_off, h_perm;
     float h2d_ms = 0.f, pack_ms = 0.f;
     void release() {
         b_ascii.release(), b_off.release(), b_len.release(), b_cbase.release(), b_cidx.release(), b_ids.release();
-        b_nrank.release(), b_bases.release(), b_amb.release(), b_ambcount.release();
+        b_nrank.release(), b_perm.release(), b_bases.release(), b_amb.release(), b_ambcount.release();
     }
 };
 
@@ -91,8 +92,8 @@ struct hlo_ctx {
     std::string err;
     LaunchCounter lc;
     hlo_timing tm;
-    int pairgen_slots_log2 = 10;
-    int verify_exact = 0, repack = 0, d2h = 1;
+    int pairgen_slots_log2 = 8;
+    int verify_exact = 0, repack = 0, d2h = 1, pairgen_generic = 0;
     cudaEvent_t ev_vf[2] = {};
     // verify tables
     DevBuf b_tab;
@@ -101,7 +102,8 @@ struct hlo_ctx {
     // workspaces
     DevBuf b_cnt, b_mzoff, b_mzx, b_mzrp, b_mzrid, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
     DevBuf b_cands, b_counters, b_ovf, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
-    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz;
+    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx;
+    std::map<uint32_t, std::vector<uint32_t>> name_order;  // N -> integers 0..N-1 in strcmp order of their decimal spelling
     PinBuf h_out, h_aux, h_coff, h_mz, h_roff, h_cands, h_rec16, h_small;
     std::vector<uint64_t> v_coff;
     hlo_reads scratch_reads;
@@ -241,7 +243,7 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
                       &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_bstart,
                       &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovfcnt, &ctx->b_gkeys,
                       &ctx->b_gmn, &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos,
-                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz};
+                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx};
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&ctx->h_out, &ctx->h_aux, &ctx->h_coff, &ctx->h_mz, &ctx->h_roff, &ctx->h_cands, &ctx->h_rec16, &ctx->h_small};
     for (PinBuf *b : pins) b->release();
@@ -310,6 +312,27 @@ static VerifyParams verify_params(const hlo_ctx *ctx) {
 // ------------------------------------------------------------------------------------------------
 // packing
 
+// integers 0..N-1 in strcmp order of their decimal spelling = preorder walk of the decimal trie
+// ("0" < "1" < "10" < "100" < "101" < ... < "11" < ... < "2" < ...); cached per N
+static const std::vector<uint32_t> &decimal_name_order(hlo_ctx *ctx, uint32_t N) {
+    auto it = ctx->name_order.find(N);
+    if (it != ctx->name_order.end()) return it->second;
+    std::vector<uint32_t> &ord = ctx->name_order[N];
+    ord.reserve(N);
+    if (N > 0) ord.push_back(0);  // "0" has no children ("00" is not a name)
+    std::vector<uint64_t> stack;
+    for (uint64_t d = 9; d >= 1; --d)
+        if (d < N) stack.push_back(d);
+    while (!stack.empty()) {
+        const uint64_t v = stack.back();
+        stack.pop_back();
+        ord.push_back((uint32_t)v);
+        for (int c = 9; c >= 0; --c)  // children pushed in reverse so that v*10 is visited next
+            if (v * 10 + (uint64_t)c < N) stack.push_back(v * 10 + (uint64_t)c);
+    }
+    return ord;
+}
+
 static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64_t *base_off, uint32_t n_reads,
                      const uint32_t *cluster_off, uint32_t n_clusters, const uint32_t *ids) {
     if (!bases || !base_off) FAIL(HLO_EINVAL, "hlo_pack_reads: null input");
@@ -330,19 +353,30 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
         R->h_len[i] = (uint32_t)l;
         max_len = std::max(max_len, (uint32_t)l);
     }
+    R->h_perm.resize(n_reads);
+    uint32_t max_cluster = 0;
     for (uint32_t c = 0; c < n_clusters; ++c) {
         if (cluster_off[c + 1] < cluster_off[c]) FAIL(HLO_EINVAL, "cluster_off not monotone");
-        const uint32_t r0 = cluster_off[c], r1 = cluster_off[c + 1];
+        const uint32_t r0 = cluster_off[c], r1 = cluster_off[c + 1], N = r1 - r0;
+        max_cluster = std::max(max_cluster, N);
         for (uint32_t i = r0; i < r1; ++i) cbase[i] = r0, R->h_cidx[i] = c, R->h_ids[i] = ids ? ids[i] : i - r0;
-        if (!ids) {
+        bool plain = true;  // names are 0..N-1 in file order (what rename_fas.py writes)
+        if (ids)
+            for (uint32_t i = r0; i < r1 && plain; ++i) plain = ids[i] == i - r0;
+        if (plain) {
             for (uint32_t i = r0; i < r1; ++i) nrank[i] = i;
+            const std::vector<uint32_t> &ord = decimal_name_order(ctx, N);
+            for (uint32_t x = 0; x < N; ++x) R->h_perm[r0 + x] = r0 + ord[x];
         } else {
-            std::vector<uint32_t> ord(r1 - r0);
-            for (uint32_t i = 0; i < r1 - r0; ++i) ord[i] = r0 + i;
+            std::vector<uint32_t> ord(N);
+            for (uint32_t i = 0; i < N; ++i) ord[i] = r0 + i;
             std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b] || (ids[a] == ids[b] && a < b); });
-            for (uint32_t i = 0; i + 1 < r1 - r0; ++i)
+            for (uint32_t i = 0; i + 1 < N; ++i)
                 if (ids[ord[i]] == ids[ord[i + 1]]) FAIL(HLO_EINVAL, "duplicate id %u in cluster %u", ids[ord[i]], c);
-            for (uint32_t i = 0; i < r1 - r0; ++i) nrank[ord[i]] = r0 + i;
+            for (uint32_t i = 0; i < N; ++i) nrank[ord[i]] = r0 + i;
+            // strcmp order of the decimal names = the order minimap2 -X compares read names in
+            std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return name_less(ids[a], ids[b]); });
+            for (uint32_t x = 0; x < N; ++x) R->h_perm[r0 + x] = ord[x];
         }
     }
     // the ungapped model equals minimap2's banded extension only while an accepted overlap cannot hold a
@@ -354,10 +388,12 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
                  ctx->P.min_identity);
     }
     const uint64_t n_bases = base_off[n_reads];
-    uint32_t words = (max_len + 15) / 16;
-    uint32_t stride_w = std::max(16u, (words + 15u) & ~15u);
+    const uint32_t words = (max_len + 15) / 16;
+    const uint32_t nv = std::max(1u, (words + 3u) / 4u);
+    const uint32_t stride_w = 4u * nv;
     DevReads &d = R->d;
-    d.n_reads = n_reads, d.n_clusters = n_clusters, d.stride_w = stride_w, d.max_len = max_len, d.n_bases = n_bases;
+    d.n_reads = n_reads, d.n_clusters = n_clusters, d.stride_w = stride_w, d.nv = nv, d.max_len = max_len, d.n_bases = n_bases;
+    d.max_cluster = max_cluster;
     const size_t plane_words = (size_t)n_reads * stride_w;
     CK(R->b_ascii.ensure(n_bases + 16));
     CK(R->b_off.ensure(((size_t)n_reads + 1) * 8));
@@ -366,12 +402,13 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     CK(R->b_cidx.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_ids.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_nrank.ensure((size_t)n_reads * 4 + 4));
-    CK(R->b_bases.ensure(plane_words * 2 * 4 + 256));
-    CK(R->b_amb.ensure(plane_words * 2 * 4 + 256));
+    CK(R->b_perm.ensure((size_t)n_reads * 4 + 4));
+    CK(R->b_bases.ensure((plane_words * 2 + 2 * HLO_PAD_WORDS) * 4));
+    CK(R->b_amb.ensure((plane_words * 2 + 2 * HLO_PAD_WORDS) * 4));
     CK(R->b_ambcount.ensure(16));
     d.len = R->b_len.as<uint32_t>(), d.cbase = R->b_cbase.as<uint32_t>(), d.cidx = R->b_cidx.as<uint32_t>();
-    d.ids = R->b_ids.as<uint32_t>(), d.nrank = R->b_nrank.as<uint32_t>();
-    d.bases = R->b_bases.as<uint32_t>(), d.amb = R->b_amb.as<uint32_t>();
+    d.ids = R->b_ids.as<uint32_t>(), d.nrank = R->b_nrank.as<uint32_t>(), d.perm = R->b_perm.as<uint32_t>();
+    d.bases = R->b_bases.as<uint32_t>() + HLO_PAD_WORDS, d.amb = R->b_amb.as<uint32_t>() + HLO_PAD_WORDS;
     CK(cudaEventRecord(ctx->ev[ST_BEGIN], s));
     if (n_reads) {
         CK(cudaMemcpyAsync(R->b_ascii.p, bases, n_bases, cudaMemcpyHostToDevice, s));
@@ -381,6 +418,7 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
         CK(cudaMemcpyAsync(d.cidx, R->h_cidx.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(d.ids, R->h_ids.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(d.nrank, nrank.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d.perm, R->h_perm.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
     }
     CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));
     CK(cudaEventRecord(ctx->ev[ST_H2D], s));
@@ -473,19 +511,18 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R) {
     CK(ctx->b_bstart.ensure((n + 2) * 4));
     CK(ctx->b_range.ensure(n * 8 + 8));
     CK(ctx->b_hits.ensure(n * 8 + 8));
-    launch_hash_keys(ctx->b_mzx.as<uint64_t>(), n, ctx->b_keys[0].as<uint64_t>(), s, &ctx->lc);
-    launch_iota(ctx->b_vals[0].as<uint32_t>(), n, s, &ctx->lc);
+    launch_hash_keys(ctx->b_mzx.as<uint64_t>(), n, ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
     const int cur = launch_radix_sort(keys, vals, n, 0, 2 * ctx->P.k, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SORT], s));
-    launch_mark_buckets(keys[cur], vals[cur], ctx->b_mzrid.as<uint32_t>(), ctx->b_mzrp.as<uint32_t>(), R->d.cbase, n,
+    launch_mark_buckets(keys[cur], vals[cur], ctx->b_mzrid.as<uint32_t>(), ctx->b_mzrp.as<uint32_t>(), R->d.cbase, R->d.len, n,
                         ctx->b_flags.as<uint32_t>(), ctx->b_hits.as<uint2>(), s, &ctx->lc);
     launch_exclusive_scan(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
     launch_bucket_starts(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_bstart.as<uint32_t>(), s, &ctx->lc);
     launch_bucket_ranges(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), vals[cur], ctx->b_bstart.as<uint32_t>(), n,
-                         ctx->b_range.as<uint2>(), s, &ctx->lc);
+                         ctx->P.mid_occ, ctx->b_range.as<uint2>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_INDEX], s));
     return HLO_OK;
@@ -497,59 +534,83 @@ static uint32_t next_pow2_u32(uint32_t v) {
     return p;
 }
 
-// candidates into b_cands; *n_out = their number
-static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, uint64_t *n_out) {
+// candidates into b_cands (CandI, or hlo_cand when external); *n_out = their number
+static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t *n_out) {
     cudaStream_t s = ctx->stream;
     const DevReads &d = R->d;
-    CK(ctx->b_counters.ensure(8 * 8));
+    CK(ctx->b_counters.ensure(16 * 8));
     CK(ctx->b_ovf.ensure((size_t)d.n_reads * 4 + 4));
-    uint64_t cap = std::max<uint64_t>(ctx->b_cands.cap / sizeof(hlo_cand), std::max<uint64_t>(ctx->n_mz * 3, 1 << 16));
+    uint64_t cap = std::max<uint64_t>(ctx->b_cands.cap / 16, std::max<uint64_t>(ctx->n_mz * 3, 1 << 16));
     PairgenArgs a;
     a.reads = d;
     a.mz_off = ctx->b_mzoff.as<uint32_t>(), a.mz_rp = ctx->b_mzrp.as<uint32_t>();
     a.range = ctx->b_range.as<uint2>(), a.hits = ctx->b_hits.as<uint2>();
-    a.k = ctx->P.k, a.mid_occ = ctx->P.mid_occ;
+    a.k = ctx->P.k;
     a.gap_min = std::max(std::max(ctx->P.min_chain_score - ctx->P.k, ctx->P.min_seeds - 1), 0);
+    a.external = external;
     a.counters = ctx->b_counters.as<unsigned long long>();
     a.overflow_reads = ctx->b_ovf.as<uint32_t>(), a.overflow_cap = d.n_reads;
+    const bool fast = pairgen_fast_supported(d, &a.dg_bits) && !ctx->pairgen_generic;
     unsigned long long hc[4];
     for (int attempt = 0; attempt < 3; ++attempt) {
-        CK(ctx->b_cands.ensure(cap * sizeof(hlo_cand)));
-        a.cands = ctx->b_cands.as<hlo_cand>(), a.cand_cap = cap;
+        CK(ctx->b_cands.ensure(cap * 16));
+        a.cands = ctx->b_cands.p, a.cand_cap = cap;
         CK(cudaMemsetAsync(ctx->b_counters.p, 0, 64, s));
-        launch_pairgen(a, ctx->pairgen_slots_log2, s, &ctx->lc);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        const uint32_t n_ovf = (uint32_t)hc[2];
-        if (n_ovf) {  // exact redo of the overflowed reads with tables in HBM
-            CK(ctx->b_ovfcnt.ensure((size_t)n_ovf * 4 + 4));
-            launch_overflow_hit_counts(a, n_ovf, ctx->b_ovfcnt.as<uint32_t>(), s, &ctx->lc);
-            std::vector<uint32_t> cnt(n_ovf), off(n_ovf + 1);
-            CK(cudaMemcpyAsync(cnt.data(), ctx->b_ovfcnt.p, (size_t)n_ovf * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            uint64_t tot = 0;
-            for (uint32_t i = 0; i < n_ovf; ++i) {
-                off[i] = (uint32_t)tot;
-                tot += next_pow2_u32(std::max(2u * cnt[i], 64u));
-                if (tot > 0xf0000000ull) FAIL(HLO_ERANGE, "overflow seed tables exceed 2^32 slots");
-            }
-            off[n_ovf] = (uint32_t)tot;
-            CK(ctx->b_gkeys.ensure(tot * 8 + 8));
-            CK(ctx->b_gmn.ensure(tot * 4 + 4));
-            CK(ctx->b_gmx.ensure(tot * 4 + 4));
-            CK(ctx->b_goff.ensure(((size_t)n_ovf + 1) * 4));
-            CK(cudaMemcpyAsync(ctx->b_goff.p, off.data(), ((size_t)n_ovf + 1) * 4, cudaMemcpyHostToDevice, s));
-            CK(cudaMemsetAsync(ctx->b_gkeys.p, 0xff, tot * 8, s));
-            CK(cudaMemsetAsync(ctx->b_gmn.p, 0xff, tot * 4, s));
-            CK(cudaMemsetAsync(ctx->b_gmx.p, 0, tot * 4, s));
-            launch_pairgen_overflow(a, n_ovf, ctx->b_gkeys.as<unsigned long long>(), ctx->b_gmn.as<uint32_t>(),
-                                    ctx->b_gmx.as<uint32_t>(), ctx->b_goff.as<uint32_t>(), s, &ctx->lc);
+        uint32_t n_list = d.n_reads;        // reads the generic kernel has to do
+        const uint32_t *list = nullptr;     // nullptr = all of them
+        if (fast) {
+            launch_pairgen(a, ctx->pairgen_slots_log2, s, &ctx->lc);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
+            n_list = (uint32_t)hc[2], list = a.overflow_reads;
         }
-        ctx->tm.n_overflow_reads = n_ovf;
+        if (n_list) {  // exact path with tables in HBM, in chunks that bound the table memory
+            CK(ctx->b_ovfcnt.ensure((size_t)n_list * 4 + 4));
+            launch_generic_hit_counts(a, list, n_list, ctx->b_ovfcnt.as<uint32_t>(), s, &ctx->lc);
+            std::vector<uint32_t> cnt(n_list);
+            CK(cudaMemcpyAsync(cnt.data(), ctx->b_ovfcnt.p, (size_t)n_list * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            const uint64_t slot_budget = 1ull << 28;  // 4 GiB of tables per chunk
+            uint32_t i0 = 0;
+            std::vector<uint64_t> off;
+            while (i0 < n_list) {
+                off.assign(1, 0);
+                uint32_t i1 = i0;
+                while (i1 < n_list) {
+                    const uint64_t sl = next_pow2_u32(std::max(2u * cnt[i1], 64u));
+                    if (i1 > i0 && off.back() + sl > slot_budget) break;
+                    off.push_back(off.back() + sl);
+                    ++i1;
+                }
+                const uint64_t tot = off.back();
+                CK(ctx->b_gkeys.ensure(tot * 8 + 8));
+                CK(ctx->b_gmn.ensure(tot * 4 + 4));
+                CK(ctx->b_gmx.ensure(tot * 4 + 4));
+                CK(ctx->b_goff.ensure(off.size() * 8));
+                CK(cudaMemcpyAsync(ctx->b_goff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+                CK(cudaMemsetAsync(ctx->b_gkeys.p, 0xff, tot * 8, s));
+                CK(cudaMemsetAsync(ctx->b_gmn.p, 0xff, tot * 4, s));
+                CK(cudaMemsetAsync(ctx->b_gmx.p, 0, tot * 4, s));
+                // a chunk is addressed by offsetting the list (or, without a list, by a list of x indices)
+                const uint32_t *chunk_list = list ? list + i0 : nullptr;
+                if (!list && i0 > 0) {
+                    std::vector<uint32_t> xs(i1 - i0);
+                    for (uint32_t i = i0; i < i1; ++i) xs[i - i0] = i;
+                    CK(cudaMemcpyAsync(ctx->b_ovf.p, xs.data(), xs.size() * 4, cudaMemcpyHostToDevice, s));
+                    CK(cudaStreamSynchronize(s));
+                    chunk_list = ctx->b_ovf.as<uint32_t>();
+                }
+                launch_pairgen_generic(a, chunk_list, i1 - i0, ctx->b_gkeys.as<unsigned long long>(), ctx->b_gmn.as<uint32_t>(),
+                                       ctx->b_gmx.as<uint32_t>(), ctx->b_goff.as<uint64_t>(), s, &ctx->lc);
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(s));
+                i0 = i1;
+            }
+            CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        ctx->tm.n_overflow_reads = fast ? n_list : 0;
         ctx->tm.n_seed_hits = hc[1];
         if (hc[0] <= cap) {
             *n_out = hc[0];
@@ -561,7 +622,7 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, uint64_t *n_out) {
 }
 
 // verify candidates (device) -> Rec16 in b_rec16; *n_acc = accepted
-static int run_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *d_cands, uint64_t n, uint64_t *n_acc) {
+static int run_verify(hlo_ctx *ctx, const hlo_reads *R, const CandI *d_cands, uint64_t n, uint64_t *n_acc) {
     cudaStream_t s = ctx->stream;
     *n_acc = 0;
     CK(ctx->b_counters.ensure(8 * 8));
@@ -574,7 +635,7 @@ static int run_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *d_cands,
     a.out = ctx->b_rec16.as<Rec16>();
     a.counters = ctx->b_counters.as<unsigned long long>();
     a.deferred = ctx->b_deferred.as<uint32_t>();
-    const bool force_exact = ctx->verify_exact != 0;
+    const bool force_exact = ctx->verify_exact != 0 || !verify_fast_supported(R->d, ctx->tab);
     unsigned long long hc[2] = {0, 0};
     if (force_exact) {
         launch_verify_exact(a, nullptr, n, s, &ctx->lc);
@@ -647,20 +708,34 @@ int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64
                        &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
+    // the device arrays are in name order (sketch.cu); hand them back in the caller's read order
     CK(ctx->h_mz.ensure(tot * sizeof(hlo_mz) + 16));
     CK(ctx->h_roff.ensure(((size_t)R->d.n_reads + 1) * 8));
     std::vector<uint32_t> off32((size_t)R->d.n_reads + 1);
-    CK(cudaMemcpyAsync(ctx->h_mz.p, ctx->b_mz.p, tot * sizeof(hlo_mz), cudaMemcpyDeviceToHost, s));
+    std::vector<hlo_mz> tmp((size_t)tot);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->b_mz.p, tot * sizeof(hlo_mz), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(off32.data(), ctx->b_mzoff.p, off32.size() * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     uint64_t *ro = ctx->h_roff.as<uint64_t>();
-    for (size_t i = 0; i < off32.size(); ++i) ro[i] = off32[i];
+    hlo_mz *hm = ctx->h_mz.as<hlo_mz>();
+    {
+        const uint32_t nr = R->d.n_reads;
+        std::vector<uint32_t> xof(nr);  // read -> x
+        for (uint32_t x = 0; x < nr; ++x) xof[R->h_perm[x]] = x;
+        uint64_t w = 0;
+        for (uint32_t r = 0; r < nr; ++r) {
+            ro[r] = w;
+            const uint32_t x = xof[r];
+            for (uint32_t m = off32[x]; m < off32[x + 1]; ++m) hm[w++] = tmp[m];
+        }
+        ro[nr] = w;
+    }
     *mz = ctx->h_mz.as<hlo_mz>(), *read_off = ro, *n = tot;
     finish_timing(ctx, R, ST_SKETCH);
     return HLO_OK;
 }
 
-static int stages_to_candidates(hlo_ctx *ctx, const hlo_reads *R, uint64_t *n_c, bool mark_start = true) {
+static int stages_to_candidates(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t *n_c, bool mark_start = true) {
     cudaStream_t s = ctx->stream;
     if (mark_start) CK(cudaEventRecord(ctx->ev[ST_PACK], s));
     int rc = run_sketch(ctx, R);
@@ -668,7 +743,7 @@ static int stages_to_candidates(hlo_ctx *ctx, const hlo_reads *R, uint64_t *n_c,
     CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
     rc = run_index(ctx, R);
     if (rc) return rc;
-    rc = run_pairgen(ctx, R, n_c);
+    rc = run_pairgen(ctx, R, external, n_c);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
     ctx->tm.n_candidates = *n_c;
@@ -680,7 +755,7 @@ int hlo_candidates(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand **cands, uin
     CK(cudaSetDevice(ctx->device));
     reset_timing(ctx);
     uint64_t n_c = 0;
-    int rc = stages_to_candidates(ctx, R, &n_c);
+    int rc = stages_to_candidates(ctx, R, 1, &n_c);
     if (rc) return rc;
     CK(ctx->h_cands.ensure(n_c * sizeof(hlo_cand) + 16));
     CK(cudaMemcpyAsync(ctx->h_cands.p, ctx->b_cands.p, n_c * sizeof(hlo_cand), cudaMemcpyDeviceToHost, ctx->stream));
@@ -705,11 +780,14 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
     cudaStream_t s = ctx->stream;
     for (uint64_t i = 0; i < n; ++i)
         if (cands[i].q >= R->d.n_reads || cands[i].t >= R->d.n_reads) FAIL(HLO_EINVAL, "candidate %llu names a read outside the batch", (unsigned long long)i);
-    CK(ctx->b_cands.ensure(n * sizeof(hlo_cand) + 16));
-    CK(cudaMemcpyAsync(ctx->b_cands.p, cands, n * sizeof(hlo_cand), cudaMemcpyHostToDevice, s));
+    CK(ctx->b_candx.ensure(n * sizeof(hlo_cand) + 16));
+    CK(ctx->b_cands.ensure(n * sizeof(CandI) + 16));
+    CK(cudaMemcpyAsync(ctx->b_candx.p, cands, n * sizeof(hlo_cand), cudaMemcpyHostToDevice, s));
+    launch_cands_to_internal(ctx->b_candx.as<hlo_cand>(), n, R->d, ctx->b_cands.as<CandI>(), s, &ctx->lc);
+    CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
     uint64_t n_acc = 0;
-    int rc = run_verify(ctx, R, ctx->b_cands.as<hlo_cand>(), n, &n_acc);
+    int rc = run_verify(ctx, R, ctx->b_cands.as<CandI>(), n, &n_acc);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
     CK(ctx->h_rec16.ensure(n_acc * sizeof(Rec16) + 16));
@@ -763,9 +841,9 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
         CK(cudaEventRecord(ctx->ev[ST_PACK], s));
         repack_ms = 0.f;
     }
-    int rc = stages_to_candidates(ctx, R, &n_c, repack_ms < 0.f);
+    int rc = stages_to_candidates(ctx, R, 0, &n_c, repack_ms < 0.f);
     if (rc) return rc;
-    rc = run_verify(ctx, R, ctx->b_cands.as<hlo_cand>(), n_c, &n_acc);
+    rc = run_verify(ctx, R, ctx->b_cands.as<CandI>(), n_c, &n_acc);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
     ctx->tm.n_accepted = n_acc;
@@ -850,6 +928,10 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
         ctx->verify_exact = value != 0;
         return HLO_OK;
     }
+    if (!strcmp(name, "pairgen_generic")) {
+        ctx->pairgen_generic = value != 0;
+        return HLO_OK;
+    }
     if (!strcmp(name, "repack")) {
         ctx->repack = value != 0;
         return HLO_OK;
@@ -859,7 +941,7 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
         return HLO_OK;
     }
     if (!strcmp(name, "pairgen_slots_log2")) {
-        if (value < 6 || value > 13) FAIL(HLO_ERANGE, "pairgen_slots_log2=%lld outside [6,13]", (long long)value);
+        if (value < 5 || value > 10) FAIL(HLO_ERANGE, "pairgen_slots_log2=%lld outside [5,10]", (long long)value);
         ctx->pairgen_slots_log2 = (int)value;
         return HLO_OK;
     }

@@ -36,53 +36,61 @@ size_t sort_tmp_words(uint64_t n);
 int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begin_bit, int end_bit, uint32_t *tmp,
                       cudaStream_t s, LaunchCounter *lc);
 
-void launch_iota(uint32_t *v, uint64_t n, cudaStream_t s, LaunchCounter *lc);
 void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, LaunchCounter *lc);
 
 // ---- pairgen.cu -----------------------------------------------------------------------------
 // index build on the hash-sorted minimizers
-void launch_hash_keys(const uint64_t *mz_x, uint64_t n, uint64_t *keys, cudaStream_t s, LaunchCounter *lc);
+void launch_hash_keys(const uint64_t *mz_x, uint64_t n, uint64_t *keys, uint32_t *vals, cudaStream_t s, LaunchCounter *lc);
 void launch_mark_buckets(const uint64_t *skeys, const uint32_t *svals, const uint32_t *mz_rid, const uint32_t *mz_rp,
-                         const uint32_t *cbase, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s, LaunchCounter *lc);
+                         const uint32_t *cbase, const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s,
+                         LaunchCounter *lc);
 void launch_bucket_starts(const uint32_t *flags, const uint32_t *bid, uint64_t n, uint32_t *bstart, cudaStream_t s,
                           LaunchCounter *lc);
 void launch_bucket_ranges(const uint32_t *flags, const uint32_t *bid, const uint32_t *svals, const uint32_t *bstart,
-                          uint64_t n, uint2 *range, cudaStream_t s, LaunchCounter *lc);
+                          uint64_t n, int mid_occ, uint2 *range, cudaStream_t s, LaunchCounter *lc);
 
 struct PairgenArgs {
     DevReads reads;
-    const uint32_t *mz_off;  // [n_reads+1]
+    const uint32_t *mz_off;  // [n_reads+1] minimizers of the x-th read (name order)
     const uint32_t *mz_rp;   // [n_mz] pos<<1|strand
-    const uint2 *range;      // [n_mz] bucket [s,e) in hits
-    const uint2 *hits;       // [n_mz] (rid, pos<<1|strand) in hash order
-    int k, mid_occ, gap_min;
-    hlo_cand *cands;         // output
+    const uint2 *range;      // [n_mz] hits [s,e) minimizer m seeds (the part of its bucket behind its own entry)
+    const uint2 *hits;       // [n_mz] (read, pos<<1|strand | len<<16 | amb<<31) in hash order
+    int k, gap_min;
+    int dg_bits;             // bits of (diagonal + max_len) in the 32-bit table key
+    int external;            // 1: emit hlo_cand (exact anchor span), 0: emit CandI
+    void *cands;             // output, 16 B per candidate
     uint64_t cand_cap;
     unsigned long long *counters;  // [0] candidates, [1] seed hits, [2] overflow reads, [3] work counter
-    uint32_t *overflow_reads;      // list of reads whose shared-memory table overflowed
+    uint32_t *overflow_reads;      // x indices of the reads whose shared-memory table overflowed
     uint32_t overflow_cap;
 };
-// fast path: one warp per query read, seed table in shared memory (slots_log2 slots per warp)
+// fast path: 8 lanes per query read, seed table in shared memory (2^slots_log2 slots per read)
+bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out);
+size_t pairgen_smem_bytes(int slots_log2);
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc);
-// exact fallback for overflowed reads: one block per read, table in global memory
-void launch_pairgen_overflow(const PairgenArgs &a, uint32_t n_overflow, unsigned long long *gtable_keys, uint32_t *gtable_mn,
-                             uint32_t *gtable_mx, const uint32_t *gtable_off, cudaStream_t s, LaunchCounter *lc);
-void launch_overflow_hit_counts(const PairgenArgs &a, uint32_t n_overflow, uint32_t *counts, cudaStream_t s, LaunchCounter *lc);
+// exact generic path: one block per listed read (list == nullptr: reads 0..n_list-1), 64-bit keys, table in HBM
+void launch_generic_hit_counts(const PairgenArgs &a, const uint32_t *list, uint32_t n_list, uint32_t *counts, cudaStream_t s,
+                               LaunchCounter *lc);
+void launch_pairgen_generic(const PairgenArgs &a, const uint32_t *list, uint32_t n_list, unsigned long long *gtable_keys,
+                            uint32_t *gtable_mn, uint32_t *gtable_mx, const uint64_t *gtable_off, cudaStream_t s,
+                            LaunchCounter *lc);
 
 // ---- verify.cu ------------------------------------------------------------------------------
 struct VerifyArgs {
     DevReads reads;
     VerifyTables tab;
     VerifyParams prm;
-    const hlo_cand *cands;
+    const CandI *cands;
     uint64_t n;
     Rec16 *out;                    // accepted records (unordered)
     unsigned long long *counters;  // [0] accepted, [1] deferred
     uint32_t *deferred;            // candidate indices for the exact path
 };
+bool verify_fast_supported(const DevReads &r, const VerifyTables &tab);
 void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc);
 // exact per-candidate path: idx == nullptr -> candidates [0,n); else the n listed candidates
 void launch_verify_exact(const VerifyArgs &a, const uint32_t *idx, uint64_t n, cudaStream_t s, LaunchCounter *lc);
+void launch_cands_to_internal(const hlo_cand *in, uint64_t n, const DevReads &r, CandI *out, cudaStream_t s, LaunchCounter *lc);
 
 // ---- records.cu -----------------------------------------------------------------------------
 void launch_record_keys(const Rec16 *rec, uint64_t n, DevReads r, uint64_t *keys, uint32_t *vals, cudaStream_t s,

@@ -8,36 +8,50 @@
 //     kept iff #anchors >= -n and score >= -m, which for -m <= 2k and -n <= 2 is
 //     (max anchor pos - min anchor pos) >= max(m - k, n - 1, 0)  (DESIGN.md §pairgen).
 //
-// One warp per query read: lanes stream the read's buckets from the hash-sorted hit array (coalesced
-// 8-byte entries) and fold every hit into a per-warp shared-memory hash table keyed by
-// (t, strand, diagonal) that keeps min/max anchor position — the warp-level dedup of the north star.
-// A read whose table overflows is redone exactly by pairgen_overflow_kernel with a table in HBM.
+// The minimizer arrays are in name order (sketch.cu), and the hash sort is stable, so every bucket lists
+// its reads in strcmp order of their names: the seeds minimap2 -X keeps for a query minimizer are exactly
+// the bucket entries AFTER its own entry (minus further entries of the same read).  No name comparison
+// and no wasted half of the bucket.
+//
+// pairgen_group_kernel: 8 lanes per query read (4 reads per warp, 16 per block).  The lanes stream the
+// suffix of each of the read's buckets from the hash-ordered hit array (coalesced 8-byte entries) and fold
+// every hit into the group's shared-memory hash table keyed by a 32-bit (t - cluster base, strand,
+// diagonal) that keeps min/max anchor position and the target's length — the warp-level dedup of the
+// north star.  Within one query minimizer all keys are distinct, so only the key claim is an atomic
+// (ATOMS.CAS); min/max are plain read-modify-writes ordered by a __syncwarp per minimizer.
+// A read whose table overflows, or a batch whose keys do not fit 32 bits, is done exactly by
+// pairgen_generic_kernel with a 64-bit-keyed table in HBM.
 // Algorithmic bytes: 8 B per seed hit in + 16 B per candidate out.
 #include "kernels.cuh"
 
 namespace hlo {
 
 #define HLO_EMPTY_KEY 0xffffffffffffffffULL
+#define HLO_EMPTY32 0xffffffffu
 
-__global__ void hash_keys_kernel(const uint64_t *__restrict__ x, uint64_t n, uint64_t *__restrict__ keys) {
+__global__ void hash_keys_kernel(const uint64_t *__restrict__ x, uint64_t n, uint64_t *__restrict__ keys,
+                                 uint32_t *__restrict__ vals) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = x[i] >> 8;
+    if (i < n) keys[i] = x[i] >> 8, vals[i] = (uint32_t)i;
 }
-void launch_hash_keys(const uint64_t *mz_x, uint64_t n, uint64_t *keys, cudaStream_t s, LaunchCounter *lc) {
+void launch_hash_keys(const uint64_t *mz_x, uint64_t n, uint64_t *keys, uint32_t *vals, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    hash_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, n, keys);
+    hash_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, n, keys, vals);
     if (lc) lc->total++;
 }
 
+// hits[i] = (read, pos<<1|strand | len<<16 | amb<<31) of the i-th minimizer in hash order;
+// flags[i] = 1 where a new (cluster, hash) bucket starts
 __global__ void mark_buckets_kernel(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
                                     const uint32_t *__restrict__ mz_rid, const uint32_t *__restrict__ mz_rp,
-                                    const uint32_t *__restrict__ cbase, uint64_t n, uint32_t *__restrict__ flags,
-                                    uint2 *__restrict__ hits) {
+                                    const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ len, uint64_t n,
+                                    uint32_t *__restrict__ flags, uint2 *__restrict__ hits) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t idx = svals[i];
     const uint32_t rid = mz_rid[idx];
-    hits[i] = make_uint2(rid, mz_rp[idx]);
+    const uint32_t lf = len[rid];
+    hits[i] = make_uint2(rid, mz_rp[idx] | (lf & 0x7fffu) << 16 | (lf & HLO_AMB_FLAG));
     uint32_t f = 1;
     if (i > 0) {
         const uint32_t prid = mz_rid[svals[i - 1]];
@@ -46,9 +60,10 @@ __global__ void mark_buckets_kernel(const uint64_t *__restrict__ skeys, const ui
     flags[i] = f;
 }
 void launch_mark_buckets(const uint64_t *skeys, const uint32_t *svals, const uint32_t *mz_rid, const uint32_t *mz_rp,
-                         const uint32_t *cbase, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s, LaunchCounter *lc) {
+                         const uint32_t *cbase, const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s,
+                         LaunchCounter *lc) {
     if (n == 0) return;
-    mark_buckets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(skeys, svals, mz_rid, mz_rp, cbase, n, flags, hits);
+    mark_buckets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(skeys, svals, mz_rid, mz_rp, cbase, len, n, flags, hits);
     if (lc) lc->total++;
 }
 
@@ -68,201 +83,255 @@ void launch_bucket_starts(const uint32_t *flags, const uint32_t *bid, uint64_t n
     if (lc) lc->total++;
 }
 
+// range[m] = the hits minimizer m seeds: the part of its bucket after its own entry, or nothing when the
+// bucket holds more than mid_occ entries
 __global__ void bucket_ranges_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ bid,
                                      const uint32_t *__restrict__ svals, const uint32_t *__restrict__ bstart, uint64_t n,
-                                     uint2 *__restrict__ range) {
+                                     int mid_occ, uint2 *__restrict__ range) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t b = bid[i] + flags[i] - 1u;
-    range[svals[i]] = make_uint2(bstart[b], bstart[b + 1]);
+    const uint32_t s = bstart[b], e = bstart[b + 1];
+    range[svals[i]] = (int)(e - s) > mid_occ ? make_uint2(0u, 0u) : make_uint2((uint32_t)i + 1u, e);
 }
 void launch_bucket_ranges(const uint32_t *flags, const uint32_t *bid, const uint32_t *svals, const uint32_t *bstart,
-                          uint64_t n, uint2 *range, cudaStream_t s, LaunchCounter *lc) {
+                          uint64_t n, int mid_occ, uint2 *range, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    bucket_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flags, bid, svals, bstart, n, range);
+    bucket_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flags, bid, svals, bstart, n, mid_occ, range);
     if (lc) lc->total++;
 }
 
 // ------------------------------------------------------------------------------------------------
-// table operations (generic pointers: shared memory in the fast kernel, HBM in the overflow kernel)
-
-__device__ __forceinline__ uint32_t slot_hash(uint64_t key, uint32_t mask) {
-    return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> 40) & mask;
-}
-
-// returns false when no slot could be claimed
-__device__ __forceinline__ bool table_insert(unsigned long long *keys, uint32_t *mn, uint32_t *mx, uint32_t mask, uint64_t key,
-                                             uint32_t qp) {
-    uint32_t slot = slot_hash(key, mask);
-    for (uint32_t probe = 0; probe <= mask; ++probe) {
-        const unsigned long long prev = atomicCAS(&keys[slot], HLO_EMPTY_KEY, (unsigned long long)key);
-        if (prev == HLO_EMPTY_KEY || prev == key) {
-            atomicMin(&mn[slot], qp);
-            atomicMax(&mx[slot], qp);
-            return true;
-        }
-        slot = (slot + 1) & mask;
+__device__ __forceinline__ void emit_cand(const PairgenArgs &a, unsigned long long p, uint32_t q, uint32_t t, uint32_t strand,
+                                          int diag, uint32_t mn, uint32_t mx, uint32_t ql, uint32_t tl, uint32_t amb) {
+    if (p >= a.cand_cap) return;  // only counted; the host grows the buffer and reruns
+    const int a_start = (int)mn - a.k + 1, a_end = (int)mx + 1;
+    uint4 o;
+    if (a.external) {
+        o = make_uint4(q, t, (uint32_t)diag, HLO_CAND_PACK(strand, a_start, a_end));
+    } else {
+        const CandI c = make_candi(q, t, diag, strand, ql, tl, a_start, a_end, amb);
+        o = make_uint4(c.q, c.t, c.z, c.w);
     }
-    return false;
+    reinterpret_cast<uint4 *>(a.cands)[p] = o;
 }
 
-__device__ __forceinline__ hlo_cand make_cand(uint32_t q, uint64_t key, uint32_t mn, uint32_t mx, int k) {
-    hlo_cand c;
-    c.q = q;
-    c.t = (uint32_t)(key >> 32);
-    const uint32_t lo = (uint32_t)key;
-    c.diag = (int32_t)(lo & 0x7fffffffu) - HLO_DIAG_BIAS;
-    c.strand_anchor = HLO_CAND_PACK(lo >> 31, mn - (uint32_t)k + 1u, mx + 1u);
-    return c;
-}
+// ------------------------------------------------------------------------------------------------
+// fast path: 8 lanes per query read, table in shared memory
+constexpr int PG_THREADS = 128;
+constexpr int PG_G = 8;                        // lanes per read
+constexpr int PG_GROUPS = PG_THREADS / PG_G;   // reads in flight per block
+constexpr int PG_PAD = 8;                      // words of padding between the groups' tables (bank spread)
 
-// fold the hits of query read q into the table; NT cooperating threads, this thread is `tid`.
-// returns (per thread) the number of hits that survived -X, and sets *ovf on table overflow.
-template <int NT_IS_WARP>
-__device__ __forceinline__ uint32_t fold_read(const PairgenArgs &a, uint32_t q, unsigned long long *keys, uint32_t *mn,
-                                              uint32_t *mx, uint32_t mask, uint32_t tid, uint32_t nt, volatile uint32_t *ovf) {
-    const uint32_t ql = a.reads.len[q] & HLO_LEN_MASK;
-    const uint32_t qid = a.reads.ids[q];
-    const uint32_t m0 = a.mz_off[q], m1 = a.mz_off[q + 1];
-    uint32_t nh = 0;
-    for (uint32_t m = m0; m < m1; ++m) {
-        const uint2 rg = a.range[m];
-        if ((int)(rg.y - rg.x) > a.mid_occ) continue;
-        if (*ovf) break;
-        const uint32_t qrp = a.mz_rp[m];
-        const uint32_t qpos = qrp >> 1;
-        for (uint32_t i = rg.x + tid; i < rg.y; i += nt) {
-            const uint2 h = a.hits[i];
-            const uint32_t t = h.x;
-            if (t == q) continue;                                // -X: no self hits
-            if (!name_less(qid, a.reads.ids[t])) continue;       // -X: query = the smaller name
-            ++nh;
-            const uint32_t strand = (h.y ^ qrp) & 1u;
-            const int32_t tp = (int32_t)(h.y >> 1);
-            const int32_t qp = strand ? (int32_t)ql - ((int32_t)qpos + 1 - a.k) - 1 : (int32_t)qpos;
-            const int32_t diag = tp - qp;
-            const uint64_t key = (uint64_t)t << 32 | (uint64_t)(strand << 31) | (uint32_t)(diag + HLO_DIAG_BIAS);
-            if (!table_insert(keys, mn, mx, mask, key, (uint32_t)qp)) *ovf = 1u;
-        }
-    }
-    return nh;
-}
-
-__global__ void __launch_bounds__(128) pairgen_kernel(PairgenArgs a, int slots_log2) {
-    extern __shared__ unsigned long long smem_u64[];
-    const uint32_t S = 1u << slots_log2, mask = S - 1u;
-    const uint32_t wp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    unsigned long long *keys = smem_u64 + (size_t)wp * S;
-    uint32_t *mn = (uint32_t *)(smem_u64 + (size_t)nw * S) + (size_t)wp * 2 * S;
-    uint32_t *mx = mn + S;
-    __shared__ uint32_t ovf_flag[8];
-    const unsigned lt_mask = (1u << lane) - 1u;
+__global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a, int slots_log2) {
+    extern __shared__ uint32_t pg_smem[];
+    const uint32_t S = 1u << slots_log2, smask = S - 1u, ST = S + PG_PAD;
+    const uint32_t g = threadIdx.x / PG_G, l = threadIdx.x % PG_G;
+    uint32_t *keys = pg_smem + (size_t)g * ST;
+    uint32_t *vals = pg_smem + (size_t)PG_GROUPS * ST + (size_t)g * ST;
+    uint16_t *aux = reinterpret_cast<uint16_t *>(pg_smem + (size_t)2 * PG_GROUPS * ST) + (size_t)g * ST;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gmask = 0xFFu << (lane & ~7u);
+    const int kshift = a.dg_bits + 1;
+    const uint32_t max_len = a.reads.max_len;
     for (;;) {
         unsigned long long qq = 0;
-        if (lane == 0) qq = atomicAdd(&a.counters[3], 1ULL);
-        qq = __shfl_sync(0xffffffffu, qq, 0);
+        if (l == 0) qq = atomicAdd(&a.counters[3], 1ULL);
+        qq = __shfl_sync(gmask, qq, 0, PG_G);
         if (qq >= a.reads.n_reads) break;
-        const uint32_t q = (uint32_t)qq;
-        if (a.mz_off[q] == a.mz_off[q + 1]) continue;
-        for (uint32_t i = lane; i < S; i += 32) keys[i] = HLO_EMPTY_KEY, mn[i] = 0xffffffffu, mx[i] = 0u;
-        if (lane == 0) ovf_flag[wp] = 0u;
-        __syncwarp();
-        uint32_t nh = fold_read<1>(a, q, keys, mn, mx, mask, lane, 32, &ovf_flag[wp]);
-        __syncwarp();
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nh += __shfl_xor_sync(0xffffffffu, nh, d);
-        if (ovf_flag[wp]) {  // redo this read exactly in the overflow kernel (its hits are counted there)
-            if (lane == 0) {
-                const unsigned long long p = atomicAdd(&a.counters[2], 1ULL);
-                if (p < a.overflow_cap) a.overflow_reads[p] = q;
+        const uint32_t xq = (uint32_t)qq;
+        const uint32_t m0 = __ldg(a.mz_off + xq), m1 = __ldg(a.mz_off + xq + 1);
+        if (m0 == m1) continue;
+        const uint32_t q = __ldg(a.reads.perm + xq);
+        const uint32_t lq = __ldg(a.reads.len + q);
+        const uint32_t ql = lq & HLO_LEN_MASK, cb = __ldg(a.reads.cbase + q);
+        for (uint32_t i = l; i < S; i += PG_G) keys[i] = HLO_EMPTY32;
+        __syncwarp(gmask);
+        uint32_t nh = 0;
+        bool ovf = false;
+        for (uint32_t m = m0; m < m1; ++m) {
+            const uint2 rg = __ldg(a.range + m);
+            const uint32_t qrp = __ldg(a.mz_rp + m);
+            const int qpos = (int)(qrp >> 1);
+            for (uint32_t i = rg.x + l; i < rg.y; i += PG_G) {
+                const uint2 h = __ldg(a.hits + i);
+                const uint32_t t = h.x;
+                if (t == q) continue;  // another minimizer of the query itself (-X: no self hits)
+                ++nh;
+                const uint32_t strand = (h.y ^ qrp) & 1u;
+                const int tp = (int)((h.y >> 1) & 0x7fffu);
+                const int qp = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
+                const int diag = tp - qp;
+                const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
+                uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
+                bool done = false;
+                for (uint32_t probe = 0; probe < S; ++probe) {
+                    const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
+                    if (old == HLO_EMPTY32) {
+                        vals[slot] = (uint32_t)qp | (uint32_t)qp << 16;
+                        aux[slot] = (uint16_t)(h.y >> 16);
+                        done = true;
+                        break;
+                    }
+                    if (old == key) {  // no other lane of the group holds this key in this iteration
+                        const uint32_t v = vals[slot];
+                        const uint32_t mn = min(v & 0xffffu, (uint32_t)qp), mx = max(v >> 16, (uint32_t)qp);
+                        vals[slot] = mn | mx << 16;
+                        done = true;
+                        break;
+                    }
+                    slot = (slot + 1u) & smask;
+                }
+                if (!done) ovf = true;
             }
-            __syncwarp();
+            __syncwarp(gmask);  // orders the plain min/max updates of consecutive minimizers
+        }
+        nh += __shfl_xor_sync(gmask, nh, 1, PG_G);
+        nh += __shfl_xor_sync(gmask, nh, 2, PG_G);
+        nh += __shfl_xor_sync(gmask, nh, 4, PG_G);
+        if (__any_sync(gmask, ovf)) {  // redo this read exactly in the generic kernel (its hits are counted there)
+            if (l == 0) {
+                const unsigned long long p = atomicAdd(&a.counters[2], 1ULL);
+                if (p < a.overflow_cap) a.overflow_reads[p] = xq;
+            }
+            __syncwarp(gmask);
             continue;
         }
         // count, reserve, write
         uint32_t cnt = 0;
-        for (uint32_t i = lane; i < S; i += 32) cnt += (keys[i] != HLO_EMPTY_KEY && (int)(mx[i] - mn[i]) >= a.gap_min);
+        for (uint32_t i = l; i < S; i += PG_G) {
+            const uint32_t v = vals[i];
+            cnt += (keys[i] != HLO_EMPTY32 && (int)((v >> 16) - (v & 0xffffu)) >= a.gap_min);
+        }
+        uint32_t inc = cnt;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        for (int d = 1; d < PG_G; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(gmask, inc, d, PG_G);
+            if ((int)l >= d) inc += o;
+        }
+        const uint32_t total = __shfl_sync(gmask, inc, PG_G - 1, PG_G);
         unsigned long long base = 0;
-        if (lane == 0) {
-            if (cnt) base = atomicAdd(&a.counters[0], (unsigned long long)cnt);
+        if (l == 0) {
+            if (total) base = atomicAdd(&a.counters[0], (unsigned long long)total);
             if (nh) atomicAdd(&a.counters[1], (unsigned long long)nh);
         }
-        base = __shfl_sync(0xffffffffu, base, 0);
+        base = __shfl_sync(gmask, base, 0, PG_G);
         if (cnt) {
-            uint32_t run = 0;
-            for (uint32_t i0 = 0; i0 < S; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                const unsigned long long key = keys[i];
-                const uint32_t lo = mn[i], hi = mx[i];
-                const bool ok = key != HLO_EMPTY_KEY && (int)(hi - lo) >= a.gap_min;
-                const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                if (ok) {
-                    const unsigned long long p = base + run + __popc(bal & lt_mask);
-                    if (p < a.cand_cap) a.cands[p] = make_cand(q, key, lo, hi, a.k);
+            unsigned long long p = base + (inc - cnt);
+            for (uint32_t i = l; i < S; i += PG_G) {
+                const uint32_t key = keys[i], v = vals[i];
+                const uint32_t mn = v & 0xffffu, mx = v >> 16;
+                if (key != HLO_EMPTY32 && (int)(mx - mn) >= a.gap_min) {
+                    const uint32_t au = aux[i];
+                    const uint32_t strand = (key >> a.dg_bits) & 1u;
+                    const int diag = (int)(key & ((1u << a.dg_bits) - 1u)) - (int)max_len;
+                    emit_cand(a, p++, q, cb + (key >> kshift), strand, diag, mn, mx, ql, au & 0x7fffu, (au >> 15) | (lq >> 31));
                 }
-                run += __popc(bal);
             }
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
+}
+
+size_t pairgen_smem_bytes(int slots_log2) {
+    const size_t ST = ((size_t)1 << slots_log2) + PG_PAD;
+    return (size_t)PG_GROUPS * ST * 10;  // keys u32 + vals u32 + aux u16
+}
+
+bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out) {
+    int dg = 1;
+    while ((1u << dg) < 2u * r.max_len + 2u) ++dg;
+    int tb = 1;
+    while ((1ull << tb) < (unsigned long long)r.max_cluster + 1ull) ++tb;
+    if (dg_bits_out) *dg_bits_out = dg;
+    return r.max_len <= 32767u && tb + dg + 1 <= 31;  // the top bit stays clear, so no key equals the empty marker
 }
 
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc) {
     if (a.reads.n_reads == 0) return;
-    const int threads = 128, nw = threads / 32;
-    const size_t smem = (size_t)nw * ((size_t)16 << slots_log2);
-    static int configured_for = -1;
-    if (configured_for != slots_log2) {
-        cudaFuncSetAttribute(pairgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-        configured_for = slots_log2;
-    }
+    const size_t smem = pairgen_smem_bytes(slots_log2);
+    cudaFuncSetAttribute(pairgen_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairgen_kernel, threads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairgen_group_kernel, PG_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = ((uint64_t)a.reads.n_reads + nw - 1) / nw;
+    uint64_t want = ((uint64_t)a.reads.n_reads + PG_GROUPS - 1) / PG_GROUPS;
     uint64_t grid = (uint64_t)sms * per_sm;
     if (grid > want) grid = want;
-    pairgen_kernel<<<(unsigned)grid, threads, smem, s>>>(a, slots_log2);
+    pairgen_group_kernel<<<(unsigned)grid, PG_THREADS, smem, s>>>(a, slots_log2);
     if (lc) lc->total++;
 }
 
 // ------------------------------------------------------------------------------------------------
-// overflow path: one block per overflowed read, table in HBM sized from the read's bucket sizes
+// generic path: one block per listed read (x index; list == nullptr -> every read), table in HBM with
+// 64-bit keys (t, strand, diagonal), sized from the read's bucket sizes
 
-__global__ void overflow_hit_counts_kernel(PairgenArgs a, uint32_t n_overflow, uint32_t *__restrict__ counts) {
+__global__ void generic_hit_counts_kernel(PairgenArgs a, const uint32_t *__restrict__ list, uint32_t n_list,
+                                          uint32_t *__restrict__ counts) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_overflow) return;
-    const uint32_t q = a.overflow_reads[i];
+    if (i >= n_list) return;
+    const uint32_t xq = list ? list[i] : i;
     uint32_t c = 0;
-    for (uint32_t m = a.mz_off[q]; m < a.mz_off[q + 1]; ++m) {
+    for (uint32_t m = a.mz_off[xq]; m < a.mz_off[xq + 1]; ++m) {
         const uint2 rg = a.range[m];
-        if ((int)(rg.y - rg.x) <= a.mid_occ) c += rg.y - rg.x;
+        c += rg.y - rg.x;
     }
     counts[i] = c;
 }
-void launch_overflow_hit_counts(const PairgenArgs &a, uint32_t n_overflow, uint32_t *counts, cudaStream_t s, LaunchCounter *lc) {
-    if (n_overflow == 0) return;
-    overflow_hit_counts_kernel<<<(n_overflow + 127) / 128, 128, 0, s>>>(a, n_overflow, counts);
+void launch_generic_hit_counts(const PairgenArgs &a, const uint32_t *list, uint32_t n_list, uint32_t *counts, cudaStream_t s,
+                               LaunchCounter *lc) {
+    if (n_list == 0) return;
+    generic_hit_counts_kernel<<<(n_list + 127) / 128, 128, 0, s>>>(a, list, n_list, counts);
     if (lc) lc->total++;
 }
 
-__global__ void __launch_bounds__(256) pairgen_overflow_kernel(PairgenArgs a, uint32_t n_overflow, unsigned long long *gkeys,
-                                                               uint32_t *gmn, uint32_t *gmx, const uint32_t *__restrict__ goff) {
-    __shared__ uint32_t ovf;
+__device__ __forceinline__ uint32_t slot_hash64(uint64_t key, uint32_t mask) {
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> 40) & mask;
+}
+
+__global__ void __launch_bounds__(256) pairgen_generic_kernel(PairgenArgs a, const uint32_t *__restrict__ list, uint32_t n_list,
+                                                              unsigned long long *gkeys, uint32_t *gmn, uint32_t *gmx,
+                                                              const uint64_t *__restrict__ goff) {
     __shared__ unsigned long long nh_tot;
-    const uint32_t i = blockIdx.x;
-    if (i >= n_overflow) return;
-    const uint32_t q = a.overflow_reads[i];
-    const uint32_t o0 = goff[i], S = goff[i + 1] - o0, mask = S - 1u;  // S is a power of two
+    const uint32_t bi = blockIdx.x;
+    if (bi >= n_list) return;
+    const uint32_t xq = list ? list[bi] : bi;
+    const uint32_t q = a.reads.perm[xq];
+    const uint32_t lq = a.reads.len[q], ql = lq & HLO_LEN_MASK;
+    const uint64_t o0 = goff[bi];
+    const uint32_t S = (uint32_t)(goff[bi + 1] - o0), mask = S - 1u;  // S is a power of two
     unsigned long long *keys = gkeys + o0;
     uint32_t *mn = gmn + o0, *mx = gmx + o0;
-    if (threadIdx.x == 0) ovf = 0u, nh_tot = 0ULL;
+    if (threadIdx.x == 0) nh_tot = 0ULL;
     __syncthreads();
-    const uint32_t nh = fold_read<0>(a, q, keys, mn, mx, mask, threadIdx.x, blockDim.x, &ovf);
+    uint32_t nh = 0;
+    for (uint32_t m = a.mz_off[xq]; m < a.mz_off[xq + 1]; ++m) {
+        const uint2 rg = a.range[m];
+        const uint32_t qrp = a.mz_rp[m];
+        const int qpos = (int)(qrp >> 1);
+        for (uint32_t i = rg.x + threadIdx.x; i < rg.y; i += blockDim.x) {
+            const uint2 h = a.hits[i];
+            const uint32_t t = h.x;
+            if (t == q) continue;
+            ++nh;
+            const uint32_t strand = (h.y ^ qrp) & 1u;
+            const int tp = (int)((h.y >> 1) & 0x7fffu);
+            const int qp = strand ? (int)ql - qpos + a.k - 2 : qpos;
+            const int diag = tp - qp;
+            const uint64_t key = (uint64_t)t << 32 | (uint64_t)(strand << 31) | (uint32_t)(diag + HLO_DIAG_BIAS);
+            uint32_t slot = slot_hash64(key, mask);
+            for (uint32_t probe = 0; probe <= mask; ++probe) {  // the table is twice the hit count: never full
+                const unsigned long long prev = atomicCAS(&keys[slot], HLO_EMPTY_KEY, (unsigned long long)key);
+                if (prev == HLO_EMPTY_KEY || prev == key) {
+                    atomicMin(&mn[slot], (uint32_t)qp);
+                    atomicMax(&mx[slot], (uint32_t)qp);
+                    break;
+                }
+                slot = (slot + 1) & mask;
+            }
+        }
+    }
     if (nh) atomicAdd(&nh_tot, (unsigned long long)nh);
     __syncthreads();
     if (threadIdx.x == 0 && nh_tot) atomicAdd(&a.counters[1], nh_tot);
@@ -271,15 +340,18 @@ __global__ void __launch_bounds__(256) pairgen_overflow_kernel(PairgenArgs a, ui
         const uint32_t lo = mn[j], hi = mx[j];
         if (key != HLO_EMPTY_KEY && (int)(hi - lo) >= a.gap_min) {
             const unsigned long long p = atomicAdd(&a.counters[0], 1ULL);
-            if (p < a.cand_cap) a.cands[p] = make_cand(q, key, lo, hi, a.k);
+            const uint32_t t = (uint32_t)(key >> 32), low = (uint32_t)key;
+            const uint32_t lt = a.reads.len[t];
+            emit_cand(a, p, q, t, low >> 31, (int)(low & 0x7fffffffu) - HLO_DIAG_BIAS, lo, hi, ql, lt & 0x7fffu, (lt | lq) >> 31);
         }
     }
 }
 
-void launch_pairgen_overflow(const PairgenArgs &a, uint32_t n_overflow, unsigned long long *gtable_keys, uint32_t *gtable_mn,
-                             uint32_t *gtable_mx, const uint32_t *gtable_off, cudaStream_t s, LaunchCounter *lc) {
-    if (n_overflow == 0) return;
-    pairgen_overflow_kernel<<<n_overflow, 256, 0, s>>>(a, n_overflow, gtable_keys, gtable_mn, gtable_mx, gtable_off);
+void launch_pairgen_generic(const PairgenArgs &a, const uint32_t *list, uint32_t n_list, unsigned long long *gtable_keys,
+                            uint32_t *gtable_mn, uint32_t *gtable_mx, const uint64_t *gtable_off, cudaStream_t s,
+                            LaunchCounter *lc) {
+    if (n_list == 0) return;
+    pairgen_generic_kernel<<<n_list, 256, 0, s>>>(a, list, n_list, gtable_keys, gtable_mn, gtable_mx, gtable_off);
     if (lc) lc->total++;
 }
 

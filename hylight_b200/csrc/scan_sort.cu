@@ -253,15 +253,6 @@ int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begi
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void iota_kernel(uint32_t *v, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = (uint32_t)i;
-}
-void launch_iota(uint32_t *v, uint64_t n, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, n);
-    if (lc) lc->total++;
-}
 __global__ void fill_kernel(uint32_t *v, uint32_t value, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = value;

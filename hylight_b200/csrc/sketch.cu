@@ -5,7 +5,7 @@
 // parity tests compare the two tuple for tuple: x = hash64(canonical k-mer) << 8 | span,
 // y = rid << 32 | last_pos << 1 | strand.
 //
-// One thread per read runs the sequential window automaton exactly (ties, the first-window special
+// One thread per read (taken in name order, see below) runs the sequential window automaton exactly (ties, the first-window special
 // case, ambiguous-base resets and the end-of-read flush are all order dependent), reading the read's
 // packed row; a count pass sizes the output, a write pass fills it, so the output is in minimap2's
 // emission order.  Integer-pipe bound: ~150 ALU ops per base; algorithmic bytes per read =
@@ -46,8 +46,12 @@ __device__ __forceinline__ void mz_push(uint32_t &n, uint64_t x, uint32_t rp, ui
 template <bool WRITE>
 __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, uint32_t *__restrict__ count,
                                                      const uint32_t *__restrict__ off, MzOut o) {
-    const uint32_t read = blockIdx.x * blockDim.x + threadIdx.x;
-    if (read >= r.n_reads) return;
+    // thread x sketches read perm[x]: the minimizer arrays are laid out in the strcmp order of the read
+    // names inside each cluster, so that after the stable hash sort every seed bucket is ordered the way
+    // minimap2's -X rule compares names (pairgen.cu)
+    const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xi >= r.n_reads) return;
+    const uint32_t read = __ldg(r.perm + xi);
     const uint32_t lenf = r.len[read];
     const int len = (int)(lenf & HLO_LEN_MASK);
     const bool has_amb = (lenf & HLO_AMB_FLAG) != 0;
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, u
     uint32_t buf_y[HLO_MAX_W];
     uint64_t min_x = INF;
     uint32_t min_y = 0xffffffffu;
-    const uint32_t base = WRITE ? off[read] : 0u;
+    const uint32_t base = WRITE ? off[xi] : 0u;
     uint32_t n = 0;
     int l = 0, buf_pos = 0, min_pos = 0;
 #pragma unroll
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, u
         if (++buf_pos == w) buf_pos = 0;
     }
     if (min_x != INF) mz_push<WRITE>(n, min_x, min_y, read, base, o);
-    if (!WRITE) count[read] = n;
+    if (!WRITE) count[xi] = n;
 }
 
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc) {

@@ -10,242 +10,179 @@
 //   from the outermost anchor.  K = mismatches in the block, blocklen = block columns - ambiguous.
 //   Accept iff blocklen >= min_len, !(matches/blocklen < min_id), !(clip_l + clip_r > min(o, maplen*r)).
 //
-// verify_fast_kernel: 4 lanes per candidate, 8 candidates per warp.  Lane s loads bases [64s, 64s+64)
-// of both rows with one 128-bit load each; the target words are re-aligned to the query with register
-// rotation + 4-lane shuffles + funnel shifts; mismatches = popc((x | x>>1) & 0x5555..) of the XOR.
-// The end rule only needs the outermost 32 bases of each target-limited end as long as the overlap holds
-// at most bad_limit (21 for -A4 -B2) bad (mismatch/ambiguous) columns; anything else (or reads > 256 bp) is deferred to
-// verify_exact_kernel, which walks base by base.  Accepted records leave through one warp-aggregated
-// atomicAdd per warp iteration.
-//
-// Bound: L1/L2 sector bandwidth + integer issue (the rows of a cluster are L2 resident); algorithmic
-// bytes per candidate = 16 (candidate) + 2*ceil(OL/4) (bases in the overlap) + 16 per accepted record
-// (SURVEY.md §8d counts 32 B for the expanded record; the expansion happens in records.cu).
+// verify_fast_kernel<NV>: ONE THREAD PER CANDIDATE.  The internal candidate (CandI) carries both read
+// lengths, so the geometry is known before a row is touched:
+//   1. overlaps shorter than min_len leave at once; pairs with an ambiguous base or with BOTH ends
+//      target-limited (query contains target, unequal lengths) go to verify_exact_kernel;
+//   2. a target-limited RIGHT end is moved to position 0 by switching both reads to their
+//      reverse-complement plane (D' = tl - ql - D), so the end rule only ever looks at bit 0.. of the
+//      mismatch words;
+//   3. the read that starts first is X (compared from its base 0), the other is Y shifted by S = |D|:
+//      NV LDG.128 per row (Y from the 16-byte vector that holds base S), a two-stage word select,
+//      funnel shifts for the residual 2-bit offset, XOR, (x|x>>1)&0x5555.. fold, popcount;
+//   4. thresholds from the host-built integer tables (shared memory), end rule on the outermost 32
+//      bases, one warp-aggregated atomicAdd per warp, 16-byte records.
+// Bound: integer (ALU) pipe and L1 wavefronts (one per 16-byte vector of the randomly addressed row);
+// rows are L2-resident.  Algorithmic bytes per candidate = 16 + 2*ceil(OL/4) (when OL >= min_len) + 16
+// per accepted record (SURVEY.md §8d counts 32 B for the expanded record; the expansion is records.cu).
 #include "kernels.cuh"
 
 namespace hlo {
 
-__device__ __forceinline__ uint32_t sel4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t r) {
-    const uint32_t lo = (r & 1u) ? x1 : x0, hi = (r & 1u) ? x3 : x2;
-    return (r & 2u) ? hi : lo;
-}
-
-// 2-bit-granular mask of positions [lo, hi) of a 16-base word (bit 2p set for position p)
-__device__ __forceinline__ uint32_t range_mask16(int lo, int hi) {
-    lo = max(lo, 0), hi = min(hi, 16);
-    const uint32_t mhi = hi >= 16 ? 0xffffffffu : (hi <= 0 ? 0u : ((1u << (2 * hi)) - 1u));
-    const uint32_t mlo = lo >= 16 ? 0xffffffffu : ((1u << (2 * lo)) - 1u);
-    return mhi & ~mlo & 0x55555555u;
-}
-
-// fetch word `w` (0..15, else 0) of the 16-word row spread over the 4 lanes of a group (lane s holds
-// words 4s..4s+3 in r0..r3).  `w` must be uniform across the group.
-__device__ __forceinline__ uint32_t group_word(unsigned gmask, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, int w) {
-    const uint32_t v = sel4(r0, r1, r2, r3, (uint32_t)w & 3u);
-    const uint32_t x = __shfl_sync(gmask, v, (w >> 2) & 3, 4);
-    return (w >= 0 && w < 16) ? x : 0u;
-}
-
-// re-align a row held as 16 words over 4 lanes so that this lane gets bases [64s + D, 64s + D + 64)
-__device__ __forceinline__ void realign_row(unsigned gmask, int sub, uint4 tv, int D, uint32_t out[4]) {
-    const int a = D >> 4, b2 = (D & 15) * 2;
-    const uint32_t ar = (uint32_t)a & 3u;
-    uint32_t u[4];
-    u[0] = sel4(tv.x, tv.y, tv.z, tv.w, ar);
-    u[1] = sel4(tv.x, tv.y, tv.z, tv.w, (ar + 1u) & 3u);
-    u[2] = sel4(tv.x, tv.y, tv.z, tv.w, (ar + 2u) & 3u);
-    u[3] = sel4(tv.x, tv.y, tv.z, tv.w, (ar + 3u) & 3u);
-    uint32_t x[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const int w = 4 * sub + a + i;
-        const uint32_t v = __shfl_sync(gmask, u[i & 3], (w >> 2) & 3, 4);
-        x[i] = (w >= 0 && w < 16) ? v : 0u;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) out[i] = __funnelshift_r(x[i], x[i + 1], b2);
-}
-
 struct ClipResult {
-    int clip, mm, amb;
+    int clip, mm;
 };
 
-// end rule on a 32-base window; bit 2(p-1) of `bad` set <=> the base at outward distance p (1 = the
-// terminal base) is a mismatch or ambiguous; `ambw` marks the ambiguous ones.
-__device__ __forceinline__ ClipResult clip_scan(uint64_t bad, uint64_t ambw, int A, int B, int N) {
-    ClipResult r{0, 0, 0};
-    int best = 0, cm = 0, ca = 0;
-    while (bad) {
-        const int bit = __ffsll((long long)bad) - 1;
-        const int p = (bit >> 1) + 1;
-        if ((ambw >> bit) & 1ull) ++ca; else ++cm;
-        const int R = A * p - (A + B) * cm - (A + N) * ca;
-        if (R <= best) best = R, r.clip = p, r.mm = cm, r.amb = ca;
-        bad &= bad - 1;
+// end rule on the outermost 32 bases of a target-limited end; bit 2(p-1) of (lo | hi<<32) set <=> the base at
+// outward distance p (1 = the terminal base) is a mismatch.  Returns the clipped length and the
+// mismatches inside it: the largest p that minimises R(p) = A*p - (A+B)*mismatches(p) over R <= 0.
+__device__ __forceinline__ ClipResult clip_scan32(uint32_t lo, uint32_t hi, int A, int B) {
+    ClipResult r{0, 0};
+    int best = 0, cm = 0;
+    while (lo) {
+        const int p = ((__ffs((int)lo) - 1) >> 1) + 1;
+        ++cm;
+        const int R = A * p - (A + B) * cm;
+        if (R <= best) best = R, r.clip = p, r.mm = cm;
+        lo &= lo - 1;
+    }
+    while (hi) {
+        const int p = ((__ffs((int)hi) - 1) >> 1) + 17;
+        ++cm;
+        const int R = A * p - (A + B) * cm;
+        if (R <= best) best = R, r.clip = p, r.mm = cm;
+        hi &= hi - 1;
     }
     return r;
 }
 
-__device__ __forceinline__ uint64_t brev_pairs64(uint64_t v) {
-    // reverse the order of the 32 two-bit fields (flags sit on the even bit of each field)
-    return __brevll(v) >> 1;
+// low n bits set, n clamped to [0, 32]
+__device__ __forceinline__ uint32_t low_mask(int n) {
+    n = max(n, 0);
+    return __funnelshift_lc(0xffffffffu, 0u, (uint32_t)n);  // (0:ones) << min(n,32), upper word
 }
 
-__global__ void __launch_bounds__(256) verify_fast_kernel(VerifyArgs a) {
+constexpr int VF_THREADS = 128;
+
+template <int NV>
+__global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
+    constexpr int NW = 4 * NV;
+    __shared__ uint16_t s_tab[3 * 1024];
+    // thresholds into shared memory (3 tables of max_len + 1 <= 1024 entries)
+    const int tl1 = a.tab.max_len + 1;
+    for (int i = threadIdx.x; i < 3 * tl1; i += VF_THREADS) s_tab[i] = a.tab.min_matches[i];
+    __syncthreads();
+    const uint16_t *t_min_matches = s_tab, *t_max_clip = s_tab + tl1, *t_max_k = s_tab + 2 * tl1;
+
     const unsigned lane = threadIdx.x & 31;
-    const int sub = (int)(lane & 3u);
-    const unsigned gmask = 0xFu << (lane & ~3u);
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint64_t n_groups_total = ((uint64_t)gridDim.x * blockDim.x) >> 2;
-    const uint64_t g0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    const uint64_t plane = (uint64_t)a.reads.n_reads * a.reads.stride_w;
-    const uint32_t sw = a.reads.stride_w;
-    const uint64_t n_round = (a.n + 7) & ~7ull;  // whole warps iterate together
-    for (uint64_t c = g0; c < n_round; c += n_groups_total) {
+    const uint64_t n_threads = (uint64_t)gridDim.x * VF_THREADS;
+    const uint64_t plane4 = (uint64_t)a.reads.n_reads * NV;  // uint4 per plane
+    const uint4 *rows = reinterpret_cast<const uint4 *>(a.reads.bases);
+    const uint4 *cands = reinterpret_cast<const uint4 *>(a.cands);
+    const uint64_t n_round = (a.n + 31) & ~31ull;  // whole warps iterate together
+    const int o = a.prm.max_overhang, min_len = a.prm.min_len;
+    for (uint64_t c = (uint64_t)blockIdx.x * VF_THREADS + threadIdx.x; c < n_round; c += n_threads) {
         bool accept = false, defer = false;
-        Rec16 rec;
-        rec.q = rec.t = rec.ds = rec.kb = 0;
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
         if (c < a.n) {
-            const uint4 cv = __ldg(reinterpret_cast<const uint4 *>(a.cands) + c);
+            const uint4 cv = __ldg(cands + c);
             const uint32_t q = cv.x, t = cv.y;
-            const int D = (int)cv.z;
-            const uint32_t strand = cv.w & 1u;
-            int aS = (int)((cv.w >> 1) & 0x7fffu), aE = (int)(cv.w >> 16);
-            const uint32_t lq = __ldg(a.reads.len + q), lt = __ldg(a.reads.len + t);
-            const int ql = (int)(lq & HLO_LEN_MASK), tl = (int)(lt & HLO_LEN_MASK);
-            const bool ambf = ((lq | lt) & HLO_AMB_FLAG) != 0;
-            const int js = D < 0 ? -D : 0, je = min(ql, tl - D);
-            const int OL = je - js;
-            if (ql > 256 || tl > 256) {
-                defer = OL >= a.prm.min_len;
-            } else if (OL >= a.prm.min_len) {
-                const uint64_t qoff = (uint64_t)strand * plane + (uint64_t)q * sw, toff = (uint64_t)t * sw;
-                const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(a.reads.bases + qoff) + sub);
-                const uint4 tv = __ldg(reinterpret_cast<const uint4 *>(a.reads.bases + toff) + sub);
-                uint32_t tw[4];
-                realign_row(gmask, sub, tv, D, tw);
-                const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
-                uint32_t mmw[4], amw[4] = {0u, 0u, 0u, 0u};
-                int mm = 0, amb = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t d = qw[i] ^ tw[i];
-                    const int base = 64 * sub + 16 * i;
-                    const uint32_t vm = range_mask16(js - base, je - base);
-                    mmw[i] = (d | (d >> 1)) & vm;
-                }
-                if (ambf) {
-                    const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(a.reads.amb + qoff) + sub);
-                    const uint4 ta = __ldg(reinterpret_cast<const uint4 *>(a.reads.amb + toff) + sub);
-                    uint32_t taw[4];
-                    realign_row(gmask, sub, ta, D, taw);
-                    const uint32_t qaw[4] = {qa.x, qa.y, qa.z, qa.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int base = 64 * sub + 16 * i;
-                        amw[i] = (qaw[i] | taw[i]) & range_mask16(js - base, je - base);
-                        mmw[i] &= ~amw[i];
-                        amb += __popc(amw[i]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) mm += __popc(mmw[i]);
-                mm += __shfl_xor_sync(gmask, mm, 1, 4);
-                mm += __shfl_xor_sync(gmask, mm, 2, 4);
-                if (ambf) {
-                    amb += __shfl_xor_sync(gmask, amb, 1, 4);
-                    amb += __shfl_xor_sync(gmask, amb, 2, 4);
-                }
-                const int o = a.prm.max_overhang;
+            const int D = (int)(cv.z & 0xffffu) - 32768;
+            const int ql = (int)((cv.z >> 16) & 0x7fffu), tl = (int)(cv.w & 0x7fffu);
+            const uint32_t strand = cv.z >> 31;
+            const int OL = min(ql, tl - D) - max(-D, 0);
+            if (OL >= min_len) {
                 const bool left_t = D < 0, right_t = (tl - D) < ql;
-                // cheap exact reject: the block keeps at least mm - o mismatches and is at most OL long
-                if (mm <= (int)__ldg(a.tab.max_k_upto + OL) + o) {
-                    int cl = 0, cr = 0, cmm = 0, camb = 0;
-                    bool ok = true;
-                    if ((mm + amb) > 0 && (left_t || right_t)) {
-                        if (mm + amb > a.prm.bad_limit) {
-                            ok = false, defer = true;
-                        } else {
-                            if (aE == 0) aS = je, aE = js;
-                            aS = max(aS, js), aE = min(aE, je);
-                            uint32_t bw[4], aw4[4];
+                if (((cv.w >> 29) & 1u) || (left_t && right_t)) {
+                    defer = true;
+                } else {
+                    // orientation in which a target-limited end, if any, is the LEFT end
+                    const uint32_t flip = right_t ? 1u : 0u;
+                    const int Dn = flip ? tl - ql - D : D;
+                    const uint4 *Qrow = rows + (uint64_t)(strand ^ flip) * plane4 + (uint64_t)q * NV;
+                    const uint4 *Trow = rows + (uint64_t)flip * plane4 + (uint64_t)t * NV;
+                    const bool neg = Dn < 0;  // then the target starts first and its end is the limited one
+                    const int S = neg ? -Dn : Dn;
+                    const uint4 *Xrow = neg ? Trow : Qrow;
+                    const uint4 *Yrow = (neg ? Qrow : Trow) + (S >> 6);
+                    uint32_t x[NW], y[NW + 1];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) bw[i] = mmw[i] | amw[i], aw4[i] = amw[i];
-                            if (left_t) {
-                                const int W0 = js >> 4, sh = (js & 15) * 2;
-                                const uint32_t b0 = group_word(gmask, bw[0], bw[1], bw[2], bw[3], W0);
-                                const uint32_t b1 = group_word(gmask, bw[0], bw[1], bw[2], bw[3], W0 + 1);
-                                const uint32_t b2 = group_word(gmask, bw[0], bw[1], bw[2], bw[3], W0 + 2);
-                                uint64_t bad = (uint64_t)__funnelshift_r(b0, b1, sh) | (uint64_t)__funnelshift_r(b1, b2, sh) << 32;
-                                uint64_t ambw = 0;
-                                if (ambf) {
-                                    const uint32_t a0 = group_word(gmask, aw4[0], aw4[1], aw4[2], aw4[3], W0);
-                                    const uint32_t a1 = group_word(gmask, aw4[0], aw4[1], aw4[2], aw4[3], W0 + 1);
-                                    const uint32_t a2 = group_word(gmask, aw4[0], aw4[1], aw4[2], aw4[3], W0 + 2);
-                                    ambw = (uint64_t)__funnelshift_r(a0, a1, sh) | (uint64_t)__funnelshift_r(a1, a2, sh) << 32;
-                                }
-                                const int EL = aS - js;
-                                if (EL < 32) bad &= (EL <= 0) ? 0ull : ((1ull << (2 * EL)) - 1ull);
-                                const ClipResult r = clip_scan(bad, ambw, a.prm.a, a.prm.b, a.prm.n);
-                                cl = r.clip, cmm += r.mm, camb += r.amb;
-                            }
-                            if (right_t) {
-                                const int E0 = je - 32;
-                                const int W0 = E0 >> 4, sh = (E0 & 15) * 2;
-                                const uint32_t b0 = group_word(gmask, bw[0], bw[1], bw[2], bw[3], W0);
-                                const uint32_t b1 = group_word(gmask, bw[0], bw[1], bw[2], bw[3], W0 + 1);
-                                const uint32_t b2 = group_word(gmask, bw[0], bw[1], bw[2], bw[3], W0 + 2);
-                                uint64_t bad = (uint64_t)__funnelshift_r(b0, b1, sh) | (uint64_t)__funnelshift_r(b1, b2, sh) << 32;
-                                uint64_t ambw = 0;
-                                if (ambf) {
-                                    const uint32_t a0 = group_word(gmask, aw4[0], aw4[1], aw4[2], aw4[3], W0);
-                                    const uint32_t a1 = group_word(gmask, aw4[0], aw4[1], aw4[2], aw4[3], W0 + 1);
-                                    const uint32_t a2 = group_word(gmask, aw4[0], aw4[1], aw4[2], aw4[3], W0 + 2);
-                                    ambw = (uint64_t)__funnelshift_r(a0, a1, sh) | (uint64_t)__funnelshift_r(a1, a2, sh) << 32;
-                                }
-                                // outward order: the terminal base je-1 becomes distance 1
-                                bad = brev_pairs64(bad), ambw = brev_pairs64(ambw);
-                                const int ER = je - aE;
-                                if (ER < 32) bad &= (ER <= 0) ? 0ull : ((1ull << (2 * ER)) - 1ull);
-                                const ClipResult r = clip_scan(bad, ambw, a.prm.a, a.prm.b, a.prm.n);
-                                cr = r.clip, cmm += r.mm, camb += r.amb;
+                    for (int v = 0; v < NV; ++v) {
+                        const uint4 xv = __ldg(Xrow + v);
+                        x[4 * v] = xv.x, x[4 * v + 1] = xv.y, x[4 * v + 2] = xv.z, x[4 * v + 3] = xv.w;
+                        // vectors of Y past the row are never compared (they lie beyond the overlap); reading
+                        // them stays inside the padded allocation
+                        const uint4 yv = __ldg(Yrow + v);
+                        y[4 * v] = yv.x, y[4 * v + 1] = yv.y, y[4 * v + 2] = yv.z, y[4 * v + 3] = yv.w;
+                    }
+                    y[NW] = 0u;
+                    // residual word shift (S/16 mod 4) by two select stages, then the 2-bit funnel shift
+                    const bool w2 = (S & 32) != 0, w1 = (S & 16) != 0;
+#pragma unroll
+                    for (int i = 0; i + 2 <= NW; ++i) y[i] = w2 ? y[i + 2] : y[i];
+#pragma unroll
+                    for (int i = 0; i + 1 <= NW; ++i) y[i] = w1 ? y[i + 1] : y[i];
+                    const uint32_t b2 = (uint32_t)(S & 15) * 2u;
+                    uint32_t f[NW];
+                    int mm = 0;
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) {
+                        const uint32_t ys = __funnelshift_r(y[i], y[i + 1], b2);
+                        const uint32_t d = x[i] ^ ys;
+                        f[i] = (d | (d >> 1)) & 0x55555555u & low_mask(2 * OL - 32 * i);
+                    }
+#pragma unroll
+                    for (int i = 0; i + 1 < NW; i += 2) mm += __popc(f[i] | (f[i + 1] << 1));
+                    if (NW & 1) mm += __popc(f[NW - 1]);
+                    // cheap exact reject: the block keeps at least mm - o mismatches and is at most OL long
+                    if (mm <= (int)t_max_k[OL] + o) {
+                        int cl = 0, cmm = 0;
+                        bool ok = true;
+                        if (mm > 0 && (left_t || right_t)) {
+                            if (mm > a.prm.bad_limit) {
+                                ok = false, defer = true;  // a 32-base window no longer decides the end rule
+                            } else {
+                                const int REG = (int)((flip ? (cv.w >> 22) : (cv.w >> 15)) & 0x7fu);
+                                uint32_t lo = f[0], hi = NW > 1 ? f[1] : 0u;
+                                if (REG < 32) lo &= low_mask(2 * REG), hi &= low_mask(2 * REG - 32);
+                                const ClipResult r = clip_scan32(lo, hi, a.prm.a, a.prm.b);
+                                cl = r.clip, cmm = r.mm;
                             }
                         }
-                    }
-                    if (ok && cl + cr <= o) {
-                        const int maplen = OL - cl - cr;
-                        const int K = mm - cmm, n_ambi = amb - camb;
-                        const int blocklen = maplen - n_ambi;
-                        if (maplen >= 1 && blocklen >= a.prm.min_len && blocklen >= 1 &&
-                            blocklen - K >= (int)__ldg(a.tab.min_matches + blocklen) &&
-                            cl + cr <= (int)__ldg(a.tab.max_clip + maplen)) {
-                            accept = true;
-                            rec.q = q, rec.t = t;
-                            rec.ds = ((uint32_t)(D + HLO_DIAG_BIAS) << 1) | strand;
-                            rec.kb = (uint32_t)K | ((uint32_t)blocklen << 16);
+                        if (ok && cl <= o) {
+                            const int maplen = OL - cl;  // no ambiguous base on this path: blocklen = maplen
+                            const int K = mm - cmm;
+                            if (maplen >= min_len && maplen >= 1 && maplen - K >= (int)t_min_matches[maplen] &&
+                                cl <= (int)t_max_clip[maplen]) {
+                                accept = true;
+                                rec = make_uint4(q, t, ((uint32_t)(D + HLO_DIAG_BIAS) << 1) | strand, (uint32_t)K | ((uint32_t)maplen << 16));
+                            }
                         }
                     }
                 }
             }
         }
         // stream compaction: one atomicAdd per warp for the accepted, one for the deferred
-        const bool lead = sub == 0;
-        const unsigned acc_b = __ballot_sync(0xffffffffu, lead && accept);
-        const unsigned def_b = __ballot_sync(0xffffffffu, lead && defer);
+        const unsigned acc_b = __ballot_sync(0xffffffffu, accept);
+        const unsigned def_b = __ballot_sync(0xffffffffu, defer);
         if (acc_b) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(acc_b));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (lead && accept)
-                reinterpret_cast<uint4 *>(a.out)[base + __popc(acc_b & lt_mask)] = make_uint4(rec.q, rec.t, rec.ds, rec.kb);
+            if (accept) reinterpret_cast<uint4 *>(a.out)[base + __popc(acc_b & lt_mask)] = rec;
         }
         if (def_b) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&a.counters[1], (unsigned long long)__popc(def_b));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (lead && defer) a.deferred[base + __popc(def_b & lt_mask)] = (uint32_t)c;
+            if (defer) a.deferred[base + __popc(def_b & lt_mask)] = (uint32_t)c;
         }
     }
+}
+
+bool verify_fast_supported(const DevReads &r, const VerifyTables &tab) {
+    return r.nv >= 1 && r.nv <= 5 && tab.max_len + 1 <= 1024 && r.n_reads > 0;
 }
 
 void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) {
@@ -253,15 +190,22 @@ void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint64_t want = (a.n * 4 + 255) / 256;
-    uint64_t grid = (uint64_t)sms * 8 * 4;  // persistent-ish: a few waves of 256-thread blocks
+    const uint64_t want = (a.n + VF_THREADS - 1) / VF_THREADS;
+    uint64_t grid = (uint64_t)sms * 16;  // persistent: every block loads the threshold tables once
     if (grid > want) grid = want;
-    verify_fast_kernel<<<(unsigned)grid, 256, 0, s>>>(a);
+    switch (a.reads.nv) {
+        case 1: verify_fast_kernel<1><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
+        case 2: verify_fast_kernel<2><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
+        case 3: verify_fast_kernel<3><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
+        case 4: verify_fast_kernel<4><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
+        default: verify_fast_kernel<5><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
+    }
     if (lc) lc->total++, lc->verify++;
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact path: one thread per candidate, base by base (any read length, any number of bad columns)
+// exact path: one thread per candidate, base by base (any read length, ambiguous bases, both ends
+// target-limited, any number of bad columns)
 
 __device__ __forceinline__ int get_base(const uint32_t *row, int j) { return (int)((row[j >> 4] >> ((j & 15) * 2)) & 3u); }
 
@@ -269,14 +213,13 @@ __global__ void __launch_bounds__(128) verify_exact_kernel(VerifyArgs a, const u
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t c = idx ? idx[i] : i;
-    const hlo_cand cd = a.cands[c];
+    const CandI cd = a.cands[c];
     const uint32_t q = cd.q, t = cd.t;
-    const int D = cd.diag;
-    const uint32_t strand = cd.strand_anchor & 1u;
-    int aS = (int)((cd.strand_anchor >> 1) & 0x7fffu), aE = (int)(cd.strand_anchor >> 16);
-    const uint32_t lq = a.reads.len[q], lt = a.reads.len[t];
-    const int ql = (int)(lq & HLO_LEN_MASK), tl = (int)(lt & HLO_LEN_MASK);
-    const bool ambf = ((lq | lt) & HLO_AMB_FLAG) != 0;
+    const int D = (int)(cd.z & 0xffffu) - 32768;
+    const uint32_t strand = cd.z >> 31;
+    const int ql = (int)((cd.z >> 16) & 0x7fffu), tl = (int)(cd.w & 0x7fffu);
+    const int EL = (int)((cd.w >> 15) & 0x7fu), ER = (int)((cd.w >> 22) & 0x7fu);
+    const bool ambf = ((cd.w >> 29) & 1u) != 0;
     const int js = D < 0 ? -D : 0, je = min(ql, tl - D);
     if (je <= js) return;
     const uint64_t plane = (uint64_t)a.reads.n_reads * a.reads.stride_w;
@@ -284,8 +227,8 @@ __global__ void __launch_bounds__(128) verify_exact_kernel(VerifyArgs a, const u
     const uint32_t *T = a.reads.bases + (uint64_t)t * a.reads.stride_w;
     const uint32_t *QA = a.reads.amb + (uint64_t)strand * plane + (uint64_t)q * a.reads.stride_w;
     const uint32_t *TA = a.reads.amb + (uint64_t)t * a.reads.stride_w;
-    if (aE == 0) aS = je, aE = js;
-    aS = max(aS, js), aE = min(aE, je);
+    // the regions between the overlap ends and the outermost anchors, capped at HLO_REGION_CAP bases
+    const int aS = min(js + EL, je), aE = max(je - ER, js);
     const int A = a.prm.a, B = a.prm.b, N = a.prm.n;
     int cl = 0, cr = 0;
     // column class: 0 match, 1 mismatch, 2 ambiguous
@@ -319,6 +262,7 @@ __global__ void __launch_bounds__(128) verify_exact_kernel(VerifyArgs a, const u
 #undef COLCLASS
     const int maplen = be - bs, blocklen = maplen - n_ambi;
     if (maplen < 1 || blocklen < 1 || blocklen < a.prm.min_len) return;
+    if (maplen > a.tab.max_len) return;
     if (blocklen - K < (int)a.tab.min_matches[blocklen]) return;
     if (cl + cr > (int)a.tab.max_clip[maplen]) return;
     const unsigned long long p = atomicAdd(&a.counters[0], 1ULL);
@@ -333,6 +277,21 @@ void launch_verify_exact(const VerifyArgs &a, const uint32_t *idx, uint64_t n, c
     if (n == 0) return;
     verify_exact_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a, idx, n);
     if (lc) lc->total++, lc->verify++;
+}
+
+// hlo_cand (ABI) -> CandI, for caller-supplied candidate lists
+__global__ void cands_to_internal_kernel(const hlo_cand *__restrict__ in, uint64_t n, DevReads r, CandI *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const hlo_cand c = in[i];
+    const uint32_t lq = r.len[c.q], lt = r.len[c.t];
+    out[i] = make_candi(c.q, c.t, c.diag, c.strand_anchor & 1u, lq & 0x7fffu, lt & 0x7fffu, (int)((c.strand_anchor >> 1) & 0x7fffu),
+                        (int)(c.strand_anchor >> 16), (lq | lt) >> 31);
+}
+void launch_cands_to_internal(const hlo_cand *in, uint64_t n, const DevReads &r, CandI *out, cudaStream_t s, LaunchCounter *lc) {
+    if (n == 0) return;
+    cands_to_internal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, n, r, out);
+    if (lc) lc->total++;
 }
 
 }  // namespace hlo
