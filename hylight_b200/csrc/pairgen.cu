@@ -117,7 +117,8 @@ __device__ __forceinline__ void emit_cand(const PairgenArgs &a, unsigned long lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast path: 8 lanes per query read, table in shared memory
+// fast path: 8 lanes per query read, 4 reads per warp in LOCKSTEP (every loop bound is the maximum over
+// the warp's 4 reads, so the warp never diverges into per-read paths), table in shared memory
 constexpr int PG_THREADS = 128;
 constexpr int PG_G = 8;                        // lanes per read
 constexpr int PG_GROUPS = PG_THREADS / PG_G;   // reads in flight per block
@@ -131,91 +132,104 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     uint32_t *vals = pg_smem + (size_t)PG_GROUPS * ST + (size_t)g * ST;
     uint16_t *aux = reinterpret_cast<uint16_t *>(pg_smem + (size_t)2 * PG_GROUPS * ST) + (size_t)g * ST;
     const unsigned lane = threadIdx.x & 31;
-    const unsigned gmask = 0xFFu << (lane & ~7u);
+    const unsigned FULL = 0xffffffffu;
     const int kshift = a.dg_bits + 1;
     const uint32_t max_len = a.reads.max_len;
+    const uint32_t n_reads = a.reads.n_reads;
+    unsigned long long nh_total = 0;
     for (;;) {
         unsigned long long qq = 0;
-        if (l == 0) qq = atomicAdd(&a.counters[3], 1ULL);
-        qq = __shfl_sync(gmask, qq, 0, PG_G);
-        if (qq >= a.reads.n_reads) break;
-        const uint32_t xq = (uint32_t)qq;
-        const uint32_t m0 = __ldg(a.mz_off + xq), m1 = __ldg(a.mz_off + xq + 1);
-        if (m0 == m1) continue;
-        const uint32_t q = __ldg(a.reads.perm + xq);
-        const uint32_t lq = __ldg(a.reads.len + q);
-        const uint32_t ql = lq & HLO_LEN_MASK, cb = __ldg(a.reads.cbase + q);
+        if (lane == 0) qq = atomicAdd(&a.counters[3], 4ULL);
+        qq = __shfl_sync(FULL, qq, 0);
+        if (qq >= n_reads) break;
+        const uint32_t xq = (uint32_t)qq + (lane >> 3);
+        const bool have_read = xq < n_reads;
+        uint32_t m0 = 0, m1 = 0, q = 0, lq = 0, cb = 0;
+        if (have_read) {
+            m0 = __ldg(a.mz_off + xq), m1 = __ldg(a.mz_off + xq + 1);
+            q = __ldg(a.reads.perm + xq);
+            lq = __ldg(a.reads.len + q);
+            cb = __ldg(a.reads.cbase + q);
+        }
+        const uint32_t ql = lq & HLO_LEN_MASK;
+        const uint32_t nm = m1 - m0;
+        const uint32_t nm_max = __reduce_max_sync(FULL, nm);
+        if (nm_max == 0) continue;
         for (uint32_t i = l; i < S; i += PG_G) keys[i] = HLO_EMPTY32;
-        __syncwarp(gmask);
+        __syncwarp();
         uint32_t nh = 0;
         bool ovf = false;
-        for (uint32_t m = m0; m < m1; ++m) {
-            const uint2 rg = __ldg(a.range + m);
-            const uint32_t qrp = __ldg(a.mz_rp + m);
+        for (uint32_t s = 0; s < nm_max; ++s) {
+            uint2 rg = make_uint2(0u, 0u);
+            uint32_t qrp = 0;
+            if (s < nm) rg = __ldg(a.range + m0 + s), qrp = __ldg(a.mz_rp + m0 + s);
             const int qpos = (int)(qrp >> 1);
-            for (uint32_t i = rg.x + l; i < rg.y; i += PG_G) {
-                const uint2 h = __ldg(a.hits + i);
-                const uint32_t t = h.x;
-                if (t == q) continue;  // another minimizer of the query itself (-X: no self hits)
-                ++nh;
-                const uint32_t strand = (h.y ^ qrp) & 1u;
-                const int tp = (int)((h.y >> 1) & 0x7fffu);
-                const int qp = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
-                const int diag = tp - qp;
-                const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
-                uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
-                bool done = false;
-                for (uint32_t probe = 0; probe < S; ++probe) {
-                    const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
-                    if (old == HLO_EMPTY32) {
-                        vals[slot] = (uint32_t)qp | (uint32_t)qp << 16;
-                        aux[slot] = (uint16_t)(h.y >> 16);
-                        done = true;
-                        break;
+            const uint32_t nchunk_max = __reduce_max_sync(FULL, (rg.y - rg.x + PG_G - 1) / PG_G);
+            uint32_t i = rg.x + l;
+            for (uint32_t c = 0; c < nchunk_max; ++c, i += PG_G) {
+                if (i < rg.y) {
+                    const uint2 h = __ldg(a.hits + i);
+                    const uint32_t t = h.x;
+                    if (t != q) {  // t == q: another minimizer of the query itself (-X: no self hits)
+                        ++nh;
+                        const uint32_t strand = (h.y ^ qrp) & 1u;
+                        const int tp = (int)((h.y >> 1) & 0x7fffu);
+                        const int qp = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
+                        const int diag = tp - qp;
+                        const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
+                        uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
+                        bool done = false;
+                        for (uint32_t probe = 0; probe < S; ++probe) {
+                            const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
+                            if (old == HLO_EMPTY32) {
+                                vals[slot] = (uint32_t)qp | (uint32_t)qp << 16;
+                                aux[slot] = (uint16_t)(h.y >> 16);
+                                done = true;
+                                break;
+                            }
+                            if (old == key) {  // no other lane of the group holds this key in this step
+                                const uint32_t v = vals[slot];
+                                const uint32_t mn = min(v & 0xffffu, (uint32_t)qp), mx = max(v >> 16, (uint32_t)qp);
+                                vals[slot] = mn | mx << 16;
+                                done = true;
+                                break;
+                            }
+                            slot = (slot + 1u) & smask;
+                        }
+                        if (!done) ovf = true;
                     }
-                    if (old == key) {  // no other lane of the group holds this key in this iteration
-                        const uint32_t v = vals[slot];
-                        const uint32_t mn = min(v & 0xffffu, (uint32_t)qp), mx = max(v >> 16, (uint32_t)qp);
-                        vals[slot] = mn | mx << 16;
-                        done = true;
-                        break;
-                    }
-                    slot = (slot + 1u) & smask;
                 }
-                if (!done) ovf = true;
             }
-            __syncwarp(gmask);  // orders the plain min/max updates of consecutive minimizers
+            __syncwarp();  // orders the plain min/max updates of consecutive minimizers
         }
-        nh += __shfl_xor_sync(gmask, nh, 1, PG_G);
-        nh += __shfl_xor_sync(gmask, nh, 2, PG_G);
-        nh += __shfl_xor_sync(gmask, nh, 4, PG_G);
-        if (__any_sync(gmask, ovf)) {  // redo this read exactly in the generic kernel (its hits are counted there)
-            if (l == 0) {
+        // per-read reductions inside the 8-lane groups (uniform across the warp)
+        unsigned gmask = 0xFFu << (lane & ~7u);
+        const bool ovf_any = (__ballot_sync(FULL, ovf) & gmask) != 0u;
+        if (ovf_any) {  // redo this read exactly in the generic kernel (its hits are counted there)
+            if (l == 0 && have_read) {
                 const unsigned long long p = atomicAdd(&a.counters[2], 1ULL);
                 if (p < a.overflow_cap) a.overflow_reads[p] = xq;
             }
-            __syncwarp(gmask);
-            continue;
+        } else {
+            nh_total += nh;
         }
         // count, reserve, write
         uint32_t cnt = 0;
-        for (uint32_t i = l; i < S; i += PG_G) {
-            const uint32_t v = vals[i];
-            cnt += (keys[i] != HLO_EMPTY32 && (int)((v >> 16) - (v & 0xffffu)) >= a.gap_min);
-        }
-        uint32_t inc = cnt;
+        if (!ovf_any && nm)
+            for (uint32_t i = l; i < S; i += PG_G) {
+                const uint32_t v = vals[i];
+                cnt += (keys[i] != HLO_EMPTY32 && (int)((v >> 16) - (v & 0xffffu)) >= a.gap_min);
+            }
+        uint32_t inc = cnt;  // inclusive scan over the whole warp: groups are laid out consecutively
 #pragma unroll
-        for (int d = 1; d < PG_G; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(gmask, inc, d, PG_G);
-            if ((int)l >= d) inc += o;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if ((int)lane >= d) inc += o;
         }
-        const uint32_t total = __shfl_sync(gmask, inc, PG_G - 1, PG_G);
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
         unsigned long long base = 0;
-        if (l == 0) {
-            if (total) base = atomicAdd(&a.counters[0], (unsigned long long)total);
-            if (nh) atomicAdd(&a.counters[1], (unsigned long long)nh);
-        }
-        base = __shfl_sync(gmask, base, 0, PG_G);
+        if (lane == 0 && total) base = atomicAdd(&a.counters[0], (unsigned long long)total);
+        base = __shfl_sync(FULL, base, 0);
         if (cnt) {
             unsigned long long p = base + (inc - cnt);
             for (uint32_t i = l; i < S; i += PG_G) {
@@ -229,8 +243,12 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                 }
             }
         }
-        __syncwarp(gmask);
+        __syncwarp();
     }
+    // seed-hit statistic: one atomic per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nh_total += __shfl_xor_sync(FULL, nh_total, d);
+    if (lane == 0 && nh_total) atomicAdd(&a.counters[1], nh_total);
 }
 
 size_t pairgen_smem_bytes(int slots_log2) {
@@ -256,7 +274,7 @@ void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, Launch
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairgen_group_kernel, PG_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = ((uint64_t)a.reads.n_reads + PG_GROUPS - 1) / PG_GROUPS;
+    uint64_t want = ((uint64_t)a.reads.n_reads + PG_GROUPS - 1) / PG_GROUPS;  // 4 reads per warp, 4 warps per block
     uint64_t grid = (uint64_t)sms * per_sm;
     if (grid > want) grid = want;
     pairgen_group_kernel<<<(unsigned)grid, PG_THREADS, smem, s>>>(a, slots_log2);

@@ -10,7 +10,7 @@
 //   from the outermost anchor.  K = mismatches in the block, blocklen = block columns - ambiguous.
 //   Accept iff blocklen >= min_len, !(matches/blocklen < min_id), !(clip_l + clip_r > min(o, maplen*r)).
 //
-// verify_fast_kernel<NV>: ONE THREAD PER CANDIDATE.  The internal candidate (CandI) carries both read
+// verify_fast_kernel<W, FULLW>: ONE THREAD PER CANDIDATE.  The internal candidate (CandI) carries both read
 // lengths, so the geometry is known before a row is touched:
 //   1. overlaps shorter than min_len leave at once; pairs with an ambiguous base or with BOTH ends
 //      target-limited (query contains target, unequal lengths) go to verify_exact_kernel;
@@ -21,7 +21,9 @@
 //      NV LDG.128 per row (Y from the 16-byte vector that holds base S), a two-stage word select,
 //      funnel shifts for the residual 2-bit offset, XOR, (x|x>>1)&0x5555.. fold, popcount;
 //   4. thresholds from the host-built integer tables (shared memory), end rule on the outermost 32
-//      bases, one warp-aggregated atomicAdd per warp, 16-byte records.
+//      bases; accepted 16-byte records are staged per block in shared memory and leave with one global
+//      atomicAdd per ~400 records and coalesced stores (a per-warp global atomic on one address was the
+//      top stall of the first version: profiles/r1b).  The next candidate is loaded one iteration ahead.
 // Bound: integer (ALU) pipe and L1 wavefronts (one per 16-byte vector of the randomly addressed row);
 // rows are L2-resident.  Algorithmic bytes per candidate = 16 + 2*ceil(OL/4) (when OL >= min_len) + 16
 // per accepted record (SURVEY.md §8d counts 32 B for the expanded record; the expansion is records.cu).
@@ -63,14 +65,21 @@ __device__ __forceinline__ uint32_t low_mask(int n) {
 }
 
 constexpr int VF_THREADS = 128;
+constexpr int VF_STAGE = 512;  // records staged per block before one flush (one global atomic per flush)
 
-template <int NV>
+// W = 32-bit data words per row actually compared (ceil(max_len / 16)); the row stride is NV = ceil(W/4)
+// 16-byte vectors.  FULLW = words that every overlap of at least min_len bases covers completely (no mask).
+template <int W, int FULLW>
 __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
-    constexpr int NW = 4 * NV;
+    constexpr int NV = (W + 3) / 4, NW = 4 * NV;
     __shared__ uint16_t s_tab[3 * 1024];
+    __shared__ uint4 s_out[VF_STAGE];
+    __shared__ uint32_t s_cnt;
+    __shared__ unsigned long long s_base;
     // thresholds into shared memory (3 tables of max_len + 1 <= 1024 entries)
     const int tl1 = a.tab.max_len + 1;
     for (int i = threadIdx.x; i < 3 * tl1; i += VF_THREADS) s_tab[i] = a.tab.min_matches[i];
+    if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const uint16_t *t_min_matches = s_tab, *t_max_clip = s_tab + tl1, *t_max_k = s_tab + 2 * tl1;
 
@@ -80,13 +89,18 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     const uint64_t plane4 = (uint64_t)a.reads.n_reads * NV;  // uint4 per plane
     const uint4 *rows = reinterpret_cast<const uint4 *>(a.reads.bases);
     const uint4 *cands = reinterpret_cast<const uint4 *>(a.cands);
-    const uint64_t n_round = (a.n + 31) & ~31ull;  // whole warps iterate together
+    const uint64_t n_round = (a.n + VF_THREADS - 1) / VF_THREADS * VF_THREADS;  // whole blocks iterate together
     const int o = a.prm.max_overhang, min_len = a.prm.min_len;
-    for (uint64_t c = (uint64_t)blockIdx.x * VF_THREADS + threadIdx.x; c < n_round; c += n_threads) {
+    uint64_t c = (uint64_t)blockIdx.x * VF_THREADS + threadIdx.x;
+    uint4 cv_next = make_uint4(0u, 0u, 0u, 0u);
+    if (c < a.n) cv_next = __ldg(cands + c);
+    for (; c < n_round; c += n_threads) {
         bool accept = false, defer = false;
         uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-        if (c < a.n) {
-            const uint4 cv = __ldg(cands + c);
+        const uint4 cv = cv_next;
+        const bool live = c < a.n;
+        if (c + n_threads < a.n) cv_next = __ldg(cands + c + n_threads);  // next iteration's candidate, in flight early
+        if (live) {
             const uint32_t q = cv.x, t = cv.y;
             const int D = (int)(cv.z & 0xffffu) - 32768;
             const int ql = (int)((cv.z >> 16) & 0x7fffu), tl = (int)(cv.w & 0x7fffu);
@@ -124,17 +138,18 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
 #pragma unroll
                     for (int i = 0; i + 1 <= NW; ++i) y[i] = w1 ? y[i + 1] : y[i];
                     const uint32_t b2 = (uint32_t)(S & 15) * 2u;
-                    uint32_t f[NW];
+                    uint32_t f[W];
                     int mm = 0;
 #pragma unroll
-                    for (int i = 0; i < NW; ++i) {
+                    for (int i = 0; i < W; ++i) {
                         const uint32_t ys = __funnelshift_r(y[i], y[i + 1], b2);
                         const uint32_t d = x[i] ^ ys;
-                        f[i] = (d | (d >> 1)) & 0x55555555u & low_mask(2 * OL - 32 * i);
+                        f[i] = (d | (d >> 1)) & 0x55555555u;
+                        if (i >= FULLW) f[i] &= low_mask(2 * OL - 32 * i);
                     }
 #pragma unroll
-                    for (int i = 0; i + 1 < NW; i += 2) mm += __popc(f[i] | (f[i + 1] << 1));
-                    if (NW & 1) mm += __popc(f[NW - 1]);
+                    for (int i = 0; i + 1 < W; i += 2) mm += __popc(f[i] | (f[i + 1] << 1));
+                    if (W & 1) mm += __popc(f[W - 1]);
                     // cheap exact reject: the block keeps at least mm - o mismatches and is at most OL long
                     if (mm <= (int)t_max_k[OL] + o) {
                         int cl = 0, cmm = 0;
@@ -144,7 +159,7 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
                                 ok = false, defer = true;  // a 32-base window no longer decides the end rule
                             } else {
                                 const int REG = (int)((flip ? (cv.w >> 22) : (cv.w >> 15)) & 0x7fu);
-                                uint32_t lo = f[0], hi = NW > 1 ? f[1] : 0u;
+                                uint32_t lo = f[0], hi = W > 1 ? f[1] : 0u;
                                 if (REG < 32) lo &= low_mask(2 * REG), hi &= low_mask(2 * REG - 32);
                                 const ClipResult r = clip_scan32(lo, hi, a.prm.a, a.prm.b);
                                 cl = r.clip, cmm = r.mm;
@@ -163,26 +178,46 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
                 }
             }
         }
-        // stream compaction: one atomicAdd per warp for the accepted, one for the deferred
+        // stream compaction: accepted records are staged in shared memory (one shared atomic per warp) and a
+        // full stage leaves with ONE global atomicAdd and coalesced 16-byte stores
         const unsigned acc_b = __ballot_sync(0xffffffffu, accept);
-        const unsigned def_b = __ballot_sync(0xffffffffu, defer);
         if (acc_b) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(acc_b));
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_cnt, (uint32_t)__popc(acc_b));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (accept) reinterpret_cast<uint4 *>(a.out)[base + __popc(acc_b & lt_mask)] = rec;
+            if (accept) s_out[base + __popc(acc_b & lt_mask)] = rec;
         }
-        if (def_b) {
+        const unsigned def_b = __ballot_sync(0xffffffffu, defer);
+        if (def_b) {  // rare
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&a.counters[1], (unsigned long long)__popc(def_b));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (defer) a.deferred[base + __popc(def_b & lt_mask)] = (uint32_t)c;
         }
+        __syncthreads();
+        const uint32_t staged = s_cnt;
+        const bool last = c + n_threads >= n_round;
+        if (staged > VF_STAGE - VF_THREADS || (last && staged)) {  // the next iteration might not fit
+            if (threadIdx.x == 0) s_base = atomicAdd(&a.counters[0], (unsigned long long)staged);
+            __syncthreads();
+            const unsigned long long gb = s_base;
+            for (uint32_t i = threadIdx.x; i < staged; i += VF_THREADS) reinterpret_cast<uint4 *>(a.out)[gb + i] = s_out[i];
+            __syncthreads();
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+        }
     }
 }
 
 bool verify_fast_supported(const DevReads &r, const VerifyTables &tab) {
-    return r.nv >= 1 && r.nv <= 5 && tab.max_len + 1 <= 1024 && r.n_reads > 0;
+    return r.max_len >= 1 && r.max_len <= 320 && tab.max_len + 1 <= 1024 && r.n_reads > 0;
+}
+
+template <int W>
+static void launch_vf(const VerifyArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr int F3 = W >= 3 ? 3 : 0;
+    if (a.prm.min_len >= 48 && F3) verify_fast_kernel<W, F3><<<grid, VF_THREADS, 0, s>>>(a);
+    else verify_fast_kernel<W, 0><<<grid, VF_THREADS, 0, s>>>(a);
 }
 
 void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) {
@@ -191,14 +226,16 @@ void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint64_t want = (a.n + VF_THREADS - 1) / VF_THREADS;
-    uint64_t grid = (uint64_t)sms * 16;  // persistent: every block loads the threshold tables once
-    if (grid > want) grid = want;
-    switch (a.reads.nv) {
-        case 1: verify_fast_kernel<1><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
-        case 2: verify_fast_kernel<2><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
-        case 3: verify_fast_kernel<3><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
-        case 4: verify_fast_kernel<4><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
-        default: verify_fast_kernel<5><<<(unsigned)grid, VF_THREADS, 0, s>>>(a); break;
+    uint64_t grid64 = (uint64_t)sms * 12;  // persistent: every block loads the threshold tables once
+    if (grid64 > want) grid64 = want;
+    const unsigned grid = (unsigned)grid64;
+    const int W = (int)((a.reads.max_len + 15) / 16);
+    switch (W) {
+#define VF_CASE(w) case w: launch_vf<w>(a, grid, s); break;
+        VF_CASE(1) VF_CASE(2) VF_CASE(3) VF_CASE(4) VF_CASE(5) VF_CASE(6) VF_CASE(7) VF_CASE(8) VF_CASE(9) VF_CASE(10)
+        VF_CASE(11) VF_CASE(12) VF_CASE(13) VF_CASE(14) VF_CASE(15) VF_CASE(16) VF_CASE(17) VF_CASE(18) VF_CASE(19)
+        default: launch_vf<20>(a, grid, s); break;
+#undef VF_CASE
     }
     if (lc) lc->total++, lc->verify++;
 }
