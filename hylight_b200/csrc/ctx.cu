@@ -93,7 +93,8 @@ struct hlo_ctx {
     LaunchCounter lc;
     hlo_timing tm;
     int pairgen_slots_log2 = 8;
-    int verify_exact = 0, repack = 0, d2h = 1, pairgen_generic = 0;
+    int verify_exact = 0, repack = 0, d2h = 1, pairgen_generic = 0, sketch_generic = 0;
+    bool keys_ready = false;
     cudaEvent_t ev_vf[2] = {};
     // verify tables
     DevBuf b_tab;
@@ -102,7 +103,7 @@ struct hlo_ctx {
     // workspaces
     DevBuf b_cnt, b_mzoff, b_mzx, b_mzrp, b_mzrid, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
     DevBuf b_cands, b_counters, b_ovf, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
-    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx;
+    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp;
     std::map<uint32_t, std::vector<uint32_t>> name_order;  // N -> integers 0..N-1 in strcmp order of their decimal spelling
     PinBuf h_out, h_aux, h_coff, h_mz, h_roff, h_cands, h_rec16, h_small;
     std::vector<uint64_t> v_coff;
@@ -243,7 +244,7 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
                       &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_bstart,
                       &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovfcnt, &ctx->b_gkeys,
                       &ctx->b_gmn, &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos,
-                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx};
+                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx, &ctx->b_sx, &ctx->b_srp};
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&ctx->h_out, &ctx->h_aux, &ctx->h_coff, &ctx->h_mz, &ctx->h_roff, &ctx->h_cands, &ctx->h_rec16, &ctx->h_small};
     for (PinBuf *b : pins) b->release();
@@ -462,37 +463,64 @@ extern "C" void hlo_reads_free(hlo_reads *R) {
 // ------------------------------------------------------------------------------------------------
 // stages
 
-static int read_u32(hlo_ctx *ctx, const uint32_t *dptr, uint32_t *out) {
-    CK(cudaMemcpyAsync(out, dptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return HLO_OK;
-}
-
-// sketch: count -> scan -> write.  Leaves mz_off (n_reads+1), mz_x, mz_rp, mz_rid on the device.
+// sketch.  Leaves mz_off (n_reads+1, name order), mz_x, mz_rp, mz_rid on the device; with the single-pass
+// fast kernel also the radix sort's input pairs (keys_ready).
 static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
     const DevReads &d = R->d;
     cudaStream_t s = ctx->stream;
     const uint32_t n = d.n_reads;
+    if ((uint64_t)d.n_bases > 0xffffffffull) FAIL(HLO_ERANGE, "batch of %llu bases exceeds the 2^32 minimizer index range", (unsigned long long)d.n_bases);
     CK(ctx->b_cnt.ensure(((size_t)n + 1) * 4));
     CK(ctx->b_mzoff.ensure(((size_t)n + 2) * 4));
     CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)n + 1) * 4));
-    CK(cudaMemsetAsync(ctx->b_cnt.p, 0, ((size_t)n + 1) * 4, s));
-    launch_sketch_count(d, ctx->P.w, ctx->P.k, ctx->b_cnt.as<uint32_t>(), s, &ctx->lc);
+    CK(ctx->b_counters.ensure(16 * 8));
+    ctx->keys_ready = false;
+    const bool fast = sketch_fast_supported(ctx->P.w, ctx->P.k) && !ctx->sketch_generic && n > 0;
+    uint32_t cap = 0;
+    if (fast) {
+        // strip capacity: 3.5x the expected density 2/(w+1) plus slack, never more than one per k-mer
+        const uint32_t kmers = d.max_len >= (uint32_t)ctx->P.k ? d.max_len - (uint32_t)ctx->P.k + 1 : 0;
+        cap = std::min<uint32_t>(std::max<uint32_t>(kmers, 1u), (uint32_t)(7.0 * kmers / (ctx->P.w + 1)) + 8u);
+        CK(ctx->b_sx.ensure((size_t)n * cap * 8 + 8));
+        CK(ctx->b_srp.ensure((size_t)n * cap * 4 + 4));
+        CK(ctx->b_ovf.ensure((size_t)n * 4 + 4));
+        CK(cudaMemsetAsync(ctx->b_cnt.as<uint32_t>() + n, 0, 4, s));
+        CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 10, 0, 8, s));
+        launch_sketch_fast(d, ctx->P.w, ctx->P.k, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
+                           ctx->b_ovf.as<uint32_t>(), ctx->b_counters.as<unsigned long long>() + 10, s, &ctx->lc);
+    } else {
+        CK(cudaMemsetAsync(ctx->b_cnt.p, 0, ((size_t)n + 1) * 4, s));
+        launch_sketch_count(d, ctx->P.w, ctx->P.k, ctx->b_cnt.as<uint32_t>(), s, &ctx->lc);
+    }
     // scanning n+1 counts (the last is 0) puts the total at mz_off[n]
     launch_exclusive_scan(ctx->b_cnt.as<uint32_t>(), ctx->b_mzoff.as<uint32_t>(), (uint64_t)n + 1, ctx->b_tmp.as<uint32_t>(), nullptr,
                           s, &ctx->lc);
     CK(cudaGetLastError());
     uint32_t total = 0;
-    int rc = read_u32(ctx, ctx->b_mzoff.as<uint32_t>() + n, &total);
-    if (rc) return rc;
-    // guard against u32 wrap of the scan
-    if ((uint64_t)d.n_bases > 0xffffffffull) FAIL(HLO_ERANGE, "batch of %llu bases exceeds the 2^32 minimizer index range", (unsigned long long)d.n_bases);
+    unsigned long long n_ovf = 0;
+    CK(cudaMemcpyAsync(&total, ctx->b_mzoff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, s));
+    if (fast) CK(cudaMemcpyAsync(&n_ovf, ctx->b_counters.as<unsigned long long>() + 10, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     ctx->n_mz = total;
     CK(ctx->b_mzx.ensure((size_t)total * 8 + 8));
     CK(ctx->b_mzrp.ensure((size_t)total * 4 + 4));
     CK(ctx->b_mzrid.ensure((size_t)total * 4 + 4));
-    launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
-                        ctx->b_mzrid.as<uint32_t>(), s, &ctx->lc);
+    if (fast) {
+        for (int i = 0; i < 2; ++i) {
+            CK(ctx->b_keys[i].ensure((size_t)total * 8 + 8));
+            CK(ctx->b_vals[i].ensure((size_t)total * 4 + 4));
+        }
+        launch_sketch_compact(d, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
+                              ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
+                              ctx->b_mzrid.as<uint32_t>(), ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
+        ctx->keys_ready = n_ovf == 0;
+        if (n_ovf)  // reads with more minimizers than a strip holds: the generic kernel writes them in place
+            launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
+                                ctx->b_mzrid.as<uint32_t>(), ctx->b_ovf.as<uint32_t>(), (uint32_t)n_ovf, s, &ctx->lc);
+    } else {
+        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
+                            ctx->b_mzrid.as<uint32_t>(), nullptr, 0, s, &ctx->lc);
+    }
     CK(cudaGetLastError());
     return HLO_OK;
 }
@@ -511,7 +539,8 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R) {
     CK(ctx->b_bstart.ensure((n + 2) * 4));
     CK(ctx->b_range.ensure(n * 8 + 8));
     CK(ctx->b_hits.ensure(n * 8 + 8));
-    launch_hash_keys(ctx->b_mzx.as<uint64_t>(), n, ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
+    if (!ctx->keys_ready)
+        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), n, ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
     const int cur = launch_radix_sort(keys, vals, n, 0, 2 * ctx->P.k, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
@@ -926,6 +955,10 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return HLO_EINVAL;
     if (!strcmp(name, "verify_exact")) {
         ctx->verify_exact = value != 0;
+        return HLO_OK;
+    }
+    if (!strcmp(name, "sketch_generic")) {
+        ctx->sketch_generic = value != 0;
         return HLO_OK;
     }
     if (!strcmp(name, "pairgen_generic")) {

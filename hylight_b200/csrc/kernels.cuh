@@ -17,8 +17,16 @@ void launch_pack(const uint8_t *ascii, const uint64_t *base_off, DevReads r, uin
 // ---- sketch.cu ------------------------------------------------------------------------------
 // pass 0: count[r] = number of minimizers of read r;  pass 1: write them at off[r].
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc);
+// list != nullptr: only the n_list listed reads (x indices)
 void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp,
-                         uint32_t *mz_rid, cudaStream_t s, LaunchCounter *lc);
+                         uint32_t *mz_rid, const uint32_t *list, uint32_t n_list, cudaStream_t s, LaunchCounter *lc);
+// single-pass fast path (static window, k odd): per-read strips of `cap` entries + counts, then a gather
+bool sketch_fast_supported(int w, int k);
+void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
+                        uint32_t *ovf_list, unsigned long long *ovf_cnt, cudaStream_t s, LaunchCounter *lc);
+void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
+                           const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp, uint32_t *mz_rid, uint64_t *keys, uint32_t *vals,
+                           cudaStream_t s, LaunchCounter *lc);
 void launch_mz_assemble(const uint64_t *mz_x, const uint32_t *mz_rp, const uint32_t *mz_rid, uint64_t n, hlo_mz *out,
                         cudaStream_t s, LaunchCounter *lc);
 

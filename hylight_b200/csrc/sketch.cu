@@ -10,6 +10,8 @@
 // packed row; a count pass sizes the output, a write pass fills it, so the output is in minimap2's
 // emission order.  Integer-pipe bound: ~150 ALU ops per base; algorithmic bytes per read =
 // ceil(L/4) in + 16 B per minimizer out.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace hlo {
@@ -45,12 +47,14 @@ __device__ __forceinline__ void mz_push(uint32_t &n, uint64_t x, uint32_t rp, ui
 
 template <bool WRITE>
 __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, uint32_t *__restrict__ count,
-                                                     const uint32_t *__restrict__ off, MzOut o) {
+                                                     const uint32_t *__restrict__ off, MzOut o,
+                                                     const uint32_t *__restrict__ list, uint32_t n_list) {
     // thread x sketches read perm[x]: the minimizer arrays are laid out in the strcmp order of the read
     // names inside each cluster, so that after the stable hash sort every seed bucket is ordered the way
     // minimap2's -X rule compares names (pairgen.cu)
-    const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (xi >= r.n_reads) return;
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= (list ? n_list : r.n_reads)) return;
+    const uint32_t xi = list ? list[ti] : ti;
     const uint32_t read = __ldg(r.perm + xi);
     const uint32_t lenf = r.len[read];
     const int len = (int)(lenf & HLO_LEN_MASK);
@@ -125,15 +129,172 @@ __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, u
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc) {
     if (r.n_reads == 0) return;
     MzOut o{nullptr, nullptr, nullptr};
-    sketch_kernel<false><<<(r.n_reads + 127) / 128, 128, 0, s>>>(r, w, k, count, nullptr, o);
+    sketch_kernel<false><<<(r.n_reads + 127) / 128, 128, 0, s>>>(r, w, k, count, nullptr, o, nullptr, 0);
     if (lc) lc->total++;
 }
 
 void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp,
-                         uint32_t *mz_rid, cudaStream_t s, LaunchCounter *lc) {
-    if (r.n_reads == 0) return;
+                         uint32_t *mz_rid, const uint32_t *list, uint32_t n_list, cudaStream_t s, LaunchCounter *lc) {
+    const uint32_t n = list ? n_list : r.n_reads;
+    if (n == 0) return;
     MzOut o{mz_x, mz_rp, mz_rid};
-    sketch_kernel<true><<<(r.n_reads + 127) / 128, 128, 0, s>>>(r, w, k, nullptr, off, o);
+    sketch_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(r, w, k, nullptr, off, o, list, n_list);
+    if (lc) lc->total++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: window size WW known at compile time and k odd (no k-mer equals its own reverse complement,
+// so the "strand-symmetric k-mer" skip of mm_sketch never fires and buffer slot = position mod w).
+// The step loop is unrolled WW times: the ring buffer lives in registers with static indices, the rescan
+// when the minimum leaves the window is a straight-line select chain, and nothing touches local memory.
+// ONE pass: the automaton writes its minimizers into a per-read scratch strip of `cap` entries and counts
+// them; after the prefix sum a gather kernel compacts the strips (and writes the sort keys on the way).
+// A read that emits more than `cap` minimizers is listed and redone by the generic kernel.
+// compile-time loop: the body sees its index as a constant expression, so the window arrays below are
+// indexed by constants from the first optimisation pass on and live in registers (a `#pragma unroll` loop
+// left them in local memory)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+template <int WW>
+__global__ void __launch_bounds__(128) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+                                                          uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
+                                                          uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt) {
+    const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xi >= r.n_reads) return;
+    const uint32_t read = __ldg(r.perm + xi);
+    const uint32_t lenf = __ldg(r.len + read);
+    const int len = (int)(lenf & HLO_LEN_MASK);
+    const bool has_amb = (lenf & HLO_AMB_FLAG) != 0;
+    const uint32_t *row = r.bases + (uint64_t)read * r.stride_w;
+    const uint32_t *arow = r.amb + (uint64_t)read * r.stride_w;
+    const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
+    const uint64_t INF = ~0ULL;
+    uint64_t kmer0 = 0, kmer1 = 0;
+    uint64_t bx[WW];
+    uint32_t by[WW];
+    static_for<0, WW>([&](auto J) { bx[J] = INF, by[J] = 0xffffffffu; });
+    uint64_t min_x = INF;
+    uint32_t min_y = 0xffffffffu;
+    int min_slot = 0, l = 0;
+    uint32_t n = 0;
+    const uint64_t sbase = (uint64_t)xi * cap;
+    auto emit = [&](uint64_t X, uint32_t Y) {
+        if (n < cap) sx[sbase + n] = X, srp[sbase + n] = Y;
+        ++n;
+    };
+    uint32_t word = 0, aword = 0;
+    for (int i0 = 0; i0 < len; i0 += WW) {
+        static_for<0, WW>([&](auto SS) {
+            constexpr int s = SS;
+            const int i = i0 + s;
+            if (i < len) {
+                if ((i & 15) == 0) {
+                    word = __ldg(row + (i >> 4));
+                    aword = has_amb ? __ldg(arow + (i >> 4)) : 0u;
+                }
+                const uint32_t c = word & 3u, amb = aword & 1u;
+                word >>= 2, aword >>= 2;
+                uint64_t info_x = INF;
+                uint32_t info_y = 0xffffffffu;
+                if (!amb) {
+                    const int kmer_span = l + 1 < k ? l + 1 : k;
+                    kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
+                    kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+                    const uint32_t z = kmer0 < kmer1 ? 0u : 1u;  // k odd: kmer0 != kmer1 always
+                    ++l;
+                    if (l >= k) {
+                        info_x = mm_hash64(z ? kmer1 : kmer0, mask) << 8 | (uint64_t)kmer_span;
+                        info_y = (uint32_t)i << 1 | z;
+                    }
+                } else
+                    l = 0;
+                bx[s] = info_x, by[s] = info_y;
+                if (l == WW + k - 1 && min_x != INF) {  // first full window: identical k-mers were not stored yet
+                    static_for<s + 1, WW>([&](auto J) {
+                        if (min_x == bx[J] && by[J] != min_y) emit(bx[J], by[J]);
+                    });
+                    static_for<0, s>([&](auto J) {
+                        if (min_x == bx[J] && by[J] != min_y) emit(bx[J], by[J]);
+                    });
+                }
+                if (info_x <= min_x) {  // a new minimum; write the old one
+                    if (l >= WW + k && min_x != INF) emit(min_x, min_y);
+                    min_x = info_x, min_y = info_y, min_slot = s;
+                } else if (min_slot == s) {  // the old minimum left the window
+                    if (l >= WW + k - 1 && min_x != INF) emit(min_x, min_y);
+                    min_x = INF;
+                    bool tie = false;  // at least two buffer entries share the new minimum
+                    auto scan = [&](auto J) {  // >= : the rightmost smallest wins
+                        if (min_x >= bx[J]) tie = min_x == bx[J], min_x = bx[J], min_y = by[J], min_slot = J;
+                    };
+                    static_for<s + 1, WW>(scan);
+                    static_for<0, s + 1>(scan);
+                    if (tie && l >= WW + k - 1 && min_x != INF) {
+                        auto dup = [&](auto J) {
+                            if (min_x == bx[J] && min_y != by[J]) emit(bx[J], by[J]);
+                        };
+                        static_for<s + 1, WW>(dup);
+                        static_for<0, s + 1>(dup);
+                    }
+                }
+            }
+        });
+    }
+    if (min_x != INF) emit(min_x, min_y);
+    count[xi] = n;
+    if (n > cap) {
+        const unsigned long long p = atomicAdd(ovf_cnt, 1ULL);
+        ovf_list[p] = xi;
+    }
+}
+
+bool sketch_fast_supported(int w, int k) { return (k & 1) && k >= 1 && k <= 28 && (w == 11 || w == 5 || w == 19); }
+
+void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
+                        uint32_t *ovf_list, unsigned long long *ovf_cnt, cudaStream_t s, LaunchCounter *lc) {
+    if (r.n_reads == 0) return;
+    const unsigned grid = (r.n_reads + 127) / 128;
+    if (w == 11) sketch_fast_kernel<11><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
+    else if (w == 5) sketch_fast_kernel<5><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
+    else sketch_fast_kernel<19><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
+    if (lc) lc->total++;
+}
+
+// strips -> dense arrays in name order, plus the (hash, index) pairs the radix sort starts from.
+// One thread per (read, strip slot); strips of reads that overflowed are skipped (the generic kernel
+// writes those reads afterwards).
+__global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_t cap, const uint64_t *__restrict__ sx,
+                                                             const uint32_t *__restrict__ srp, const uint32_t *__restrict__ count,
+                                                             const uint32_t *__restrict__ off, uint64_t *__restrict__ mz_x,
+                                                             uint32_t *__restrict__ mz_rp, uint32_t *__restrict__ mz_rid,
+                                                             uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)r.n_reads * cap;
+    if (gid >= total) return;
+    const uint32_t xi = (uint32_t)(gid / cap), j = (uint32_t)(gid % cap);
+    const uint32_t n = count[xi];
+    if (j >= n || n > cap) return;
+    const uint32_t dst = off[xi] + j;
+    const uint64_t x = sx[gid];
+    mz_x[dst] = x;
+    mz_rp[dst] = srp[gid];
+    mz_rid[dst] = r.perm[xi];
+    keys[dst] = x >> 8;
+    vals[dst] = dst;
+}
+
+void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
+                           const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp, uint32_t *mz_rid, uint64_t *keys, uint32_t *vals,
+                           cudaStream_t s, LaunchCounter *lc) {
+    const uint64_t total = (uint64_t)r.n_reads * cap;
+    if (total == 0) return;
+    sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rp, mz_rid, keys, vals);
     if (lc) lc->total++;
 }
 

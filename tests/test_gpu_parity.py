@@ -25,19 +25,23 @@ def ctx():
 
 
 def sketch_case(ctx, seqs_per_cluster, **pkw):
+    """both sketch kernels (single-pass static-window kernel where it applies, generic two-pass kernel) vs the oracle"""
     b = orc.Batch(seqs_per_cluster)
     c = ctx if not pkw else api.Context(0, **pkw)
-    try:
-        R = c.pack(b)
-        mz, ro = c.sketch(R)
-        R.free()
-    finally:
-        if pkw:
-            c.close()
     p = orc.default_params(**pkw)
     mz_o, ro_o = orc.sketch_all(b, p)
-    assert np.array_equal(ro, ro_o)
-    assert np.array_equal(mz["x"], mz_o["x"]) and np.array_equal(mz["y"], mz_o["y"])
+    try:
+        for generic in (0, 1):
+            c.set_option("sketch_generic", generic)
+            R = c.pack(b)
+            mz, ro = c.sketch(R)
+            R.free()
+            assert np.array_equal(ro, ro_o)
+            assert np.array_equal(mz["x"], mz_o["x"]) and np.array_equal(mz["y"], mz_o["y"])
+    finally:
+        c.set_option("sketch_generic", 0)
+        if pkw:
+            c.close()
     return len(mz)
 
 
