@@ -9,6 +9,7 @@
 // kernels through the C ABI of include/hlovlp.h; this file only parses text, batches clusters, drives
 // one worker thread per GPU (clusters are independent: dynamic queue, host-side gather, no NCCL) and
 // writes text.  There is no CPU code path for the overlap computation.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -36,6 +37,7 @@ struct Options {
     hlo_params P;
     std::vector<int> devices;
     uint64_t batch_bases = 256ull << 20;
+    int workers_per_device = 2;
     bool rename = false;
     std::string stats;
     std::vector<Cluster> clusters;
@@ -140,6 +142,8 @@ void usage() {
             "  --rename            name reads 0..N-1 in file order (what rename_fas.py does)\n"
             "  --devices 0,1,..|all   GPUs to use (default all)\n"
             "  --batch_bases N     bases per device batch (default 268435456)\n"
+            "  --workers_per_device N  host workers (context + stream each) per GPU; 2 overlaps one batch's copies\n"
+            "                      and text output with another's kernels (default 2)\n"
             "  --stats FILE        JSON-lines per batch\n");
 }
 
@@ -178,6 +182,7 @@ bool parse_args(int argc, char **argv, Options &o, std::string &err) {
         else if (a == "--mid_occ") o.P.mid_occ = atoi(v);
         else if (a == "--devices") devs = v;
         else if (a == "--batch_bases") o.batch_bases = strtoull(v, nullptr, 10);
+        else if (a == "--workers_per_device") o.workers_per_device = std::max(1, atoi(v));
         else if (a == "--stats") o.stats = v;
         else {
             err = "unknown option " + a;
@@ -387,8 +392,8 @@ int main(int argc, char **argv) {
         }
     }
     std::vector<std::thread> th;
-    const size_t n_workers = std::min(o.devices.size(), S.batches.size());
-    for (size_t i = 0; i < n_workers; ++i) th.emplace_back(worker, &S, o.devices[i]);
+    const size_t n_workers = std::min(o.devices.size() * (size_t)o.workers_per_device, S.batches.size());
+    for (size_t i = 0; i < n_workers; ++i) th.emplace_back(worker, &S, o.devices[i % o.devices.size()]);
     for (auto &t : th) t.join();
     if (S.stats && S.stats != stderr) fclose(S.stats);
     return S.failed ? 1 : 0;
