@@ -16,9 +16,12 @@
 // pairgen_group_kernel: 8 lanes per query read (4 reads per warp, 16 per block).  The lanes stream the
 // suffix of each of the read's buckets from the hash-ordered hit array (coalesced 8-byte entries) and fold
 // every hit into the group's shared-memory hash table keyed by a 32-bit (t - cluster base, strand,
-// diagonal) that keeps min/max anchor position and the target's length — the warp-level dedup of the
-// north star.  Within one query minimizer all keys are distinct, so only the key claim is an atomic
-// (ATOMS.CAS); min/max are plain read-modify-writes ordered by a __syncwarp per minimizer.
+// diagonal) that keeps min/max anchor position — the warp-level dedup of the north star.  Within one
+// query minimizer all keys are distinct, so only the key claim is an atomic (ATOMS.CAS; a claim by plain
+// store + read-back after __syncwarp was measured slower); min/max are plain read-modify-writes ordered
+// by a __syncwarp per minimizer.  Claimed slots go to a per-read list and the number of qualifying chains
+// is counted while inserting, so the emission is one pass over ~100 list entries instead of two over the
+// table.  Bucket ranges and hits are loaded one step ahead of their use.
 // A read whose table overflows, or a batch whose keys do not fit 32 bits, is done exactly by
 // pairgen_generic_kernel with a 64-bit-keyed table in HBM.
 // Algorithmic bytes: 8 B per seed hit in + 16 B per candidate out.
@@ -128,14 +131,17 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     extern __shared__ uint32_t pg_smem[];
     const uint32_t S = 1u << slots_log2, smask = S - 1u, ST = S + PG_PAD;
     const uint32_t g = threadIdx.x / PG_G, l = threadIdx.x % PG_G;
-    uint32_t *keys = pg_smem + (size_t)g * ST;
-    uint32_t *vals = pg_smem + (size_t)PG_GROUPS * ST + (size_t)g * ST;
-    uint16_t *aux = reinterpret_cast<uint16_t *>(pg_smem + (size_t)2 * PG_GROUPS * ST) + (size_t)g * ST;
+    uint32_t *keys = pg_smem + (size_t)g * ST;                                // (t - cluster base, strand, diagonal)
+    uint32_t *vals = pg_smem + (size_t)PG_GROUPS * ST + (size_t)g * ST;       // min anchor pos | max anchor pos << 16
+    uint16_t *list = reinterpret_cast<uint16_t *>(pg_smem + (size_t)2 * PG_GROUPS * ST) + (size_t)g * ST;  // claimed slots
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
+    const unsigned gshift = lane & ~7u;
+    const unsigned lt8 = (1u << l) - 1u;
     const int kshift = a.dg_bits + 1;
     const uint32_t max_len = a.reads.max_len;
     const uint32_t n_reads = a.reads.n_reads;
+    const int gap_min = a.gap_min;
     unsigned long long nh_total = 0;
     for (;;) {
         unsigned long long qq = 0;
@@ -155,72 +161,86 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         const uint32_t nm = m1 - m0;
         const uint32_t nm_max = __reduce_max_sync(FULL, nm);
         if (nm_max == 0) continue;
-        for (uint32_t i = l; i < S; i += PG_G) keys[i] = HLO_EMPTY32;
+        {
+            uint4 *k4 = reinterpret_cast<uint4 *>(keys);
+            const uint4 e4 = make_uint4(HLO_EMPTY32, HLO_EMPTY32, HLO_EMPTY32, HLO_EMPTY32);
+            for (uint32_t i = l; i < S / 4; i += PG_G) k4[i] = e4;
+        }
         __syncwarp();
-        uint32_t nh = 0;
+        uint32_t nh = 0, nq = 0, list_n = 0;
         bool ovf = false;
+        // the bucket range of the next minimizer and the next chunk of hits are loaded one step ahead, so
+        // that their (L2) latency overlaps the table work of the current chunk
+        uint2 rg_n = make_uint2(0u, 0u);
+        uint32_t qrp_n = 0;
+        if (nm) rg_n = __ldg(a.range + m0), qrp_n = __ldg(a.mz_rp + m0);
         for (uint32_t s = 0; s < nm_max; ++s) {
-            uint2 rg = make_uint2(0u, 0u);
-            uint32_t qrp = 0;
-            if (s < nm) rg = __ldg(a.range + m0 + s), qrp = __ldg(a.mz_rp + m0 + s);
+            const uint2 rg = rg_n;
+            const uint32_t qrp = qrp_n;
+            rg_n = make_uint2(0u, 0u);
+            if (s + 1 < nm) rg_n = __ldg(a.range + m0 + s + 1), qrp_n = __ldg(a.mz_rp + m0 + s + 1);
             const int qpos = (int)(qrp >> 1);
             const uint32_t nchunk_max = __reduce_max_sync(FULL, (rg.y - rg.x + PG_G - 1) / PG_G);
             uint32_t i = rg.x + l;
+            uint2 h_n = make_uint2(q, 0u);
+            if (i < rg.y) h_n = __ldg(a.hits + i);
             for (uint32_t c = 0; c < nchunk_max; ++c, i += PG_G) {
-                if (i < rg.y) {
-                    const uint2 h = __ldg(a.hits + i);
+                const uint2 h = h_n;
+                const bool in_range = i < rg.y;
+                if (i + PG_G < rg.y) h_n = __ldg(a.hits + i + PG_G);
+                int newslot = -1;
+                if (in_range && h.x != q) {  // h.x == q: another minimizer of the query itself (-X: no self hits)
                     const uint32_t t = h.x;
-                    if (t != q) {  // t == q: another minimizer of the query itself (-X: no self hits)
-                        ++nh;
-                        const uint32_t strand = (h.y ^ qrp) & 1u;
-                        const int tp = (int)((h.y >> 1) & 0x7fffu);
-                        const int qp = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
-                        const int diag = tp - qp;
-                        const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
-                        uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
-                        bool done = false;
-                        for (uint32_t probe = 0; probe < S; ++probe) {
-                            const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
-                            if (old == HLO_EMPTY32) {
-                                vals[slot] = (uint32_t)qp | (uint32_t)qp << 16;
-                                aux[slot] = (uint16_t)(h.y >> 16);
-                                done = true;
-                                break;
-                            }
-                            if (old == key) {  // no other lane of the group holds this key in this step
-                                const uint32_t v = vals[slot];
-                                const uint32_t mn = min(v & 0xffffu, (uint32_t)qp), mx = max(v >> 16, (uint32_t)qp);
-                                vals[slot] = mn | mx << 16;
-                                done = true;
-                                break;
-                            }
-                            slot = (slot + 1u) & smask;
+                    ++nh;
+                    const uint32_t strand = (h.y ^ qrp) & 1u;
+                    const int tp = (int)((h.y >> 1) & 0x7fffu);
+                    const int qpi = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
+                    const int diag = tp - qpi;
+                    const uint32_t qp = (uint32_t)qpi;
+                    const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
+                    uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
+                    bool done = false;
+                    for (uint32_t probe = 0; probe < S; ++probe) {
+                        const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
+                        if (old == HLO_EMPTY32) {
+                            vals[slot] = qp | qp << 16;
+                            nq += gap_min <= 0;
+                            newslot = (int)slot;
+                            done = true;
+                            break;
                         }
-                        if (!done) ovf = true;
+                        if (old == key) {  // no other lane of the group holds this key in this step
+                            const uint32_t v = vals[slot];
+                            const uint32_t mn = min(v & 0xffffu, qp), mx = max(v >> 16, qp);
+                            vals[slot] = mn | mx << 16;
+                            nq += ((int)((v >> 16) - (v & 0xffffu)) < gap_min) && ((int)(mx - mn) >= gap_min);
+                            done = true;
+                            break;
+                        }
+                        slot = (slot + 1u) & smask;
                     }
+                    if (!done) ovf = true;
                 }
+                // remember the claimed slots (per-group list, positions from a ballot: no atomics)
+                const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & 0xFFu;
+                if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (uint16_t)newslot;
+                list_n += __popc(gb);
             }
             __syncwarp();  // orders the plain min/max updates of consecutive minimizers
         }
         // per-read reductions inside the 8-lane groups (uniform across the warp)
-        unsigned gmask = 0xFFu << (lane & ~7u);
-        const bool ovf_any = (__ballot_sync(FULL, ovf) & gmask) != 0u;
+        const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & 0xFFu) != 0u;
         if (ovf_any) {  // redo this read exactly in the generic kernel (its hits are counted there)
             if (l == 0 && have_read) {
                 const unsigned long long p = atomicAdd(&a.counters[2], 1ULL);
                 if (p < a.overflow_cap) a.overflow_reads[p] = xq;
             }
+            nq = 0, list_n = 0;
         } else {
             nh_total += nh;
         }
-        // count, reserve, write
-        uint32_t cnt = 0;
-        if (!ovf_any && nm)
-            for (uint32_t i = l; i < S; i += PG_G) {
-                const uint32_t v = vals[i];
-                cnt += (keys[i] != HLO_EMPTY32 && (int)((v >> 16) - (v & 0xffffu)) >= a.gap_min);
-            }
-        uint32_t inc = cnt;  // inclusive scan over the whole warp: groups are laid out consecutively
+        // candidates of the read = group sum of nq; reserve space for the warp's 4 reads with one atomic
+        uint32_t inc = nq;  // inclusive scan over the whole warp: groups are laid out consecutively
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, inc, d);
@@ -230,18 +250,28 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         unsigned long long base = 0;
         if (lane == 0 && total) base = atomicAdd(&a.counters[0], (unsigned long long)total);
         base = __shfl_sync(FULL, base, 0);
-        if (cnt) {
-            unsigned long long p = base + (inc - cnt);
-            for (uint32_t i = l; i < S; i += PG_G) {
-                const uint32_t key = keys[i], v = vals[i];
-                const uint32_t mn = v & 0xffffu, mx = v >> 16;
-                if (key != HLO_EMPTY32 && (int)(mx - mn) >= a.gap_min) {
-                    const uint32_t au = aux[i];
-                    const uint32_t strand = (key >> a.dg_bits) & 1u;
-                    const int diag = (int)(key & ((1u << a.dg_bits) - 1u)) - (int)max_len;
-                    emit_cand(a, p++, q, cb + (key >> kshift), strand, diag, mn, mx, ql, au & 0x7fffu, (au >> 15) | (lq >> 31));
-                }
+        // exclusive prefix of my group = inclusive prefix of the last lane of the previous group
+        const uint32_t gprev = __shfl_sync(FULL, inc, (gshift + 31u) & 31u);
+        unsigned long long p = base + (gshift ? gprev : 0u);
+        const uint32_t list_max = __reduce_max_sync(FULL, list_n);
+        for (uint32_t j0 = 0; j0 < list_max; j0 += PG_G) {
+            const uint32_t j = j0 + l;
+            bool okc = false;
+            uint32_t key = 0, v = 0;
+            if (j < list_n) {
+                const uint32_t e = list[j];
+                key = keys[e], v = vals[e];
+                okc = (int)((v >> 16) - (v & 0xffffu)) >= gap_min;
             }
+            const unsigned ob = (__ballot_sync(FULL, okc) >> gshift) & 0xFFu;
+            if (okc) {
+                const uint32_t t = cb + (key >> kshift);
+                const uint32_t lt = __ldg(a.reads.len + t);
+                const uint32_t strand = (key >> a.dg_bits) & 1u;
+                const int diag = (int)(key & ((1u << a.dg_bits) - 1u)) - (int)max_len;
+                emit_cand(a, p + __popc(ob & lt8), q, t, strand, diag, v & 0xffffu, v >> 16, ql, lt & 0x7fffu, (lt | lq) >> 31);
+            }
+            p += __popc(ob);
         }
         __syncwarp();
     }
@@ -253,7 +283,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
 
 size_t pairgen_smem_bytes(int slots_log2) {
     const size_t ST = ((size_t)1 << slots_log2) + PG_PAD;
-    return (size_t)PG_GROUPS * ST * 10;  // keys u32 + vals u32 + aux u16
+    return (size_t)PG_GROUPS * ST * 10;  // keys u32 + vals u32 + list u16
 }
 
 bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out) {
