@@ -37,6 +37,23 @@ UNIT = "overlaps/s"
 CLUSTER_KW = dict(n_fragments=15000, read_len=150, n_strains=5, strain_cov=10.0, snp_rate=0.01, err_rate=0.005)
 
 
+def rank_cluster_seeds(rank, c_per_gpu):
+    """independent clusters per rank (weak scaling): rank r works on seeds 1000 + r*C .. 1000 + (r+1)*C - 1"""
+    return [1000 + rank * c_per_gpu + c for c in range(c_per_gpu)]
+
+
+def whole_job(dist, torch, device, ms_local, n_local):
+    """value of the whole job: units of all ranks / max-over-ranks time (no data-path collective: clusters are
+    independent; these two reductions are the only communication)"""
+    if dist is None:
+        return ms_local, float(n_local)
+    t = torch.tensor([ms_local], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c = torch.tensor([float(n_local)], device=device, dtype=torch.float64)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(c.item())
+
+
 def workload_config(c_per_gpu):
     return {"workload": "BASELINE configs[1] cluster (15000 fragments = 30000 reads x 150 bp, 5 strains, 0.5%% error), "
                         "%d such clusters per step per GPU (a shard of configs[2])" % c_per_gpu,
@@ -170,6 +187,40 @@ def verify_algorithmic_bytes(cands, lens, min_len, n_acc):
     return int(16 * len(cands) + (2 * ((ol + 3) // 4)).sum() + 16 * n_acc), float(ol[ol > 0].mean()) if (ol > 0).any() else 0.0
 
 
+def concordance_check(api, synth):
+    """Correctness reported with the timing: one config-2 cluster through the CUDA path vs the CPU
+    chain (oracle/): (1) records bit-exact; (2) Jaccard of the (ID1,ID2,POS1,ORI1,ORI2,LEN1) tuples of the two
+    13-column files, floor 0.999."""
+    import tempfile
+    from oracle import orc
+    b = synth.cluster_batch(1, seed0=4242, **CLUSTER_KW)
+    with api.Context(0) as c:
+        R = c.pack(b)
+        cands = c.candidates(R)
+        rec_v, aux_v = c.verify(R, cands)          # hlo_verify on the candidate list
+        rec, aux, coff = c.overlap_batch(R)        # full path
+        R.free()
+    ob = orc.Batch.from_arrays(b.bases, b.base_off, b.cluster_off)
+    oc, _ = orc.candidates(ob)
+    key = lambda a: np.lexsort((a["diag"], a["strand_anchor"] & 1, a["t"], a["q"]))
+    cands_equal = len(oc) == len(cands) and bool(np.array_equal(oc[key(oc)], cands[key(cands)]))
+    rv_o, _, _ = orc.verify(ob, oc)
+    srt = lambda r: r[np.lexsort((r["K"], r["OHB"], r["OHA"], r["ori"], r["idB"], r["idA"]))]
+    verify_equal = len(rv_o) == len(rec_v) and bool(np.array_equal(srt(rv_o), srt(rec_v)))
+    rec_o, _, _, _ = orc.overlap_batch(ob)
+    with tempfile.TemporaryDirectory() as d:
+        api.write_overlaps(rec, os.path.join(d, "g.txt"))
+        orc.write_overlaps(rec_o, os.path.join(d, "c.txt"))
+        tup = lambda p: {(a[0], a[1], a[2], a[5], a[6], a[9]) for a in (l.rstrip("\n").split("\t") for l in open(p))}
+        g, cset = tup(os.path.join(d, "g.txt")), tup(os.path.join(d, "c.txt"))
+        byte_identical = open(os.path.join(d, "g.txt"), "rb").read() == open(os.path.join(d, "c.txt"), "rb").read()
+    jac = len(g & cset) / float(len(g | cset)) if (g or cset) else 1.0
+    return {"cluster": "config-2, seed 4242", "candidates": int(len(cands)), "candidates_bit_exact": cands_equal,
+            "verified_records": int(len(rec_v)), "verify_records_bit_exact": verify_equal, "records": int(len(rec)),
+            "overlaps_file_byte_identical": byte_identical, "jaccard": jac, "jaccard_floor": 0.999,
+            "against": "CPU restatement of the minimap2->filter->sfo->overlaps chain (oracle/; minimap2 binary unavailable)"}
+
+
 def run_ours(args):
     import torch
     from hylight_b200 import api, synth
@@ -185,7 +236,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     C = args.clusters
-    batch = synth.cluster_batch(C, seed0=1000 + rank * C, **CLUSTER_KW)
+    seeds = rank_cluster_seeds(rank, C)
+    batch = synth.cluster_batch(C, seed0=seeds[0], **CLUSTER_KW)
     lens = np.diff(batch.base_off).astype(np.int64)
     ctx = api.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local))
@@ -297,10 +349,8 @@ def run_ours(args):
     for c in ctxs[1:]:
         c.close()
     h2d = batch.bases.nbytes + batch.base_off.nbytes + 5 * 4 * batch.n_reads
-    tot = torch.tensor([n_rec, n_rec2], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tot)
-    n_rec_all, n_rec2_all = float(tot[0].item()), float(tot[1].item())
+    _, n_rec_all = whole_job(dist, torch, "cuda", ms_dev, n_rec)
+    _, n_rec2_all = whole_job(dist, torch, "cuda", ms_e2e, n_rec2)
     ctx.close()
     for p in (pb, po, pc):
         p.free()
@@ -319,6 +369,7 @@ def run_ours(args):
                         "timing": "wall clock between device synchronisations, max over ranks"},
                 "gpu_launches": int(launches), "roofline": roofline, "stages_ms": stages}
         if world == 1 and not args.no_cpu:
+            line["concordance"] = concordance_check(api, synth)
             cores = os.cpu_count() or 1
             n_cl = max(1, min(cores, 32))
             cl = [synth.cluster_batch(1, seed0=5000 + c, **CLUSTER_KW) for c in range(n_cl)]

@@ -348,8 +348,9 @@ def test_host_binary_end_to_end(tmp_path):
         lst.append("%s\t%s\t%s" % (os.path.join(GOLDEN, tag + ".fasta"), tmp_path / (tag + ".txt"), tmp_path / (tag + ".sfo")))
     # same thresholds for both: cluster3 was generated with 50 -> compare against the oracle instead of the golden
     (tmp_path / "list.tsv").write_text("\n".join(lst) + "\n")
+    # --batch_bases 1: one cluster per batch, so both host workers of the device get work
     r = subprocess.run([exe, "--clusters", str(tmp_path / "list.tsv"), "--stats", str(tmp_path / "stats.jsonl"),
-                        "--min_ovlp_len", "60"], capture_output=True, text=True)
+                        "--min_ovlp_len", "60", "--batch_bases", "1", "--workers_per_device", "2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     for tag in ["cluster1", "cluster3"]:
         seqs = read_fasta(os.path.join(GOLDEN, tag + ".fasta"))
@@ -384,6 +385,24 @@ def test_config2_full_cluster_matches_oracle(ctx):
     b = synth.cluster_batch(1, seed0=1, **synth.CONFIGS["config2"])
     rec, coff, tm = check_full(ctx, b)
     assert len(rec) > 300000
+
+
+def test_config4_long_reads_many_strains(ctx):
+    """BASELINE config 4 shape (2x250 bp, 20 strains, --min_identity 0.95) at 3000 fragments: vs the oracle"""
+    kw = dict(synth.CONFIGS["config4"], n_fragments=3000)
+    b = synth.cluster_batch(1, seed0=77, **kw)
+    rec, coff, tm = check_full(ctx, b, min_identity=0.95)
+    assert len(rec) > 20000 and tm["n_deferred"] == 0
+
+
+def test_config5_oversized_cluster(ctx):
+    """BASELINE config 5 (one cluster of 100 000 fragments = 200 000 reads): memory sizing of sort and pair
+    generation; batch invariance against the same reads split... no: a cluster cannot be split, so the check is
+    against the oracle on the full cluster (about half a minute of CPU)"""
+    b = synth.cluster_batch(1, seed0=5, **synth.CONFIGS["config5"])
+    assert b.n_reads == 200000
+    rec, coff, tm = check_full(ctx, b)
+    assert len(rec) > 2000000 and tm["n_overflow_reads"] == 0
 
 
 def test_properties_at_scale(ctx):
