@@ -311,6 +311,8 @@ def run_ours(args):
     # GPU (main.cpp, --workers_per_device).  Every step still copies its own inputs in and its own records out.
     n_workers = 2
     ctxs = [ctx] + [api.Context(local) for _ in range(n_workers - 1)]
+    for c_ in ctxs:
+        c_.set_option("aux", 0)  # what hylight-ovlp asks for: records + per-cluster offsets
     d2h = [0]
 
     def run_steps(n_steps):
@@ -327,7 +329,7 @@ def run_ours(args):
                     nxt[0] += 1
                 r = c.overlap_host_raw(pb.ptr, po.ptr, batch.n_reads, pc.ptr, batch.n_clusters)
                 tot[wi] += int(r.n)
-                d2h[0] = int(r.n) * (api.REC_DT.itemsize + api.AUX_DT.itemsize) + 8 * (batch.n_clusters + 1)
+                d2h[0] = int(r.n) * api.REC_DT.itemsize + 8 * (batch.n_clusters + 1)
 
         th = [threading.Thread(target=work, args=(wi,)) for wi in range(n_workers)]
         for t in th:
@@ -348,7 +350,7 @@ def run_ours(args):
         ms_e2e = float(t.item())
     for c in ctxs[1:]:
         c.close()
-    h2d = batch.bases.nbytes + batch.base_off.nbytes + 5 * 4 * batch.n_reads
+    h2d = batch.bases.nbytes + batch.base_off.nbytes + batch.cluster_off.nbytes
     _, n_rec_all = whole_job(dist, torch, "cuda", ms_dev, n_rec)
     _, n_rec2_all = whole_job(dist, torch, "cuda", ms_e2e, n_rec2)
     ctx.close()

@@ -216,7 +216,7 @@ class Context:
 
     def _recs(self, r, copy=True):
         rec = _copy_out(r.rec, r.n, REC_DT)
-        aux = _copy_out(r.aux, r.n, AUX_DT)
+        aux = _copy_out(r.aux, r.n, AUX_DT) if r.aux else None
         coff = _copy_out(r.cluster_off, r.n_clusters + 1, np.dtype("<u8")) if r.cluster_off else None
         return rec, aux, coff
 

@@ -9,7 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -75,11 +75,11 @@ struct hlo_reads {
     hlo_ctx *ctx = nullptr;
     int device = -1;
     DevReads d;
-    DevBuf b_ascii, b_off, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_bases, b_amb, b_ambcount;
+    DevBuf b_ascii, b_off, b_coff, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_bases, b_amb, b_ambcount;
     std::vector<uint32_t> h_len, h_ids, h_cidx, h_cluster_off, h_perm;
     float h2d_ms = 0.f, pack_ms = 0.f;
     void release() {
-        b_ascii.release(), b_off.release(), b_len.release(), b_cbase.release(), b_cidx.release(), b_ids.release();
+        b_ascii.release(), b_off.release(), b_coff.release(), b_len.release(), b_cbase.release(), b_cidx.release(), b_ids.release();
         b_nrank.release(), b_perm.release(), b_bases.release(), b_amb.release(), b_ambcount.release();
     }
 };
@@ -93,8 +93,9 @@ struct hlo_ctx {
     LaunchCounter lc;
     hlo_timing tm;
     int pairgen_slots_log2 = 8;
-    int verify_exact = 0, repack = 0, d2h = 1, pairgen_generic = 0, sketch_generic = 0;
+    int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, pairgen_generic = 0, sketch_generic = 0;
     bool keys_ready = false;
+    uint32_t *mapped_host = nullptr, *mapped_dev = nullptr;  // 256 B of mapped pinned memory (fetch_small)
     cudaEvent_t ev_vf[2] = {};
     // verify tables
     DevBuf b_tab;
@@ -104,7 +105,6 @@ struct hlo_ctx {
     DevBuf b_cnt, b_mzoff, b_mzx, b_mzrp, b_mzrid, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
     DevBuf b_cands, b_counters, b_ovf, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
     DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp;
-    std::map<uint32_t, std::vector<uint32_t>> name_order;  // N -> integers 0..N-1 in strcmp order of their decimal spelling
     PinBuf h_out, h_aux, h_coff, h_mz, h_roff, h_cands, h_rec16, h_small;
     std::vector<uint64_t> v_coff;
     hlo_reads scratch_reads;
@@ -124,6 +124,15 @@ struct hlo_ctx {
         }                                                                                             \
     } while (0)
 
+// Small device -> host read-backs (counters) go through a kernel that stores into mapped pinned memory, not
+// through the copy engine: a 4-byte cudaMemcpy queues behind another context's multi-hundred-MB record
+// download on the same engine and stalls the whole pipeline for milliseconds.
+#define FETCH(dst, dev_src, nbytes)                                              \
+    do {                                                                         \
+        int rc__ = fetch_small(ctx, (dst), (dev_src), (nbytes));                 \
+        if (rc__) return rc__;                                                   \
+    } while (0)
+
 #define FAIL(code, ...)                              \
     do {                                             \
         char buf__[512];                             \
@@ -131,6 +140,24 @@ struct hlo_ctx {
         ctx->err = buf__;                            \
         return (code);                               \
     } while (0)
+
+// Kernels of different contexts on one device are serialised (one compute section at a time), so that with
+// two or more host workers per GPU one worker's uploads/downloads overlap another's kernels instead of every
+// worker sharing the SMs and then the PCIe link in lockstep (measured: 18.5 -> ~11 ms per 32-cluster step).
+static std::mutex g_compute_mutex[64];
+
+// copies nbytes (multiple of 4, <= 256) from device memory to host memory and waits for it
+static int fetch_small(hlo_ctx *ctx, void *dst, const void *dev_src, size_t nbytes) {
+    if (nbytes > 256 || (nbytes & 3)) {
+        ctx->err = "fetch_small: bad size";
+        return HLO_EINVAL;
+    }
+    launch_copy_words(reinterpret_cast<const uint32_t *>(dev_src), ctx->mapped_dev, (uint32_t)(nbytes / 4), ctx->stream, &ctx->lc);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(dst, ctx->mapped_host, nbytes);
+    return HLO_OK;
+}
 
 extern "C" {
 
@@ -230,6 +257,12 @@ int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out) {
     }
     for (int i = 0; i <= ST_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaEventCreate(&ctx->ev_vf[0]), cudaEventCreate(&ctx->ev_vf[1]);
+    if (cudaHostAlloc((void **)&ctx->mapped_host, 256, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&ctx->mapped_dev, ctx->mapped_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        hlo_ctx_destroy(ctx);
+        return HLO_ENOMEM;
+    }
     memset(&ctx->tm, 0, sizeof ctx->tm);
     ctx->scratch_reads.ctx = ctx;
     *out = ctx;
@@ -253,6 +286,7 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i)
         if (ctx->ev_vf[i]) cudaEventDestroy(ctx->ev_vf[i]);
+    if (ctx->mapped_host) cudaFreeHost(ctx->mapped_host);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -313,25 +347,23 @@ static VerifyParams verify_params(const hlo_ctx *ctx) {
 // ------------------------------------------------------------------------------------------------
 // packing
 
-// integers 0..N-1 in strcmp order of their decimal spelling = preorder walk of the decimal trie
-// ("0" < "1" < "10" < "100" < "101" < ... < "11" < ... < "2" < ...); cached per N
-static const std::vector<uint32_t> &decimal_name_order(hlo_ctx *ctx, uint32_t N) {
-    auto it = ctx->name_order.find(N);
-    if (it != ctx->name_order.end()) return it->second;
-    std::vector<uint32_t> &ord = ctx->name_order[N];
-    ord.reserve(N);
-    if (N > 0) ord.push_back(0);  // "0" has no children ("00" is not a name)
-    std::vector<uint64_t> stack;
-    for (uint64_t d = 9; d >= 1; --d)
-        if (d < N) stack.push_back(d);
-    while (!stack.empty()) {
-        const uint64_t v = stack.back();
-        stack.pop_back();
-        ord.push_back((uint32_t)v);
-        for (int c = 9; c >= 0; --c)  // children pushed in reverse so that v*10 is visited next
-            if (v * 10 + (uint64_t)c < N) stack.push_back(v * 10 + (uint64_t)c);
+// host copies of the per-read metadata, needed only by the parity entry points (hlo_sketch, hlo_verify);
+// when the metadata was built on the device they are fetched on first use
+static int ensure_host_meta(hlo_ctx *ctx, const hlo_reads *Rc) {
+    hlo_reads *R = const_cast<hlo_reads *>(Rc);
+    const uint32_t n = R->d.n_reads;
+    if (R->h_len.size() == n && R->h_perm.size() == n) return HLO_OK;
+    R->h_len.resize(n), R->h_ids.resize(n), R->h_cidx.resize(n), R->h_perm.resize(n);
+    if (n) {
+        cudaStream_t s = ctx->stream;
+        CK(cudaMemcpyAsync(R->h_len.data(), R->d.len, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(R->h_ids.data(), R->d.ids, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(R->h_cidx.data(), R->d.cidx, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(R->h_perm.data(), R->d.perm, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < n; ++i) R->h_len[i] &= HLO_LEN_MASK;
     }
-    return ord;
+    return HLO_OK;
 }
 
 static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64_t *base_off, uint32_t n_reads,
@@ -343,32 +375,40 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     R->ctx = ctx, R->device = ctx->device;
-    R->h_len.resize(n_reads), R->h_ids.resize(n_reads), R->h_cidx.resize(n_reads);
     R->h_cluster_off.assign(cluster_off, cluster_off + n_clusters + 1);
-    std::vector<uint32_t> cbase(n_reads), nrank(n_reads);
+    R->h_len.clear(), R->h_ids.clear(), R->h_cidx.clear(), R->h_perm.clear();
+    // one lean pass over the offsets: monotone, length limit, longest read (sizes the rows)
     uint32_t max_len = 0;
-    for (uint32_t i = 0; i < n_reads; ++i) {
-        if (base_off[i + 1] < base_off[i]) FAIL(HLO_EINVAL, "base_off not monotone at read %u", i);
-        const uint64_t l = base_off[i + 1] - base_off[i];
-        if (l > 32767) FAIL(HLO_ERANGE, "read %u is %llu bp; limit is 32767 (anchor fields of hlo_cand)", i, (unsigned long long)l);
-        R->h_len[i] = (uint32_t)l;
-        max_len = std::max(max_len, (uint32_t)l);
+    {
+        uint64_t worst = 0;
+        bool mono = true;
+        for (uint32_t i = 0; i < n_reads; ++i) {
+            mono &= base_off[i + 1] >= base_off[i];
+            const uint64_t l = base_off[i + 1] - base_off[i];
+            worst = l > worst ? l : worst;
+        }
+        if (!mono) FAIL(HLO_EINVAL, "base_off is not monotone");
+        if (worst > 32767) FAIL(HLO_ERANGE, "a read of %llu bp exceeds the limit of 32767 (anchor fields of hlo_cand)", (unsigned long long)worst);
+        max_len = (uint32_t)worst;
     }
-    R->h_perm.resize(n_reads);
     uint32_t max_cluster = 0;
     for (uint32_t c = 0; c < n_clusters; ++c) {
         if (cluster_off[c + 1] < cluster_off[c]) FAIL(HLO_EINVAL, "cluster_off not monotone");
-        const uint32_t r0 = cluster_off[c], r1 = cluster_off[c + 1], N = r1 - r0;
-        max_cluster = std::max(max_cluster, N);
-        for (uint32_t i = r0; i < r1; ++i) cbase[i] = r0, R->h_cidx[i] = c, R->h_ids[i] = ids ? ids[i] : i - r0;
-        bool plain = true;  // names are 0..N-1 in file order (what rename_fas.py writes)
-        if (ids)
-            for (uint32_t i = r0; i < r1 && plain; ++i) plain = ids[i] == i - r0;
-        if (plain) {
-            for (uint32_t i = r0; i < r1; ++i) nrank[i] = i;
-            const std::vector<uint32_t> &ord = decimal_name_order(ctx, N);
-            for (uint32_t x = 0; x < N; ++x) R->h_perm[r0 + x] = r0 + ord[x];
-        } else {
+        max_cluster = std::max(max_cluster, cluster_off[c + 1] - cluster_off[c]);
+    }
+    // names 0..N-1 in file order (what rename_fas.py writes): all per-read metadata is derived on the device
+    bool plain = true;
+    if (ids)
+        for (uint32_t c = 0; c < n_clusters && plain; ++c)
+            for (uint32_t i = cluster_off[c]; i < cluster_off[c + 1] && plain; ++i) plain = ids[i] == i - cluster_off[c];
+    std::vector<uint32_t> cbase, nrank;
+    if (!plain) {
+        R->h_len.resize(n_reads), R->h_ids.resize(n_reads), R->h_cidx.resize(n_reads), R->h_perm.resize(n_reads);
+        cbase.resize(n_reads), nrank.resize(n_reads);
+        for (uint32_t i = 0; i < n_reads; ++i) R->h_len[i] = (uint32_t)(base_off[i + 1] - base_off[i]);
+        for (uint32_t c = 0; c < n_clusters; ++c) {
+            const uint32_t r0 = cluster_off[c], r1 = cluster_off[c + 1], N = r1 - r0;
+            for (uint32_t i = r0; i < r1; ++i) cbase[i] = r0, R->h_cidx[i] = c, R->h_ids[i] = ids[i];
             std::vector<uint32_t> ord(N);
             for (uint32_t i = 0; i < N; ++i) ord[i] = r0 + i;
             std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b] || (ids[a] == ids[b] && a < b); });
@@ -398,6 +438,7 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     const size_t plane_words = (size_t)n_reads * stride_w;
     CK(R->b_ascii.ensure(n_bases + 16));
     CK(R->b_off.ensure(((size_t)n_reads + 1) * 8));
+    CK(R->b_coff.ensure(((size_t)n_clusters + 1) * 4));
     CK(R->b_len.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_cbase.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_cidx.ensure((size_t)n_reads * 4 + 4));
@@ -414,21 +455,25 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     if (n_reads) {
         CK(cudaMemcpyAsync(R->b_ascii.p, bases, n_bases, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(R->b_off.p, base_off, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(d.len, R->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(d.cbase, cbase.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(d.cidx, R->h_cidx.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(d.ids, R->h_ids.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(d.nrank, nrank.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(d.perm, R->h_perm.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        if (plain) {
+            CK(cudaMemcpyAsync(R->b_coff.p, cluster_off, ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
+        } else {
+            CK(cudaMemcpyAsync(d.len, R->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d.cbase, cbase.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d.cidx, R->h_cidx.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d.ids, R->h_ids.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d.nrank, nrank.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d.perm, R->h_perm.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        }
     }
     CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));
     CK(cudaEventRecord(ctx->ev[ST_H2D], s));
+    if (plain && n_reads) launch_read_meta(R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), d, s, &ctx->lc);
     launch_pack(R->b_ascii.as<uint8_t>(), R->b_off.as<uint64_t>(), d, R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_PACK], s));
     uint32_t amb = 0;
-    CK(cudaMemcpyAsync(&amb, R->b_ambcount.p, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));  // also keeps the caller's host buffers alive until the copies are done
+    FETCH(&amb, R->b_ambcount.p, 4);  // the wait also keeps the caller's host buffers alive until the copies are done
     d.has_amb = amb != 0;
     CK(cudaEventElapsedTime(&R->h2d_ms, ctx->ev[ST_BEGIN], ctx->ev[ST_H2D]));
     CK(cudaEventElapsedTime(&R->pack_ms, ctx->ev[ST_H2D], ctx->ev[ST_PACK]));
@@ -485,7 +530,7 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
         CK(ctx->b_srp.ensure((size_t)n * cap * 4 + 4));
         CK(ctx->b_ovf.ensure((size_t)n * 4 + 4));
         CK(cudaMemsetAsync(ctx->b_cnt.as<uint32_t>() + n, 0, 4, s));
-        CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 10, 0, 8, s));
+        CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 10, 0, 16, s));
         launch_sketch_fast(d, ctx->P.w, ctx->P.k, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
                            ctx->b_ovf.as<uint32_t>(), ctx->b_counters.as<unsigned long long>() + 10, s, &ctx->lc);
     } else {
@@ -493,14 +538,18 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
         launch_sketch_count(d, ctx->P.w, ctx->P.k, ctx->b_cnt.as<uint32_t>(), s, &ctx->lc);
     }
     // scanning n+1 counts (the last is 0) puts the total at mz_off[n]
-    launch_exclusive_scan(ctx->b_cnt.as<uint32_t>(), ctx->b_mzoff.as<uint32_t>(), (uint64_t)n + 1, ctx->b_tmp.as<uint32_t>(), nullptr,
-                          s, &ctx->lc);
+    launch_exclusive_scan(ctx->b_cnt.as<uint32_t>(), ctx->b_mzoff.as<uint32_t>(), (uint64_t)n + 1, ctx->b_tmp.as<uint32_t>(),
+                          ctx->b_counters.as<uint32_t>() + 22, s, &ctx->lc);  // grand total -> low word of counters[11]
     CK(cudaGetLastError());
     uint32_t total = 0;
     unsigned long long n_ovf = 0;
-    CK(cudaMemcpyAsync(&total, ctx->b_mzoff.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, s));
-    if (fast) CK(cudaMemcpyAsync(&n_ovf, ctx->b_counters.as<unsigned long long>() + 10, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    if (fast) {  // one fetch for both: the scan leaves the total right behind the sketch overflow counter
+        unsigned long long two[2] = {0, 0};
+        FETCH(two, ctx->b_counters.as<unsigned long long>() + 10, 16);
+        n_ovf = two[0], total = (uint32_t)two[1];
+    } else {
+        FETCH(&total, ctx->b_counters.as<uint32_t>() + 22, 4);
+    }
     ctx->n_mz = total;
     CK(ctx->b_mzx.ensure((size_t)total * 8 + 8));
     CK(ctx->b_mzrp.ensure((size_t)total * 4 + 4));
@@ -590,8 +639,7 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
         if (fast) {
             launch_pairgen(a, ctx->pairgen_slots_log2, s, &ctx->lc);
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            FETCH(hc, ctx->b_counters.p, sizeof hc);
             n_list = (uint32_t)hc[2], list = a.overflow_reads;
         }
         if (n_list) {  // exact path with tables in HBM, in chunks that bound the table memory
@@ -636,8 +684,7 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
                 CK(cudaStreamSynchronize(s));
                 i0 = i1;
             }
-            CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            FETCH(hc, ctx->b_counters.p, sizeof hc);
         }
         ctx->tm.n_overflow_reads = fast ? n_list : 0;
         ctx->tm.n_seed_hits = hc[1];
@@ -673,15 +720,13 @@ static int run_verify(hlo_ctx *ctx, const hlo_reads *R, const CandI *d_cands, ui
         launch_verify_fast(a, s, &ctx->lc);
         CK(cudaEventRecord(ctx->ev_vf[1], s));
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        FETCH(hc, ctx->b_counters.p, sizeof hc);
         if (n && cudaEventElapsedTime(&ctx->tm.verify_fast_ms, ctx->ev_vf[0], ctx->ev_vf[1]) != cudaSuccess) cudaGetLastError();
         if (hc[1]) launch_verify_exact(a, a.deferred, hc[1], s, &ctx->lc);
     }
     CK(cudaGetLastError());
     const unsigned long long n_def = hc[1];
-    CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    if (force_exact || n_def) FETCH(hc, ctx->b_counters.p, sizeof hc);  // else the count fetched after the fast kernel is final
     ctx->tm.n_deferred = force_exact ? n : n_def;
     *n_acc = hc[0];
     return HLO_OK;
@@ -738,6 +783,8 @@ int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
     // the device arrays are in name order (sketch.cu); hand them back in the caller's read order
+    rc = ensure_host_meta(ctx, R);
+    if (rc) return rc;
     CK(ctx->h_mz.ensure(tot * sizeof(hlo_mz) + 16));
     CK(ctx->h_roff.ensure(((size_t)R->d.n_reads + 1) * 8));
     std::vector<uint32_t> off32((size_t)R->d.n_reads + 1);
@@ -807,6 +854,10 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
     CK(cudaSetDevice(ctx->device));
     reset_timing(ctx);
     cudaStream_t s = ctx->stream;
+    {
+        const int rcm = ensure_host_meta(ctx, R);
+        if (rcm) return rcm;
+    }
     for (uint64_t i = 0; i < n; ++i)
         if (cands[i].q >= R->d.n_reads || cands[i].t >= R->d.n_reads) FAIL(HLO_EINVAL, "candidate %llu names a read outside the batch", (unsigned long long)i);
     CK(ctx->b_candx.ensure(n * sizeof(hlo_cand) + 16));
@@ -861,6 +912,7 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     const DevReads &d = R->d;
     uint64_t n_c = 0, n_acc = 0;
     float repack_ms = -1.f;
+    std::unique_lock<std::mutex> compute_lock(g_compute_mutex[ctx->device & 63]);
     if (ctx->repack && d.n_reads) {
         // the packer again, from the ASCII bases still resident in HBM (results are identical; the
         // ambiguity flags it ORs into len[] are idempotent)
@@ -909,24 +961,24 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     launch_expand_records(ctx->b_flags.as<uint32_t>(), ctx->b_pos.as<uint32_t>(), ctx->b_best.as<uint32_t>(), ctx->b_rec16.as<Rec16>(),
                           n_acc, d, ctx->b_out.as<hlo_rec>(), ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    FETCH(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4);
     const uint64_t n_out = n_out32;
     launch_cluster_offsets(ctx->b_aux.as<hlo_rec_aux>(), n_out, d.n_clusters, ctx->b_coff.as<unsigned long long>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_DEDUP], s));
+    compute_lock.unlock();  // the download below overlaps the next worker's kernels
     if (ctx->d2h) {
         CK(ctx->h_out.ensure(n_out * sizeof(hlo_rec) + 32));
         CK(ctx->h_aux.ensure(n_out * sizeof(hlo_rec_aux) + 32));
         CK(ctx->h_coff.ensure(((size_t)d.n_clusters + 2) * 8));
         CK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, n_out * sizeof(hlo_rec), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_aux.p, ctx->b_aux.p, n_out * sizeof(hlo_rec_aux), cudaMemcpyDeviceToHost, s));
+        if (ctx->aux_out) CK(cudaMemcpyAsync(ctx->h_aux.p, ctx->b_aux.p, n_out * sizeof(hlo_rec_aux), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_coff.p, ctx->b_coff.p, ((size_t)d.n_clusters + 1) * 8, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ctx->ev[ST_D2H], s));
     CK(cudaStreamSynchronize(s));
     if (ctx->d2h) {
-        out->rec = ctx->h_out.as<hlo_rec>(), out->aux = ctx->h_aux.as<hlo_rec_aux>();
+        out->rec = ctx->h_out.as<hlo_rec>(), out->aux = ctx->aux_out ? ctx->h_aux.as<hlo_rec_aux>() : nullptr;
         out->cluster_off = ctx->h_coff.as<uint64_t>();
     } else {
         out->rec = nullptr, out->aux = nullptr, out->cluster_off = nullptr;
@@ -967,6 +1019,10 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
     }
     if (!strcmp(name, "repack")) {
         ctx->repack = value != 0;
+        return HLO_OK;
+    }
+    if (!strcmp(name, "aux")) {
+        ctx->aux_out = value != 0;
         return HLO_OK;
     }
     if (!strcmp(name, "d2h")) {

@@ -14,6 +14,9 @@ struct LaunchCounter {
 void launch_pack(const uint8_t *ascii, const uint64_t *base_off, DevReads r, uint32_t *amb_count, cudaStream_t s,
                  LaunchCounter *lc);
 
+// per-read metadata (len, cbase, cidx, ids, nrank, perm) on the device for names 0..N-1 in file order
+void launch_read_meta(const uint64_t *base_off, const uint32_t *cluster_off, DevReads r, cudaStream_t s, LaunchCounter *lc);
+
 // ---- sketch.cu ------------------------------------------------------------------------------
 // pass 0: count[r] = number of minimizers of read r;  pass 1: write them at off[r].
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc);
@@ -44,6 +47,8 @@ size_t sort_tmp_words(uint64_t n);
 int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begin_bit, int end_bit, uint32_t *tmp,
                       cudaStream_t s, LaunchCounter *lc);
 
+// up to 64 words from device memory to (mapped) host memory: the read-back path for counters
+void launch_copy_words(const uint32_t *src, uint32_t *dst, uint32_t n, cudaStream_t s, LaunchCounter *lc);
 void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, LaunchCounter *lc);
 
 // ---- pairgen.cu -----------------------------------------------------------------------------

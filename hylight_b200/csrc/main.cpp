@@ -278,6 +278,7 @@ void worker(Shared *S, int device) {
         S->failed = 1;
         return;
     }
+    hlo_set_option(ctx, "aux", 0);  // the files need the records and the per-cluster offsets only
     for (;;) {
         const size_t b = S->next.fetch_add(1);
         if (b >= S->batches.size() || S->failed) break;

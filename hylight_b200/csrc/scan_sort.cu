@@ -253,6 +253,14 @@ int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begi
 }
 
 // ------------------------------------------------------------------------------------------------
+__global__ void copy_words_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint32_t n) {
+    if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+void launch_copy_words(const uint32_t *src, uint32_t *dst, uint32_t n, cudaStream_t s, LaunchCounter *lc) {
+    if (n == 0) return;
+    copy_words_kernel<<<1, 64, 0, s>>>(src, dst, n);
+    if (lc) lc->total++;
+}
 __global__ void fill_kernel(uint32_t *v, uint32_t value, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = value;

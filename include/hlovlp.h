@@ -187,7 +187,10 @@ int hlo_get_timing(const hlo_ctx *ctx, hlo_timing *t);
  * kernel; "pairgen_slots_log2" (6..13): slots of the per-warp shared-memory seed table;
  * "repack" (0|1): hlo_overlap_batch re-runs the 2-bit packer from the ASCII bases kept in HBM (so a
  * device-resident measurement covers the packer); "d2h" (0|1): copy the records back to the host
- * (with 0 hlo_overlap_batch returns n only; rec/aux/cluster_off are NULL). */
+ * (with 0 hlo_overlap_batch returns n only; rec/aux/cluster_off are NULL); "aux" (0|1): also copy the
+ * hlo_rec_aux array back (with 0 hlo_recs.aux is NULL: a caller that only writes the files needs rec and
+ * cluster_off); "sketch_generic" / "pairgen_generic" (0|1): force the generic (any w, k / 64-bit keyed)
+ * kernels instead of the specialised ones. */
 int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value);
 
 /* The CUDA stream (cudaStream_t) every call on this ctx enqueues its work on, so that a caller can
