@@ -561,7 +561,7 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
         }
         launch_sketch_compact(d, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
                               ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
-                              ctx->b_mzrid.as<uint32_t>(), ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
+                              ctx->b_mzrid.as<uint32_t>(), ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, s, &ctx->lc);
         ctx->keys_ready = n_ovf == 0;
         if (n_ovf)  // reads with more minimizers than a strip holds: the generic kernel writes them in place
             launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
@@ -572,6 +572,12 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
     }
     CK(cudaGetLastError());
     return HLO_OK;
+}
+
+static int bits_for(uint64_t v) {
+    int b = 1;
+    while (b < 63 && (1ull << b) < v) ++b;
+    return b;
 }
 
 // hash sort + bucket index.  Leaves range[] (per minimizer, read order) and hits[] (hash order).
@@ -589,13 +595,17 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R) {
     CK(ctx->b_range.ensure(n * 8 + 8));
     CK(ctx->b_hits.ensure(n * 8 + 8));
     if (!ctx->keys_ready)
-        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), n, ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
+        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrid.as<uint32_t>(), R->d.cidx, 2 * ctx->P.k, n, ctx->b_keys[0].as<uint64_t>(),
+                         ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
-    const int cur = launch_radix_sort(keys, vals, n, 0, 2 * ctx->P.k, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+    // key = cluster index << 2k | hash: 2k hash bits + the bits of the cluster count
+    const int key_bits = 2 * ctx->P.k + (R->d.n_clusters > 1 ? bits_for(R->d.n_clusters) : 0);
+    if (key_bits > 64) FAIL(HLO_ERANGE, "%u clusters with k=%d need a %d-bit sort key (limit 64): use smaller batches", R->d.n_clusters, ctx->P.k, key_bits);
+    const int cur = launch_radix_sort(keys, vals, n, 0, key_bits, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SORT], s));
-    launch_mark_buckets(keys[cur], vals[cur], ctx->b_mzrid.as<uint32_t>(), ctx->b_mzrp.as<uint32_t>(), R->d.cbase, R->d.len, n,
+    launch_mark_buckets(keys[cur], vals[cur], ctx->b_mzrid.as<uint32_t>(), ctx->b_mzrp.as<uint32_t>(), R->d.len, n,
                         ctx->b_flags.as<uint32_t>(), ctx->b_hits.as<uint2>(), s, &ctx->lc);
     launch_exclusive_scan(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
     launch_bucket_starts(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_bstart.as<uint32_t>(), s, &ctx->lc);
@@ -732,11 +742,6 @@ static int run_verify(hlo_ctx *ctx, const hlo_reads *R, const CandI *d_cands, ui
     return HLO_OK;
 }
 
-static int bits_for(uint64_t v) {
-    int b = 1;
-    while (b < 63 && (1ull << b) < v) ++b;
-    return b;
-}
 
 static void finish_timing(hlo_ctx *ctx, const hlo_reads *R, int last_stage) {
     auto el = [&](int a, int b) {

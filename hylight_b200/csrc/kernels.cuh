@@ -29,7 +29,7 @@ void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t 
                         uint32_t *ovf_list, unsigned long long *ovf_cnt, cudaStream_t s, LaunchCounter *lc);
 void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
                            const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp, uint32_t *mz_rid, uint64_t *keys, uint32_t *vals,
-                           cudaStream_t s, LaunchCounter *lc);
+                           int hash_bits, cudaStream_t s, LaunchCounter *lc);
 void launch_mz_assemble(const uint64_t *mz_x, const uint32_t *mz_rp, const uint32_t *mz_rid, uint64_t n, hlo_mz *out,
                         cudaStream_t s, LaunchCounter *lc);
 
@@ -53,10 +53,11 @@ void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, La
 
 // ---- pairgen.cu -----------------------------------------------------------------------------
 // index build on the hash-sorted minimizers
-void launch_hash_keys(const uint64_t *mz_x, uint64_t n, uint64_t *keys, uint32_t *vals, cudaStream_t s, LaunchCounter *lc);
+// sort key = cluster index << hash_bits | minimizer hash (cluster-major: buckets of one cluster stay together)
+void launch_hash_keys(const uint64_t *mz_x, const uint32_t *mz_rid, const uint32_t *cidx, int hash_bits, uint64_t n, uint64_t *keys,
+                      uint32_t *vals, cudaStream_t s, LaunchCounter *lc);
 void launch_mark_buckets(const uint64_t *skeys, const uint32_t *svals, const uint32_t *mz_rid, const uint32_t *mz_rp,
-                         const uint32_t *cbase, const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s,
-                         LaunchCounter *lc);
+                         const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s, LaunchCounter *lc);
 void launch_bucket_starts(const uint32_t *flags, const uint32_t *bid, uint64_t n, uint32_t *bstart, cudaStream_t s,
                           LaunchCounter *lc);
 void launch_bucket_ranges(const uint32_t *flags, const uint32_t *bid, const uint32_t *svals, const uint32_t *bstart,

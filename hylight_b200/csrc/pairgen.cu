@@ -32,41 +32,38 @@ namespace hlo {
 #define HLO_EMPTY_KEY 0xffffffffffffffffULL
 #define HLO_EMPTY32 0xffffffffu
 
-__global__ void hash_keys_kernel(const uint64_t *__restrict__ x, uint64_t n, uint64_t *__restrict__ keys,
+__global__ void hash_keys_kernel(const uint64_t *__restrict__ x, const uint32_t *__restrict__ mz_rid,
+                                 const uint32_t *__restrict__ cidx, int hash_bits, uint64_t n, uint64_t *__restrict__ keys,
                                  uint32_t *__restrict__ vals) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = x[i] >> 8, vals[i] = (uint32_t)i;
+    if (i < n) keys[i] = (x[i] >> 8) | (uint64_t)cidx[mz_rid[i]] << hash_bits, vals[i] = (uint32_t)i;
 }
-void launch_hash_keys(const uint64_t *mz_x, uint64_t n, uint64_t *keys, uint32_t *vals, cudaStream_t s, LaunchCounter *lc) {
+void launch_hash_keys(const uint64_t *mz_x, const uint32_t *mz_rid, const uint32_t *cidx, int hash_bits, uint64_t n, uint64_t *keys,
+                      uint32_t *vals, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    hash_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, n, keys, vals);
+    hash_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, mz_rid, cidx, hash_bits, n, keys, vals);
     if (lc) lc->total++;
 }
 
-// hits[i] = (read, pos<<1|strand | len<<16 | amb<<31) of the i-th minimizer in hash order;
-// flags[i] = 1 where a new (cluster, hash) bucket starts
+// hits[i] = (read, pos<<1|strand | len<<16 | amb<<31) of the i-th minimizer in (cluster, hash) order;
+// flags[i] = 1 where a new (cluster, hash) bucket starts.  The sort key is cluster-major, so the gathers
+// below stay inside one cluster's few MB (L2-resident) instead of wandering over the whole batch.
 __global__ void mark_buckets_kernel(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
                                     const uint32_t *__restrict__ mz_rid, const uint32_t *__restrict__ mz_rp,
-                                    const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ len, uint64_t n,
-                                    uint32_t *__restrict__ flags, uint2 *__restrict__ hits) {
+                                    const uint32_t *__restrict__ len, uint64_t n, uint32_t *__restrict__ flags,
+                                    uint2 *__restrict__ hits) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t idx = svals[i];
     const uint32_t rid = mz_rid[idx];
     const uint32_t lf = len[rid];
     hits[i] = make_uint2(rid, mz_rp[idx] | (lf & 0x7fffu) << 16 | (lf & HLO_AMB_FLAG));
-    uint32_t f = 1;
-    if (i > 0) {
-        const uint32_t prid = mz_rid[svals[i - 1]];
-        f = (skeys[i] != skeys[i - 1]) || (cbase[rid] != cbase[prid]);
-    }
-    flags[i] = f;
+    flags[i] = i == 0 || skeys[i] != skeys[i - 1];
 }
 void launch_mark_buckets(const uint64_t *skeys, const uint32_t *svals, const uint32_t *mz_rid, const uint32_t *mz_rp,
-                         const uint32_t *cbase, const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s,
-                         LaunchCounter *lc) {
+                         const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    mark_buckets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(skeys, svals, mz_rid, mz_rp, cbase, len, n, flags, hits);
+    mark_buckets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(skeys, svals, mz_rid, mz_rp, len, n, flags, hits);
     if (lc) lc->total++;
 }
 

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_
                                                              const uint32_t *__restrict__ srp, const uint32_t *__restrict__ count,
                                                              const uint32_t *__restrict__ off, uint64_t *__restrict__ mz_x,
                                                              uint32_t *__restrict__ mz_rp, uint32_t *__restrict__ mz_rid,
-                                                             uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                                             uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int hash_bits) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)r.n_reads * cap;
     if (gid >= total) return;
@@ -284,17 +284,18 @@ __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_
     const uint64_t x = sx[gid];
     mz_x[dst] = x;
     mz_rp[dst] = srp[gid];
-    mz_rid[dst] = r.perm[xi];
-    keys[dst] = x >> 8;
+    const uint32_t read = r.perm[xi];
+    mz_rid[dst] = read;
+    keys[dst] = (x >> 8) | (uint64_t)r.cidx[read] << hash_bits;  // cluster-major: a cluster's buckets stay together
     vals[dst] = dst;
 }
 
 void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
                            const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp, uint32_t *mz_rid, uint64_t *keys, uint32_t *vals,
-                           cudaStream_t s, LaunchCounter *lc) {
+                           int hash_bits, cudaStream_t s, LaunchCounter *lc) {
     const uint64_t total = (uint64_t)r.n_reads * cap;
     if (total == 0) return;
-    sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rp, mz_rid, keys, vals);
+    sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rp, mz_rid, keys, vals, hash_bits);
     if (lc) lc->total++;
 }
 
