@@ -934,37 +934,33 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
     ctx->tm.n_accepted = n_acc;
     if (n_acc > 0xfffffff0ull) FAIL(HLO_ERANGE, "more than 2^32 accepted overlaps in one batch");
-    // per-pair keep-longest + (idA, idB) order + expansion
-    for (int i = 0; i < 2; ++i) {
-        CK(ctx->b_keys[i].ensure(n_acc * 8 + 8));
-        CK(ctx->b_vals[i].ensure(n_acc * 4 + 4));
-    }
-    CK(ctx->b_tmp.ensure(std::max(sort_tmp_words(n_acc), scan_tmp_words(n_acc + 1)) * 4));
-    CK(ctx->b_flags.ensure(n_acc * 4 + 4));
-    CK(ctx->b_best.ensure(n_acc * 4 + 4));
-    CK(ctx->b_pos.ensure(n_acc * 4 + 8));
+    // per-pair keep-longest + (idA, idB) order + expansion: group by idA, sort the small groups (records.cu)
+    const uint32_t ng = d.n_reads;
+    CK(ctx->b_flags.ensure(((size_t)ng + 2) * 4));   // records per idA
+    CK(ctx->b_bid.ensure(((size_t)ng + 2) * 4));     // group offsets
+    CK(ctx->b_best.ensure(((size_t)ng + 2) * 4));    // distinct idB per idA
+    CK(ctx->b_pos.ensure(((size_t)ng + 2) * 4));     // output offsets
+    CK(ctx->b_vals[0].ensure(n_acc * 4 + 4));        // slot of a record inside its group
+    CK(ctx->b_keys[0].ensure(n_acc * 8 + 8));        // (rank of idB, record index) entries
+    CK(ctx->b_vals[1].ensure(n_acc * 4 + 4));        // group of an entry
+    CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)ng + 1) * 4));
     CK(ctx->b_out.ensure(n_acc * sizeof(hlo_rec) + 32));
     CK(ctx->b_aux.ensure(n_acc * sizeof(hlo_rec_aux) + 32));
     CK(ctx->b_coff.ensure(((size_t)d.n_clusters + 2) * 8));
-    uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
-    uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
-    launch_record_keys(ctx->b_rec16.as<Rec16>(), n_acc, d, keys[0], vals[0], s, &ctx->lc);
-    const int nb = bits_for(std::max<uint64_t>(d.n_reads, 2));
-    int cur = launch_radix_sort(keys, vals, n_acc, 0, nb, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
-    {
-        uint64_t *k2[2] = {keys[cur], keys[cur ^ 1]};
-        uint32_t *v2[2] = {vals[cur], vals[cur ^ 1]};
-        const int c2 = launch_radix_sort(k2, v2, n_acc, 32, 32 + nb, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
-        cur = c2 ? cur ^ 1 : cur;
-    }
-    launch_dedup_flags(keys[cur], vals[cur], ctx->b_rec16.as<Rec16>(), n_acc, 1, ctx->b_flags.as<uint32_t>(), ctx->b_best.as<uint32_t>(),
-                       s, &ctx->lc);
+    uint32_t *g_cnt = ctx->b_flags.as<uint32_t>(), *g_off = ctx->b_bid.as<uint32_t>();
+    uint32_t *g_uniq = ctx->b_best.as<uint32_t>(), *g_uoff = ctx->b_pos.as<uint32_t>();
+    uint2 *g_ent = ctx->b_keys[0].as<uint2>();
+    CK(cudaMemsetAsync(g_cnt, 0, ((size_t)ng + 1) * 4, s));
+    CK(cudaMemsetAsync(g_uniq, 0, ((size_t)ng + 1) * 4, s));
+    launch_group_count(ctx->b_rec16.as<Rec16>(), n_acc, d, g_cnt, ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
+    launch_exclusive_scan(g_cnt, g_off, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
+    uint32_t *g_entg = ctx->b_vals[1].as<uint32_t>();
+    launch_group_scatter(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, ctx->b_vals[0].as<uint32_t>(), g_ent, g_entg, s, &ctx->lc);
+    launch_group_mark(ctx->b_rec16.as<Rec16>(), n_acc, g_off, g_entg, 1, g_ent, g_uniq, s, &ctx->lc);
     uint32_t n_out32 = 0;
-    CK(ctx->h_small.ensure(64));
-    launch_exclusive_scan(ctx->b_flags.as<uint32_t>(), ctx->b_pos.as<uint32_t>(), n_acc, ctx->b_tmp.as<uint32_t>(),
-                          ctx->b_counters.as<uint32_t>() + 8, s, &ctx->lc);
-    launch_expand_records(ctx->b_flags.as<uint32_t>(), ctx->b_pos.as<uint32_t>(), ctx->b_best.as<uint32_t>(), ctx->b_rec16.as<Rec16>(),
-                          n_acc, d, ctx->b_out.as<hlo_rec>(), ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
+    launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), ctx->b_counters.as<uint32_t>() + 8, s, &ctx->lc);
+    launch_group_expand(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, g_uoff, g_entg, g_ent, ctx->b_out.as<hlo_rec>(),
+                        ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
     CK(cudaGetLastError());
     FETCH(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4);
     const uint64_t n_out = n_out32;

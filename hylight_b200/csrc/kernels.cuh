@@ -107,13 +107,14 @@ void launch_verify_exact(const VerifyArgs &a, const uint32_t *idx, uint64_t n, c
 void launch_cands_to_internal(const hlo_cand *in, uint64_t n, const DevReads &r, CandI *out, cudaStream_t s, LaunchCounter *lc);
 
 // ---- records.cu -----------------------------------------------------------------------------
-void launch_record_keys(const Rec16 *rec, uint64_t n, DevReads r, uint64_t *keys, uint32_t *vals, cudaStream_t s,
-                        LaunchCounter *lc);
-// per run of equal keys choose the best record; flags[i] = 1 at the run start, best[i] = chosen index
-void launch_dedup_flags(const uint64_t *skeys, const uint32_t *svals, const Rec16 *rec, uint64_t n, int dedup, uint32_t *flags,
-                        uint32_t *best, cudaStream_t s, LaunchCounter *lc);
-void launch_expand_records(const uint32_t *flags, const uint32_t *pos, const uint32_t *best, const Rec16 *rec, uint64_t n,
-                           DevReads r, hlo_rec *out, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc);
+// group the accepted records by idA, sort the small groups by idB, keep the best record of every pair
+void launch_group_count(const Rec16 *rec, uint64_t n, DevReads r, uint32_t *cnt, uint32_t *slot, cudaStream_t s, LaunchCounter *lc);
+void launch_group_scatter(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *slot, uint2 *ent,
+                          uint32_t *entg, cudaStream_t s, LaunchCounter *lc);
+void launch_group_mark(const Rec16 *rec, uint64_t n, const uint32_t *off, const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq,
+                       cudaStream_t s, LaunchCounter *lc);
+void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *uoff, const uint32_t *entg,
+                         const uint2 *ent, hlo_rec *out, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc);
 void launch_cluster_offsets(const hlo_rec_aux *aux, uint64_t n, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,
                             LaunchCounter *lc);
 

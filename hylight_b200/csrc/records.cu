@@ -6,26 +6,18 @@
 // fewest mismatches, then '+' before '-', then the smaller diagonal.  The reference keeps the first-seen
 // longest inside each 1000-line chunk of minimap2's output order; that order is not reproducible
 // without minimap2, so the canonical rule is global.
+//
+// No global sort: the output order is (cluster, idA, idB) with idA < idB numerically, and a read has
+// only a dozen overlaps as idA.  So: (1) count the records per idA (one L2 atomic each; its return
+// value is the record's slot inside its group), (2) exclusive scan, (3) scatter 8-byte (rank of idB,
+// record index) entries into the groups, (4) one thread per record decides whether it is the record to
+// keep for its pair (marks its entry, counts per idA), (5) scan, (6) one thread per kept record counts
+// the kept entries of its group with a smaller idB and expands the record at that place.  Every pass is
+// record-parallel and coalesced on the record array; the group loops (a dozen entries) run out of L1.
+// Algorithmic bytes per record: 3 * 16 (Rec16 read by three passes) + 8 (entry) + 40 (out).
 #include "kernels.cuh"
 
 namespace hlo {
-
-__global__ void record_keys_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r, uint64_t *__restrict__ keys,
-                                   uint32_t *__restrict__ vals) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t q = rec[i].q, t = rec[i].t;
-    const uint32_t nq = r.nrank[q], nt = r.nrank[t];
-    const uint32_t lo = nq < nt ? nq : nt, hi = nq < nt ? nt : nq;
-    keys[i] = (uint64_t)lo << 32 | hi;
-    vals[i] = (uint32_t)i;
-}
-void launch_record_keys(const Rec16 *rec, uint64_t n, DevReads r, uint64_t *keys, uint32_t *vals, cudaStream_t s,
-                        LaunchCounter *lc) {
-    if (n == 0) return;
-    record_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, keys, vals);
-    if (lc) lc->total++;
-}
 
 __device__ __forceinline__ bool rec_better(const Rec16 &x, const Rec16 &y) {
     const uint32_t bx = x.kb >> 16, by = y.kb >> 16;
@@ -37,57 +29,106 @@ __device__ __forceinline__ bool rec_better(const Rec16 &x, const Rec16 &y) {
     return (x.ds >> 1) < (y.ds >> 1);
 }
 
-__global__ void dedup_flags_kernel(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
-                                   const Rec16 *__restrict__ rec, uint64_t n, int dedup, uint32_t *__restrict__ flags,
-                                   uint32_t *__restrict__ best) {
+// group = numeric rank (batch-global) of the record's idA; slot[i] = position of record i inside its group
+__global__ void __launch_bounds__(256) group_count_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
+                                                          uint32_t *__restrict__ cnt, uint32_t *__restrict__ slot) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (!dedup) {
-        flags[i] = 1u, best[i] = svals[i];
-        return;
-    }
-    const uint64_t key = skeys[i];
-    if (i > 0 && skeys[i - 1] == key) {
-        flags[i] = 0u, best[i] = 0u;
-        return;
-    }
-    uint32_t bi = svals[i];
-    Rec16 br = rec[bi];
-    for (uint64_t j = i + 1; j < n && skeys[j] == key; ++j) {
-        const uint32_t cj = svals[j];
-        const Rec16 cr = rec[cj];
-        if (rec_better(cr, br)) br = cr, bi = cj;
-    }
-    flags[i] = 1u, best[i] = bi;
+    const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
+    const uint32_t nq = __ldg(r.nrank + qt.x), nt = __ldg(r.nrank + qt.y);
+    slot[i] = atomicAdd(&cnt[min(nq, nt)], 1u);
 }
-void launch_dedup_flags(const uint64_t *skeys, const uint32_t *svals, const Rec16 *rec, uint64_t n, int dedup, uint32_t *flags,
-                        uint32_t *best, cudaStream_t s, LaunchCounter *lc) {
+void launch_group_count(const Rec16 *rec, uint64_t n, DevReads r, uint32_t *cnt, uint32_t *slot, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    dedup_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(skeys, svals, rec, n, dedup, flags, best);
+    group_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, cnt, slot);
     if (lc) lc->total++;
 }
 
-__global__ void expand_records_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos,
-                                      const uint32_t *__restrict__ best, const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
-                                      hlo_rec *__restrict__ out, hlo_rec_aux *__restrict__ aux) {
+// entry = (rank of idB, record index) at off[group] + slot; entg = its group
+__global__ void __launch_bounds__(256) group_scatter_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
+                                                            const uint32_t *__restrict__ off, const uint32_t *__restrict__ slot,
+                                                            uint2 *__restrict__ ent, uint32_t *__restrict__ entg) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !flags[i]) return;
-    const Rec16 x = rec[best[i]];
+    if (i >= n) return;
+    const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
+    const uint32_t nq = __ldg(r.nrank + qt.x), nt = __ldg(r.nrank + qt.y);
+    const uint32_t g = min(nq, nt), p = off[g] + slot[i];
+    ent[p] = make_uint2(max(nq, nt), (uint32_t)i);
+    entg[p] = g;
+}
+void launch_group_scatter(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *slot, uint2 *ent,
+                          uint32_t *entg, cudaStream_t s, LaunchCounter *lc) {
+    if (n == 0) return;
+    group_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, slot, ent, entg);
+    if (lc) lc->total++;
+}
+
+// Pass A, one thread per ENTRY (entries are laid out group by group, so the lanes of a warp walk the same one
+// or two groups and their loads coalesce): is my record the one to keep for its pair?  (No other entry of the
+// group with the same idB is better.)  The answer goes to the top bit of the entry and is counted per group.
+__global__ void __launch_bounds__(256) group_mark_kernel(const Rec16 *__restrict__ rec, uint64_t n, const uint32_t *__restrict__ off,
+                                                         const uint32_t *__restrict__ entg, int dedup, uint2 *ent,
+                                                         uint32_t *__restrict__ uniq) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint2 me = ent[p];
+    const uint32_t g = entg[p];
+    bool keep = true;
+    if (dedup) {
+        const uint32_t b = off[g], e = off[g + 1];
+        for (uint32_t j = b; j < e; ++j) {
+            const uint2 y = ent[j];
+            if (y.x == me.x && j != p && rec_better(rec[y.y & 0x7fffffffu], rec[me.y])) keep = false;  // same pair, better record
+        }
+    }
+    if (keep) {
+        ent[p].y = me.y | 0x80000000u;
+        atomicAdd(&uniq[g], 1u);
+    }
+}
+void launch_group_mark(const Rec16 *rec, uint64_t n, const uint32_t *off, const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq,
+                       cudaStream_t s, LaunchCounter *lc) {
+    if (n == 0) return;
+    group_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, off, entg, dedup, ent, uniq);
+    if (lc) lc->total++;
+}
+
+// Pass B, one thread per kept entry: its place inside the group = number of kept entries with a smaller idB
+// (ties between kept entries cannot occur with dedup; without dedup the better record goes first); expand it there.
+__global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
+                                                           const uint32_t *__restrict__ off, const uint32_t *__restrict__ uoff,
+                                                           const uint32_t *__restrict__ entg, const uint2 *__restrict__ ent,
+                                                           hlo_rec *__restrict__ out, hlo_rec_aux *__restrict__ aux) {
+    const uint64_t pe = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pe >= n) return;
+    const uint2 me = ent[pe];
+    if (!(me.y >> 31)) return;
+    const uint32_t g = entg[pe];
+    const uint32_t b = off[g], e = off[g + 1];
+    const Rec16 x = rec[me.y & 0x7fffffffu];
+    uint32_t rank = 0;
+    for (uint32_t j = b; j < e; ++j) {
+        const uint2 y = ent[j];
+        if (!(y.y >> 31) || j == pe) continue;
+        rank += y.x < me.x || (y.x == me.x && rec_better(rec[y.y & 0x7fffffffu], x));
+    }
+    const uint32_t p = uoff[g] + rank;
     const int ql = (int)(r.len[x.q] & HLO_LEN_MASK), tl = (int)(r.len[x.t] & HLO_LEN_MASK);
     const int diag = (int)(x.ds >> 1) - HLO_DIAG_BIAS;
     hlo_rec o;
     expand_record(r.ids[x.q], r.ids[x.t], ql, tl, diag, (int)(x.ds & 1u), x.kb & 0xffffu, &o);
-    const uint32_t p = pos[i];
-    out[p] = o;
+    uint4 *dst = reinterpret_cast<uint4 *>(out + p);
+    dst[0] = make_uint4(o.idA, o.idB, (uint32_t)o.OHA, (uint32_t)o.OHB);
+    dst[1] = make_uint4(o.OLA, o.OLB, o.K, o.ori);
     hlo_rec_aux ax;
     ax.cluster = r.cidx[x.q];
     ax.blocklen = x.kb >> 16;
     aux[p] = ax;
 }
-void launch_expand_records(const uint32_t *flags, const uint32_t *pos, const uint32_t *best, const Rec16 *rec, uint64_t n,
-                           DevReads r, hlo_rec *out, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc) {
+void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *uoff, const uint32_t *entg,
+                         const uint2 *ent, hlo_rec *out, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    expand_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flags, pos, best, rec, n, r, out, aux);
+    group_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, uoff, entg, ent, out, aux);
     if (lc) lc->total++;
 }
 
