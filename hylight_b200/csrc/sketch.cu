@@ -18,14 +18,17 @@ namespace hlo {
 
 #define HLO_MAX_W HLO_MAX_W_PUBLIC
 
+// minimap2's hash64 (Thomas Wang's 64-bit mix, every step masked to 2k bits).  The shift-add steps are
+// written as multiplications by constants (key + (key << 3) + (key << 8) = key * 265, ...): they run on
+// the FMA pipe as IMADs and leave the ALU pipe, which bounds the sketch kernels, to the xor-shifts.
 __device__ __forceinline__ uint64_t mm_hash64(uint64_t key, uint64_t mask) {
-    key = (~key + (key << 21)) & mask;
+    key = (key * 2097151ULL - 1ULL) & mask;  // ~key + (key << 21)  (~key = -key - 1)
     key = key ^ key >> 24;
-    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = (key * 265ULL) & mask;             // key + (key << 3) + (key << 8)
     key = key ^ key >> 14;
-    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = (key * 21ULL) & mask;              // key + (key << 2) + (key << 4)
     key = key ^ key >> 28;
-    key = (key + (key << 31)) & mask;
+    key = (key * 2147483649ULL) & mask;      // key + (key << 31)
     return key;
 }
 
@@ -176,10 +179,27 @@ __global__ void __launch_bounds__(128) sketch_fast_kernel(DevReads r, int k, uin
     const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
     const uint64_t INF = ~0ULL;
     uint64_t kmer0 = 0, kmer1 = 0;
+    // ring buffer of the last WW entries: slot = step mod WW, a compile-time constant in the unrolled body
     uint64_t bx[WW];
     uint32_t by[WW];
     static_for<0, WW>([&](auto J) { bx[J] = INF, by[J] = 0xffffffffu; });
-    uint64_t min_x = INF;
+    // mm_sketch's `min` is at every step the RIGHTMOST SMALLEST entry of the window.  Instead of rescanning the
+    // window when the minimum leaves it (a per-lane event: the warp would run the rescan with a handful of active
+    // lanes at almost every step), the window minimum is kept by block decomposition: steps are grouped in
+    // blocks of WW (one pass of the unrolled body); suf[j] = rightmost smallest of the previous block's slots
+    // j..WW-1, computed for all j at the block boundary (the same step for every lane), and the minimum of the
+    // current block's slots 0..s runs along.  Window minimum after step s = the smaller of the two, ties to the
+    // running one (it lies to the right).
+    uint64_t sufx[WW];
+    uint32_t sufy[WW];
+    uint32_t suf_tie = 0;          // bit j: the suffix minimum of j.. occurs more than once in j..WW-1
+    uint32_t sufs[WW];             // its slot
+    static_for<0, WW>([&](auto J) { sufx[J] = INF, sufy[J] = 0xffffffffu, sufs[J] = WW - 1; });  // all-INF window: rightmost slot
+    uint64_t px = INF;             // running minimum of the current block
+    uint32_t py = 0xffffffffu;
+    int pslot = 0;
+    bool ptie = false;
+    uint64_t min_x = INF;          // mm_sketch's `min`
     uint32_t min_y = 0xffffffffu;
     int min_slot = 0, l = 0;
     uint32_t n = 0;
@@ -190,6 +210,18 @@ __global__ void __launch_bounds__(128) sketch_fast_kernel(DevReads r, int k, uin
     };
     uint32_t word = 0, aword = 0;
     for (int i0 = 0; i0 < len; i0 += WW) {
+        if (i0 > 0) {  // block boundary: suffix minima of the block just finished (the ring holds exactly it)
+            uint64_t cx = INF;
+            uint32_t cy = 0xffffffffu, cs = WW - 1, tie = 0;
+            suf_tie = 0;
+            static_for<0, WW>([&](auto JJ) {
+                constexpr int j = WW - 1 - JJ;
+                if (j == WW - 1 || bx[j] < cx) cx = bx[j], cy = by[j], cs = j, tie = 0;  // strict <: the rightmost stays
+                else if (bx[j] == cx) tie = 1;
+                sufx[j] = cx, sufy[j] = cy, sufs[j] = cs;
+                suf_tie |= tie << j;
+            });
+        }
         static_for<0, WW>([&](auto SS) {
             constexpr int s = SS;
             const int i = i0 + s;
@@ -223,25 +255,28 @@ __global__ void __launch_bounds__(128) sketch_fast_kernel(DevReads r, int k, uin
                         if (min_x == bx[J] && by[J] != min_y) emit(bx[J], by[J]);
                     });
                 }
-                if (info_x <= min_x) {  // a new minimum; write the old one
-                    if (l >= WW + k && min_x != INF) emit(min_x, min_y);
-                    min_x = info_x, min_y = info_y, min_slot = s;
-                } else if (min_slot == s) {  // the old minimum left the window
-                    if (l >= WW + k - 1 && min_x != INF) emit(min_x, min_y);
-                    min_x = INF;
-                    bool tie = false;  // at least two buffer entries share the new minimum
-                    auto scan = [&](auto J) {  // >= : the rightmost smallest wins
-                        if (min_x >= bx[J]) tie = min_x == bx[J], min_x = bx[J], min_y = by[J], min_slot = J;
+                // running minimum of the current block (<=: the rightmost smallest)
+                if (s == 0 || info_x <= px) ptie = (s != 0) && info_x == px, px = info_x, py = info_y, pslot = s;
+                // the events of mm_sketch, decided against the OLD minimum
+                const bool ev_a = info_x <= min_x;                 // a new minimum
+                const bool ev_b = !ev_a && min_slot == s;          // the old minimum left the window
+                if (((ev_a && l >= WW + k) || (ev_b && l >= WW + k - 1)) && min_x != INF) emit(min_x, min_y);
+                // the new window minimum
+                bool tie;
+                if (s == WW - 1 || px <= sufx[s + 1 < WW ? s + 1 : 0]) {
+                    tie = ptie || (s != WW - 1 && px == sufx[s + 1 < WW ? s + 1 : 0]);
+                    min_x = px, min_y = py, min_slot = pslot;
+                } else {
+                    constexpr int j = s + 1 < WW ? s + 1 : 0;
+                    tie = (suf_tie >> j) & 1u;
+                    min_x = sufx[j], min_y = sufy[j], min_slot = (int)sufs[j];
+                }
+                if (ev_b && tie && l >= WW + k - 1 && min_x != INF) {  // rare: other entries share the new minimum
+                    auto dup = [&](auto J) {
+                        if (min_x == bx[J] && min_y != by[J]) emit(bx[J], by[J]);
                     };
-                    static_for<s + 1, WW>(scan);
-                    static_for<0, s + 1>(scan);
-                    if (tie && l >= WW + k - 1 && min_x != INF) {
-                        auto dup = [&](auto J) {
-                            if (min_x == bx[J] && min_y != by[J]) emit(bx[J], by[J]);
-                        };
-                        static_for<s + 1, WW>(dup);
-                        static_for<0, s + 1>(dup);
-                    }
+                    static_for<s + 1, WW>(dup);
+                    static_for<0, s + 1>(dup);
                 }
             }
         });
