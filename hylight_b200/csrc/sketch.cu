@@ -301,34 +301,38 @@ void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t 
     if (lc) lc->total++;
 }
 
-// strips -> dense arrays in name order, plus the (hash, index) pairs the radix sort starts from.
-// One thread per (read, strip slot); strips of reads that overflowed are skipped (the generic kernel
-// writes those reads afterwards).
+// strips -> dense arrays in name order, plus the (cluster, hash | index) pairs the radix sort starts from.
+// 8 lanes per read walk its strip (a strip holds ~22 of `cap` entries); strips of reads that overflowed are
+// skipped (the generic kernel writes those reads afterwards).
 __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_t cap, const uint64_t *__restrict__ sx,
                                                              const uint32_t *__restrict__ srp, const uint32_t *__restrict__ count,
                                                              const uint32_t *__restrict__ off, uint64_t *__restrict__ mz_x,
                                                              uint32_t *__restrict__ mz_rp, uint32_t *__restrict__ mz_rid,
                                                              uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int hash_bits) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t total = (uint64_t)r.n_reads * cap;
-    if (gid >= total) return;
-    const uint32_t xi = (uint32_t)(gid / cap), j = (uint32_t)(gid % cap);
+    const uint32_t xi = (uint32_t)(gid >> 3), l = (uint32_t)(gid & 7);
+    if (xi >= r.n_reads) return;
     const uint32_t n = count[xi];
-    if (j >= n || n > cap) return;
-    const uint32_t dst = off[xi] + j;
-    const uint64_t x = sx[gid];
-    mz_x[dst] = x;
-    mz_rp[dst] = srp[gid];
+    if (n > cap) return;
     const uint32_t read = r.perm[xi];
-    mz_rid[dst] = read;
-    keys[dst] = (x >> 8) | (uint64_t)r.cidx[read] << hash_bits;  // cluster-major: a cluster's buckets stay together
-    vals[dst] = dst;
+    const uint64_t chi = (uint64_t)r.cidx[read] << hash_bits;  // cluster-major: a cluster's buckets stay together
+    const uint32_t o = off[xi];
+    const uint64_t sb = (uint64_t)xi * cap;
+    for (uint32_t j = l; j < n; j += 8) {
+        const uint32_t dst = o + j;
+        const uint64_t x = sx[sb + j];
+        mz_x[dst] = x;
+        mz_rp[dst] = srp[sb + j];
+        mz_rid[dst] = read;
+        keys[dst] = (x >> 8) | chi;
+        vals[dst] = dst;
+    }
 }
 
 void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
                            const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp, uint32_t *mz_rid, uint64_t *keys, uint32_t *vals,
                            int hash_bits, cudaStream_t s, LaunchCounter *lc) {
-    const uint64_t total = (uint64_t)r.n_reads * cap;
+    const uint64_t total = (uint64_t)r.n_reads * 8;
     if (total == 0) return;
     sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rp, mz_rid, keys, vals, hash_bits);
     if (lc) lc->total++;
