@@ -306,10 +306,10 @@ def run_ours(args):
     pb.array[:] = batch.bases
     po.array[:] = batch.base_off.view(np.uint8)
     pc.array[:] = batch.cluster_off.view(np.uint8)
-    # Two host workers, each with its own context (stream + workspaces), take the steps alternately: the H2D copy
+    # A few host workers, each with its own context (stream + workspaces), take the steps alternately: the H2D copy
     # of one step, the kernels of another and the D2H copy of a third overlap, which is how the host binary drives a
     # GPU (main.cpp, --workers_per_device).  Every step still copies its own inputs in and its own records out.
-    n_workers = 2
+    n_workers = args.e2e_workers
     ctxs = [ctx] + [api.Context(local) for _ in range(n_workers - 1)]
     for c_ in ctxs:
         c_.set_option("aux", 0)  # what hylight-ovlp asks for: records + per-cluster offsets
@@ -394,6 +394,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clusters", type=int, default=32, help="clusters per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="pipelined host workers (context + stream each) in the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

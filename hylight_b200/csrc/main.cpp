@@ -37,7 +37,7 @@ struct Options {
     hlo_params P;
     std::vector<int> devices;
     uint64_t batch_bases = 256ull << 20;
-    int workers_per_device = 2;
+    int workers_per_device = 3;
     bool rename = false;
     std::string stats;
     std::vector<Cluster> clusters;
@@ -142,8 +142,8 @@ void usage() {
             "  --rename            name reads 0..N-1 in file order (what rename_fas.py does)\n"
             "  --devices 0,1,..|all   GPUs to use (default all)\n"
             "  --batch_bases N     bases per device batch (default 268435456)\n"
-            "  --workers_per_device N  host workers (context + stream each) per GPU; 2 overlaps one batch's copies\n"
-            "                      and text output with another's kernels (default 2)\n"
+            "  --workers_per_device N  host workers (context + stream each) per GPU; one computes while the others\n"
+            "                      upload, download and write text (default 3)\n"
             "  --stats FILE        JSON-lines per batch\n");
 }
 
