@@ -80,7 +80,7 @@ struct PairgenArgs {
 };
 // fast path: 8 lanes per query read, seed table in shared memory (2^slots_log2 slots per read)
 bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out);
-size_t pairgen_smem_bytes(int slots_log2);
+size_t pairgen_smem_bytes(int slots_log2, bool narrow);
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc);
 // exact generic path: one block per listed read (list == nullptr: reads 0..n_list-1), 64-bit keys, table in HBM
 void launch_generic_hit_counts(const PairgenArgs &a, const uint32_t *list, uint32_t n_list, uint32_t *counts, cudaStream_t s,

@@ -25,6 +25,8 @@
 // A read whose table overflows, or a batch whose keys do not fit 32 bits, is done exactly by
 // pairgen_generic_kernel with a 64-bit-keyed table in HBM.
 // Algorithmic bytes: 8 B per seed hit in + 16 B per candidate out.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace hlo {
@@ -124,13 +126,21 @@ constexpr int PG_G = 8;                        // lanes per read
 constexpr int PG_GROUPS = PG_THREADS / PG_G;   // reads in flight per block
 constexpr int PG_PAD = 8;                      // words of padding between the groups' tables (bank spread)
 
+// NARROW: reads of at most 255 bases and tables of at most 256 slots: min/max anchor positions are bytes and
+// the slot list is bytes, 7 instead of 10 bytes of shared memory per slot (more resident warps)
+template <bool NARROW>
 __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a, int slots_log2) {
     extern __shared__ uint32_t pg_smem[];
+    typedef typename std::conditional<NARROW, uint16_t, uint32_t>::type val_t;
+    typedef typename std::conditional<NARROW, uint8_t, uint16_t>::type list_t;
+    constexpr int VSH = NARROW ? 8 : 16;
+    constexpr uint32_t VMASK = NARROW ? 0xffu : 0xffffu;
     const uint32_t S = 1u << slots_log2, smask = S - 1u, ST = S + PG_PAD;
     const uint32_t g = threadIdx.x / PG_G, l = threadIdx.x % PG_G;
     uint32_t *keys = pg_smem + (size_t)g * ST;                                // (t - cluster base, strand, diagonal)
-    uint32_t *vals = pg_smem + (size_t)PG_GROUPS * ST + (size_t)g * ST;       // min anchor pos | max anchor pos << 16
-    uint16_t *list = reinterpret_cast<uint16_t *>(pg_smem + (size_t)2 * PG_GROUPS * ST) + (size_t)g * ST;  // claimed slots
+    val_t *vals = reinterpret_cast<val_t *>(pg_smem + (size_t)PG_GROUPS * ST) + (size_t)g * ST;  // min | max << VSH anchor position
+    list_t *list = reinterpret_cast<list_t *>(reinterpret_cast<val_t *>(pg_smem + (size_t)PG_GROUPS * ST) + (size_t)PG_GROUPS * ST) +
+                   (size_t)g * ST;                                            // claimed slots
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const unsigned gshift = lane & ~7u;
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                     for (uint32_t probe = 0; probe < S; ++probe) {
                         const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
                         if (old == HLO_EMPTY32) {
-                            vals[slot] = qp | qp << 16;
+                            vals[slot] = (val_t)(qp | qp << VSH);
                             nq += gap_min <= 0;
                             newslot = (int)slot;
                             done = true;
@@ -208,9 +218,9 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                         }
                         if (old == key) {  // no other lane of the group holds this key in this step
                             const uint32_t v = vals[slot];
-                            const uint32_t mn = min(v & 0xffffu, qp), mx = max(v >> 16, qp);
-                            vals[slot] = mn | mx << 16;
-                            nq += ((int)((v >> 16) - (v & 0xffffu)) < gap_min) && ((int)(mx - mn) >= gap_min);
+                            const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
+                            vals[slot] = (val_t)(mn | mx << VSH);
+                            nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
                             done = true;
                             break;
                         }
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                 }
                 // remember the claimed slots (per-group list, positions from a ballot: no atomics)
                 const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & 0xFFu;
-                if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (uint16_t)newslot;
+                if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
                 list_n += __popc(gb);
             }
             __syncwarp();  // orders the plain min/max updates of consecutive minimizers
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
             if (j < list_n) {
                 const uint32_t e = list[j];
                 key = keys[e], v = vals[e];
-                okc = (int)((v >> 16) - (v & 0xffffu)) >= gap_min;
+                okc = (int)((v >> VSH) - (v & VMASK)) >= gap_min;
             }
             const unsigned ob = (__ballot_sync(FULL, okc) >> gshift) & 0xFFu;
             if (okc) {
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                 const uint32_t lt = __ldg(a.reads.len + t);
                 const uint32_t strand = (key >> a.dg_bits) & 1u;
                 const int diag = (int)(key & ((1u << a.dg_bits) - 1u)) - (int)max_len;
-                emit_cand(a, p + __popc(ob & lt8), q, t, strand, diag, v & 0xffffu, v >> 16, ql, lt & 0x7fffu, (lt | lq) >> 31);
+                emit_cand(a, p + __popc(ob & lt8), q, t, strand, diag, v & VMASK, v >> VSH, ql, lt & 0x7fffu, (lt | lq) >> 31);
             }
             p += __popc(ob);
         }
@@ -278,9 +288,10 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     if (lane == 0 && nh_total) atomicAdd(&a.counters[1], nh_total);
 }
 
-size_t pairgen_smem_bytes(int slots_log2) {
+static bool pairgen_narrow(const DevReads &r, int slots_log2) { return r.max_len <= 255 && slots_log2 <= 8; }
+size_t pairgen_smem_bytes(int slots_log2, bool narrow) {
     const size_t ST = ((size_t)1 << slots_log2) + PG_PAD;
-    return (size_t)PG_GROUPS * ST * 10;  // keys u32 + vals u32 + list u16
+    return (size_t)PG_GROUPS * ST * (narrow ? 7 : 10);  // keys u32 + vals u16|u32 + list u8|u16
 }
 
 bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out) {
@@ -294,17 +305,19 @@ bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out) {
 
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc) {
     if (a.reads.n_reads == 0) return;
-    const size_t smem = pairgen_smem_bytes(slots_log2);
-    cudaFuncSetAttribute(pairgen_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+    const bool narrow = pairgen_narrow(a.reads, slots_log2);
+    const size_t smem = pairgen_smem_bytes(slots_log2, narrow);
+    void (*kern)(PairgenArgs, int) = narrow ? pairgen_group_kernel<true> : pairgen_group_kernel<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairgen_group_kernel, PG_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PG_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     uint64_t want = ((uint64_t)a.reads.n_reads + PG_GROUPS - 1) / PG_GROUPS;  // 4 reads per warp, 4 warps per block
     uint64_t grid = (uint64_t)sms * per_sm;
     if (grid > want) grid = want;
-    pairgen_group_kernel<<<(unsigned)grid, PG_THREADS, smem, s>>>(a, slots_log2);
+    kern<<<(unsigned)grid, PG_THREADS, smem, s>>>(a, slots_log2);
     if (lc) lc->total++;
 }
 
