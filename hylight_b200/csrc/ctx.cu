@@ -1010,6 +1010,10 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
         ctx->verify_exact = value != 0;
         return HLO_OK;
     }
+    if (!strcmp(name, "sort_onesweep")) {
+        radix_sort_use_onesweep(value != 0);
+        return HLO_OK;
+    }
     if (!strcmp(name, "sketch_generic")) {
         ctx->sketch_generic = value != 0;
         return HLO_OK;

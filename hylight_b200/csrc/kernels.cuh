@@ -44,6 +44,7 @@ void launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint64_t n, uint32
 // keys/vals are double buffers of n elements each; returns which buffer (0/1) holds the result.
 // `tmp` must hold sort_tmp_words(n) u32.
 size_t sort_tmp_words(uint64_t n);
+void radix_sort_use_onesweep(bool on);  // false: the classic histogram / scan / scatter passes
 int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begin_bit, int end_bit, uint32_t *tmp,
                       cudaStream_t s, LaunchCounter *lc);
 
