@@ -294,10 +294,16 @@ def run_ours(args):
     R.free()
     peak, peak_src = peaks()
     ach = vbytes / (stages["verify_fast_ms"] * 1e-3) / 1e9 if stages["verify_fast_ms"] > 0 else 0.0
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+    tj = os.path.join(ROOT, "profiles", "verify_traffic.json")
+    if os.path.exists(tj):
+        t = json.load(open(tj))
+        traffic = int((t["dram_bytes_read"] + t["dram_bytes_write"]) * counts["n_candidates"] / float(t["candidates_per_launch"]))
     roofline = {"kernel": "verify_fast_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": vbytes,
+                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": vbytes,
                 "ms_per_launch": stages["verify_fast_ms"], "mean_overlap_len": mean_ol, "peak_source": peak_src,
-                "note": "rows of a cluster are L2-resident (3.8 MB/cluster); see profiles/ for dram bytes and pipe utilisation"}
+                "note": "traffic < algorithmic bytes: the rows of a cluster (1.4 MB per strand) are re-read from L2; the kernel is "
+                        "bound by the integer (ALU) pipe, 63% utilised (profiles/r1h_verify.md)"}
 
     # ---- end-to-end leg: pinned host buffers -> hlo_overlap_host -> records on the host
     pb = api.PinnedArray(batch.bases.nbytes)
