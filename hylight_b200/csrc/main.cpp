@@ -259,8 +259,26 @@ bool parse_args(int argc, char **argv, Options &o, std::string &err) {
     return true;
 }
 
+// fn(i) for i in [0, n) on up to `threads` host threads
+template <class F>
+void parallel_for(size_t n, size_t threads, F fn) {
+    if (threads <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    const size_t nt = std::min(threads, n);
+    for (size_t t = 0; t < nt; ++t)
+        th.emplace_back([&] {
+            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto &t : th) t.join();
+}
+
 struct Shared {
     Options *o;
+    size_t helpers = 1;  // host threads a worker may use to parse and to write the clusters of its batch
     std::vector<std::vector<size_t>> batches;  // cluster indices per batch
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
@@ -284,22 +302,30 @@ void worker(Shared *S, int device) {
         if (b >= S->batches.size() || S->failed) break;
         const auto t0 = std::chrono::steady_clock::now();
         const std::vector<size_t> &idx = S->batches[b];
-        // load + concatenate
+        // parse the clusters of the batch (in parallel), then concatenate
         std::string bases;
         std::vector<uint64_t> off{0};
         std::vector<uint32_t> ids, coff{0};
-        bool ok = true;
-        for (size_t ci : idx) {
-            Cluster &c = o.clusters[ci];
-            ok = parse_reads(c.in1, c, o.rename) && (c.in2.empty() || parse_reads(c.in2, c, o.rename));
-            if (!ok) break;
-            for (size_t r = 1; r < c.off.size(); ++r) off.push_back(bases.size() + c.off[r]);
-            bases += c.bases;
-            ids.insert(ids.end(), c.ids.begin(), c.ids.end());
-            coff.push_back((uint32_t)ids.size());
-            std::string().swap(c.bases);
-            std::vector<uint64_t>().swap(c.off);
-            std::vector<uint32_t>().swap(c.ids);
+        std::atomic<bool> parse_ok{true};
+        parallel_for(idx.size(), S->helpers, [&](size_t j) {
+            Cluster &c = o.clusters[idx[j]];
+            if (!(parse_reads(c.in1, c, o.rename) && (c.in2.empty() || parse_reads(c.in2, c, o.rename)))) parse_ok = false;
+        });
+        bool ok = parse_ok;
+        if (ok) {
+            size_t nb = 0, nr = 0;
+            for (size_t ci : idx) nb += o.clusters[ci].bases.size(), nr += o.clusters[ci].ids.size();
+            bases.reserve(nb), off.reserve(nr + 1), ids.reserve(nr);
+            for (size_t ci : idx) {
+                Cluster &c = o.clusters[ci];
+                for (size_t r = 1; r < c.off.size(); ++r) off.push_back(bases.size() + c.off[r]);
+                bases += c.bases;
+                ids.insert(ids.end(), c.ids.begin(), c.ids.end());
+                coff.push_back((uint32_t)ids.size());
+                std::string().swap(c.bases);
+                std::vector<uint64_t>().swap(c.off);
+                std::vector<uint32_t>().swap(c.ids);
+            }
         }
         hlo_reads *R = nullptr;
         hlo_recs out{};
@@ -312,16 +338,20 @@ void worker(Shared *S, int device) {
             if (!rc) rc = hlo_overlap_batch(ctx, R, &out);
             if (rc) err = std::string(hlo_strerror(rc)) + ": " + hlo_last_error(ctx);
         }
-        if (err.empty()) {
-            for (size_t j = 0; j < idx.size() && err.empty(); ++j) {
+        if (err.empty()) {  // per-cluster files, written in parallel
+            std::mutex emu;
+            parallel_for(idx.size(), S->helpers, [&](size_t j) {
                 Cluster &c = o.clusters[idx[j]];
                 const hlo_rec *r0 = out.rec + out.cluster_off[j];
                 const uint64_t n = out.cluster_off[j + 1] - out.cluster_off[j];
                 c.n_records = n;
-                rc = hlo_write_overlaps(r0, n, c.out.c_str());
-                if (!rc && !c.sfo.empty()) rc = hlo_write_sfo(r0, n, c.sfo.c_str());
-                if (rc) err = std::string(hlo_strerror(rc)) + " writing " + c.out;
-            }
+                int wrc = hlo_write_overlaps(r0, n, c.out.c_str());
+                if (!wrc && !c.sfo.empty()) wrc = hlo_write_sfo(r0, n, c.sfo.c_str());
+                if (wrc) {
+                    std::lock_guard<std::mutex> g(emu);
+                    err = std::string(hlo_strerror(wrc)) + " writing " + c.out;
+                }
+            });
         }
         hlo_timing tm{};
         hlo_get_timing(ctx, &tm);
@@ -394,6 +424,7 @@ int main(int argc, char **argv) {
     }
     std::vector<std::thread> th;
     const size_t n_workers = std::min(o.devices.size() * (size_t)o.workers_per_device, S.batches.size());
+    S.helpers = std::max<size_t>(1, std::thread::hardware_concurrency() / std::max<size_t>(1, n_workers));
     for (size_t i = 0; i < n_workers; ++i) th.emplace_back(worker, &S, o.devices[i % o.devices.size()]);
     for (auto &t : th) t.join();
     if (S.stats && S.stats != stderr) fclose(S.stats);
