@@ -27,6 +27,8 @@
 // Bound: integer (ALU) pipe and L1 wavefronts (one per 16-byte vector of the randomly addressed row);
 // rows are L2-resident.  Algorithmic bytes per candidate = 16 + 2*ceil(OL/4) (when OL >= min_len) + 16
 // per accepted record (SURVEY.md §8d counts 32 B for the expanded record; the expansion is records.cu).
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace hlo {
@@ -65,7 +67,8 @@ __device__ __forceinline__ uint32_t low_mask(int n) {
 }
 
 constexpr int VF_THREADS = 128;
-constexpr int VF_STAGE = 512;  // records staged per block before one flush (one global atomic per flush)
+constexpr int VF_WARPS = VF_THREADS / 32;
+constexpr int VF_STAGE = 128;  // records staged per WARP before one flush (one global atomic per flush)
 
 // W = 32-bit data words per row actually compared (ceil(max_len / 16)); the row stride is NV = ceil(W/4)
 // 16-byte vectors.  FULLW = words that every overlap of at least min_len bases covers completely (no mask).
@@ -73,15 +76,14 @@ template <int W, int FULLW>
 __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     constexpr int NV = (W + 3) / 4, NW = 4 * NV;
     __shared__ uint16_t s_tab[3 * 1024];
-    __shared__ uint4 s_out[VF_STAGE];
-    __shared__ uint32_t s_cnt;
-    __shared__ unsigned long long s_base;
+    __shared__ uint4 s_out[VF_WARPS][VF_STAGE];
     // thresholds into shared memory (3 tables of max_len + 1 <= 1024 entries)
     const int tl1 = a.tab.max_len + 1;
     for (int i = threadIdx.x; i < 3 * tl1; i += VF_THREADS) s_tab[i] = a.tab.min_matches[i];
-    if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const uint16_t *t_min_matches = s_tab, *t_max_clip = s_tab + tl1, *t_max_k = s_tab + 2 * tl1;
+    uint4 *w_out = s_out[threadIdx.x >> 5];
+    uint32_t w_cnt = 0;  // records staged by this warp (warp-uniform)
 
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -89,9 +91,10 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     const uint64_t plane4 = (uint64_t)a.reads.n_reads * NV;  // uint4 per plane
     const uint4 *rows = reinterpret_cast<const uint4 *>(a.reads.bases);
     const uint4 *cands = reinterpret_cast<const uint4 *>(a.cands);
-    const uint64_t n_round = (a.n + VF_THREADS - 1) / VF_THREADS * VF_THREADS;  // whole blocks iterate together
+    const uint64_t n_round = (a.n + 31) & ~31ull;  // whole warps iterate together
     const int o = a.prm.max_overhang, min_len = a.prm.min_len;
     uint64_t c = (uint64_t)blockIdx.x * VF_THREADS + threadIdx.x;
+    if (c >= n_round) return;  // (after the only block barrier)
     uint4 cv_next = make_uint4(0u, 0u, 0u, 0u);
     if (c < a.n) cv_next = __ldg(cands + c);
     for (; c < n_round; c += n_threads) {
@@ -178,15 +181,11 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
                 }
             }
         }
-        // stream compaction: accepted records are staged in shared memory (one shared atomic per warp) and a
-        // full stage leaves with ONE global atomicAdd and coalesced 16-byte stores
+        // stream compaction: accepted records are staged per warp in shared memory (positions from a ballot, no
+        // atomics) and a full stage leaves with ONE global atomicAdd and coalesced 16-byte stores; no block barrier
         const unsigned acc_b = __ballot_sync(0xffffffffu, accept);
-        if (acc_b) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_cnt, (uint32_t)__popc(acc_b));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (accept) s_out[base + __popc(acc_b & lt_mask)] = rec;
-        }
+        if (accept) w_out[w_cnt + __popc(acc_b & lt_mask)] = rec;
+        w_cnt += __popc(acc_b);
         const unsigned def_b = __ballot_sync(0xffffffffu, defer);
         if (def_b) {  // rare
             unsigned long long base = 0;
@@ -194,17 +193,15 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
             base = __shfl_sync(0xffffffffu, base, 0);
             if (defer) a.deferred[base + __popc(def_b & lt_mask)] = (uint32_t)c;
         }
-        __syncthreads();
-        const uint32_t staged = s_cnt;
         const bool last = c + n_threads >= n_round;
-        if (staged > VF_STAGE - VF_THREADS || (last && staged)) {  // the next iteration might not fit
-            if (threadIdx.x == 0) s_base = atomicAdd(&a.counters[0], (unsigned long long)staged);
-            __syncthreads();
-            const unsigned long long gb = s_base;
-            for (uint32_t i = threadIdx.x; i < staged; i += VF_THREADS) reinterpret_cast<uint4 *>(a.out)[gb + i] = s_out[i];
-            __syncthreads();
-            if (threadIdx.x == 0) s_cnt = 0;
-            __syncthreads();
+        if (w_cnt > VF_STAGE - 32 || (last && w_cnt)) {  // the next iteration might not fit
+            __syncwarp();
+            unsigned long long gb = 0;
+            if (lane == 0) gb = atomicAdd(&a.counters[0], (unsigned long long)w_cnt);
+            gb = __shfl_sync(0xffffffffu, gb, 0);
+            for (uint32_t i = lane; i < w_cnt; i += 32) reinterpret_cast<uint4 *>(a.out)[gb + i] = w_out[i];
+            __syncwarp();
+            w_cnt = 0;
         }
     }
 }
@@ -213,11 +210,19 @@ bool verify_fast_supported(const DevReads &r, const VerifyTables &tab) {
     return r.max_len >= 1 && r.max_len <= 320 && tab.max_len + 1 <= 1024 && r.n_reads > 0;
 }
 
+template <int W, int F>
+static void launch_vf2(const VerifyArgs &a, int sms, cudaStream_t s) {
+    int per_sm = 8;  // persistent grid: as many blocks as are resident at once (each builds its tables once)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, verify_fast_kernel<W, F>, VF_THREADS, 0);
+    const uint64_t want = (a.n + VF_THREADS - 1) / VF_THREADS;
+    const uint64_t grid = std::min<uint64_t>(want, (uint64_t)sms * (per_sm > 0 ? per_sm : 1));
+    verify_fast_kernel<W, F><<<(unsigned)grid, VF_THREADS, 0, s>>>(a);
+}
 template <int W>
-static void launch_vf(const VerifyArgs &a, unsigned grid, cudaStream_t s) {
+static void launch_vf(const VerifyArgs &a, int sms, cudaStream_t s) {
     constexpr int F3 = W >= 3 ? 3 : 0;
-    if (a.prm.min_len >= 48 && F3) verify_fast_kernel<W, F3><<<grid, VF_THREADS, 0, s>>>(a);
-    else verify_fast_kernel<W, 0><<<grid, VF_THREADS, 0, s>>>(a);
+    if (a.prm.min_len >= 48 && F3) launch_vf2<W, F3>(a, sms, s);
+    else launch_vf2<W, 0>(a, sms, s);
 }
 
 void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) {
@@ -225,16 +230,12 @@ void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint64_t want = (a.n + VF_THREADS - 1) / VF_THREADS;
-    uint64_t grid64 = (uint64_t)sms * 12;  // persistent: every block loads the threshold tables once
-    if (grid64 > want) grid64 = want;
-    const unsigned grid = (unsigned)grid64;
     const int W = (int)((a.reads.max_len + 15) / 16);
     switch (W) {
-#define VF_CASE(w) case w: launch_vf<w>(a, grid, s); break;
+#define VF_CASE(w) case w: launch_vf<w>(a, sms, s); break;
         VF_CASE(1) VF_CASE(2) VF_CASE(3) VF_CASE(4) VF_CASE(5) VF_CASE(6) VF_CASE(7) VF_CASE(8) VF_CASE(9) VF_CASE(10)
         VF_CASE(11) VF_CASE(12) VF_CASE(13) VF_CASE(14) VF_CASE(15) VF_CASE(16) VF_CASE(17) VF_CASE(18) VF_CASE(19)
-        default: launch_vf<20>(a, grid, s); break;
+        default: launch_vf<20>(a, sms, s); break;
 #undef VF_CASE
     }
     if (lc) lc->total++, lc->verify++;
