@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "hlo_params_default", "hlo_abi_version", "hlo_strerror", "hlo_last_error", "hlo_device_count",
     "hlo_ctx_create", "hlo_ctx_destroy", "hlo_host_alloc", "hlo_host_free", "hlo_pack_reads", "hlo_reads_free",
     "hlo_sketch", "hlo_candidates", "hlo_verify", "hlo_overlap_batch", "hlo_overlap_host", "hlo_get_timing",
-    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream",
+    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records",
 ]
 
 
@@ -90,6 +90,8 @@ def lib():
         L.hlo_write_overlaps.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p]
         L.hlo_format_overlap_line.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.hlo_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.hlo_score_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double,
+                                        C.c_uint32, C.POINTER(C.c_void_p)]
         L.hlo_stream.restype = C.c_void_p
         L.hlo_stream.argtypes = [C.c_void_p]
         _lib = L
@@ -243,6 +245,16 @@ class Context:
         coff = np.ascontiguousarray(batch.cluster_off, dtype=np.uint32)
         r = self.overlap_host_raw(_ptr(bases), _ptr(off), len(off) - 1, _ptr(coff), len(coff) - 1)
         return self._recs(r)
+
+    def score_records(self, reads, quals, rec, rec_cluster=None, mismatch_prob=0.0, min_read_len=0):
+        """HaploConduct's overlap_score per record (EdgeCalculator.cpp:67-139): array (n, 2) of (score, mismatch_rate)."""
+        quals = np.ascontiguousarray(quals, dtype=np.uint8)
+        rec = np.ascontiguousarray(rec, dtype=REC_DT)
+        rc = None if rec_cluster is None else np.ascontiguousarray(rec_cluster, dtype=np.uint32)
+        out = C.c_void_p()
+        self._check(lib().hlo_score_records(self.h, reads.handle, _ptr(quals), _ptr(rec), _ptr(rc), len(rec), float(mismatch_prob),
+                                            int(min_read_len), C.byref(out)))
+        return _copy_out(out.value, len(rec), np.dtype([("score", "<f8"), ("mismatch_rate", "<f8")]))
 
     def stream_handle(self):
         """cudaStream_t of the ctx as an integer (wrap with torch.cuda.ExternalStream to record events on it)."""

@@ -104,7 +104,9 @@ struct hlo_ctx {
     // workspaces
     DevBuf b_cnt, b_mzoff, b_mzx, b_mzrp, b_mzrid, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
     DevBuf b_cands, b_counters, b_ovf, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
-    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp;
+    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp, b_qual, b_screc, b_scclu, b_scout, b_prob;
+    PinBuf h_score;
+    bool prob_ready = false;
     PinBuf h_out, h_aux, h_coff, h_mz, h_roff, h_cands, h_rec16, h_small;
     std::vector<uint64_t> v_coff;
     hlo_reads scratch_reads;
@@ -277,9 +279,9 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
                       &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_bstart,
                       &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovfcnt, &ctx->b_gkeys,
                       &ctx->b_gmn, &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos,
-                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx, &ctx->b_sx, &ctx->b_srp};
+                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx, &ctx->b_sx, &ctx->b_srp, &ctx->b_qual, &ctx->b_screc, &ctx->b_scclu, &ctx->b_scout, &ctx->b_prob};
     for (DevBuf *b : bufs) b->release();
-    PinBuf *pins[] = {&ctx->h_out, &ctx->h_aux, &ctx->h_coff, &ctx->h_mz, &ctx->h_roff, &ctx->h_cands, &ctx->h_rec16, &ctx->h_small};
+    PinBuf *pins[] = {&ctx->h_score, &ctx->h_out, &ctx->h_aux, &ctx->h_coff, &ctx->h_mz, &ctx->h_roff, &ctx->h_cands, &ctx->h_rec16, &ctx->h_small};
     for (PinBuf *b : pins) b->release();
     ctx->scratch_reads.release();
     for (int i = 0; i <= ST_COUNT; ++i)
@@ -1040,6 +1042,48 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
         return HLO_OK;
     }
     FAIL(HLO_EINVAL, "unknown option %s", name);
+}
+
+int hlo_score_records(hlo_ctx *ctx, const hlo_reads *R, const char *quals, const hlo_rec *rec, const uint32_t *rec_cluster, uint64_t n,
+                      double mismatch_prob, uint32_t min_read_len, const hlo_score **out) {
+    if (!ctx || !R || !quals || (!rec && n) || !out) return HLO_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const DevReads &d = R->d;
+    if (d.n_clusters > 1 && !rec_cluster) FAIL(HLO_EINVAL, "hlo_score_records: rec_cluster is required for a multi-cluster batch");
+    {   // records name reads by their decimal names: only names 0..N-1 in file order are resolved here
+        const int rcm = ensure_host_meta(ctx, R);
+        if (rcm) return rcm;
+        for (uint32_t c = 0; c < d.n_clusters; ++c)
+            for (uint32_t i = R->h_cluster_off[c]; i < R->h_cluster_off[c + 1]; ++i)
+                if (R->h_ids[i] != i - R->h_cluster_off[c]) FAIL(HLO_EUNSUPPORTED, "hlo_score_records needs read names 0..N-1 in file order");
+    }
+    if (!ctx->prob_ready) {  // phred_to_prob (EdgeCalculator.cpp:59-63) for every byte value, the reference's own expression
+        double tab[128];
+        for (int b = 0; b < 128; ++b) tab[b] = pow(10, -(b - 33) / 10.0);
+        CK(ctx->b_prob.ensure(sizeof tab));
+        CK(cudaMemcpyAsync(ctx->b_prob.p, tab, sizeof tab, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        ctx->prob_ready = true;
+    }
+    CK(ctx->b_qual.ensure(d.n_bases + 16));
+    CK(ctx->b_screc.ensure(n * sizeof(hlo_rec) + 32));
+    CK(ctx->b_scclu.ensure(n * 4 + 4));
+    CK(ctx->b_scout.ensure(n * sizeof(hlo_score) + 16));
+    CK(ctx->h_score.ensure(n * sizeof(hlo_score) + 16));
+    CK(const_cast<hlo_reads *>(R)->b_coff.ensure(((size_t)d.n_clusters + 1) * 4));
+    CK(cudaMemcpyAsync(R->b_coff.p, R->h_cluster_off.data(), ((size_t)d.n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->b_qual.p, quals, d.n_bases, cudaMemcpyHostToDevice, s));
+    if (n) CK(cudaMemcpyAsync(ctx->b_screc.p, rec, n * sizeof(hlo_rec), cudaMemcpyHostToDevice, s));
+    if (n && rec_cluster) CK(cudaMemcpyAsync(ctx->b_scclu.p, rec_cluster, n * 4, cudaMemcpyHostToDevice, s));
+    launch_score_records(d, ctx->b_qual.as<uint8_t>(), R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), ctx->b_screc.as<hlo_rec>(),
+                         rec_cluster ? ctx->b_scclu.as<uint32_t>() : nullptr, n, ctx->b_prob.as<double>(), mismatch_prob, min_read_len,
+                         ctx->b_scout.as<hlo_score>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    if (n) CK(cudaMemcpyAsync(ctx->h_score.p, ctx->b_scout.p, n * sizeof(hlo_score), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *out = ctx->h_score.as<hlo_score>();
+    return HLO_OK;
 }
 
 void *hlo_stream(const hlo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

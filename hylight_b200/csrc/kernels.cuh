@@ -119,4 +119,9 @@ void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_
 void launch_cluster_offsets(const hlo_rec_aux *aux, uint64_t n, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,
                             LaunchCounter *lc);
 
+// ---- score.cu -------------------------------------------------------------------------------
+void launch_score_records(const DevReads &r, const uint8_t *quals, const uint64_t *base_off, const uint32_t *cluster_off, const hlo_rec *rec,
+                          const uint32_t *rec_cluster, uint64_t n, const double *prob_tab, double mismatch_thr, uint32_t min_read_len,
+                          hlo_score *out, cudaStream_t s, LaunchCounter *lc);
+
 }  // namespace hlo

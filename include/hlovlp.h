@@ -183,6 +183,23 @@ int hlo_overlap_host(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, 
 
 int hlo_get_timing(const hlo_ctx *ctx, hlo_timing *t);
 
+/* Next step of the path: what the consumer computes for every line of the .overlaps
+ * file, tools/HaploConduct/src/EdgeCalculator.cpp:26-139 (score, overlap_score) in the S-S case of
+ * compute_overlap (:199-233): orient read ID1 by ORI1 and read ID2 by ORI2 (sequence reverse-complemented,
+ * phreds reversed), compare seq1[POS1 + i] with seq2[i] over L = min(L1 - POS1, L2), skip positions with an
+ * ambiguous base, per position p(same strain) from the two phred error probabilities, score = exp(mean log p),
+ * mismatch_rate = mismatches / compared positions; score 0 when a position has p < mismatch_prob, when a read is
+ * shorter than min_read_len, or when nothing was compared.  FP64, accumulated in position order.
+ *   quals : phred+33 strings, concatenated with the same offsets as the bases given to hlo_pack_reads
+ *   rec_cluster : cluster index of every record (hlo_rec_aux.cluster), or NULL when the batch has one cluster
+ * Only for read names 0..N-1 in file order (HLO_EUNSUPPORTED otherwise). */
+typedef struct hlo_score {
+    double score;
+    double mismatch_rate;
+} hlo_score;
+int hlo_score_records(hlo_ctx *ctx, const hlo_reads *reads, const char *quals, const hlo_rec *rec, const uint32_t *rec_cluster,
+                      uint64_t n, double mismatch_prob, uint32_t min_read_len, const hlo_score **out);
+
 /* Tuning / test knobs.  "verify_exact" (0|1): route every candidate through the base-by-base verify
  * kernel; "pairgen_slots_log2" (6..13): slots of the per-warp shared-memory seed table;
  * "repack" (0|1): hlo_overlap_batch re-runs the 2-bit packer from the ASCII bases kept in HBM (so a

@@ -848,3 +848,73 @@ uint64_t orc_paf_rows_to_recs(const orc_paf *rows, const uint64_t *idx, uint64_t
 }
 
 size_t orc_sizeof_paf(void) { return sizeof(orc_paf); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* (3) the consumer's phred-weighted overlap score: EdgeCalculator.cpp:26-56 (score), :59-63        */
+/*     (phred_to_prob), :67-139 (overlap_score), S-S orientation handling :199-221                  */
+
+static double orc_phred_to_prob(int phred) { return pow(10, -phred / 10.0); }
+
+/* score(): returns log p (<= 0), 1 for an N position, 2 for an unacceptable mismatch */
+static double orc_score(char nt1, char nt2, double p1, double p2, double mismatch_thr, int *mismatch_count) {
+    double p;
+    if (nt1 == 'N' || nt2 == 'N') return 1;
+    else if (nt1 == nt2) p = (1 - p1) * (1 - p2) + (p1 * p2) / 3.0;
+    else {
+        p = p1 * (1 - p2) / 3.0 + p2 * (1 - p1) / 3.0 + (2 / 9.0) * p1 * p2;
+        ++*mismatch_count;
+    }
+    if (p < mismatch_thr) return 2;
+    return log(p);
+}
+
+static char orc_up(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+static char orc_comp(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N'; }
+
+/* one record -> (score, mismatch_rate), reads named 0..N-1 inside cluster `cb` (first read of the cluster) */
+void orc_overlap_score(const char *bases, const char *quals, const uint64_t *base_off, uint32_t cb, const hlo_rec *r,
+                       double mismatch_thr, uint32_t min_read_len, double *score_out, double *mismatch_rate_out) {
+    /* the 13-column fields of sfo2overlaps.py:150-200 */
+    const int OHA = r->OHA;
+    uint32_t id1, id2;
+    int pos1, ori1, ori2; /* ori: 1 = '+' */
+    if (OHA >= 0) id1 = r->idA, id2 = r->idB, pos1 = OHA, ori1 = 1, ori2 = !r->ori;
+    else id1 = r->idB, id2 = r->idA, pos1 = -OHA, ori1 = !r->ori, ori2 = 1;
+    const char *s1 = bases + base_off[cb + id1], *s2 = bases + base_off[cb + id2];
+    const char *q1 = quals + base_off[cb + id1], *q2 = quals + base_off[cb + id2];
+    const int L1 = (int)(base_off[cb + id1 + 1] - base_off[cb + id1]), L2 = (int)(base_off[cb + id2 + 1] - base_off[cb + id2]);
+    *mismatch_rate_out = 1.0;
+    *score_out = 0.0;
+    if (pos1 >= L1) return;
+    if ((uint32_t)L1 < min_read_len || (uint32_t)L2 < min_read_len) return;
+    const int L = (L1 - pos1) < L2 ? (L1 - pos1) : L2;
+    double total_score = 0.0, total_len = 0.0;
+    int mismatch_count = 0;
+    for (int i = 0; i < L; ++i) {
+        const int j1 = pos1 + i, j2 = i;
+        /* FastqStorage upper-cases on load (FastqStorage.cpp:123); anything but ACGT is treated as N here */
+        char n1 = ori1 ? orc_up(s1[j1]) : orc_comp(orc_up(s1[L1 - 1 - j1]));
+        char n2 = ori2 ? orc_up(s2[j2]) : orc_comp(orc_up(s2[L2 - 1 - j2]));
+        if (n1 == 'U') n1 = 'T';
+        if (n2 == 'U') n2 = 'T';
+        if (n1 != 'A' && n1 != 'C' && n1 != 'G' && n1 != 'T') n1 = 'N';
+        if (n2 != 'A' && n2 != 'C' && n2 != 'G' && n2 != 'T') n2 = 'N';
+        const int Q1 = (int)(ori1 ? q1[j1] : q1[L1 - 1 - j1]) - 33, Q2 = (int)(ori2 ? q2[j2] : q2[L2 - 1 - j2]) - 33;
+        const double s = orc_score(n1, n2, orc_phred_to_prob(Q1), orc_phred_to_prob(Q2), mismatch_thr, &mismatch_count);
+        if (s <= 0) total_score += s, total_len += 1;
+        else if (s == 1) continue;
+        else return; /* unacceptable mismatch: score 0, mismatch_rate stays 1 */
+    }
+    if (total_len == 0) return;
+    *mismatch_rate_out = (float)mismatch_count / total_len;
+    *score_out = exp((1.0 / total_len) * total_score);
+}
+
+void orc_score_records(const char *bases, const char *quals, const uint64_t *base_off, const uint32_t *cluster_off,
+                       const hlo_rec *rec, const uint32_t *rec_cluster, uint64_t n, double mismatch_thr, uint32_t min_read_len,
+                       double *out /* 2 per record */) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t cb = (cluster_off && rec_cluster) ? cluster_off[rec_cluster[i]] : 0u;
+        orc_overlap_score(bases, quals, base_off, cb, &rec[i], mismatch_thr, min_read_len, &out[2 * i], &out[2 * i + 1]);
+    }
+}

@@ -239,3 +239,14 @@ def overlap_line(rec_row):
 
 def name_cmp(a, b):
     return lib().orc_name_cmp(C.c_uint32(a), C.c_uint32(b))
+
+
+def score_records(b, quals, rec, rec_cluster=None, mismatch_prob=0.0, min_read_len=0):
+    """HaploConduct's overlap_score (EdgeCalculator.cpp:67-139) per record: array (n, 2) of (score, mismatch_rate)."""
+    rec = np.ascontiguousarray(rec, dtype=REC_DT)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    rc = None if rec_cluster is None else np.ascontiguousarray(rec_cluster, dtype=np.uint32)
+    out = np.zeros((max(len(rec), 1), 2), dtype=np.float64)
+    lib().orc_score_records(_ptr(b.bases), _ptr(quals), _ptr(b.base_off), _ptr(b.cluster_off), _ptr(rec), _ptr(rc),
+                            C.c_uint64(len(rec)), C.c_double(mismatch_prob), C.c_uint32(min_read_len), _ptr(out))
+    return out[:len(rec)]
