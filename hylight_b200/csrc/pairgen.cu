@@ -122,7 +122,9 @@ __device__ __forceinline__ void emit_cand(const PairgenArgs &a, unsigned long lo
 // fast path: 8 lanes per query read, 4 reads per warp in LOCKSTEP (every loop bound is the maximum over
 // the warp's 4 reads, so the warp never diverges into per-read paths), table in shared memory
 constexpr int PG_THREADS = 128;
-constexpr int PG_G = 8;                        // lanes per read
+constexpr int PG_G = 16;                       // lanes per read (8 and 16 measured; 16: fewer, fuller chunks and less smem per block)
+constexpr unsigned PG_GMASK = PG_G == 32 ? 0xffffffffu : ((1u << PG_G) - 1u);
+constexpr int PG_RPW = 32 / PG_G;              // reads per warp
 constexpr int PG_GROUPS = PG_THREADS / PG_G;   // reads in flight per block
 constexpr int PG_PAD = 8;                      // words of padding between the groups' tables (bank spread)
 
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                    (size_t)g * ST;                                            // claimed slots
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    const unsigned gshift = lane & ~7u;
+    const unsigned gshift = lane & ~(unsigned)(PG_G - 1);
     const unsigned lt8 = (1u << l) - 1u;
     const int kshift = a.dg_bits + 1;
     const uint32_t max_len = a.reads.max_len;
@@ -152,10 +154,10 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     unsigned long long nh_total = 0;
     for (;;) {
         unsigned long long qq = 0;
-        if (lane == 0) qq = atomicAdd(&a.counters[3], 4ULL);
+        if (lane == 0) qq = atomicAdd(&a.counters[3], (unsigned long long)PG_RPW);
         qq = __shfl_sync(FULL, qq, 0);
         if (qq >= n_reads) break;
-        const uint32_t xq = (uint32_t)qq + (lane >> 3);
+        const uint32_t xq = (uint32_t)qq + lane / PG_G;
         const bool have_read = xq < n_reads;
         uint32_t m0 = 0, m1 = 0, q = 0, lq = 0, cb = 0;
         if (have_read) {
@@ -229,14 +231,14 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                     if (!done) ovf = true;
                 }
                 // remember the claimed slots (per-group list, positions from a ballot: no atomics)
-                const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & 0xFFu;
+                const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & PG_GMASK;
                 if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
                 list_n += __popc(gb);
             }
             __syncwarp();  // orders the plain min/max updates of consecutive minimizers
         }
         // per-read reductions inside the 8-lane groups (uniform across the warp)
-        const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & 0xFFu) != 0u;
+        const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & PG_GMASK) != 0u;
         if (ovf_any) {  // redo this read exactly in the generic kernel (its hits are counted there)
             if (l == 0 && have_read) {
                 const unsigned long long p = atomicAdd(&a.counters[2], 1ULL);
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                 key = keys[e], v = vals[e];
                 okc = (int)((v >> VSH) - (v & VMASK)) >= gap_min;
             }
-            const unsigned ob = (__ballot_sync(FULL, okc) >> gshift) & 0xFFu;
+            const unsigned ob = (__ballot_sync(FULL, okc) >> gshift) & PG_GMASK;
             if (okc) {
                 const uint32_t t = cb + (key >> kshift);
                 const uint32_t lt = __ldg(a.reads.len + t);
