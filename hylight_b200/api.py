@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "hlo_params_default", "hlo_abi_version", "hlo_strerror", "hlo_last_error", "hlo_device_count",
     "hlo_ctx_create", "hlo_ctx_destroy", "hlo_host_alloc", "hlo_host_free", "hlo_pack_reads", "hlo_reads_free",
     "hlo_sketch", "hlo_candidates", "hlo_verify", "hlo_overlap_batch", "hlo_overlap_host", "hlo_get_timing",
-    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records",
+    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records", "hlo_write_overlaps_scored",
 ]
 
 

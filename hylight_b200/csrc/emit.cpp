@@ -128,7 +128,16 @@ int hlo_write_sfo(const hlo_rec *rec, uint64_t n, const char *path) {
     return HLO_OK;
 }
 
-int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path) {
+static int write_overlaps_impl(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path);
+
+int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path) { return write_overlaps_impl(rec, nullptr, n, path); }
+
+int hlo_write_overlaps_scored(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path) {
+    if (!score && n) return HLO_EINVAL;
+    return write_overlaps_impl(rec, score, n, path);
+}
+
+static int write_overlaps_impl(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path) {
     if ((!rec && n) || !path) return HLO_EINVAL;
     std::string tmp = std::string(path) + ".tmp";
     FILE *f = fopen(tmp.c_str(), "w");
@@ -147,6 +156,11 @@ int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path) {
         }
         if (i && strcmp(line, prev) == 0) continue;  // `uniq`
         out.append(line, (size_t)len);
+        if (score) {  // two more columns: overlap score and mismatch rate, round-trip precision
+            char sc[64];
+            const int sl = snprintf(sc, sizeof sc, "\t%.17g\t%.17g", score[i].score, score[i].mismatch_rate);
+            out.append(sc, (size_t)sl);
+        }
         out.push_back('\n');
         memcpy(prev, line, (size_t)len + 1);
         if (out.size() >= BUF) {

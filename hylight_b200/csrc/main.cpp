@@ -26,7 +26,7 @@ namespace {
 
 struct Cluster {
     std::string in1, in2, out, sfo;
-    std::string bases;
+    std::string bases, quals;
     std::vector<uint64_t> off{0};
     std::vector<uint32_t> ids;
     std::string err;
@@ -39,6 +39,9 @@ struct Options {
     uint64_t batch_bases = 256ull << 20;
     int workers_per_device = 3;
     bool rename = false;
+    bool scores = false;          // also write <out>.scored: 13 columns + HaploConduct's overlap score and mismatch rate
+    double mismatch_prob = 0.0;   // ViralQuasispecies --mismatch
+    uint32_t min_read_len = 0;    // ViralQuasispecies --min_read_len
     std::string stats;
     std::vector<Cluster> clusters;
 };
@@ -75,7 +78,7 @@ bool parse_id(const char *s, const char *e, uint32_t &id) {
 }
 
 // FASTA (multi-line) or FASTQ (4-line records, fastq2fasta.py:32-40) -> appended to c
-bool parse_reads(const std::string &path, Cluster &c, bool rename) {
+bool parse_reads(const std::string &path, Cluster &c, bool rename, bool want_quals = false) {
     std::string data;
     if (!read_file(path, data, c.err)) return false;
     const char *p = data.data(), *end = p + data.size();
@@ -88,6 +91,10 @@ bool parse_reads(const std::string &path, Cluster &c, bool rename) {
     const bool fq = *p == '@';
     if (!fq && *p != '>') {
         c.err = path + ": neither FASTA nor FASTQ";
+        return false;
+    }
+    if (!fq && want_quals) {
+        c.err = path + ": --scores needs FASTQ input (phred qualities)";
         return false;
     }
     while (p < end) {
@@ -112,9 +119,19 @@ bool parse_reads(const std::string &path, Cluster &c, bool rename) {
             const char *s_end = se;
             while (s_end > p && s_end[-1] == '\r') --s_end;
             c.bases.append(p, s_end);
+            const size_t slen = (size_t)(s_end - p);
             p = se < end ? se + 1 : end;
             for (int k = 0; k < 2 && p < end; ++k) {  // '+' line and the qualities
                 const char *e2 = line_end(p);
+                if (k == 1 && want_quals) {
+                    const char *q_end = e2;
+                    while (q_end > p && q_end[-1] == '\r') --q_end;
+                    if ((size_t)(q_end - p) != slen) {
+                        c.err = path + ": quality string and sequence differ in length";
+                        return false;
+                    }
+                    c.quals.append(p, q_end);
+                }
                 p = e2 < end ? e2 + 1 : end;
             }
         } else {
@@ -144,6 +161,8 @@ void usage() {
             "  --batch_bases N     bases per device batch (default 268435456)\n"
             "  --workers_per_device N  host workers (context + stream each) per GPU; one computes while the others\n"
             "                      upload, download and write text (default 3)\n"
+            "  --scores            also write <out>.scored = the 13 columns + HaploConduct's phred-weighted overlap score and\n"
+            "                      mismatch rate (EdgeCalculator.cpp:67-139); FASTQ input; [--mismatch_prob P] [--min_read_len L]\n"
             "  --stats FILE        JSON-lines per batch\n");
 }
 
@@ -161,6 +180,7 @@ bool parse_args(int argc, char **argv, Options &o, std::string &err) {
         };
         const char *v = nullptr;
         if (a == "--rename") o.rename = true;
+        else if (a == "--scores") o.scores = true;
         else if (a == "-h" || a == "--help") return false;
         else if (!val(v)) {
             err = "missing value for " + a;
@@ -184,6 +204,8 @@ bool parse_args(int argc, char **argv, Options &o, std::string &err) {
         else if (a == "--batch_bases") o.batch_bases = strtoull(v, nullptr, 10);
         else if (a == "--workers_per_device") o.workers_per_device = std::max(1, atoi(v));
         else if (a == "--stats") o.stats = v;
+        else if (a == "--mismatch_prob") o.mismatch_prob = atof(v);
+        else if (a == "--min_read_len") o.min_read_len = (uint32_t)atoi(v);
         else {
             err = "unknown option " + a;
             return false;
@@ -303,13 +325,13 @@ void worker(Shared *S, int device) {
         const auto t0 = std::chrono::steady_clock::now();
         const std::vector<size_t> &idx = S->batches[b];
         // parse the clusters of the batch (in parallel), then concatenate
-        std::string bases;
+        std::string bases, quals;
         std::vector<uint64_t> off{0};
         std::vector<uint32_t> ids, coff{0};
         std::atomic<bool> parse_ok{true};
         parallel_for(idx.size(), S->helpers, [&](size_t j) {
             Cluster &c = o.clusters[idx[j]];
-            if (!(parse_reads(c.in1, c, o.rename) && (c.in2.empty() || parse_reads(c.in2, c, o.rename)))) parse_ok = false;
+            if (!(parse_reads(c.in1, c, o.rename, o.scores) && (c.in2.empty() || parse_reads(c.in2, c, o.rename, o.scores)))) parse_ok = false;
         });
         bool ok = parse_ok;
         if (ok) {
@@ -320,6 +342,7 @@ void worker(Shared *S, int device) {
                 Cluster &c = o.clusters[ci];
                 for (size_t r = 1; r < c.off.size(); ++r) off.push_back(bases.size() + c.off[r]);
                 bases += c.bases;
+                if (o.scores) quals += c.quals, std::string().swap(c.quals);
                 ids.insert(ids.end(), c.ids.begin(), c.ids.end());
                 coff.push_back((uint32_t)ids.size());
                 std::string().swap(c.bases);
@@ -328,6 +351,7 @@ void worker(Shared *S, int device) {
             }
         }
         hlo_reads *R = nullptr;
+        const hlo_score *scores = nullptr;
         hlo_recs out{};
         std::string err;
         if (!ok) {
@@ -336,6 +360,12 @@ void worker(Shared *S, int device) {
         } else {
             rc = hlo_pack_reads(ctx, bases.data(), off.data(), (uint32_t)ids.size(), coff.data(), (uint32_t)idx.size(), ids.data(), &R);
             if (!rc) rc = hlo_overlap_batch(ctx, R, &out);
+            if (!rc && o.scores) {
+                std::vector<uint32_t> rc_of(out.n);  // cluster of every record, from the per-cluster offsets
+                for (size_t j = 0; j < idx.size(); ++j)
+                    for (uint64_t k = out.cluster_off[j]; k < out.cluster_off[j + 1]; ++k) rc_of[k] = (uint32_t)j;
+                rc = hlo_score_records(ctx, R, quals.data(), out.rec, rc_of.data(), out.n, o.mismatch_prob, o.min_read_len, &scores);
+            }
             if (rc) err = std::string(hlo_strerror(rc)) + ": " + hlo_last_error(ctx);
         }
         if (err.empty()) {  // per-cluster files, written in parallel
@@ -347,6 +377,7 @@ void worker(Shared *S, int device) {
                 c.n_records = n;
                 int wrc = hlo_write_overlaps(r0, n, c.out.c_str());
                 if (!wrc && !c.sfo.empty()) wrc = hlo_write_sfo(r0, n, c.sfo.c_str());
+                if (!wrc && scores) wrc = hlo_write_overlaps_scored(r0, scores + out.cluster_off[j], n, (c.out + ".scored").c_str());
                 if (wrc) {
                     std::lock_guard<std::mutex> g(emu);
                     err = std::string(hlo_strerror(wrc)) + " writing " + c.out;

@@ -220,6 +220,9 @@ void *hlo_stream(const hlo_ctx *ctx);
 int hlo_write_sfo(const hlo_rec *rec, uint64_t n, const char *path);
 /* 13-field SAVAGE .overlaps lines (sfo2overlaps.py:150-200), written to a temp file then renamed. */
 int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path);
+/* The same lines with two more columns, hlo_score.score and .mismatch_rate (%.17g): the file a HaploConduct whose
+ * reader takes the precomputed score would consume (15 fields; the stock reader wants exactly 13). */
+int hlo_write_overlaps_scored(const hlo_rec *rec, const struct hlo_score *score, uint64_t n, const char *path);
 /* Format one 13-field line into buf (>= 128 bytes); returns its length. */
 int hlo_format_overlap_line(const hlo_rec *rec, char *buf, size_t cap);
 

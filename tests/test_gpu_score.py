@@ -67,3 +67,38 @@ def test_scores_need_plain_names():
             c.score_records(R, np.full(b.n_bases, 70, dtype=np.uint8), rec, aux["cluster"])
         assert e.value.status == -5
         R.free()
+
+
+def test_host_binary_scored_file(tmp_path):
+    """hylight-ovlp --scores: FASTQ in, <out>.scored = the 13 columns + score and mismatch rate (%.17g)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "hylight_b200", "hylight-ovlp")
+    rng = np.random.default_rng(9)
+    b = small_cluster(66, n_fragments=80)
+    quals = random_quals(rng, b.n_bases)
+    fq = tmp_path / "s_p1_p2.fastq"
+    with open(fq, "wb") as f:
+        for i in range(b.n_reads):
+            lo, hi = int(b.base_off[i]), int(b.base_off[i + 1])
+            f.write(b"@%d\n" % i + b.bases[lo:hi].tobytes() + b"\n+\n" + quals[lo:hi].tobytes() + b"\n")
+    out = tmp_path / "o.txt"
+    r = subprocess.run([exe, "--in", str(fq), "--out", str(out), "--scores"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ob = to_orc_batch(b)
+    rec, blk, coff, st = orc.overlap_batch(ob)
+    want = orc.score_records(ob, quals, rec)
+    plain = open(out).read().splitlines()
+    scored = open(str(out) + ".scored").read().splitlines()
+    assert len(plain) == len(scored) == len(rec)
+    for k, (p, s) in enumerate(zip(plain, scored)):
+        f = s.split("\t")
+        assert len(f) == 15 and "\t".join(f[:13]) == p
+        assert float(f[14]) == want[k, 1]
+        assert abs(float(f[13]) - want[k, 0]) <= REL_TOL * want[k, 0]
+    # FASTA input has no qualities
+    fa = tmp_path / "r.fa"
+    synth.write_fasta(b, 0, str(fa))
+    r = subprocess.run([exe, "--in", str(fa), "--out", str(tmp_path / "x.txt"), "--scores"], capture_output=True, text=True)
+    assert r.returncode != 0 and "FASTQ" in r.stderr
