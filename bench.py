@@ -221,6 +221,25 @@ def concordance_check(api, synth):
             "against": "CPU restatement of the minimap2->filter->sfo->overlaps chain (oracle/; minimap2 binary unavailable)"}
 
 
+def bind_to_gpu_cpus(local):
+    """Run this rank (and the host workers it starts) on the CPUs NVML reports as closest to its GPU, so that the
+    pinned buffers are first-touched on that NUMA node and the PCIe traffic does not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._nvml_index(local))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1 and 64 * w + b < n_cpu}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001
+        pass
+    return 0
+
+
 def run_ours(args):
     import torch
     from hylight_b200 import api, synth
@@ -230,6 +249,7 @@ def run_ours(args):
     if not torch.cuda.is_available() or api.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; the overlap stage has no CPU fallback")
     torch.cuda.set_device(local)
+    bound = 0 if args.no_bind else bind_to_gpu_cpus(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -318,7 +338,8 @@ def run_ours(args):
     n_workers = args.e2e_workers
     ctxs = [ctx] + [api.Context(local) for _ in range(n_workers - 1)]
     for c_ in ctxs:
-        c_.set_option("aux", 0)  # what hylight-ovlp asks for: records + per-cluster offsets
+        c_.set_option("aux", 0)      # what hylight-ovlp asks for: records + per-cluster offsets,
+        c_.set_option("compact", 1)  # in the 16-byte form (hlo_rec16)
     d2h = [0]
 
     def run_steps(n_steps):
@@ -335,7 +356,7 @@ def run_ours(args):
                     nxt[0] += 1
                 r = c.overlap_host_raw(pb.ptr, po.ptr, batch.n_reads, pc.ptr, batch.n_clusters)
                 tot[wi] += int(r.n)
-                d2h[0] = int(r.n) * api.REC_DT.itemsize + 8 * (batch.n_clusters + 1)
+                d2h[0] = int(r.n) * api.REC16_DT.itemsize + 8 * (batch.n_clusters + 1)
 
         th = [threading.Thread(target=work, args=(wi,)) for wi in range(n_workers)]
         for t in th:
@@ -373,7 +394,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": n_rec2_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": ms_e2e / args.steps, "host_workers": n_workers,
+                        "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": ms_e2e / args.steps, "host_workers": n_workers, "cpus_bound": bound,
                         "timing": "wall clock between device synchronisations, max over ranks"},
                 "gpu_launches": int(launches), "roofline": roofline, "stages_ms": stages}
         if world == 1 and not args.no_cpu:
@@ -400,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clusters", type=int, default=32, help="clusters per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to the CPUs closest to its GPU")
     ap.add_argument("--e2e-workers", type=int, default=3, help="pipelined host workers (context + stream each) in the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

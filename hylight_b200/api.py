@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libhlovlp.so")
 CAND_DT = np.dtype([("q", "<u4"), ("t", "<u4"), ("diag", "<i4"), ("strand_anchor", "<u4")])
 REC_DT = np.dtype([("idA", "<u4"), ("idB", "<u4"), ("OHA", "<i4"), ("OHB", "<i4"), ("OLA", "<u4"), ("OLB", "<u4"),
                    ("K", "<u4"), ("ori", "<u4")])
+REC16_DT = np.dtype([("idA", "<u4"), ("idB", "<u4"), ("OHA", "<i2"), ("OHB", "<i2"), ("OLA", "<u2"), ("K_ori", "<u2")])
 AUX_DT = np.dtype([("cluster", "<u4"), ("blocklen", "<u4")])
 MZ_DT = np.dtype([("x", "<u8"), ("y", "<u8")])
 
@@ -22,7 +23,7 @@ ABI_SYMBOLS = [
     "hlo_params_default", "hlo_abi_version", "hlo_strerror", "hlo_last_error", "hlo_device_count",
     "hlo_ctx_create", "hlo_ctx_destroy", "hlo_host_alloc", "hlo_host_free", "hlo_pack_reads", "hlo_reads_free",
     "hlo_sketch", "hlo_candidates", "hlo_verify", "hlo_overlap_batch", "hlo_overlap_host", "hlo_get_timing",
-    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records", "hlo_write_overlaps_scored",
+    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records", "hlo_write_overlaps_scored", "hlo_write_overlaps16", "hlo_write_sfo16",
 ]
 
 
@@ -42,7 +43,7 @@ class Params(C.Structure):
 
 class Recs(C.Structure):
     _fields_ = [("rec", C.c_void_p), ("aux", C.c_void_p), ("n", C.c_uint64), ("cluster_off", C.c_void_p),
-                ("n_clusters", C.c_uint32)]
+                ("n_clusters", C.c_uint32), ("rec16", C.c_void_p)]
 
 
 class Timing(C.Structure):
@@ -217,7 +218,7 @@ class Context:
         return _copy_out(p.value, n.value, CAND_DT)
 
     def _recs(self, r, copy=True):
-        rec = _copy_out(r.rec, r.n, REC_DT)
+        rec = _copy_out(r.rec16, r.n, REC16_DT) if (r.rec16 and not r.rec) else _copy_out(r.rec, r.n, REC_DT)
         aux = _copy_out(r.aux, r.n, AUX_DT) if r.aux else None
         coff = _copy_out(r.cluster_off, r.n_clusters + 1, np.dtype("<u8")) if r.cluster_off else None
         return rec, aux, coff
@@ -264,6 +265,26 @@ class Context:
         t = Timing()
         self._check(lib().hlo_get_timing(self.h, C.byref(t)))
         return t.as_dict()
+
+
+def expand_rec16(rec16):
+    """hlo_rec16 array -> hlo_rec array (hlo_rec16_expand of the header)"""
+    out = np.zeros(len(rec16), dtype=REC_DT)
+    for f in ("idA", "idB", "OHA", "OHB", "OLA"):
+        out[f] = rec16[f]
+    out["OLB"] = rec16["OLA"]
+    out["K"] = rec16["K_ori"] & 0x7fff
+    out["ori"] = rec16["K_ori"] >> 15
+    return out
+
+
+def write_overlaps16(rec16, path):
+    rec16 = np.ascontiguousarray(rec16, dtype=REC16_DT)
+    L = lib()
+    L.hlo_write_overlaps16.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p]
+    rc = L.hlo_write_overlaps16(_ptr(rec16), len(rec16), os.fsencode(path))
+    if rc:
+        raise HloError(rc, L.hlo_strerror(rc).decode())
 
 
 def write_sfo(rec, path):

@@ -93,7 +93,7 @@ struct hlo_ctx {
     LaunchCounter lc;
     hlo_timing tm;
     int pairgen_slots_log2 = 8;
-    int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, pairgen_generic = 0, sketch_generic = 0;
+    int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0;
     bool keys_ready = false;
     uint32_t *mapped_host = nullptr, *mapped_dev = nullptr;  // 256 B of mapped pinned memory (fetch_small)
     cudaEvent_t ev_vf[2] = {};
@@ -898,7 +898,7 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
                       (int)(x.ds & 1u), x.kb & 0xffffu, &ro[i]);
         ao[i].cluster = R->h_cidx[x.q], ao[i].blocklen = x.kb >> 16;
     }
-    out->rec = ro, out->aux = ao, out->n = n_acc, out->cluster_off = nullptr, out->n_clusters = R->d.n_clusters;
+    out->rec = ro, out->rec16 = nullptr, out->aux = ao, out->n = n_acc, out->cluster_off = nullptr, out->n_clusters = R->d.n_clusters;
     ctx->tm.n_candidates = n, ctx->tm.n_accepted = n_acc, ctx->tm.n_records = n_acc;
     {
         float v = 0.f;
@@ -962,7 +962,7 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     uint32_t n_out32 = 0;
     launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), ctx->b_counters.as<uint32_t>() + 8, s, &ctx->lc);
     launch_group_expand(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, g_uoff, g_entg, g_ent, ctx->b_out.as<hlo_rec>(),
-                        ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
+                        ctx->compact ? ctx->b_out.as<hlo_rec16>() : nullptr, ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
     CK(cudaGetLastError());
     FETCH(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4);
     const uint64_t n_out = n_out32;
@@ -974,17 +974,19 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
         CK(ctx->h_out.ensure(n_out * sizeof(hlo_rec) + 32));
         CK(ctx->h_aux.ensure(n_out * sizeof(hlo_rec_aux) + 32));
         CK(ctx->h_coff.ensure(((size_t)d.n_clusters + 2) * 8));
-        CK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, n_out * sizeof(hlo_rec), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, n_out * (ctx->compact ? sizeof(hlo_rec16) : sizeof(hlo_rec)), cudaMemcpyDeviceToHost, s));
         if (ctx->aux_out) CK(cudaMemcpyAsync(ctx->h_aux.p, ctx->b_aux.p, n_out * sizeof(hlo_rec_aux), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_coff.p, ctx->b_coff.p, ((size_t)d.n_clusters + 1) * 8, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ctx->ev[ST_D2H], s));
     CK(cudaStreamSynchronize(s));
     if (ctx->d2h) {
-        out->rec = ctx->h_out.as<hlo_rec>(), out->aux = ctx->aux_out ? ctx->h_aux.as<hlo_rec_aux>() : nullptr;
+        out->rec = ctx->compact ? nullptr : ctx->h_out.as<hlo_rec>();
+        out->rec16 = ctx->compact ? ctx->h_out.as<hlo_rec16>() : nullptr;
+        out->aux = ctx->aux_out ? ctx->h_aux.as<hlo_rec_aux>() : nullptr;
         out->cluster_off = ctx->h_coff.as<uint64_t>();
     } else {
-        out->rec = nullptr, out->aux = nullptr, out->cluster_off = nullptr;
+        out->rec = nullptr, out->rec16 = nullptr, out->aux = nullptr, out->cluster_off = nullptr;
     }
     out->n = n_out, out->n_clusters = d.n_clusters;
     ctx->tm.n_records = n_out;
@@ -1026,6 +1028,10 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
     }
     if (!strcmp(name, "repack")) {
         ctx->repack = value != 0;
+        return HLO_OK;
+    }
+    if (!strcmp(name, "compact")) {
+        ctx->compact = value != 0;
         return HLO_OK;
     }
     if (!strcmp(name, "aux")) {

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/hlovlp.h"
 #include "common.cuh"
@@ -129,6 +130,17 @@ int hlo_write_sfo(const hlo_rec *rec, uint64_t n, const char *path) {
 }
 
 static int write_overlaps_impl(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path);
+
+// 16-byte records are expanded block-wise and written through the 32-byte code
+static int write16_blocks(const hlo_rec16 *rec, uint64_t n, const char *path, bool sfo) {
+    if ((!rec && n) || !path) return HLO_EINVAL;
+    std::string all;
+    std::vector<hlo_rec> tmp((size_t)n);
+    for (uint64_t i = 0; i < n; ++i) hlo_rec16_expand(&rec[i], &tmp[(size_t)i]);
+    return sfo ? hlo_write_sfo(tmp.data(), n, path) : write_overlaps_impl(tmp.data(), nullptr, n, path);
+}
+int hlo_write_overlaps16(const hlo_rec16 *rec, uint64_t n, const char *path) { return write16_blocks(rec, n, path, false); }
+int hlo_write_sfo16(const hlo_rec16 *rec, uint64_t n, const char *path) { return write16_blocks(rec, n, path, true); }
 
 int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path) { return write_overlaps_impl(rec, nullptr, n, path); }
 

@@ -319,6 +319,8 @@ void worker(Shared *S, int device) {
         return;
     }
     hlo_set_option(ctx, "aux", 0);  // the files need the records and the per-cluster offsets only
+    const bool compact = !o.scores;  // 16-byte records: half the download (the scorer takes the 32-byte form)
+    hlo_set_option(ctx, "compact", compact ? 1 : 0);
     for (;;) {
         const size_t b = S->next.fetch_add(1);
         if (b >= S->batches.size() || S->failed) break;
@@ -372,11 +374,12 @@ void worker(Shared *S, int device) {
             std::mutex emu;
             parallel_for(idx.size(), S->helpers, [&](size_t j) {
                 Cluster &c = o.clusters[idx[j]];
-                const hlo_rec *r0 = out.rec + out.cluster_off[j];
                 const uint64_t n = out.cluster_off[j + 1] - out.cluster_off[j];
                 c.n_records = n;
-                int wrc = hlo_write_overlaps(r0, n, c.out.c_str());
-                if (!wrc && !c.sfo.empty()) wrc = hlo_write_sfo(r0, n, c.sfo.c_str());
+                const hlo_rec *r0 = compact ? nullptr : out.rec + out.cluster_off[j];
+                const hlo_rec16 *c0 = compact ? out.rec16 + out.cluster_off[j] : nullptr;
+                int wrc = compact ? hlo_write_overlaps16(c0, n, c.out.c_str()) : hlo_write_overlaps(r0, n, c.out.c_str());
+                if (!wrc && !c.sfo.empty()) wrc = compact ? hlo_write_sfo16(c0, n, c.sfo.c_str()) : hlo_write_sfo(r0, n, c.sfo.c_str());
                 if (!wrc && scores) wrc = hlo_write_overlaps_scored(r0, scores + out.cluster_off[j], n, (c.out + ".scored").c_str());
                 if (wrc) {
                     std::lock_guard<std::mutex> g(emu);

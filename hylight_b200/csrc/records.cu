@@ -98,7 +98,8 @@ void launch_group_mark(const Rec16 *rec, uint64_t n, const uint32_t *off, const 
 __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
                                                            const uint32_t *__restrict__ off, const uint32_t *__restrict__ uoff,
                                                            const uint32_t *__restrict__ entg, const uint2 *__restrict__ ent,
-                                                           hlo_rec *__restrict__ out, hlo_rec_aux *__restrict__ aux) {
+                                                           hlo_rec *__restrict__ out, hlo_rec16 *__restrict__ out16,
+                                                           hlo_rec_aux *__restrict__ aux) {
     const uint64_t pe = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pe >= n) return;
     const uint2 me = ent[pe];
@@ -117,18 +118,23 @@ __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restri
     const int diag = (int)(x.ds >> 1) - HLO_DIAG_BIAS;
     hlo_rec o;
     expand_record(r.ids[x.q], r.ids[x.t], ql, tl, diag, (int)(x.ds & 1u), x.kb & 0xffffu, &o);
-    uint4 *dst = reinterpret_cast<uint4 *>(out + p);
-    dst[0] = make_uint4(o.idA, o.idB, (uint32_t)o.OHA, (uint32_t)o.OHB);
-    dst[1] = make_uint4(o.OLA, o.OLB, o.K, o.ori);
+    if (out16) {  // 16-byte form (hlo_rec16): OLB == OLA, 16-bit overhangs and lengths
+        reinterpret_cast<uint4 *>(out16)[p] = make_uint4(o.idA, o.idB, ((uint32_t)o.OHA & 0xffffu) | (uint32_t)o.OHB << 16,
+                                                          o.OLA | (o.K | o.ori << 15) << 16);
+    } else {
+        uint4 *dst = reinterpret_cast<uint4 *>(out + p);
+        dst[0] = make_uint4(o.idA, o.idB, (uint32_t)o.OHA, (uint32_t)o.OHB);
+        dst[1] = make_uint4(o.OLA, o.OLB, o.K, o.ori);
+    }
     hlo_rec_aux ax;
     ax.cluster = r.cidx[x.q];
     ax.blocklen = x.kb >> 16;
     aux[p] = ax;
 }
 void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *uoff, const uint32_t *entg,
-                         const uint2 *ent, hlo_rec *out, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc) {
+                         const uint2 *ent, hlo_rec *out, hlo_rec16 *out16, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    group_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, uoff, entg, ent, out, aux);
+    group_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, uoff, entg, ent, out, out16, aux);
     if (lc) lc->total++;
 }
 

@@ -94,6 +94,21 @@ typedef struct hlo_rec {
     uint32_t ori;
 } hlo_rec; /* 32 bytes */
 
+/* The same record in 16 bytes (option "compact"): half the device->host traffic of the result, which is what
+ * bounds the end-to-end rate once several GPUs share a host.  Valid because reads are at most 32767 bases:
+ * OLB == OLA always, |OHA|, |OHB| < 32768, K < 32768. */
+typedef struct hlo_rec16 {
+    uint32_t idA, idB;
+    int16_t OHA, OHB;
+    uint16_t OLA;
+    uint16_t K_ori; /* K | ori << 15 */
+} hlo_rec16; /* 16 bytes */
+
+static inline void hlo_rec16_expand(const hlo_rec16 *c, hlo_rec *r) {
+    r->idA = c->idA, r->idB = c->idB, r->OHA = c->OHA, r->OHB = c->OHB;
+    r->OLA = c->OLA, r->OLB = c->OLA, r->K = c->K_ori & 0x7fffu, r->ori = c->K_ori >> 15;
+}
+
 /* Extra per-record facts the reference computes on the way (PAF columns 10/11) */
 typedef struct hlo_rec_aux {
     uint32_t cluster; /* cluster index inside the batch */
@@ -106,6 +121,7 @@ typedef struct hlo_recs {
     uint64_t n;
     const uint64_t *cluster_off; /* n_clusters + 1 offsets into rec (NULL for hlo_verify) */
     uint32_t n_clusters;
+    const hlo_rec16 *rec16;     /* with option "compact" = 1: the n records in 16-byte form, and rec == NULL */
 } hlo_recs;
 
 /* minimizer tuple, same two words as minimap2's mm128_t: x = hash<<8 | span, y = rid<<32 | pos<<1 | strand */
@@ -206,7 +222,8 @@ int hlo_score_records(hlo_ctx *ctx, const hlo_reads *reads, const char *quals, c
  * device-resident measurement covers the packer); "d2h" (0|1): copy the records back to the host
  * (with 0 hlo_overlap_batch returns n only; rec/aux/cluster_off are NULL); "aux" (0|1): also copy the
  * hlo_rec_aux array back (with 0 hlo_recs.aux is NULL: a caller that only writes the files needs rec and
- * cluster_off); "sketch_generic" / "pairgen_generic" (0|1): force the generic (any w, k / 64-bit keyed)
+ * cluster_off); "compact" (0|1): hlo_overlap_batch / hlo_overlap_host return hlo_recs.rec16
+ * (16-byte records) instead of rec; "sketch_generic" / "pairgen_generic" (0|1): force the generic (any w, k / 64-bit keyed)
  * kernels instead of the specialised ones. */
 int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value);
 
@@ -220,6 +237,9 @@ void *hlo_stream(const hlo_ctx *ctx);
 int hlo_write_sfo(const hlo_rec *rec, uint64_t n, const char *path);
 /* 13-field SAVAGE .overlaps lines (sfo2overlaps.py:150-200), written to a temp file then renamed. */
 int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path);
+/* hlo_write_overlaps / hlo_write_sfo for 16-byte records */
+int hlo_write_overlaps16(const hlo_rec16 *rec, uint64_t n, const char *path);
+int hlo_write_sfo16(const hlo_rec16 *rec, uint64_t n, const char *path);
 /* The same lines with two more columns, hlo_score.score and .mismatch_rate (%.17g): the file a HaploConduct whose
  * reader takes the precomputed score would consume (15 fields; the stock reader wants exactly 13). */
 int hlo_write_overlaps_scored(const hlo_rec *rec, const struct hlo_score *score, uint64_t n, const char *path);

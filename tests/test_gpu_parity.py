@@ -303,6 +303,24 @@ def test_full_path_multi_cluster_ids_and_params(ctx):
     check_full(ctx, b, min_ovlp_len=50, min_identity=0.95, max_overhang=2)
 
 
+def test_compact_records_expand_to_the_same_records(ctx, tmp_path):
+    b = small_cluster(47)
+    ob = to_orc_batch(b)
+    R = ctx.pack(ob)
+    rec, aux, coff = ctx.overlap_batch(R)
+    ctx.set_option("compact", 1)
+    try:
+        rec16, aux16, coff16 = ctx.overlap_batch(R)
+    finally:
+        ctx.set_option("compact", 0)
+    R.free()
+    assert rec16.dtype == api.REC16_DT and len(rec16) == len(rec) > 0
+    assert np.array_equal(api.expand_rec16(rec16), rec) and np.array_equal(coff, coff16)
+    api.write_overlaps(rec, str(tmp_path / "a.txt"))
+    api.write_overlaps16(rec16, str(tmp_path / "b.txt"))
+    assert open(tmp_path / "a.txt").read() == open(tmp_path / "b.txt").read()
+
+
 def test_full_path_empty_inputs(ctx):
     b = synth.ReadBatch.from_seqs([[], [b"ACGT"], []])
     rec, coff, tm = check_full(ctx, b)
