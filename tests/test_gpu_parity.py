@@ -321,6 +321,50 @@ def test_compact_records_expand_to_the_same_records(ctx, tmp_path):
     assert open(tmp_path / "a.txt").read() == open(tmp_path / "b.txt").read()
 
 
+def test_full_path_longer_reads_take_the_wide_and_generic_kernels(ctx):
+    """300 bp: 32-bit table values in pair generation (reads > 255 bp), 19-word verify kernel;
+    600 bp: generic pack kernel (> 512 bp) and the exact verify kernel (> 320 bp)"""
+    rec, coff, tm = check_full(ctx, small_cluster(48, n_fragments=120, read_len=300, n_strains=2))
+    assert len(rec) > 200 and tm["n_deferred"] == 0
+    rec, coff, tm = check_full(ctx, small_cluster(49, n_fragments=60, read_len=600, n_strains=2, insert_mean=900.0))
+    assert len(rec) > 50 and tm["n_deferred"] == tm["n_candidates"]
+
+
+def test_full_path_generic_kernels_forced(ctx):
+    """the generic pair generator (64-bit keys, table in HBM) and the classic / one-sweep sorts give the same records"""
+    b = small_cluster(50, n_fragments=150)
+    for opt in ("pairgen_generic", "sort_onesweep"):
+        ctx.set_option(opt, 1)
+        try:
+            check_full(ctx, b)
+        finally:
+            ctx.set_option(opt, 0)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_full_path_random_parameters(seed):
+    """random thresholds inside the supported domain, ragged lengths, some N and lower-case bases"""
+    rng = np.random.default_rng(1000 + seed)
+    L = int(rng.integers(90, 260))
+    b = small_cluster(500 + seed, n_fragments=int(rng.integers(60, 200)), read_len=L, n_strains=int(rng.integers(1, 5)),
+                      err_rate=float(rng.choice([0.0, 0.003, 0.01])), n_rate=float(rng.choice([0.0, 0.002])))
+    seqs = []
+    for s_ in b.cluster_reads(0):
+        s_ = bytearray(s_[:int(rng.integers(max(L - 40, 30), L + 1))])
+        if rng.random() < 0.3:
+            for j in rng.integers(0, len(s_), size=3):
+                s_[j] |= 0x20
+        seqs.append(bytes(s_))
+    rb = synth.ReadBatch.from_seqs([seqs])
+    pkw = dict(min_ovlp_len=int(rng.integers(30, 80)), min_identity=float(rng.choice([0.9, 0.95, 0.98, 0.99, 1.0])),
+               max_overhang=int(rng.integers(0, 6)), overhang_ratio=float(rng.choice([0.0, 0.02, 0.8])),
+               mid_occ=int(rng.choice([30, 1000])), min_seeds=int(rng.integers(1, 3)))
+    if pkw["min_ovlp_len"] * pkw["min_identity"] < 30:
+        pkw["min_ovlp_len"] = 40
+    with api.Context(0) as c:
+        check_full(c, rb, **pkw)
+
+
 def test_full_path_empty_inputs(ctx):
     b = synth.ReadBatch.from_seqs([[], [b"ACGT"], []])
     rec, coff, tm = check_full(ctx, b)
