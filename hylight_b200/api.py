@@ -48,7 +48,7 @@ class Recs(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "pack_ms", "sketch_ms", "sort_ms", "index_ms", "pairgen_ms",
-                                         "verify_ms", "dedup_ms", "d2h_ms", "total_ms", "verify_fast_ms", "reserved0")] + \
+                                         "verify_ms", "dedup_ms", "d2h_ms", "total_ms", "verify_fast_ms", "sort_fallback")] + \
                [(n, C.c_uint64) for n in ("n_reads", "n_bases", "n_minimizers", "n_seed_hits", "n_candidates",
                                           "n_accepted", "n_records", "n_deferred", "n_overflow_reads",
                                           "verify_launches", "total_launches")]

@@ -93,7 +93,8 @@ struct hlo_ctx {
     LaunchCounter lc;
     hlo_timing tm;
     int pairgen_slots_log2 = 8;
-    int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0;
+    int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0, sort_prefix = 1, sort_hash_bits = 0, sort_segmented = 1;
+    bool prefix_used = false, prefix_failed = false;
     bool keys_ready = false;
     uint32_t *mapped_host = nullptr, *mapped_dev = nullptr;  // 256 B of mapped pinned memory (fetch_small)
     cudaEvent_t ev_vf[2] = {};
@@ -457,9 +458,8 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     if (n_reads) {
         CK(cudaMemcpyAsync(R->b_ascii.p, bases, n_bases, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(R->b_off.p, base_off, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-        if (plain) {
-            CK(cudaMemcpyAsync(R->b_coff.p, cluster_off, ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
-        } else {
+        CK(cudaMemcpyAsync(R->b_coff.p, cluster_off, ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
+        if (!plain) {
             CK(cudaMemcpyAsync(d.len, R->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(d.cbase, cbase.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(d.cidx, R->h_cidx.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
@@ -583,20 +583,20 @@ static int bits_for(uint64_t v) {
 }
 
 // hash sort + bucket index.  Leaves range[] (per minimizer, read order) and hits[] (hash order).
-static int run_index(hlo_ctx *ctx, const hlo_reads *R) {
+static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
     cudaStream_t s = ctx->stream;
     const uint64_t n = ctx->n_mz;
     for (int i = 0; i < 2; ++i) {
         CK(ctx->b_keys[i].ensure(n * 8 + 8));
         CK(ctx->b_vals[i].ensure(n * 4 + 4));
     }
-    CK(ctx->b_tmp.ensure(std::max(sort_tmp_words(n), scan_tmp_words(n + 1)) * 4));
+    CK(ctx->b_tmp.ensure(std::max(std::max(sort_tmp_words(n), sort_segmented_tmp_words(n, R->d.n_clusters)), scan_tmp_words(n + 1)) * 4));
     CK(ctx->b_flags.ensure(n * 4 + 4));
     CK(ctx->b_bid.ensure(n * 4 + 4));
     CK(ctx->b_bstart.ensure((n + 2) * 4));
     CK(ctx->b_range.ensure(n * 8 + 8));
     CK(ctx->b_hits.ensure(n * 8 + 8));
-    if (!ctx->keys_ready)
+    if (!ctx->keys_ready || !allow_prefix)  // (a redo after a prefix attempt starts from fresh keys)
         launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrid.as<uint32_t>(), R->d.cidx, 2 * ctx->P.k, n, ctx->b_keys[0].as<uint64_t>(),
                          ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
@@ -604,7 +604,29 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R) {
     // key = cluster index << 2k | hash: 2k hash bits + the bits of the cluster count
     const int key_bits = 2 * ctx->P.k + (R->d.n_clusters > 1 ? bits_for(R->d.n_clusters) : 0);
     if (key_bits > 64) FAIL(HLO_ERANGE, "%u clusters with k=%d need a %d-bit sort key (limit 64): use smaller batches", R->d.n_clusters, ctx->P.k, key_bits);
-    const int cur = launch_radix_sort(keys, vals, n, 0, key_bits, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+    // (1) The minimizer array is cluster-major already, so every cluster is sorted as its own segment: the cluster bits
+    //     of the key cost no pass.  (2) Grouping needs equal keys adjacent and stable, not a total order: only the top
+    //     24 hash bits are sorted (3 passes instead of 6) and the rare groups in which two hashes share that prefix are
+    //     repaired afterwards.
+    const int hash_bits = 2 * ctx->P.k;
+    const bool segmented = ctx->sort_segmented && n < (1ull << 32);
+    const int top = segmented ? hash_bits : key_bits;          // sorted bits end here
+    const int avail = segmented ? hash_bits : key_bits;        // ... and this many exist below
+    int sort_bits = ctx->sort_hash_bits > 0 ? (segmented ? 0 : key_bits - hash_bits) + ctx->sort_hash_bits : (segmented ? 24 : ((key_bits - hash_bits + 19 + 7) / 8) * 8);
+    const bool prefix = allow_prefix && ctx->sort_prefix && sort_bits < avail && n > 1;
+    ctx->prefix_used = prefix;
+    if (!prefix) sort_bits = avail;
+    int cur;
+    if (segmented)
+        cur = launch_radix_sort_segmented(keys, vals, n, top - sort_bits, top, ctx->b_mzoff.as<uint32_t>(), R->b_coff.as<uint32_t>(), R->d.n_clusters,
+                                          ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+    else
+        cur = launch_radix_sort(keys, vals, n, top - sort_bits, top, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+    if (prefix) {  // counters[12] = (groups repaired, 1 if one was too large: run_pairgen's fetch sees it and the index is redone)
+        CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 12, 0, 8, s));
+        launch_collision_fix(keys[cur], vals[cur], n, top - sort_bits, ctx->b_flags.as<uint32_t>(), ctx->b_counters.as<uint32_t>() + 24, s,
+                             &ctx->lc);
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SORT], s));
     launch_mark_buckets(keys[cur], vals[cur], ctx->b_mzrid.as<uint32_t>(), ctx->b_mzrp.as<uint32_t>(), R->d.len, n,
@@ -641,7 +663,17 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
     a.counters = ctx->b_counters.as<unsigned long long>();
     a.overflow_reads = ctx->b_ovf.as<uint32_t>(), a.overflow_cap = d.n_reads;
     const bool fast = pairgen_fast_supported(d, &a.dg_bits) && !ctx->pairgen_generic;
-    unsigned long long hc[4];
+    unsigned long long hc[13];
+    ctx->prefix_failed = false;
+    if (ctx->prefix_used && !fast) {  // the fast path reads the prefix sort's flag with its own counters below
+        unsigned long long flag = 0;
+        FETCH(&flag, ctx->b_counters.as<unsigned long long>() + 12, 8);
+        if (flag >> 32) {
+            ctx->prefix_failed = true;
+            *n_out = 0;
+            return HLO_OK;
+        }
+    }
     for (int attempt = 0; attempt < 3; ++attempt) {
         CK(ctx->b_cands.ensure(cap * 16));
         a.cands = ctx->b_cands.p, a.cand_cap = cap;
@@ -652,6 +684,11 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
             launch_pairgen(a, ctx->pairgen_slots_log2, s, &ctx->lc);
             CK(cudaGetLastError());
             FETCH(hc, ctx->b_counters.p, sizeof hc);
+            if (ctx->prefix_used && (hc[12] >> 32)) {  // a mixed prefix group was too large to repair: the caller redoes the index
+                ctx->prefix_failed = true;
+                *n_out = 0;
+                return HLO_OK;
+            }
             n_list = (uint32_t)hc[2], list = a.overflow_reads;
         }
         if (n_list) {  // exact path with tables in HBM, in chunks that bound the table memory
@@ -824,10 +861,17 @@ static int stages_to_candidates(hlo_ctx *ctx, const hlo_reads *R, int external, 
     int rc = run_sketch(ctx, R);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
-    rc = run_index(ctx, R);
+    rc = run_index(ctx, R, true);
     if (rc) return rc;
     rc = run_pairgen(ctx, R, external, n_c);
     if (rc) return rc;
+    if (ctx->prefix_failed) {  // rare: two heavily repeated minimizers share a hash prefix — sort on all bits instead
+        ctx->tm.sort_fallback = 1.0f;
+        rc = run_index(ctx, R, false);
+        if (rc) return rc;
+        rc = run_pairgen(ctx, R, external, n_c);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
     ctx->tm.n_candidates = *n_c;
     return HLO_OK;
@@ -1020,6 +1064,19 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
     }
     if (!strcmp(name, "sketch_generic")) {
         ctx->sketch_generic = value != 0;
+        return HLO_OK;
+    }
+    if (!strcmp(name, "sort_segmented")) {
+        ctx->sort_segmented = value != 0;
+        return HLO_OK;
+    }
+    if (!strcmp(name, "sort_prefix")) {
+        ctx->sort_prefix = value != 0;
+        return HLO_OK;
+    }
+    if (!strcmp(name, "sort_hash_bits")) {  // 0 = automatic
+        if (value < 0 || value > 64) return HLO_EINVAL;
+        ctx->sort_hash_bits = (int)value;
         return HLO_OK;
     }
     if (!strcmp(name, "pairgen_generic")) {

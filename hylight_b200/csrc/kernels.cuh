@@ -48,6 +48,19 @@ void radix_sort_use_onesweep(bool on);  // false: the classic histogram / scan /
 int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begin_bit, int end_bit, uint32_t *tmp,
                       cudaStream_t s, LaunchCounter *lc);
 
+// The same sort applied to every segment of the array on its own (segment c = elements [elem_off[seg_off[c]],
+// elem_off[seg_off[c + 1]]): the minimizers of cluster c, elem_off = per-read minimizer offsets, seg_off = the
+// cluster offsets, both on the device).  Segments need no key bits and no pass.
+size_t sort_segmented_tmp_words(uint64_t n, uint32_t n_seg);
+int launch_radix_sort_segmented(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begin_bit, int end_bit, const uint32_t *elem_off,
+                                const uint32_t *seg_off, uint32_t n_seg, uint32_t *tmp, cudaStream_t s, LaunchCounter *lc);
+
+// Equal keys adjacent + stable is all the index needs: after a sort on key bits [shift, ...) only, list the groups
+// (runs of equal key >> shift) that mix different keys and order those by the full key.  list: n/2 + 1 words;
+// state (2 device words, zeroed by the caller): [0] groups fixed, [1] = 1 when a group was too large (redo with a full sort).
+void launch_collision_fix(uint64_t *keys, uint32_t *vals, uint64_t n, int shift, uint32_t *list, uint32_t *state, cudaStream_t s,
+                          LaunchCounter *lc);
+
 // up to 64 words from device memory to (mapped) host memory: the read-back path for counters
 void launch_copy_words(const uint32_t *src, uint32_t *dst, uint32_t n, cudaStream_t s, LaunchCounter *lc);
 void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, LaunchCounter *lc);

@@ -141,26 +141,80 @@ constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
+// Segments: the array is a sequence of independent segments (the clusters: their minimizers are contiguous), each
+// sorted on its own.  Tiles never straddle a segment and the histogram is laid out (segment, digit, tile), so the one
+// exclusive scan still yields final positions — the cluster index costs no key bits and no pass.
+// seg_start[c] = first element of segment c, seg_tile[c] = its first tile; seg_start == nullptr: one segment.
+struct RsSeg {
+    const uint32_t *seg_start = nullptr;
+    const uint32_t *seg_tile = nullptr;
+    uint32_t n_seg = 0;
+};
+struct RsTile {
+    uint64_t base;      // first element
+    uint32_t n;         // elements (0: no such tile)
+    uint64_t hist0;     // index of (digit 0, this tile) in the histogram
+    uint32_t hstride;   // distance between digits there
+};
+__device__ __forceinline__ RsTile rs_tile(const RsSeg &g, uint64_t n, uint32_t n_tiles) {
+    RsTile t;
+    const uint32_t b = blockIdx.x;
+    if (!g.seg_start) {
+        t.base = (uint64_t)b * RS_TILE;
+        t.n = (uint32_t)((n - t.base) < (uint64_t)RS_TILE ? (n - t.base) : (uint64_t)RS_TILE);
+        t.hist0 = b, t.hstride = n_tiles;
+        return t;
+    }
+    t.base = 0, t.n = 0, t.hist0 = 0, t.hstride = 0;
+    if (b >= g.seg_tile[g.n_seg]) return t;
+    uint32_t lo = 0, hi = g.n_seg;  // the segment with seg_tile[lo] <= b < seg_tile[lo + 1]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (g.seg_tile[mid] <= b) lo = mid; else hi = mid;
+    }
+    const uint32_t t0 = g.seg_tile[lo], nt = g.seg_tile[lo + 1] - t0, lt = b - t0;
+    t.base = (uint64_t)g.seg_start[lo] + (uint64_t)lt * RS_TILE;
+    const uint64_t left = (uint64_t)g.seg_start[lo + 1] - t.base;
+    t.n = (uint32_t)(left < (uint64_t)RS_TILE ? left : (uint64_t)RS_TILE);
+    t.hist0 = (uint64_t)RS_BINS * t0 + lt, t.hstride = nt;
+    return t;
+}
+
+__global__ void rs_segments_kernel(const uint32_t *__restrict__ elem_off, const uint32_t *__restrict__ seg_off, uint32_t n_seg,
+                                   uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_tile) {
+    for (uint32_t c = threadIdx.x; c <= n_seg; c += blockDim.x) seg_start[c] = elem_off[seg_off[c]];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (uint32_t c = 0; c < n_seg; ++c) {
+            seg_tile[c] = t;
+            t += (seg_start[c + 1] - seg_start[c] + RS_TILE - 1) / RS_TILE;
+        }
+        seg_tile[n_seg] = t;
+    }
+}
+
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift,
-                                                             uint32_t n_tiles, uint32_t *__restrict__ hist) {
+                                                             uint32_t n_tiles, uint32_t *__restrict__ hist, RsSeg seg) {
     __shared__ uint32_t h[RS_BINS];
+    const RsTile t = rs_tile(seg, n, n_tiles);
+    if (t.n == 0) return;
     h[threadIdx.x] = 0;
     __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-        const uint64_t i = base + (uint64_t)j * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & (RS_BINS - 1)], 1u);
+        const uint32_t e = (uint32_t)j * RS_THREADS + threadIdx.x;
+        if (e < t.n) atomicAdd(&h[(uint32_t)(keys[t.base + e] >> shift) & (RS_BINS - 1)], 1u);
     }
     __syncthreads();
-    hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+    hist[t.hist0 + (uint64_t)threadIdx.x * t.hstride] = h[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const uint64_t *__restrict__ keys_in,
                                                                 const uint32_t *__restrict__ vals_in,
                                                                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                                                                 uint64_t n, int shift, uint32_t n_tiles,
-                                                                const uint32_t *__restrict__ hist_scanned) {
+                                                                const uint32_t *__restrict__ hist_scanned, RsSeg seg) {
     __shared__ uint32_t wcnt[RS_WARPS][RS_BINS];
     __shared__ uint32_t tile_start[RS_BINS];
     __shared__ uint32_t gbase[RS_BINS];
@@ -168,8 +222,10 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const uint64_
     __shared__ uint64_t stage_k[RS_TILE];
     __shared__ uint32_t stage_v[RS_TILE];
     const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-    const uint32_t tile_n = (uint32_t)((n - base) < (uint64_t)RS_TILE ? (n - base) : (uint64_t)RS_TILE);
+    const RsTile tl = rs_tile(seg, n, n_tiles);
+    if (tl.n == 0) return;
+    const uint64_t base = tl.base;
+    const uint32_t tile_n = tl.n;
 #pragma unroll
     for (int w2 = 0; w2 < RS_WARPS; ++w2) wcnt[w2][threadIdx.x] = 0;
     __syncthreads();
@@ -205,7 +261,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const uint64_
         uint32_t tot;
         const uint32_t ex = block_excl_scan(off, &tot, sm);
         tile_start[d] = ex;
-        gbase[d] = hist_scanned[(uint64_t)d * n_tiles + blockIdx.x];
+        gbase[d] = hist_scanned[tl.hist0 + (uint64_t)d * tl.hstride];
     }
     __syncthreads();
 #pragma unroll
@@ -405,11 +461,43 @@ int launch_radix_sort(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begi
     uint32_t *hist = tmp;
     uint32_t *scan_tmp = tmp + ((hist_n + 63) & ~63ull);
     for (int shift = begin_bit; shift < end_bit; shift += RS_BITS) {
-        rs_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(keys[cur], n, shift, n_tiles, hist);
+        rs_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(keys[cur], n, shift, n_tiles, hist, RsSeg());
         if (lc) lc->total++;
         launch_exclusive_scan(hist, hist, hist_n, scan_tmp, nullptr, s, lc);
         rs_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, n_tiles,
-                                                         hist);
+                                                         hist, RsSeg());
+        if (lc) lc->total++;
+        cur ^= 1;
+    }
+    return cur;
+}
+
+static uint64_t seg_tile_bound(uint64_t n, uint32_t n_seg) { return ceil_div_u64(n, RS_TILE) + n_seg; }
+
+size_t sort_segmented_tmp_words(uint64_t n, uint32_t n_seg) {
+    const uint64_t hist_n = (uint64_t)RS_BINS * seg_tile_bound(n, n_seg);
+    return (size_t)(((hist_n + 63) & ~63ull) + scan_tmp_words(hist_n) + 2 * (((uint64_t)n_seg + 64) & ~63ull));
+}
+
+int launch_radix_sort_segmented(uint64_t *keys[2], uint32_t *vals[2], uint64_t n, int begin_bit, int end_bit, const uint32_t *elem_off,
+                                const uint32_t *seg_off, uint32_t n_seg, uint32_t *tmp, cudaStream_t s, LaunchCounter *lc) {
+    int cur = 0;
+    if (n == 0 || begin_bit >= end_bit) return cur;
+    const uint32_t t_bound = (uint32_t)seg_tile_bound(n, n_seg);  // the tile count lives on the device: launch the bound
+    const uint64_t hist_n = (uint64_t)RS_BINS * t_bound;
+    uint32_t *hist = tmp;
+    uint32_t *scan_tmp = tmp + ((hist_n + 63) & ~63ull);
+    uint32_t *seg_start = scan_tmp + scan_tmp_words(hist_n);
+    uint32_t *seg_tile = seg_start + (((uint64_t)n_seg + 64) & ~63ull);
+    rs_segments_kernel<<<1, 256, 0, s>>>(elem_off, seg_off, n_seg, seg_start, seg_tile);
+    if (lc) lc->total++;
+    RsSeg g;
+    g.seg_start = seg_start, g.seg_tile = seg_tile, g.n_seg = n_seg;
+    for (int shift = begin_bit; shift < end_bit; shift += RS_BITS) {
+        rs_hist_kernel<<<t_bound, RS_THREADS, 0, s>>>(keys[cur], n, shift, t_bound, hist, g);
+        if (lc) lc->total++;
+        launch_exclusive_scan(hist, hist, hist_n, scan_tmp, nullptr, s, lc);
+        rs_scatter_kernel<<<t_bound, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, t_bound, hist, g);
         if (lc) lc->total++;
         cur ^= 1;
     }
@@ -434,5 +522,82 @@ void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, La
     fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, value, n);
     if (lc) lc->total++;
 }
+
+// ---- grouping by a PREFIX of the key -------------------------------------------------------------------------
+// The index only needs equal keys adjacent, in stable order — not the order between different keys.  Sorting on
+// the top `sort_bits` of the key therefore suffices wherever the keys of a group (a run of equal prefixes) are all
+// equal; the few groups that mix two or more keys (a prefix collision) are listed by collision_find_kernel and put
+// in full-key order, stably, by collision_fix_kernel.  state[0] = groups listed, state[1] = 1 if a mixed group was
+// too large for the one-warp fix (the caller then redoes the sort on all bits).
+constexpr uint32_t CF_MAX_GROUP = 512;
+constexpr int CF_WARPS = 4;
+
+__global__ void collision_find_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint32_t *__restrict__ list,
+                                      uint32_t *__restrict__ state) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 || i >= n) return;
+    const uint64_t b = keys[i];
+    uint64_t a = keys[i - 1];
+    if (a == b || (a >> shift) != (b >> shift)) return;  // not a witness of a mixed group
+    // first witness of its group?  walk back to the group start; an earlier key change inside the group = no
+    uint64_t j = i - 1;
+    while (j > 0) {
+        const uint64_t c = keys[j - 1];
+        if ((c >> shift) != (b >> shift)) break;
+        if (c != a) return;
+        --j;
+    }
+    list[atomicAdd(&state[0], 1u)] = (uint32_t)j;
+}
+
+// one warp per listed group: the group is staged in shared memory, every element counts the elements that must
+// precede it (smaller key, or equal key and earlier position) and is written to that rank
+__global__ void __launch_bounds__(CF_WARPS * 32) collision_fix_kernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, uint64_t n,
+                                                                      int shift, const uint32_t *__restrict__ list,
+                                                                      uint32_t *__restrict__ state) {
+    __shared__ uint64_t sk[CF_WARPS][CF_MAX_GROUP];
+    __shared__ uint32_t sv[CF_WARPS][CF_MAX_GROUP];
+    const uint32_t n_groups = state[0];
+    const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (uint32_t g = blockIdx.x * CF_WARPS + wp; g < n_groups; g += gridDim.x * CF_WARPS) {
+        const uint64_t b0 = list[g];
+        const uint64_t pre = keys[b0] >> shift;
+        uint32_t m = 0;
+        for (;;) {
+            const uint64_t idx = b0 + m + lane;
+            const uint64_t kx = idx < n ? keys[idx] : 0ull;
+            const bool ok = idx < n && (kx >> shift) == pre;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            const uint32_t cnt = bal == 0xffffffffu ? 32u : (uint32_t)__ffs(~bal) - 1u;  // leading lanes still inside the group
+            if (lane < cnt && m + lane < CF_MAX_GROUP) sk[wp][m + lane] = kx, sv[wp][m + lane] = vals[idx];
+            m += cnt;
+            if (cnt < 32u || m > CF_MAX_GROUP) break;
+        }
+        if (m > CF_MAX_GROUP) {
+            if (lane == 0) state[1] = 1u;
+            continue;
+        }
+        __syncwarp();
+        for (uint32_t e = lane; e < m; e += 32) {
+            const uint64_t ke = sk[wp][e];
+            uint32_t r = 0;
+            for (uint32_t f = 0; f < m; ++f) {
+                const uint64_t kf = sk[wp][f];
+                r += (kf < ke || (kf == ke && f < e)) ? 1u : 0u;
+            }
+            keys[b0 + r] = ke, vals[b0 + r] = sv[wp][e];
+        }
+        __syncwarp();
+    }
+}
+
+void launch_collision_fix(uint64_t *keys, uint32_t *vals, uint64_t n, int shift, uint32_t *list, uint32_t *state, cudaStream_t s,
+                          LaunchCounter *lc) {
+    if (n < 2) return;
+    collision_find_kernel<<<(unsigned)ceil_div_u64(n, 256), 256, 0, s>>>(keys, n, shift, list, state);
+    collision_fix_kernel<<<148 * 8, CF_WARPS * 32, 0, s>>>(keys, vals, n, shift, list, state);
+    if (lc) lc->total += 2;
+}
+
 
 }  // namespace hlo

@@ -133,7 +133,7 @@ typedef struct hlo_mz {
 typedef struct hlo_timing {
     float h2d_ms, pack_ms, sketch_ms, sort_ms, index_ms, pairgen_ms, verify_ms, dedup_ms, d2h_ms, total_ms;
     float verify_fast_ms;  /* the warp-per-pair verify kernel alone (one launch) */
-    float reserved0;
+    float sort_fallback;   /* 1 = the in-shared-memory bucket sort overflowed and the plain radix passes redid the index */
     uint64_t n_reads, n_bases, n_minimizers, n_seed_hits, n_candidates, n_accepted, n_records;
     uint64_t n_deferred;     /* candidates that took the exact slow verify path */
     uint64_t n_overflow_reads; /* query reads whose seed table overflowed shared memory */

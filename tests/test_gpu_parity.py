@@ -333,12 +333,38 @@ def test_full_path_longer_reads_take_the_wide_and_generic_kernels(ctx):
 def test_full_path_generic_kernels_forced(ctx):
     """the generic pair generator (64-bit keys, table in HBM) and the classic / one-sweep sorts give the same records"""
     b = small_cluster(50, n_fragments=150)
-    for opt in ("pairgen_generic", "sort_onesweep"):
-        ctx.set_option(opt, 1)
+    for opts in (("pairgen_generic",), ("sort_onesweep", "sort_segmented")):
+        ctx.set_option(opts[0], 1)
+        if len(opts) > 1:
+            ctx.set_option(opts[1], 0)  # the one-sweep passes exist for the unsegmented sort only
         try:
             check_full(ctx, b)
         finally:
-            ctx.set_option(opt, 0)
+            ctx.set_option(opts[0], 0)
+            ctx.set_option("sort_segmented", 1)
+
+
+def test_full_path_sort_paths(ctx):
+    """prefix sort + collision repair (default) vs the sort on all key bits; a short prefix forces many repairs,
+    a 2-bit prefix makes groups too large to repair and the index is redone with the full sort"""
+    b = synth.ReadBatch.concat([small_cluster(71, n_fragments=90), synth.ReadBatch.from_seqs([[]]), small_cluster(72, n_fragments=300),
+                                small_cluster(73, n_fragments=10), small_cluster(74, n_fragments=150, read_len=101)])
+    rec, coff, tm = check_full(ctx, b)
+    assert tm["sort_fallback"] == 0
+    try:
+        for segmented in (1, 0):
+            ctx.set_option("sort_segmented", segmented)
+            for prefix, bits, fallback in ((0, 0, 0), (1, 0, 0), (1, 12, 0), (1, 7, None), (1, 2, 1)):
+                ctx.set_option("sort_prefix", prefix)
+                ctx.set_option("sort_hash_bits", bits)
+                rec2, coff2, tm2 = check_full(ctx, b)
+                assert np.array_equal(rec, rec2) and np.array_equal(coff, coff2)
+                if fallback is not None:
+                    assert tm2["sort_fallback"] == fallback
+    finally:
+        ctx.set_option("sort_segmented", 1)
+        ctx.set_option("sort_prefix", 1)
+        ctx.set_option("sort_hash_bits", 0)
 
 
 @pytest.mark.parametrize("seed", range(8))
