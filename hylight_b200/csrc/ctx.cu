@@ -103,7 +103,7 @@ struct hlo_ctx {
     int tab_len = -1;
     VerifyTables tab{};
     // workspaces
-    DevBuf b_cnt, b_mzoff, b_mzx, b_mzrp, b_mzrid, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
+    DevBuf b_cnt, b_mzoff, b_mzx, b_mzrr, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
     DevBuf b_cands, b_counters, b_ovf, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
     DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp, b_qual, b_screc, b_scclu, b_scout, b_prob;
     PinBuf h_score;
@@ -276,7 +276,7 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->b_tab, &ctx->b_cnt, &ctx->b_mzoff, &ctx->b_mzx, &ctx->b_mzrp, &ctx->b_mzrid, &ctx->b_keys[0],
+    DevBuf *bufs[] = {&ctx->b_tab, &ctx->b_cnt, &ctx->b_mzoff, &ctx->b_mzx, &ctx->b_mzrr, &ctx->b_keys[0],
                       &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_bstart,
                       &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovfcnt, &ctx->b_gkeys,
                       &ctx->b_gmn, &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos,
@@ -554,23 +554,22 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
     }
     ctx->n_mz = total;
     CK(ctx->b_mzx.ensure((size_t)total * 8 + 8));
-    CK(ctx->b_mzrp.ensure((size_t)total * 4 + 4));
-    CK(ctx->b_mzrid.ensure((size_t)total * 4 + 4));
+    CK(ctx->b_mzrr.ensure((size_t)total * 8 + 8));
     if (fast) {
         for (int i = 0; i < 2; ++i) {
             CK(ctx->b_keys[i].ensure((size_t)total * 8 + 8));
             CK(ctx->b_vals[i].ensure((size_t)total * 4 + 4));
         }
         launch_sketch_compact(d, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
-                              ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
-                              ctx->b_mzrid.as<uint32_t>(), ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, s, &ctx->lc);
+                              ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(),
+                              ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, s, &ctx->lc);
         ctx->keys_ready = n_ovf == 0;
         if (n_ovf)  // reads with more minimizers than a strip holds: the generic kernel writes them in place
-            launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
-                                ctx->b_mzrid.as<uint32_t>(), ctx->b_ovf.as<uint32_t>(), (uint32_t)n_ovf, s, &ctx->lc);
+            launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(),
+                                ctx->b_ovf.as<uint32_t>(), (uint32_t)n_ovf, s, &ctx->lc);
     } else {
-        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(),
-                            ctx->b_mzrid.as<uint32_t>(), nullptr, 0, s, &ctx->lc);
+        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(),
+                            nullptr, 0, s, &ctx->lc);
     }
     CK(cudaGetLastError());
     return HLO_OK;
@@ -592,12 +591,10 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
     }
     CK(ctx->b_tmp.ensure(std::max(std::max(sort_tmp_words(n), sort_segmented_tmp_words(n, R->d.n_clusters)), scan_tmp_words(n + 1)) * 4));
     CK(ctx->b_flags.ensure(n * 4 + 4));
-    CK(ctx->b_bid.ensure(n * 4 + 4));
-    CK(ctx->b_bstart.ensure((n + 2) * 4));
     CK(ctx->b_range.ensure(n * 8 + 8));
     CK(ctx->b_hits.ensure(n * 8 + 8));
     if (!ctx->keys_ready || !allow_prefix)  // (a redo after a prefix attempt starts from fresh keys)
-        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrid.as<uint32_t>(), R->d.cidx, 2 * ctx->P.k, n, ctx->b_keys[0].as<uint64_t>(),
+        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(), R->d.cidx, 2 * ctx->P.k, n, ctx->b_keys[0].as<uint64_t>(),
                          ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
@@ -629,12 +626,8 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SORT], s));
-    launch_mark_buckets(keys[cur], vals[cur], ctx->b_mzrid.as<uint32_t>(), ctx->b_mzrp.as<uint32_t>(), R->d.len, n,
-                        ctx->b_flags.as<uint32_t>(), ctx->b_hits.as<uint2>(), s, &ctx->lc);
-    launch_exclusive_scan(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
-    launch_bucket_starts(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), n, ctx->b_bstart.as<uint32_t>(), s, &ctx->lc);
-    launch_bucket_ranges(ctx->b_flags.as<uint32_t>(), ctx->b_bid.as<uint32_t>(), vals[cur], ctx->b_bstart.as<uint32_t>(), n,
-                         ctx->P.mid_occ, ctx->b_range.as<uint2>(), s, &ctx->lc);
+    launch_bucket_index(keys[cur], vals[cur], ctx->b_mzrr.as<uint2>(), n, ctx->P.mid_occ, ctx->b_hits.as<uint2>(), ctx->b_range.as<uint2>(), s,
+                        &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_INDEX], s));
     return HLO_OK;
@@ -655,7 +648,7 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
     uint64_t cap = std::max<uint64_t>(ctx->b_cands.cap / 16, std::max<uint64_t>(ctx->n_mz * 3, 1 << 16));
     PairgenArgs a;
     a.reads = d;
-    a.mz_off = ctx->b_mzoff.as<uint32_t>(), a.mz_rp = ctx->b_mzrp.as<uint32_t>();
+    a.mz_off = ctx->b_mzoff.as<uint32_t>(), a.mz_rr = ctx->b_mzrr.as<uint2>();
     a.range = ctx->b_range.as<uint2>(), a.hits = ctx->b_hits.as<uint2>();
     a.k = ctx->P.k;
     a.gap_min = std::max(std::max(ctx->P.min_chain_score - ctx->P.k, ctx->P.min_seeds - 1), 0);
@@ -822,7 +815,7 @@ int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64
     if (rc) return rc;
     const uint64_t tot = ctx->n_mz;
     CK(ctx->b_mz.ensure(tot * sizeof(hlo_mz) + 16));
-    launch_mz_assemble(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrp.as<uint32_t>(), ctx->b_mzrid.as<uint32_t>(), tot, ctx->b_mz.as<hlo_mz>(), s,
+    launch_mz_assemble(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(), tot, ctx->b_mz.as<hlo_mz>(), s,
                        &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));

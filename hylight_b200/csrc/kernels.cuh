@@ -21,17 +21,16 @@ void launch_read_meta(const uint64_t *base_off, const uint32_t *cluster_off, Dev
 // pass 0: count[r] = number of minimizers of read r;  pass 1: write them at off[r].
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc);
 // list != nullptr: only the n_list listed reads (x indices)
-void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp,
-                         uint32_t *mz_rid, const uint32_t *list, uint32_t n_list, cudaStream_t s, LaunchCounter *lc);
+void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, const uint32_t *list,
+                         uint32_t n_list, cudaStream_t s, LaunchCounter *lc);
 // single-pass fast path (static window, k odd): per-read strips of `cap` entries + counts, then a gather
 bool sketch_fast_supported(int w, int k);
 void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
                         uint32_t *ovf_list, unsigned long long *ovf_cnt, cudaStream_t s, LaunchCounter *lc);
 void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
-                           const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp, uint32_t *mz_rid, uint64_t *keys, uint32_t *vals,
-                           int hash_bits, cudaStream_t s, LaunchCounter *lc);
-void launch_mz_assemble(const uint64_t *mz_x, const uint32_t *mz_rp, const uint32_t *mz_rid, uint64_t n, hlo_mz *out,
-                        cudaStream_t s, LaunchCounter *lc);
+                           const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, uint64_t *keys, uint32_t *vals, int hash_bits,
+                           cudaStream_t s, LaunchCounter *lc);
+void launch_mz_assemble(const uint64_t *mz_x, const uint2 *mz_rr, uint64_t n, hlo_mz *out, cudaStream_t s, LaunchCounter *lc);
 
 // ---- scan_sort.cu ---------------------------------------------------------------------------
 // Exclusive prefix sum of n u32 values (in may alias out).  `tmp` must hold scan_tmp_words(n) u32.
@@ -68,21 +67,19 @@ void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, La
 // ---- pairgen.cu -----------------------------------------------------------------------------
 // index build on the hash-sorted minimizers
 // sort key = cluster index << hash_bits | minimizer hash (cluster-major: buckets of one cluster stay together)
-void launch_hash_keys(const uint64_t *mz_x, const uint32_t *mz_rid, const uint32_t *cidx, int hash_bits, uint64_t n, uint64_t *keys,
+void launch_hash_keys(const uint64_t *mz_x, const uint2 *mz_rr, const uint32_t *cidx, int hash_bits, uint64_t n, uint64_t *keys,
                       uint32_t *vals, cudaStream_t s, LaunchCounter *lc);
-void launch_mark_buckets(const uint64_t *skeys, const uint32_t *svals, const uint32_t *mz_rid, const uint32_t *mz_rp,
-                         const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s, LaunchCounter *lc);
-void launch_bucket_starts(const uint32_t *flags, const uint32_t *bid, uint64_t n, uint32_t *bstart, cudaStream_t s,
-                          LaunchCounter *lc);
-void launch_bucket_ranges(const uint32_t *flags, const uint32_t *bid, const uint32_t *svals, const uint32_t *bstart,
-                          uint64_t n, int mid_occ, uint2 *range, cudaStream_t s, LaunchCounter *lc);
+// hits[i] = (read, pos<<1|strand) of the i-th grouped entry; range[m] = (i + 1, bucket end) of minimizer m, or (0, 0)
+// when its bucket holds more than mid_occ entries.  skeys: equal keys adjacent (the grouped order), svals: their m.
+void launch_bucket_index(const uint64_t *skeys, const uint32_t *svals, const uint2 *mz_rr, uint64_t n, int mid_occ, uint2 *hits,
+                         uint2 *range, cudaStream_t s, LaunchCounter *lc);
 
 struct PairgenArgs {
     DevReads reads;
     const uint32_t *mz_off;  // [n_reads+1] minimizers of the x-th read (name order)
-    const uint32_t *mz_rp;   // [n_mz] pos<<1|strand
+    const uint2 *mz_rr;      // [n_mz] (read, pos<<1|strand), read order
     const uint2 *range;      // [n_mz] hits [s,e) minimizer m seeds (the part of its bucket behind its own entry)
-    const uint2 *hits;       // [n_mz] (read, pos<<1|strand | len<<16 | amb<<31) in hash order
+    const uint2 *hits;       // [n_mz] (read, pos<<1|strand) in hash order
     int k, gap_min;
     int dg_bits;             // bits of (diagonal + max_len) in the 32-bit table key
     int external;            // 1: emit hlo_cand (exact anchor span), 0: emit CandI

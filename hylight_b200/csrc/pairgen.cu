@@ -34,72 +34,129 @@ namespace hlo {
 #define HLO_EMPTY_KEY 0xffffffffffffffffULL
 #define HLO_EMPTY32 0xffffffffu
 
-__global__ void hash_keys_kernel(const uint64_t *__restrict__ x, const uint32_t *__restrict__ mz_rid,
+__global__ void hash_keys_kernel(const uint64_t *__restrict__ x, const uint2 *__restrict__ mz_rr,
                                  const uint32_t *__restrict__ cidx, int hash_bits, uint64_t n, uint64_t *__restrict__ keys,
                                  uint32_t *__restrict__ vals) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = (x[i] >> 8) | (uint64_t)cidx[mz_rid[i]] << hash_bits, vals[i] = (uint32_t)i;
+    if (i < n) keys[i] = (x[i] >> 8) | (uint64_t)cidx[mz_rr[i].x] << hash_bits, vals[i] = (uint32_t)i;
 }
-void launch_hash_keys(const uint64_t *mz_x, const uint32_t *mz_rid, const uint32_t *cidx, int hash_bits, uint64_t n, uint64_t *keys,
+void launch_hash_keys(const uint64_t *mz_x, const uint2 *mz_rr, const uint32_t *cidx, int hash_bits, uint64_t n, uint64_t *keys,
                       uint32_t *vals, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    hash_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, mz_rid, cidx, hash_bits, n, keys, vals);
+    hash_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, mz_rr, cidx, hash_bits, n, keys, vals);
     if (lc) lc->total++;
 }
 
-// hits[i] = (read, pos<<1|strand | len<<16 | amb<<31) of the i-th minimizer in (cluster, hash) order;
-// flags[i] = 1 where a new (cluster, hash) bucket starts.  The sort key is cluster-major, so the gathers
-// below stay inside one cluster's few MB (L2-resident) instead of wandering over the whole batch.
-__global__ void mark_buckets_kernel(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
-                                    const uint32_t *__restrict__ mz_rid, const uint32_t *__restrict__ mz_rp,
-                                    const uint32_t *__restrict__ len, uint64_t n, uint32_t *__restrict__ flags,
-                                    uint2 *__restrict__ hits) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t idx = svals[i];
-    const uint32_t rid = mz_rid[idx];
-    const uint32_t lf = len[rid];
-    hits[i] = make_uint2(rid, mz_rp[idx] | (lf & 0x7fffu) << 16 | (lf & HLO_AMB_FLAG));
-    flags[i] = i == 0 || skeys[i] != skeys[i - 1];
-}
-void launch_mark_buckets(const uint64_t *skeys, const uint32_t *svals, const uint32_t *mz_rid, const uint32_t *mz_rp,
-                         const uint32_t *len, uint64_t n, uint32_t *flags, uint2 *hits, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    mark_buckets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(skeys, svals, mz_rid, mz_rp, len, n, flags, hits);
-    if (lc) lc->total++;
-}
+// The whole bucket index in one pass over the (cluster, hash)-grouped minimizers:
+//   hits[i]  = (read, pos<<1|strand) of the i-th entry (one 8-byte gather from the read-order array);
+//   range[m] = the hits minimizer m seeds: the part of its bucket behind its own entry (i + 1 .. bucket end),
+//              or nothing when the bucket holds more than mid_occ entries (scatter to read order).
+// A tile of 1024 entries finds its bucket boundaries from warp ballots of "key differs from the previous key";
+// only the two buckets that stick out of the tile need a look at the neighbouring tiles' keys, and that search
+// stops after mid_occ entries (a longer bucket is dropped anyway).  The keys are cluster-major, so the gather
+// and the scatter stay inside one cluster's few MB.
+constexpr int IX_THREADS = 256;
+constexpr int IX_ITEMS = 4;
+constexpr int IX_TILE = IX_THREADS * IX_ITEMS;
+constexpr int IX_RUNS = IX_TILE / 32;
 
-// bid = exclusive scan of flags; bucket of element i = bid[i] + flags[i] - 1
-__global__ void bucket_starts_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ bid, uint64_t n,
-                                     uint32_t *__restrict__ bstart) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t b = bid[i] + flags[i] - 1u;
-    if (flags[i]) bstart[b] = (uint32_t)i;
-    if (i == n - 1) bstart[b + 1] = (uint32_t)n;
+__global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
+                                                                  const uint2 *__restrict__ mz_rr, uint64_t n, int mid_occ,
+                                                                  uint2 *__restrict__ hits, uint2 *__restrict__ range) {
+    __shared__ int run_first[IX_RUNS], run_last[IX_RUNS];     // first / last bucket start inside a run of 32 entries (tile-relative)
+    __shared__ int next_after[IX_RUNS], last_before[IX_RUNS]; // first start in a later run / last start in an earlier run
+    __shared__ uint32_t tile_prev, tile_next;                 // start of the tile's first bucket, end of its last (global)
+    const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const uint64_t base = (uint64_t)blockIdx.x * IX_TILE;
+    const uint32_t tn = (uint32_t)((n - base) < (uint64_t)IX_TILE ? (n - base) : (uint64_t)IX_TILE);
+    unsigned bal[IX_ITEMS];
+    uint32_t idx[IX_ITEMS];
+#pragma unroll
+    for (int j = 0; j < IX_ITEMS; ++j) {
+        const uint32_t r = (uint32_t)j * (IX_THREADS / 32) + wp, e = r * 32 + lane;
+        const uint64_t i = base + e;
+        const bool ok = e < tn;
+        bool flag = false;
+        idx[j] = 0;
+        if (ok) {
+            const uint64_t kx = skeys[i];
+            flag = i == 0 || kx != skeys[i - 1];
+            idx[j] = svals[i];
+            hits[i] = mz_rr[idx[j]];
+        }
+        bal[j] = __ballot_sync(FULL, flag);
+        if (lane == 0) {
+            run_first[r] = bal[j] ? (int)(r * 32) + __ffs(bal[j]) - 1 : INT_MAX;
+            run_last[r] = bal[j] ? (int)(r * 32) + 31 - __clz(bal[j]) : -1;
+        }
+    }
+    __syncthreads();
+    if (wp == 0) {  // IX_RUNS == 32: one lane per run
+        int nf = run_first[lane], lb = run_last[lane];
+        // inclusive suffix minimum / prefix maximum, then shift by one run
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a = __shfl_down_sync(FULL, nf, d), c = __shfl_up_sync(FULL, lb, d);
+            if (lane + d < 32) nf = min(nf, a);
+            if ((int)lane >= d) lb = max(lb, c);
+        }
+        const int nf_x = __shfl_down_sync(FULL, nf, 1), lb_x = __shfl_up_sync(FULL, lb, 1);
+        next_after[lane] = lane == 31 ? INT_MAX : nf_x;
+        last_before[lane] = lane == 0 ? -1 : lb_x;
+    } else if (wp == 1) {  // end of the bucket the tile's last entry belongs to
+        uint64_t end = base + tn;
+        if (end < n) {
+            const uint64_t key_last = skeys[end - 1];
+            for (;;) {
+                const uint64_t i = end + lane;
+                const bool differs = i >= n || skeys[i] != key_last;
+                const unsigned b = __ballot_sync(FULL, differs);
+                if (b) {
+                    end += (uint64_t)(__ffs(b) - 1);
+                    break;
+                }
+                end += 32;
+                if (end - (base + tn) > (uint64_t)max(mid_occ, 0)) break;  // already larger than mid_occ: dropped anyway
+            }
+        }
+        if (lane == 0) tile_next = (uint32_t)end;
+    } else if (wp == 2) {  // start of the bucket the tile's first entry belongs to
+        uint64_t start = base;
+        if (base > 0 && tn > 0) {
+            const uint64_t key_first = skeys[base];
+            for (;;) {
+                // lane l looks at entry start - 1 - l
+                const bool differs = start < (uint64_t)lane + 1 || skeys[start - 1 - lane] != key_first;
+                const unsigned b = __ballot_sync(FULL, differs);
+                if (b) {
+                    start -= (uint64_t)(__ffs(b) - 1);
+                    break;
+                }
+                start -= 32;
+                if (base - start > (uint64_t)max(mid_occ, 0)) break;
+            }
+        }
+        if (lane == 0) tile_prev = (uint32_t)start;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < IX_ITEMS; ++j) {
+        const uint32_t r = (uint32_t)j * (IX_THREADS / 32) + wp, e = r * 32 + lane;
+        if (e >= tn) continue;
+        const unsigned above = lane == 31 ? 0u : bal[j] >> (lane + 1);
+        const unsigned upto = bal[j] & (0xffffffffu >> (31 - lane));
+        const int nb = above ? (int)e + __ffs(above) : next_after[r];
+        const int pb = upto ? (int)(r * 32) + 31 - __clz(upto) : last_before[r];
+        const uint32_t en = nb == INT_MAX ? tile_next : (uint32_t)(base + (uint32_t)nb);
+        const uint32_t st = pb < 0 ? tile_prev : (uint32_t)(base + (uint32_t)pb);
+        range[idx[j]] = (int)(en - st) > mid_occ ? make_uint2(0u, 0u) : make_uint2((uint32_t)(base + e) + 1u, en);
+    }
 }
-void launch_bucket_starts(const uint32_t *flags, const uint32_t *bid, uint64_t n, uint32_t *bstart, cudaStream_t s,
-                          LaunchCounter *lc) {
+void launch_bucket_index(const uint64_t *skeys, const uint32_t *svals, const uint2 *mz_rr, uint64_t n, int mid_occ, uint2 *hits,
+                         uint2 *range, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    bucket_starts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flags, bid, n, bstart);
-    if (lc) lc->total++;
-}
-
-// range[m] = the hits minimizer m seeds: the part of its bucket after its own entry, or nothing when the
-// bucket holds more than mid_occ entries
-__global__ void bucket_ranges_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ bid,
-                                     const uint32_t *__restrict__ svals, const uint32_t *__restrict__ bstart, uint64_t n,
-                                     int mid_occ, uint2 *__restrict__ range) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t b = bid[i] + flags[i] - 1u;
-    const uint32_t s = bstart[b], e = bstart[b + 1];
-    range[svals[i]] = (int)(e - s) > mid_occ ? make_uint2(0u, 0u) : make_uint2((uint32_t)i + 1u, e);
-}
-void launch_bucket_ranges(const uint32_t *flags, const uint32_t *bid, const uint32_t *svals, const uint32_t *bstart,
-                          uint64_t n, int mid_occ, uint2 *range, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    bucket_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flags, bid, svals, bstart, n, mid_occ, range);
+    bucket_index_kernel<<<(unsigned)((n + IX_TILE - 1) / IX_TILE), IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n, mid_occ, hits, range);
     if (lc) lc->total++;
 }
 
@@ -174,6 +231,9 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
             uint4 *k4 = reinterpret_cast<uint4 *>(keys);
             const uint4 e4 = make_uint4(HLO_EMPTY32, HLO_EMPTY32, HLO_EMPTY32, HLO_EMPTY32);
             for (uint32_t i = l; i < S / 4; i += PG_G) k4[i] = e4;
+            const uint32_t f = NARROW ? VMASK * 0x10001u : VMASK;  // every value: min = VMASK, max = 0
+            uint4 *v4 = reinterpret_cast<uint4 *>(vals);
+            for (uint32_t i = l; i < S * (uint32_t)sizeof(val_t) / 16; i += PG_G) v4[i] = make_uint4(f, f, f, f);
         }
         __syncwarp();
         uint32_t nh = 0, nq = 0, list_n = 0;
@@ -182,12 +242,12 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         // that their (L2) latency overlaps the table work of the current chunk
         uint2 rg_n = make_uint2(0u, 0u);
         uint32_t qrp_n = 0;
-        if (nm) rg_n = __ldg(a.range + m0), qrp_n = __ldg(a.mz_rp + m0);
+        if (nm) rg_n = __ldg(a.range + m0), qrp_n = __ldg(&a.mz_rr[m0].y);
         for (uint32_t s = 0; s < nm_max; ++s) {
             const uint2 rg = rg_n;
             const uint32_t qrp = qrp_n;
             rg_n = make_uint2(0u, 0u);
-            if (s + 1 < nm) rg_n = __ldg(a.range + m0 + s + 1), qrp_n = __ldg(a.mz_rp + m0 + s + 1);
+            if (s + 1 < nm) rg_n = __ldg(a.range + m0 + s + 1), qrp_n = __ldg(&a.mz_rr[m0 + s + 1].y);
             const int qpos = (int)(qrp >> 1);
             const uint32_t nchunk_max = __reduce_max_sync(FULL, (rg.y - rg.x + PG_G - 1) / PG_G);
             uint32_t i = rg.x + l;
@@ -208,25 +268,24 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                     const uint32_t qp = (uint32_t)qpi;
                     const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
                     uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
+                    // claim-or-find, then ONE update path for both outcomes: a fresh slot holds (min = all ones, max = 0),
+                    // so "min/max with qp" initialises it and its old span (negative) is below any threshold
                     bool done = false;
+                    uint32_t old = 0;
                     for (uint32_t probe = 0; probe < S; ++probe) {
-                        const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
-                        if (old == HLO_EMPTY32) {
-                            vals[slot] = (val_t)(qp | qp << VSH);
-                            nq += gap_min <= 0;
-                            newslot = (int)slot;
-                            done = true;
-                            break;
-                        }
-                        if (old == key) {  // no other lane of the group holds this key in this step
-                            const uint32_t v = vals[slot];
-                            const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
-                            vals[slot] = (val_t)(mn | mx << VSH);
-                            nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
+                        old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
+                        if (old == HLO_EMPTY32 || old == key) {
                             done = true;
                             break;
                         }
                         slot = (slot + 1u) & smask;
+                    }
+                    if (done) {  // no other lane of the group holds this key in this step: plain read-modify-write
+                        const uint32_t v = vals[slot];
+                        const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
+                        vals[slot] = (val_t)(mn | mx << VSH);
+                        nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
+                        if (old == HLO_EMPTY32) newslot = (int)slot;
                     }
                     if (!done) ovf = true;
                 }
@@ -368,7 +427,7 @@ __global__ void __launch_bounds__(256) pairgen_generic_kernel(PairgenArgs a, con
     uint32_t nh = 0;
     for (uint32_t m = a.mz_off[xq]; m < a.mz_off[xq + 1]; ++m) {
         const uint2 rg = a.range[m];
-        const uint32_t qrp = a.mz_rp[m];
+        const uint32_t qrp = a.mz_rr[m].y;
         const int qpos = (int)(qrp >> 1);
         for (uint32_t i = rg.x + threadIdx.x; i < rg.y; i += blockDim.x) {
             const uint2 h = a.hits[i];

@@ -34,16 +34,14 @@ __device__ __forceinline__ uint64_t mm_hash64(uint64_t key, uint64_t mask) {
 
 struct MzOut {
     uint64_t *x;
-    uint32_t *rp;
-    uint32_t *rid;
+    uint2 *rr;  // (read, pos << 1 | strand)
 };
 
 template <bool WRITE>
 __device__ __forceinline__ void mz_push(uint32_t &n, uint64_t x, uint32_t rp, uint32_t rid, uint32_t base, const MzOut &o) {
     if (WRITE) {
         o.x[base + n] = x;
-        o.rp[base + n] = rp;
-        o.rid[base + n] = rid;
+        o.rr[base + n] = make_uint2(rid, rp);
     }
     ++n;
 }
@@ -131,16 +129,16 @@ __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, u
 
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc) {
     if (r.n_reads == 0) return;
-    MzOut o{nullptr, nullptr, nullptr};
+    MzOut o{nullptr, nullptr};
     sketch_kernel<false><<<(r.n_reads + 127) / 128, 128, 0, s>>>(r, w, k, count, nullptr, o, nullptr, 0);
     if (lc) lc->total++;
 }
 
-void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp,
-                         uint32_t *mz_rid, const uint32_t *list, uint32_t n_list, cudaStream_t s, LaunchCounter *lc) {
+void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, const uint32_t *list,
+                         uint32_t n_list, cudaStream_t s, LaunchCounter *lc) {
     const uint32_t n = list ? n_list : r.n_reads;
     if (n == 0) return;
-    MzOut o{mz_x, mz_rp, mz_rid};
+    MzOut o{mz_x, mz_rr};
     sketch_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(r, w, k, nullptr, off, o, list, n_list);
     if (lc) lc->total++;
 }
@@ -307,7 +305,7 @@ void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t 
 __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_t cap, const uint64_t *__restrict__ sx,
                                                              const uint32_t *__restrict__ srp, const uint32_t *__restrict__ count,
                                                              const uint32_t *__restrict__ off, uint64_t *__restrict__ mz_x,
-                                                             uint32_t *__restrict__ mz_rp, uint32_t *__restrict__ mz_rid,
+                                                             uint2 *__restrict__ mz_rr,
                                                              uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int hash_bits) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t xi = (uint32_t)(gid >> 3), l = (uint32_t)(gid & 7);
@@ -322,36 +320,34 @@ __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_
         const uint32_t dst = o + j;
         const uint64_t x = sx[sb + j];
         mz_x[dst] = x;
-        mz_rp[dst] = srp[sb + j];
-        mz_rid[dst] = read;
+        mz_rr[dst] = make_uint2(read, srp[sb + j]);
         keys[dst] = (x >> 8) | chi;
         vals[dst] = dst;
     }
 }
 
 void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
-                           const uint32_t *off, uint64_t *mz_x, uint32_t *mz_rp, uint32_t *mz_rid, uint64_t *keys, uint32_t *vals,
+                           const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, uint64_t *keys, uint32_t *vals,
                            int hash_bits, cudaStream_t s, LaunchCounter *lc) {
     const uint64_t total = (uint64_t)r.n_reads * 8;
     if (total == 0) return;
-    sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rp, mz_rid, keys, vals, hash_bits);
+    sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rr, keys, vals, hash_bits);
     if (lc) lc->total++;
 }
 
-__global__ void mz_assemble_kernel(const uint64_t *__restrict__ x, const uint32_t *__restrict__ rp,
-                                   const uint32_t *__restrict__ rid, uint64_t n, hlo_mz *__restrict__ out) {
+__global__ void mz_assemble_kernel(const uint64_t *__restrict__ x, const uint2 *__restrict__ rr, uint64_t n,
+                                   hlo_mz *__restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     hlo_mz m;
     m.x = x[i];
-    m.y = (uint64_t)rid[i] << 32 | rp[i];
+    m.y = (uint64_t)rr[i].x << 32 | rr[i].y;
     out[i] = m;
 }
 
-void launch_mz_assemble(const uint64_t *mz_x, const uint32_t *mz_rp, const uint32_t *mz_rid, uint64_t n, hlo_mz *out,
-                        cudaStream_t s, LaunchCounter *lc) {
+void launch_mz_assemble(const uint64_t *mz_x, const uint2 *mz_rr, uint64_t n, hlo_mz *out, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    mz_assemble_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, mz_rp, mz_rid, n, out);
+    mz_assemble_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, mz_rr, n, out);
     if (lc) lc->total++;
 }
 
