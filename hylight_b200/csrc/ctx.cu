@@ -526,7 +526,10 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
     uint32_t cap = 0;
     if (fast) {
         // strip capacity: 3.5x the expected density 2/(w+1) plus slack, never more than one per k-mer
-        const uint32_t kmers = d.max_len >= (uint32_t)ctx->P.k ? d.max_len - (uint32_t)ctx->P.k + 1 : 0;
+        // (sized for reads of at most 1024 bp: in a batch that mixes short reads with a few contigs the long ones overflow
+        // their strip and take the generic kernel, instead of every read paying for a contig-sized strip)
+        const uint32_t cap_len = std::min<uint32_t>(d.max_len, 1024u);
+        const uint32_t kmers = cap_len >= (uint32_t)ctx->P.k ? cap_len - (uint32_t)ctx->P.k + 1 : 0;
         cap = std::min<uint32_t>(std::max<uint32_t>(kmers, 1u), (uint32_t)(7.0 * kmers / (ctx->P.w + 1)) + 8u);
         CK(ctx->b_sx.ensure((size_t)n * cap * 8 + 8));
         CK(ctx->b_srp.ensure((size_t)n * cap * 4 + 4));

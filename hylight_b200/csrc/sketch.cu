@@ -163,7 +163,7 @@ __device__ __forceinline__ void static_for(F &&f) {
 }
 
 template <int WW>
-__global__ void __launch_bounds__(128) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+__global__ void __launch_bounds__(128, 5) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
                                                           uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
                                                           uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt) {
     const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;

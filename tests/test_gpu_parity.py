@@ -544,3 +544,42 @@ def test_properties_at_scale(ctx):
         mm = int(np.count_nonzero(a[sa:sa + ol] != bq[sb:sb + ol]))
         assert int(r["K"]) <= mm <= int(r["K"]) + 1
         assert ol >= 60 and (ol - 1 - int(r["K"])) >= 0.98 * (ol - 1) - 1
+
+
+def _contig_cluster(seed, n_contigs, lo, hi, genome_len=30000, n_strains=2, snp_rate=0.01):
+    """variable-length 'contigs' (the sequences run_sfo re-overlaps, polyte.tune_params.py:534-579): error-free
+    substrings of a few strain genomes, random strand"""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 4, size=genome_len).astype(np.uint8)
+    comp = np.array([3, 2, 1, 0], dtype=np.uint8)
+    seqs = []
+    for _ in range(n_contigs):
+        g = base.copy()
+        srng = np.random.default_rng(seed * 100 + int(rng.integers(0, n_strains)))
+        m = srng.random(genome_len) < snp_rate
+        g[m] = (g[m] + srng.integers(1, 4, size=int(m.sum()))) % 4
+        L = int(rng.integers(lo, hi + 1))
+        s0 = int(rng.integers(0, genome_len - L + 1))
+        c = g[s0:s0 + L]
+        if rng.random() < 0.5:
+            c = comp[c[::-1]]
+        seqs.append(np.frombuffer(b"ACGT", dtype=np.uint8)[c].tobytes())
+    return seqs
+
+
+def test_full_path_contigs_variable_length():
+    """the same chain on contigs (min_overlap_len 50), alone and in one batch with clusters of
+    short reads (the long sequences take the generic sketch / pack kernels and the exact verify kernel).  The
+    ungapped extension model holds while (1 - min_identity) * length * B < end bonus, i.e. up to 2499 bp at 0.98;
+    longer sequences are refused (test below)"""
+    contigs = _contig_cluster(7, 120, 150, 2400, genome_len=9000)
+    mid = _contig_cluster(8, 150, 200, 1500, genome_len=12000, n_strains=3)
+    short = [bytes(s_) for s_ in small_cluster(75, n_fragments=150).cluster_reads(0)]
+    with api.Context(0, min_ovlp_len=50) as c:
+        rec, coff, tm = check_full(c, synth.ReadBatch.from_seqs([contigs]), min_ovlp_len=50)
+        assert len(rec) > 50
+        rec, coff, tm = check_full(c, synth.ReadBatch.from_seqs([short, contigs, mid, short[:50]]), min_ovlp_len=50)
+        assert coff[1] > 0 and coff[2] > coff[1] and coff[3] > coff[2]
+        with pytest.raises(api.HloError) as ei:
+            c.pack(to_orc_batch(synth.ReadBatch.from_seqs([_contig_cluster(9, 3, 2600, 2700, genome_len=9000)])))
+        assert "ungapped" in str(ei.value)
