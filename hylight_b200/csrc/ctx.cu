@@ -95,6 +95,7 @@ struct hlo_ctx {
     int pairgen_slots_log2 = 8;
     int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0, sort_prefix = 1, sort_hash_bits = 0, sort_segmented = 1;
     bool prefix_used = false, prefix_failed = false;
+    int sorted_buf = 0;  // which of b_keys / b_vals holds the grouped pairs of the last run_index
     bool keys_ready = false;
     uint32_t *mapped_host = nullptr, *mapped_dev = nullptr;  // 256 B of mapped pinned memory (fetch_small)
     cudaEvent_t ev_vf[2] = {};
@@ -512,7 +513,7 @@ extern "C" void hlo_reads_free(hlo_reads *R) {
 
 // sketch.  Leaves mz_off (n_reads+1, name order), mz_x, mz_rp, mz_rid on the device; with the single-pass
 // fast kernel also the radix sort's input pairs (keys_ready).
-static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
+static int run_sketch(hlo_ctx *ctx, const hlo_reads *R, bool want_x) {
     const DevReads &d = R->d;
     cudaStream_t s = ctx->stream;
     const uint32_t n = d.n_reads;
@@ -556,7 +557,12 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
         FETCH(&total, ctx->b_counters.as<uint32_t>() + 22, 4);
     }
     ctx->n_mz = total;
-    CK(ctx->b_mzx.ensure((size_t)total * 8 + 8));
+    // the hash words themselves are only wanted by hlo_sketch: the index is built from the sort keys
+    uint64_t *mz_x = nullptr;
+    if (want_x || !fast) {
+        CK(ctx->b_mzx.ensure((size_t)total * 8 + 8));
+        mz_x = ctx->b_mzx.as<uint64_t>();
+    }
     CK(ctx->b_mzrr.ensure((size_t)total * 8 + 8));
     if (fast) {
         for (int i = 0; i < 2; ++i) {
@@ -564,15 +570,15 @@ static int run_sketch(hlo_ctx *ctx, const hlo_reads *R) {
             CK(ctx->b_vals[i].ensure((size_t)total * 4 + 4));
         }
         launch_sketch_compact(d, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
-                              ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(),
-                              ctx->b_keys[0].as<uint64_t>(), ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, s, &ctx->lc);
-        ctx->keys_ready = n_ovf == 0;
-        if (n_ovf)  // reads with more minimizers than a strip holds: the generic kernel writes them in place
-            launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(),
-                                ctx->b_ovf.as<uint32_t>(), (uint32_t)n_ovf, s, &ctx->lc);
+                              ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), ctx->b_keys[0].as<uint64_t>(),
+                              ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, s, &ctx->lc);
+        ctx->keys_ready = true;
+        if (n_ovf)  // reads with more minimizers than a strip holds, or low-complexity reads: the generic kernel writes them in place
+            launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), ctx->b_keys[0].as<uint64_t>(),
+                                ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, ctx->b_ovf.as<uint32_t>(), (uint32_t)n_ovf, s, &ctx->lc);
     } else {
-        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(),
-                            nullptr, 0, s, &ctx->lc);
+        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), nullptr, nullptr, 0, nullptr, 0, s,
+                            &ctx->lc);
     }
     CK(cudaGetLastError());
     return HLO_OK;
@@ -596,11 +602,17 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
     CK(ctx->b_flags.ensure(n * 4 + 4));
     CK(ctx->b_range.ensure(n * 8 + 8));
     CK(ctx->b_hits.ensure(n * 8 + 8));
-    if (!ctx->keys_ready || !allow_prefix)  // (a redo after a prefix attempt starts from fresh keys)
-        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(), R->d.cidx, 2 * ctx->P.k, n, ctx->b_keys[0].as<uint64_t>(),
-                         ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
+    if (!allow_prefix) {
+        // a redo after a prefix attempt: the (key, index) pairs are intact but permuted — put every pair back at its
+        // index, into the other buffer, and sort from there
+        const int from = ctx->sorted_buf;
+        launch_unpermute_pairs(keys[from], vals[from], n, keys[from ^ 1], vals[from ^ 1], s, &ctx->lc);
+        if (from == 0) std::swap(keys[0], keys[1]), std::swap(vals[0], vals[1]);
+    } else if (!ctx->keys_ready) {
+        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(), R->d.cidx, 2 * ctx->P.k, n, keys[0], vals[0], s, &ctx->lc);
+    }
     // key = cluster index << 2k | hash: 2k hash bits + the bits of the cluster count
     const int key_bits = 2 * ctx->P.k + (R->d.n_clusters > 1 ? bits_for(R->d.n_clusters) : 0);
     if (key_bits > 64) FAIL(HLO_ERANGE, "%u clusters with k=%d need a %d-bit sort key (limit 64): use smaller batches", R->d.n_clusters, ctx->P.k, key_bits);
@@ -629,6 +641,7 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SORT], s));
+    ctx->sorted_buf = keys[cur] == ctx->b_keys[0].as<uint64_t>() ? 0 : 1;
     launch_bucket_index(keys[cur], vals[cur], ctx->b_mzrr.as<uint2>(), n, ctx->P.mid_occ, ctx->b_hits.as<uint2>(), ctx->b_range.as<uint2>(), s,
                         &ctx->lc);
     CK(cudaGetLastError());
@@ -814,7 +827,7 @@ int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64
     reset_timing(ctx);
     cudaStream_t s = ctx->stream;
     CK(cudaEventRecord(ctx->ev[ST_PACK], s));
-    int rc = run_sketch(ctx, R);
+    int rc = run_sketch(ctx, R, true);
     if (rc) return rc;
     const uint64_t tot = ctx->n_mz;
     CK(ctx->b_mz.ensure(tot * sizeof(hlo_mz) + 16));
@@ -854,7 +867,7 @@ int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64
 static int stages_to_candidates(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t *n_c, bool mark_start = true) {
     cudaStream_t s = ctx->stream;
     if (mark_start) CK(cudaEventRecord(ctx->ev[ST_PACK], s));
-    int rc = run_sketch(ctx, R);
+    int rc = run_sketch(ctx, R, false);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
     rc = run_index(ctx, R, true);

@@ -21,8 +21,9 @@ void launch_read_meta(const uint64_t *base_off, const uint32_t *cluster_off, Dev
 // pass 0: count[r] = number of minimizers of read r;  pass 1: write them at off[r].
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc);
 // list != nullptr: only the n_list listed reads (x indices)
-void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, const uint32_t *list,
-                         uint32_t n_list, cudaStream_t s, LaunchCounter *lc);
+// mz_x == nullptr: hash words not wanted; keys != nullptr: also the sort pairs (cluster << hash_bits | hash, own index)
+void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, uint64_t *keys, uint32_t *vals,
+                         int hash_bits, const uint32_t *list, uint32_t n_list, cudaStream_t s, LaunchCounter *lc);
 // single-pass fast path (static window, k odd): per-read strips of `cap` entries + counts, then a gather
 bool sketch_fast_supported(int w, int k);
 void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
@@ -59,6 +60,10 @@ int launch_radix_sort_segmented(uint64_t *keys[2], uint32_t *vals[2], uint64_t n
 // state (2 device words, zeroed by the caller): [0] groups fixed, [1] = 1 when a group was too large (redo with a full sort).
 void launch_collision_fix(uint64_t *keys, uint32_t *vals, uint64_t n, int shift, uint32_t *list, uint32_t *state, cudaStream_t s,
                           LaunchCounter *lc);
+
+// pairs (key, index) in any order -> keys_out[index] = key, vals_out[index] = index
+void launch_unpermute_pairs(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint64_t *keys_out, uint32_t *vals_out, cudaStream_t s,
+                            LaunchCounter *lc);
 
 // up to 64 words from device memory to (mapped) host memory: the read-back path for counters
 void launch_copy_words(const uint32_t *src, uint32_t *dst, uint32_t n, cudaStream_t s, LaunchCounter *lc);

@@ -600,4 +600,18 @@ void launch_collision_fix(uint64_t *keys, uint32_t *vals, uint64_t n, int shift,
 }
 
 
+__global__ void unpermute_pairs_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n,
+                                       uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = vals[i];
+    keys_out[v] = keys[i], vals_out[v] = v;
+}
+void launch_unpermute_pairs(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint64_t *keys_out, uint32_t *vals_out, cudaStream_t s,
+                            LaunchCounter *lc) {
+    if (n == 0) return;
+    unpermute_pairs_kernel<<<(unsigned)ceil_div_u64(n, 256), 256, 0, s>>>(keys, vals, n, keys_out, vals_out);
+    if (lc) lc->total++;
+}
+
 }  // namespace hlo

@@ -63,6 +63,39 @@ def test_sketch_edge_cases(ctx):
     sketch_case(ctx, [seqs])
 
 
+def test_sketch_low_complexity_stress(ctx):
+    """thousands of reads in which the same k-mer recurs inside one window (tandem repeats of period 1..40 with a few
+    point changes, two-letter sequence, repeats next to random sequence, N inside repeats): the fast kernel has to
+    notice every such read and hand it to the exact kernel"""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = []
+    for _ in range(4000):
+        L = int(rng.integers(60, 260))
+        kind = int(rng.integers(0, 5))
+        if kind <= 2:  # tandem repeat, possibly mutated, possibly flanked by random sequence
+            period = int(rng.integers(1, 41))
+            unit = acgt[rng.integers(0, 4, size=period)]
+            s_ = np.tile(unit, L // period + 2)[:L].copy()
+            for _m in range(int(rng.integers(0, 4))):
+                s_[int(rng.integers(0, L))] = acgt[int(rng.integers(0, 4))]
+            if kind == 1:
+                cut = int(rng.integers(0, L))
+                s_[cut:] = acgt[rng.integers(0, 4, size=L - cut)]
+            if kind == 2 and rng.random() < 0.5:
+                s_[int(rng.integers(0, L))] = ord("N")
+        elif kind == 3:  # two-letter sequence
+            two = acgt[rng.choice(4, size=2, replace=False)]
+            s_ = two[rng.integers(0, 2, size=L)]
+        else:  # a random segment repeated after a short gap
+            seg = acgt[rng.integers(0, 4, size=int(rng.integers(22, 60)))]
+            gap = acgt[rng.integers(0, 4, size=int(rng.integers(0, 12)))]
+            s_ = np.concatenate([seg, gap, seg, gap, seg, acgt[rng.integers(0, 4, size=L)]])[:L]
+        seqs.append(s_.tobytes())
+    for w, k in [(11, 21), (5, 15), (19, 11)]:
+        sketch_case(ctx, [seqs], w=w, k=k, min_chain_score=min(30, 2 * k))
+
+
 def test_sketch_other_wk(ctx):
     rng = np.random.default_rng(3)
     seqs = random_reads(rng, 200, 40, 200, n_rate=0.01)
