@@ -439,6 +439,7 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     DevReads &d = R->d;
     d.n_reads = n_reads, d.n_clusters = n_clusters, d.stride_w = stride_w, d.nv = nv, d.max_len = max_len, d.n_bases = n_bases;
     d.max_cluster = max_cluster;
+    d.plain_names = plain ? 1 : 0;
     const size_t plane_words = (size_t)n_reads * stride_w;
     CK(R->b_ascii.ensure(n_bases + 16));
     CK(R->b_off.ensure(((size_t)n_reads + 1) * 8));
@@ -1011,10 +1012,11 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     launch_exclusive_scan(g_cnt, g_off, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
     uint32_t *g_entg = ctx->b_vals[1].as<uint32_t>();
     launch_group_scatter(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, ctx->b_vals[0].as<uint32_t>(), g_ent, g_entg, s, &ctx->lc);
-    launch_group_mark(ctx->b_rec16.as<Rec16>(), n_acc, g_off, g_entg, 1, g_ent, g_uniq, s, &ctx->lc);
+    uint32_t *g_lt = ctx->b_vals[0].as<uint32_t>();  // (the slots are consumed by the scatter)
+    launch_group_mark(ctx->b_rec16.as<Rec16>(), n_acc, g_off, g_entg, 1, g_ent, g_uniq, g_lt, s, &ctx->lc);
     uint32_t n_out32 = 0;
     launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), ctx->b_counters.as<uint32_t>() + 8, s, &ctx->lc);
-    launch_group_expand(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, g_uoff, g_entg, g_ent, ctx->b_out.as<hlo_rec>(),
+    launch_group_expand(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, g_uoff, g_entg, g_ent, g_lt, ctx->b_out.as<hlo_rec>(),
                         ctx->compact ? ctx->b_out.as<hlo_rec16>() : nullptr, ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
     CK(cudaGetLastError());
     FETCH(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4);

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) group_count_kernel(const Rec16 *__restric
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
-    const uint32_t nq = __ldg(r.nrank + qt.x), nt = __ldg(r.nrank + qt.y);
+    const uint32_t nq = r.plain_names ? qt.x : __ldg(r.nrank + qt.x), nt = r.plain_names ? qt.y : __ldg(r.nrank + qt.y);
     slot[i] = atomicAdd(&cnt[min(nq, nt)], 1u);
 }
 void launch_group_count(const Rec16 *rec, uint64_t n, DevReads r, uint32_t *cnt, uint32_t *slot, cudaStream_t s, LaunchCounter *lc) {
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) group_scatter_kernel(const Rec16 *__restr
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
-    const uint32_t nq = __ldg(r.nrank + qt.x), nt = __ldg(r.nrank + qt.y);
+    const uint32_t nq = r.plain_names ? qt.x : __ldg(r.nrank + qt.x), nt = r.plain_names ? qt.y : __ldg(r.nrank + qt.y);
     const uint32_t g = min(nq, nt), p = off[g] + slot[i];
     ent[p] = make_uint2(max(nq, nt), (uint32_t)i);
     entg[p] = g;
@@ -68,37 +68,39 @@ void launch_group_scatter(const Rec16 *rec, uint64_t n, DevReads r, const uint32
 // group with the same idB is better.)  The answer goes to the top bit of the entry and is counted per group.
 __global__ void __launch_bounds__(256) group_mark_kernel(const Rec16 *__restrict__ rec, uint64_t n, const uint32_t *__restrict__ off,
                                                          const uint32_t *__restrict__ entg, int dedup, uint2 *ent,
-                                                         uint32_t *__restrict__ uniq) {
+                                                         uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint2 me = ent[p];
     const uint32_t g = entg[p];
     bool keep = true;
-    if (dedup) {
-        const uint32_t b = off[g], e = off[g + 1];
-        for (uint32_t j = b; j < e; ++j) {
-            const uint2 y = ent[j];
-            if (y.x == me.x && j != p && rec_better(rec[y.y & 0x7fffffffu], rec[me.y])) keep = false;  // same pair, better record
-        }
+    uint32_t lt = 0;  // entries of the group with a smaller idB: my place in the group when it holds no duplicate pair
+    const uint32_t b = off[g], e = off[g + 1];
+    for (uint32_t j = b; j < e; ++j) {
+        const uint2 y = ent[j];
+        lt += y.x < me.x;
+        if (dedup && y.x == me.x && j != p && rec_better(rec[y.y & 0x7fffffffu], rec[me.y])) keep = false;  // same pair, better record
     }
+    lt_out[p] = lt;
     if (keep) {
         ent[p].y = me.y | 0x80000000u;
         atomicAdd(&uniq[g], 1u);
     }
 }
 void launch_group_mark(const Rec16 *rec, uint64_t n, const uint32_t *off, const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq,
-                       cudaStream_t s, LaunchCounter *lc) {
+                       uint32_t *lt, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    group_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, off, entg, dedup, ent, uniq);
+    group_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, off, entg, dedup, ent, uniq, lt);
     if (lc) lc->total++;
 }
 
 // Pass B, one thread per kept entry: its place inside the group = number of kept entries with a smaller idB
+// (= the count pass A left when the group has no duplicate pair; otherwise counted here)
 // (ties between kept entries cannot occur with dedup; without dedup the better record goes first); expand it there.
 __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
                                                            const uint32_t *__restrict__ off, const uint32_t *__restrict__ uoff,
                                                            const uint32_t *__restrict__ entg, const uint2 *__restrict__ ent,
-                                                           hlo_rec *__restrict__ out, hlo_rec16 *__restrict__ out16,
+                                                           const uint32_t *__restrict__ lt, hlo_rec *__restrict__ out, hlo_rec16 *__restrict__ out16,
                                                            hlo_rec_aux *__restrict__ aux) {
     const uint64_t pe = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pe >= n) return;
@@ -107,11 +109,14 @@ __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restri
     const uint32_t g = entg[pe];
     const uint32_t b = off[g], e = off[g + 1];
     const Rec16 x = rec[me.y & 0x7fffffffu];
-    uint32_t rank = 0;
-    for (uint32_t j = b; j < e; ++j) {
-        const uint2 y = ent[j];
-        if (!(y.y >> 31) || j == pe) continue;
-        rank += y.x < me.x || (y.x == me.x && rec_better(rec[y.y & 0x7fffffffu], x));
+    uint32_t rank = lt[pe];  // exact when every entry of the group was kept (no duplicate pair: the usual case)
+    if (uoff[g + 1] - uoff[g] != e - b) {
+        rank = 0;
+        for (uint32_t j = b; j < e; ++j) {
+            const uint2 y = ent[j];
+            if (!(y.y >> 31) || j == pe) continue;
+            rank += y.x < me.x || (y.x == me.x && rec_better(rec[y.y & 0x7fffffffu], x));
+        }
     }
     const uint32_t p = uoff[g] + rank;
     const int ql = (int)(r.len[x.q] & HLO_LEN_MASK), tl = (int)(r.len[x.t] & HLO_LEN_MASK);
@@ -132,9 +137,10 @@ __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restri
     aux[p] = ax;
 }
 void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *uoff, const uint32_t *entg,
-                         const uint2 *ent, hlo_rec *out, hlo_rec16 *out16, hlo_rec_aux *aux, cudaStream_t s, LaunchCounter *lc) {
+                         const uint2 *ent, const uint32_t *lt, hlo_rec *out, hlo_rec16 *out16, hlo_rec_aux *aux, cudaStream_t s,
+                         LaunchCounter *lc) {
     if (n == 0) return;
-    group_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, uoff, entg, ent, out, out16, aux);
+    group_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, uoff, entg, ent, lt, out, out16, aux);
     if (lc) lc->total++;
 }
 
