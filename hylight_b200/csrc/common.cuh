@@ -33,6 +33,7 @@ struct DevReads {
     uint32_t *ids = nullptr;    // [n] decimal name
     uint32_t *nrank = nullptr;  // [n] cbase + numeric rank of the name inside the cluster
     int plain_names = 0;        // names are 0..N-1 in file order: nrank[i] == i, no lookup needed
+    uint4 *meta = nullptr;      // [n] (length, name, cluster, cluster base): one gather where a record needs them all
     uint32_t *perm = nullptr;   // [n] x -> read: reads of a cluster in strcmp order of their decimal names
     uint32_t *bases = nullptr;  // [2][n][stride_w]
     uint32_t *amb = nullptr;    // [2][n][stride_w]

@@ -75,12 +75,12 @@ struct hlo_reads {
     hlo_ctx *ctx = nullptr;
     int device = -1;
     DevReads d;
-    DevBuf b_ascii, b_off, b_coff, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_bases, b_amb, b_ambcount;
+    DevBuf b_ascii, b_off, b_coff, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_meta, b_bases, b_amb, b_ambcount;
     std::vector<uint32_t> h_len, h_ids, h_cidx, h_cluster_off, h_perm;
     float h2d_ms = 0.f, pack_ms = 0.f;
     void release() {
         b_ascii.release(), b_off.release(), b_coff.release(), b_len.release(), b_cbase.release(), b_cidx.release(), b_ids.release();
-        b_nrank.release(), b_perm.release(), b_bases.release(), b_amb.release(), b_ambcount.release();
+        b_nrank.release(), b_perm.release(), b_meta.release(), b_bases.release(), b_amb.release(), b_ambcount.release();
     }
 };
 
@@ -449,12 +449,14 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     CK(R->b_cidx.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_ids.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_nrank.ensure((size_t)n_reads * 4 + 4));
+    CK(R->b_meta.ensure((size_t)n_reads * 16 + 16));
     CK(R->b_perm.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_bases.ensure((plane_words * 2 + 2 * HLO_PAD_WORDS) * 4));
     CK(R->b_amb.ensure((plane_words * 2 + 2 * HLO_PAD_WORDS) * 4));
     CK(R->b_ambcount.ensure(16));
     d.len = R->b_len.as<uint32_t>(), d.cbase = R->b_cbase.as<uint32_t>(), d.cidx = R->b_cidx.as<uint32_t>();
     d.ids = R->b_ids.as<uint32_t>(), d.nrank = R->b_nrank.as<uint32_t>(), d.perm = R->b_perm.as<uint32_t>();
+    d.meta = R->b_meta.as<uint4>();
     d.bases = R->b_bases.as<uint32_t>() + HLO_PAD_WORDS, d.amb = R->b_amb.as<uint32_t>() + HLO_PAD_WORDS;
     CK(cudaEventRecord(ctx->ev[ST_BEGIN], s));
     if (n_reads) {
@@ -467,6 +469,10 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
             CK(cudaMemcpyAsync(d.cidx, R->h_cidx.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(d.ids, R->h_ids.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(d.nrank, nrank.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+            std::vector<uint4> meta(n_reads);
+            for (uint32_t i = 0; i < n_reads; ++i) meta[i] = make_uint4(R->h_len[i], R->h_ids[i], R->h_cidx[i], cbase[i]);
+            CK(cudaMemcpyAsync(d.meta, meta.data(), (size_t)n_reads * 16, cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));  // (meta is a local)
             CK(cudaMemcpyAsync(d.perm, R->h_perm.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
         }
     }

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256) read_meta_kernel(const uint64_t *__restri
     r.cidx[i] = lo;
     r.ids[i] = i - cb;
     r.nrank[i] = i;
+    r.meta[i] = make_uint4((uint32_t)(base_off[i + 1] - base_off[i]), i - cb, lo, cb);
     r.perm[i] = cb + dec_order_kth(N, i - cb);
 }
 

@@ -119,10 +119,11 @@ __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restri
         }
     }
     const uint32_t p = uoff[g] + rank;
-    const int ql = (int)(r.len[x.q] & HLO_LEN_MASK), tl = (int)(r.len[x.t] & HLO_LEN_MASK);
+    const uint4 mq = __ldg(r.meta + x.q), mt = __ldg(r.meta + x.t);  // (length, name, cluster, cluster base)
+    const int ql = (int)mq.x, tl = (int)mt.x;
     const int diag = (int)(x.ds >> 1) - HLO_DIAG_BIAS;
     hlo_rec o;
-    expand_record(r.ids[x.q], r.ids[x.t], ql, tl, diag, (int)(x.ds & 1u), x.kb & 0xffffu, &o);
+    expand_record(mq.y, mt.y, ql, tl, diag, (int)(x.ds & 1u), x.kb & 0xffffu, &o);
     if (out16) {  // 16-byte form (hlo_rec16): OLB == OLA, 16-bit overhangs and lengths
         reinterpret_cast<uint4 *>(out16)[p] = make_uint4(o.idA, o.idB, ((uint32_t)o.OHA & 0xffffu) | (uint32_t)o.OHB << 16,
                                                           o.OLA | (o.K | o.ori << 15) << 16);
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restri
         dst[1] = make_uint4(o.OLA, o.OLB, o.K, o.ori);
     }
     hlo_rec_aux ax;
-    ax.cluster = r.cidx[x.q];
+    ax.cluster = mq.z;
     ax.blocklen = x.kb >> 16;
     aux[p] = ax;
 }
