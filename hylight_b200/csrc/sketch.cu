@@ -138,16 +138,6 @@ __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, u
     sketch_read<WRITE>(r, w, k, count, off, o, list ? list[ti] : ti);
 }
 
-// exact counts of the reads the fast kernel listed for a redo; the list length is still on the device
-__global__ void __launch_bounds__(128) sketch_recount_kernel(DevReads r, int w, int k, uint32_t *__restrict__ count,
-                                                             const uint32_t *__restrict__ list,
-                                                             const unsigned long long *__restrict__ n_list_dev) {
-    const unsigned long long n_list = *n_list_dev;
-    MzOut o{nullptr, nullptr, nullptr, nullptr, 0};
-    for (unsigned long long ti = blockIdx.x * blockDim.x + threadIdx.x; ti < n_list; ti += (unsigned long long)gridDim.x * blockDim.x)
-        sketch_read<false>(r, w, k, count, nullptr, o, list[ti]);
-}
-
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc) {
     if (r.n_reads == 0) return;
     MzOut o{nullptr, nullptr, nullptr, nullptr, 0};
@@ -183,15 +173,136 @@ __device__ __forceinline__ void static_for(F &&f) {
     }
 }
 
+// The complete automaton (ties included) for ONE read, same strip output: the rerun of a read in which the lean
+// automaton of sketch_fast_kernel met equal hashes.  Not inlined: it is the rare path and must not set the register
+// budget of the common one.
+template <int WW>
+__device__ __noinline__ uint32_t sketch_strip_exact(const DevReads &r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+                                                    uint32_t *__restrict__ srp, uint32_t xi) {
+    const uint32_t read = __ldg(r.perm + xi);
+    const uint32_t lenf = __ldg(r.len + read);
+    const int len = (int)(lenf & HLO_LEN_MASK);
+    const bool has_amb = (lenf & HLO_AMB_FLAG) != 0;
+    const uint32_t *row = r.bases + (uint64_t)read * r.stride_w;
+    const uint32_t *arow = r.amb + (uint64_t)read * r.stride_w;
+    const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
+    const uint64_t INF = ~0ULL;
+    uint64_t kmer0 = 0, kmer1 = 0;
+    // ring buffer of the last WW entries: slot = step mod WW, a compile-time constant in the unrolled body
+    uint64_t bx[WW];
+    uint32_t by[WW];
+    static_for<0, WW>([&](auto J) { bx[J] = INF, by[J] = 0xffffffffu; });
+    // mm_sketch's `min` is at every step the RIGHTMOST SMALLEST entry of the window.  Instead of rescanning the
+    // window when the minimum leaves it (a per-lane event: the warp would run the rescan with a handful of active
+    // lanes at almost every step), the window minimum is kept by block decomposition: steps are grouped in
+    // blocks of WW (one pass of the unrolled body); suf[j] = rightmost smallest of the previous block's slots
+    // j..WW-1, computed for all j at the block boundary (the same step for every lane), and the minimum of the
+    // current block's slots 0..s runs along.  Window minimum after step s = the smaller of the two, ties to the
+    // running one (it lies to the right).
+    uint64_t sufx[WW];
+    uint32_t sufy[WW];
+    uint32_t suf_tie = 0;          // bit j: the suffix minimum of j.. occurs more than once in j..WW-1
+    uint32_t sufs[WW];             // its slot
+    static_for<0, WW>([&](auto J) { sufx[J] = INF, sufy[J] = 0xffffffffu, sufs[J] = WW - 1; });  // all-INF window: rightmost slot
+    uint64_t px = INF;             // running minimum of the current block
+    uint32_t py = 0xffffffffu;
+    int pslot = 0;
+    bool ptie = false;
+    uint64_t min_x = INF;          // mm_sketch's `min`
+    uint32_t min_y = 0xffffffffu;
+    int min_slot = 0, l = 0;
+    uint32_t n = 0;
+    const uint64_t sbase = (uint64_t)xi * cap;
+    auto emit = [&](uint64_t X, uint32_t Y) {
+        if (n < cap) sx[sbase + n] = X, srp[sbase + n] = Y;
+        ++n;
+    };
+    uint32_t word = 0, aword = 0;
+    for (int i0 = 0; i0 < len; i0 += WW) {
+        if (i0 > 0) {  // block boundary: suffix minima of the block just finished (the ring holds exactly it)
+            uint64_t cx = INF;
+            uint32_t cy = 0xffffffffu, cs = WW - 1, tie = 0;
+            suf_tie = 0;
+            static_for<0, WW>([&](auto JJ) {
+                constexpr int j = WW - 1 - JJ;
+                if (j == WW - 1 || bx[j] < cx) cx = bx[j], cy = by[j], cs = j, tie = 0;  // strict <: the rightmost stays
+                else if (bx[j] == cx) tie = 1;
+                sufx[j] = cx, sufy[j] = cy, sufs[j] = cs;
+                suf_tie |= tie << j;
+            });
+        }
+        static_for<0, WW>([&](auto SS) {
+            constexpr int s = SS;
+            const int i = i0 + s;
+            if (i < len) {
+                if ((i & 15) == 0) {
+                    word = __ldg(row + (i >> 4));
+                    aword = has_amb ? __ldg(arow + (i >> 4)) : 0u;
+                }
+                const uint32_t c = word & 3u, amb = aword & 1u;
+                word >>= 2, aword >>= 2;
+                uint64_t info_x = INF;
+                uint32_t info_y = 0xffffffffu;
+                if (!amb) {
+                    const int kmer_span = l + 1 < k ? l + 1 : k;
+                    kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
+                    kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+                    const uint32_t z = kmer0 < kmer1 ? 0u : 1u;  // k odd: kmer0 != kmer1 always
+                    ++l;
+                    if (l >= k) {
+                        info_x = mm_hash64(z ? kmer1 : kmer0, mask) << 8 | (uint64_t)kmer_span;
+                        info_y = (uint32_t)i << 1 | z;
+                    }
+                } else
+                    l = 0;
+                bx[s] = info_x, by[s] = info_y;
+                if (l == WW + k - 1 && min_x != INF) {  // first full window: identical k-mers were not stored yet
+                    static_for<s + 1, WW>([&](auto J) {
+                        if (min_x == bx[J] && by[J] != min_y) emit(bx[J], by[J]);
+                    });
+                    static_for<0, s>([&](auto J) {
+                        if (min_x == bx[J] && by[J] != min_y) emit(bx[J], by[J]);
+                    });
+                }
+                // running minimum of the current block (<=: the rightmost smallest)
+                if (s == 0 || info_x <= px) ptie = (s != 0) && info_x == px, px = info_x, py = info_y, pslot = s;
+                // the events of mm_sketch, decided against the OLD minimum
+                const bool ev_a = info_x <= min_x;                 // a new minimum
+                const bool ev_b = !ev_a && min_slot == s;          // the old minimum left the window
+                if (((ev_a && l >= WW + k) || (ev_b && l >= WW + k - 1)) && min_x != INF) emit(min_x, min_y);
+                // the new window minimum
+                bool tie;
+                if (s == WW - 1 || px <= sufx[s + 1 < WW ? s + 1 : 0]) {
+                    tie = ptie || (s != WW - 1 && px == sufx[s + 1 < WW ? s + 1 : 0]);
+                    min_x = px, min_y = py, min_slot = pslot;
+                } else {
+                    constexpr int j = s + 1 < WW ? s + 1 : 0;
+                    tie = (suf_tie >> j) & 1u;
+                    min_x = sufx[j], min_y = sufy[j], min_slot = (int)sufs[j];
+                }
+                if (ev_b && tie && l >= WW + k - 1 && min_x != INF) {  // rare: other entries share the new minimum
+                    auto dup = [&](auto J) {
+                        if (min_x == bx[J] && min_y != by[J]) emit(bx[J], by[J]);
+                    };
+                    static_for<s + 1, WW>(dup);
+                    static_for<0, s + 1>(dup);
+                }
+            }
+        });
+    }
+    if (min_x != INF) emit(min_x, min_y);
+    return n;
+}
+
+
 // mm_sketch emits an entry that equals the window minimum but is not "the" minimum only through two special
 // blocks (first full window; after the minimum left the window).  Both need two EQUAL valid entries inside one
 // window — the same canonical k-mer twice within w + k bases, i.e. low-complexity sequence.  The fast kernel does
 // not carry those blocks: it raises a sticky flag at the three places where equal values can meet (running
 // minimum, running minimum against the previous block's suffix minimum, suffix scan), and a flagged read is redone
-// by the exact generic kernel, like a read that overflows its strip.  Invalid entries (the first k-1 positions,
+// on the spot by the complete automaton (sketch_strip_exact).  Invalid entries (the first k-1 positions,
 // positions after an N) get distinct markers ~i (bit 63 set, a newer one is smaller), so they never tie, never win
 // against a valid entry and keep mm_sketch's "rightmost" choice among themselves.
-constexpr uint64_t SK_REDO = ~0ULL;  // first strip entry of a read the generic kernel has to redo
 
 template <int WW, bool AMB>
 __global__ void __launch_bounds__(128, WW <= 11 ? 5 : 2) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
@@ -289,11 +400,11 @@ __global__ void __launch_bounds__(128, WW <= 11 ? 5 : 2) sketch_fast_kernel(DevR
         });
     }
     if (valid(min_x)) emit(min_x, min_y);
+    if (tie) n = sketch_strip_exact<WW>(r, k, cap, sx, srp, xi);  // equal hashes met: the complete automaton decides
     count[xi] = n;
-    if (n > cap || tie) {
+    if (n > cap) {  // more minimizers than the strip holds: the generic kernel writes this read
         const unsigned long long p = atomicAdd(ovf_cnt, 1ULL);
         ovf_list[p] = xi;
-        sx[sbase] = SK_REDO;
     }
 }
 
@@ -307,15 +418,13 @@ static void launch_sketch_fast_w(const DevReads &r, int k, uint32_t cap, uint64_
     else sketch_fast_kernel<WW, false><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
 }
 
-// One pass: strips + tentative counts; then the exact counts of the listed (overflowing / low-complexity) reads.
 void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
                         uint32_t *ovf_list, unsigned long long *ovf_cnt, cudaStream_t s, LaunchCounter *lc) {
     if (r.n_reads == 0) return;
     if (w == 11) launch_sketch_fast_w<11>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, s);
     else if (w == 5) launch_sketch_fast_w<5>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, s);
     else launch_sketch_fast_w<19>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, s);
-    sketch_recount_kernel<<<148, 128, 0, s>>>(r, w, k, count, ovf_list, ovf_cnt);
-    if (lc) lc->total += 2;
+    if (lc) lc->total++;
 }
 
 // strips -> dense arrays in name order, plus the (cluster, hash | index) pairs the radix sort starts from.
@@ -330,7 +439,7 @@ __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_
     const uint32_t xi = (uint32_t)(gid >> 3), l = (uint32_t)(gid & 7);
     if (xi >= r.n_reads) return;
     const uint32_t n = count[xi];
-    if (n == 0 || n > cap || sx[(uint64_t)xi * cap] == SK_REDO) return;  // nothing / redone by the generic kernel
+    if (n > cap) return;  // written by the generic kernel
     const uint32_t read = r.perm[xi];
     const uint64_t chi = (uint64_t)r.cidx[read] << hash_bits;  // cluster-major: a cluster's buckets stay together
     const uint32_t o = off[xi];
