@@ -1023,12 +1023,12 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     uint32_t n_out32 = 0;
     launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), ctx->b_counters.as<uint32_t>() + 8, s, &ctx->lc);
     launch_group_expand(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, g_uoff, g_entg, g_ent, g_lt, ctx->b_out.as<hlo_rec>(),
-                        ctx->compact ? ctx->b_out.as<hlo_rec16>() : nullptr, ctx->b_aux.as<hlo_rec_aux>(), s, &ctx->lc);
+                        ctx->compact ? ctx->b_out.as<hlo_rec16>() : nullptr, ctx->aux_out ? ctx->b_aux.as<hlo_rec_aux>() : nullptr, s, &ctx->lc);
+    if (d.n_reads) launch_cluster_offsets(g_uoff, R->b_coff.as<uint32_t>(), d.n_clusters, ctx->b_coff.as<unsigned long long>(), s, &ctx->lc);
+    else CK(cudaMemsetAsync(ctx->b_coff.p, 0, ((size_t)d.n_clusters + 1) * 8, s));
     CK(cudaGetLastError());
     FETCH(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4);
     const uint64_t n_out = n_out32;
-    launch_cluster_offsets(ctx->b_aux.as<hlo_rec_aux>(), n_out, d.n_clusters, ctx->b_coff.as<unsigned long long>(), s, &ctx->lc);
-    CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_DEDUP], s));
     compute_lock.unlock();  // the download below overlaps the next worker's kernels
     if (ctx->d2h) {

@@ -132,7 +132,7 @@ void launch_group_mark(const Rec16 *rec, uint64_t n, const uint32_t *off, const 
 void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *uoff, const uint32_t *entg,
                          const uint2 *ent, const uint32_t *lt, hlo_rec *out, hlo_rec16 *out16, hlo_rec_aux *aux, cudaStream_t s,
                          LaunchCounter *lc);
-void launch_cluster_offsets(const hlo_rec_aux *aux, uint64_t n, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,
+void launch_cluster_offsets(const uint32_t *uoff, const uint32_t *cluster_off, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,
                             LaunchCounter *lc);
 
 // ---- score.cu -------------------------------------------------------------------------------

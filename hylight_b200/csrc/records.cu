@@ -132,10 +132,12 @@ __global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restri
         dst[0] = make_uint4(o.idA, o.idB, (uint32_t)o.OHA, (uint32_t)o.OHB);
         dst[1] = make_uint4(o.OLA, o.OLB, o.K, o.ori);
     }
-    hlo_rec_aux ax;
-    ax.cluster = mq.z;
-    ax.blocklen = x.kb >> 16;
-    aux[p] = ax;
+    if (aux) {
+        hlo_rec_aux ax;
+        ax.cluster = mq.z;
+        ax.blocklen = x.kb >> 16;
+        aux[p] = ax;
+    }
 }
 void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *uoff, const uint32_t *entg,
                          const uint2 *ent, const uint32_t *lt, hlo_rec *out, hlo_rec16 *out16, hlo_rec_aux *aux, cudaStream_t s,
@@ -145,24 +147,16 @@ void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_
     if (lc) lc->total++;
 }
 
-// coff[c] = index of the first output record of cluster c (records are sorted by cluster); coff[n_clusters] = n
-__global__ void cluster_offsets_kernel(const hlo_rec_aux *__restrict__ aux, uint64_t n, uint32_t n_clusters,
+// coff[c] = index of the first output record of cluster c = output offset of the cluster's first group (groups are
+// numbered cluster by cluster: cluster base + numeric rank of idA); coff[n_clusters] = number of records
+__global__ void cluster_offsets_kernel(const uint32_t *__restrict__ uoff, const uint32_t *__restrict__ cluster_off, uint32_t n_clusters,
                                        unsigned long long *__restrict__ coff) {
-    const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= n) return;
-    const long long cur = aux[o].cluster;
-    const long long prev = o ? (long long)aux[o - 1].cluster : -1;
-    for (long long c = prev + 1; c <= cur; ++c) coff[c] = o;
-    if (o == n - 1)
-        for (long long c = cur + 1; c <= (long long)n_clusters; ++c) coff[c] = n;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= n_clusters) coff[c] = uoff[cluster_off[c]];
 }
-void launch_cluster_offsets(const hlo_rec_aux *aux, uint64_t n, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,
+void launch_cluster_offsets(const uint32_t *uoff, const uint32_t *cluster_off, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,
                             LaunchCounter *lc) {
-    if (n == 0) {
-        cudaMemsetAsync(coff, 0, ((size_t)n_clusters + 1) * sizeof(unsigned long long), s);
-        return;
-    }
-    cluster_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(aux, n, n_clusters, coff);
+    cluster_offsets_kernel<<<(n_clusters + 1 + 255) / 256, 256, 0, s>>>(uoff, cluster_off, n_clusters, coff);
     if (lc) lc->total++;
 }
 
