@@ -217,14 +217,17 @@ int hlo_score_records(hlo_ctx *ctx, const hlo_reads *reads, const char *quals, c
                       uint64_t n, double mismatch_prob, uint32_t min_read_len, const hlo_score **out);
 
 /* Tuning / test knobs.  "verify_exact" (0|1): route every candidate through the base-by-base verify
- * kernel; "pairgen_slots_log2" (6..13): slots of the per-warp shared-memory seed table;
+ * kernel; "pairgen_slots_log2" (5..10): slots of the per-read shared-memory seed table;
  * "repack" (0|1): hlo_overlap_batch re-runs the 2-bit packer from the ASCII bases kept in HBM (so a
  * device-resident measurement covers the packer); "d2h" (0|1): copy the records back to the host
  * (with 0 hlo_overlap_batch returns n only; rec/aux/cluster_off are NULL); "aux" (0|1): also copy the
  * hlo_rec_aux array back (with 0 hlo_recs.aux is NULL: a caller that only writes the files needs rec and
  * cluster_off); "compact" (0|1): hlo_overlap_batch / hlo_overlap_host return hlo_recs.rec16
  * (16-byte records) instead of rec; "sketch_generic" / "pairgen_generic" (0|1): force the generic (any w, k / 64-bit keyed)
- * kernels instead of the specialised ones. */
+ * kernels instead of the specialised ones; "sort_segmented" (1|0): sort every cluster's minimizers as its own segment
+ * (0: one sort with the cluster index in the key); "sort_prefix" (1|0): sort only a prefix of the hash and repair the
+ * groups in which two hashes share it (0: all hash bits); "sort_hash_bits" (0 = automatic): length of that prefix;
+ * "sort_onesweep" (0|1, process-wide, unsegmented sort only): one-sweep radix passes.  None of them changes a result. */
 int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value);
 
 /* The CUDA stream (cudaStream_t) every call on this ctx enqueues its work on, so that a caller can
