@@ -184,6 +184,11 @@ constexpr unsigned PG_GMASK = PG_G == 32 ? 0xffffffffu : ((1u << PG_G) - 1u);
 constexpr int PG_RPW = 32 / PG_G;              // reads per warp
 constexpr int PG_GROUPS = PG_THREADS / PG_G;   // reads in flight per block
 constexpr int PG_PAD = 8;                      // words of padding between the groups' tables (bank spread)
+constexpr int PG_STAGE = 32;                   // bucket ranges of a read staged at a time (a multiple of PG_G)
+__host__ __device__ inline size_t pairgen_table_words(int slots_log2, bool narrow) {
+    const size_t ST = ((size_t)1 << slots_log2) + PG_PAD;
+    return ((size_t)PG_GROUPS * ST * (narrow ? 7 : 10) + 15) / 16 * 4;  // keys u32 + vals u16|u32 + list u8|u16, rounded to 16 B
+}
 
 // NARROW: reads of at most 255 bases and tables of at most 256 slots: min/max anchor positions are bytes and
 // the slot list is bytes, 7 instead of 10 bytes of shared memory per slot (more resident warps)
@@ -200,6 +205,8 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     val_t *vals = reinterpret_cast<val_t *>(pg_smem + (size_t)PG_GROUPS * ST) + (size_t)g * ST;  // min | max << VSH anchor position
     list_t *list = reinterpret_cast<list_t *>(reinterpret_cast<val_t *>(pg_smem + (size_t)PG_GROUPS * ST) + (size_t)PG_GROUPS * ST) +
                    (size_t)g * ST;                                            // claimed slots
+    // the read's non-empty bucket ranges, long ones first: (first hit, end, query pos<<1|strand, -)
+    uint4 *stg = reinterpret_cast<uint4 *>(pg_smem + pairgen_table_words(slots_log2, NARROW)) + (size_t)g * PG_STAGE;
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const unsigned gshift = lane & ~(unsigned)(PG_G - 1);
@@ -238,63 +245,99 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         __syncwarp();
         uint32_t nh = 0, nq = 0, list_n = 0;
         bool ovf = false;
-        // the bucket range of the next minimizer and the next chunk of hits are loaded one step ahead, so
-        // that their (L2) latency overlaps the table work of the current chunk
-        uint2 rg_n = make_uint2(0u, 0u);
-        uint32_t qrp_n = 0;
-        if (nm) rg_n = __ldg(a.range + m0), qrp_n = __ldg(&a.mz_rr[m0].y);
-        for (uint32_t s = 0; s < nm_max; ++s) {
-            const uint2 rg = rg_n;
-            const uint32_t qrp = qrp_n;
-            rg_n = make_uint2(0u, 0u);
-            if (s + 1 < nm) rg_n = __ldg(a.range + m0 + s + 1), qrp_n = __ldg(&a.mz_rr[m0 + s + 1].y);
-            const int qpos = (int)(qrp >> 1);
-            const uint32_t nchunk_max = __reduce_max_sync(FULL, (rg.y - rg.x + PG_G - 1) / PG_G);
-            uint32_t i = rg.x + l;
-            uint2 h_n = make_uint2(q, 0u);
-            if (i < rg.y) h_n = __ldg(a.hits + i);
-            for (uint32_t c = 0; c < nchunk_max; ++c, i += PG_G) {
-                const uint2 h = h_n;
-                const bool in_range = i < rg.y;
-                if (i + PG_G < rg.y) h_n = __ldg(a.hits + i + PG_G);
-                int newslot = -1;
-                if (in_range && h.x != q) {  // h.x == q: another minimizer of the query itself (-X: no self hits)
-                    const uint32_t t = h.x;
-                    ++nh;
-                    const uint32_t strand = (h.y ^ qrp) & 1u;
-                    const int tp = (int)((h.y >> 1) & 0x7fffu);
-                    const int qpi = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
-                    const int diag = tp - qpi;
-                    const uint32_t qp = (uint32_t)qpi;
-                    const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
-                    uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
-                    // claim-or-find, then ONE update path for both outcomes: a fresh slot holds (min = all ones, max = 0),
-                    // so "min/max with qp" initialises it and its old span (negative) is below any threshold
-                    bool done = false;
-                    uint32_t old = 0;
-                    for (uint32_t probe = 0; probe < S; ++probe) {
-                        old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
-                        if (old == HLO_EMPTY32 || old == key) {
-                            done = true;
-                            break;
-                        }
-                        slot = (slot + 1u) & smask;
-                    }
-                    if (done) {  // no other lane of the group holds this key in this step: plain read-modify-write
-                        const uint32_t v = vals[slot];
-                        const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
-                        vals[slot] = (val_t)(mn | mx << VSH);
-                        nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
-                        if (old == HLO_EMPTY32) newslot = (int)slot;
-                    }
-                    if (!done) ovf = true;
+        // The minimizers are taken PG_STAGE at a time.  Their bucket ranges are staged in shared memory without the empty
+        // ones and with the long ones (more than one chunk of PG_G hits) first: the two reads of the warp run in
+        // lockstep, so pairing long with long and short with short wastes fewer chunks, steps without hits vanish, and
+        // a step reads its range with one broadcast LDS instead of address arithmetic + two global loads.
+        for (uint32_t mb = 0; mb < nm_max; mb += PG_STAGE) {
+            uint32_t n_eff = 0;
+            {
+                uint2 rg_r[PG_STAGE / PG_G];
+                uint32_t qrp_r[PG_STAGE / PG_G];
+                unsigned big_b[PG_STAGE / PG_G], small_b[PG_STAGE / PG_G];
+                uint32_t n_big = 0, n_small = 0;
+#pragma unroll
+                for (int rr = 0; rr < PG_STAGE / PG_G; ++rr) {
+                    const uint32_t idx = mb + rr * PG_G + l;
+                    rg_r[rr] = make_uint2(0u, 0u), qrp_r[rr] = 0u;
+                    if (idx < nm) rg_r[rr] = __ldg(a.range + m0 + idx), qrp_r[rr] = __ldg(&a.mz_rr[m0 + idx].y);
+                    const uint32_t sz = rg_r[rr].y - rg_r[rr].x;
+                    big_b[rr] = (__ballot_sync(FULL, sz > (uint32_t)PG_G) >> gshift) & PG_GMASK;
+                    small_b[rr] = (__ballot_sync(FULL, sz != 0u && sz <= (uint32_t)PG_G) >> gshift) & PG_GMASK;
+                    n_big += __popc(big_b[rr]), n_small += __popc(small_b[rr]);
                 }
-                // remember the claimed slots (per-group list, positions from a ballot: no atomics)
-                const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & PG_GMASK;
-                if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
-                list_n += __popc(gb);
+                uint32_t pb = 0, ps = n_big;
+#pragma unroll
+                for (int rr = 0; rr < PG_STAGE / PG_G; ++rr) {
+                    const uint32_t sz = rg_r[rr].y - rg_r[rr].x;
+                    if (sz > (uint32_t)PG_G) stg[pb + __popc(big_b[rr] & lt8)] = make_uint4(rg_r[rr].x, rg_r[rr].y, qrp_r[rr], 0u);
+                    else if (sz != 0u) stg[ps + __popc(small_b[rr] & lt8)] = make_uint4(rg_r[rr].x, rg_r[rr].y, qrp_r[rr], 0u);
+                    pb += __popc(big_b[rr]), ps += __popc(small_b[rr]);
+                }
+                n_eff = n_big + n_small;
             }
-            __syncwarp();  // orders the plain min/max updates of consecutive minimizers
+            __syncwarp();
+            const uint32_t steps = __reduce_max_sync(FULL, n_eff);
+            // the range of a step and the first chunk of its hits are loaded one step ahead, later chunks one chunk ahead
+            uint4 e_n = make_uint4(0u, 0u, 0u, 0u);
+            if (n_eff) e_n = stg[0];
+            uint2 h_first = make_uint2(q, 0u);
+            if (e_n.x + l < e_n.y) h_first = __ldg(a.hits + e_n.x + l);
+            for (uint32_t s = 0; s < steps; ++s) {
+                const uint2 rg = make_uint2(e_n.x, e_n.y);
+                const uint32_t qrp = e_n.z;
+                e_n = make_uint4(0u, 0u, 0u, 0u);
+                if (s + 1 < n_eff) e_n = stg[s + 1];
+                const int qpos = (int)(qrp >> 1);
+                const uint32_t nchunk_max = __reduce_max_sync(FULL, (rg.y - rg.x + PG_G - 1) / PG_G);
+                uint32_t i = rg.x + l;
+                uint2 h_n = h_first;
+                h_first = make_uint2(q, 0u);
+                if (e_n.x + l < e_n.y) h_first = __ldg(a.hits + e_n.x + l);
+                for (uint32_t c = 0; c < nchunk_max; ++c, i += PG_G) {
+                    const uint2 h = h_n;
+                    const bool in_range = i < rg.y;
+                    if (i + PG_G < rg.y) h_n = __ldg(a.hits + i + PG_G);
+                    int newslot = -1;
+                    if (in_range && h.x != q) {  // h.x == q: another minimizer of the query itself (-X: no self hits)
+                        const uint32_t t = h.x;
+                        ++nh;
+                        const uint32_t strand = (h.y ^ qrp) & 1u;
+                        const int tp = (int)((h.y >> 1) & 0x7fffu);
+                        const int qpi = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
+                        const int diag = tp - qpi;
+                        const uint32_t qp = (uint32_t)qpi;
+                        const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
+                        uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
+                        // claim-or-find, then ONE update path for both outcomes: a fresh slot holds (min = all ones, max = 0),
+                        // so "min/max with qp" initialises it and its old span (negative) is below any threshold
+                        bool done = false;
+                        uint32_t old = 0;
+                        for (uint32_t probe = 0; probe < S; ++probe) {
+                            old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
+                            if (old == HLO_EMPTY32 || old == key) {
+                                done = true;
+                                break;
+                            }
+                            slot = (slot + 1u) & smask;
+                        }
+                        if (done) {  // no other lane of the group holds this key in this step: plain read-modify-write
+                            const uint32_t v = vals[slot];
+                            const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
+                            vals[slot] = (val_t)(mn | mx << VSH);
+                            nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
+                            if (old == HLO_EMPTY32) newslot = (int)slot;
+                        }
+                        if (!done) ovf = true;
+                    }
+                    // remember the claimed slots (per-group list, positions from a ballot: no atomics)
+                    const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & PG_GMASK;
+                    if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
+                    list_n += __popc(gb);
+                }
+                __syncwarp();  // orders the plain min/max updates of consecutive minimizers
+            }
+            __syncwarp();  // the staging area is rewritten by the next batch
         }
         // per-read reductions inside the 8-lane groups (uniform across the warp)
         const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & PG_GMASK) != 0u;
@@ -351,8 +394,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
 
 static bool pairgen_narrow(const DevReads &r, int slots_log2) { return r.max_len <= 255 && slots_log2 <= 8; }
 size_t pairgen_smem_bytes(int slots_log2, bool narrow) {
-    const size_t ST = ((size_t)1 << slots_log2) + PG_PAD;
-    return (size_t)PG_GROUPS * ST * (narrow ? 7 : 10);  // keys u32 + vals u16|u32 + list u8|u16
+    return pairgen_table_words(slots_log2, narrow) * 4 + (size_t)PG_GROUPS * PG_STAGE * sizeof(uint4);
 }
 
 bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out) {
