@@ -1141,27 +1141,46 @@ int hlo_score_records(hlo_ctx *ctx, const hlo_reads *R, const char *quals, const
     if (!ctx->prob_ready) {  // phred_to_prob (EdgeCalculator.cpp:59-63) for every byte value, the reference's own expression
         double tab[128];
         for (int b = 0; b < 128; ++b) tab[b] = pow(10, -(b - 33) / 10.0);
-        CK(ctx->b_prob.ensure(sizeof tab));
+        CK(ctx->b_prob.ensure(sizeof tab + 2 * 128 * 128 * sizeof(double)));
         CK(cudaMemcpyAsync(ctx->b_prob.p, tab, sizeof tab, cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
         ctx->prob_ready = true;
     }
-    CK(ctx->b_qual.ensure(d.n_bases + 16));
+    CK(ctx->b_qual.ensure(d.n_bases + 64 + (size_t)d.n_reads + 16));  // 32 bytes of padding on both sides, then a flag per read
     CK(ctx->b_screc.ensure(n * sizeof(hlo_rec) + 32));
     CK(ctx->b_scclu.ensure(n * 4 + 4));
     CK(ctx->b_scout.ensure(n * sizeof(hlo_score) + 16));
     CK(ctx->h_score.ensure(n * sizeof(hlo_score) + 16));
     CK(const_cast<hlo_reads *>(R)->b_coff.ensure(((size_t)d.n_clusters + 1) * 4));
+    reset_timing(ctx);
+    CK(cudaEventRecord(ctx->ev[ST_BEGIN], s));
     CK(cudaMemcpyAsync(R->b_coff.p, R->h_cluster_off.data(), ((size_t)d.n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->b_qual.p, quals, d.n_bases, cudaMemcpyHostToDevice, s));
+    uint8_t *d_qual = ctx->b_qual.as<uint8_t>() + 32, *d_qflag = d_qual + ((d.n_bases + 32 + 15) & ~(uint64_t)15);
+    CK(cudaMemsetAsync(ctx->b_qual.p, 0, 32, s));
+    CK(cudaMemsetAsync(d_qual + d.n_bases, 0, 32, s));
+    CK(cudaMemcpyAsync(d_qual, quals, d.n_bases, cudaMemcpyHostToDevice, s));
     if (n) CK(cudaMemcpyAsync(ctx->b_screc.p, rec, n * sizeof(hlo_rec), cudaMemcpyHostToDevice, s));
     if (n && rec_cluster) CK(cudaMemcpyAsync(ctx->b_scclu.p, rec_cluster, n * 4, cudaMemcpyHostToDevice, s));
-    launch_score_records(d, ctx->b_qual.as<uint8_t>(), R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), ctx->b_screc.as<hlo_rec>(),
-                         rec_cluster ? ctx->b_scclu.as<uint32_t>() : nullptr, n, ctx->b_prob.as<double>(), mismatch_prob, min_read_len,
+    CK(cudaEventRecord(ctx->ev[ST_H2D], s));
+    launch_score_table(ctx->b_prob.as<double>(), mismatch_prob, ctx->b_prob.as<double>() + 128, s, &ctx->lc);
+    launch_qual_flags(d_qual, R->b_off.as<uint64_t>(), d.n_reads, d_qflag, s, &ctx->lc);
+    launch_score_records(d, d_qual, d_qflag, R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), ctx->b_screc.as<hlo_rec>(),
+                         rec_cluster ? ctx->b_scclu.as<uint32_t>() : nullptr, n, ctx->b_prob.as<double>() + 128, min_read_len,
                          ctx->b_scout.as<hlo_score>(), s, &ctx->lc);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
     if (n) CK(cudaMemcpyAsync(ctx->h_score.p, ctx->b_scout.p, n * sizeof(hlo_score), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[ST_D2H], s));
     CK(cudaStreamSynchronize(s));
+    {  // hlo_get_timing after this call: h2d_ms = uploads (qualities, records), verify_ms = the score kernel, d2h_ms, total_ms
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, ctx->ev[ST_BEGIN], ctx->ev[ST_H2D]) == cudaSuccess) ctx->tm.h2d_ms = v;
+        if (cudaEventElapsedTime(&v, ctx->ev[ST_H2D], ctx->ev[ST_VERIFY]) == cudaSuccess) ctx->tm.verify_ms = v;
+        if (cudaEventElapsedTime(&v, ctx->ev[ST_VERIFY], ctx->ev[ST_D2H]) == cudaSuccess) ctx->tm.d2h_ms = v;
+        if (cudaEventElapsedTime(&v, ctx->ev[ST_BEGIN], ctx->ev[ST_D2H]) == cudaSuccess) ctx->tm.total_ms = v;
+        ctx->tm.n_records = n, ctx->tm.n_reads = d.n_reads, ctx->tm.n_bases = d.n_bases;
+        ctx->tm.total_launches = ctx->lc.total;
+    }
     *out = ctx->h_score.as<hlo_score>();
     return HLO_OK;
 }

@@ -136,8 +136,13 @@ void launch_cluster_offsets(const uint32_t *uoff, const uint32_t *cluster_off, u
                             LaunchCounter *lc);
 
 // ---- score.cu -------------------------------------------------------------------------------
-void launch_score_records(const DevReads &r, const uint8_t *quals, const uint64_t *base_off, const uint32_t *cluster_off, const hlo_rec *rec,
-                          const uint32_t *rec_cluster, uint64_t n, const double *prob_tab, double mismatch_thr, uint32_t min_read_len,
-                          hlo_score *out, cudaStream_t s, LaunchCounter *lc);
+// log p for (match?, phred byte 1, phred byte 2): 2 * 128 * 128 doubles from the 128-entry phred -> probability table; NaN where
+// p < mismatch_thr
+void launch_score_table(const double *prob_tab, double mismatch_thr, double *tab, cudaStream_t s, LaunchCounter *lc);
+void launch_qual_flags(const uint8_t *quals, const uint64_t *base_off, uint32_t n_reads, uint8_t *qflag, cudaStream_t s, LaunchCounter *lc);
+// quals: padded by 32 readable bytes in front and behind
+void launch_score_records(const DevReads &r, const uint8_t *quals, const uint8_t *qflag, const uint64_t *base_off, const uint32_t *cluster_off,
+                          const hlo_rec *rec, const uint32_t *rec_cluster, uint64_t n, const double *tab, uint32_t min_read_len, hlo_score *out,
+                          cudaStream_t s, LaunchCounter *lc);
 
 }  // namespace hlo

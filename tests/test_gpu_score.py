@@ -49,6 +49,28 @@ def test_scores_multi_cluster_with_ambiguous_bases_and_ragged_lengths():
     check(synth.ReadBatch.concat(parts), seed=3)
 
 
+def test_scores_unusual_phred_bytes():
+    """reads with phred bytes outside 33..126 leave the shared-memory table (per-read flag) and take the general path"""
+    b = small_cluster(67, n_fragments=120)
+    ob = to_orc_batch(b)
+    rng = np.random.default_rng(6)
+    quals = random_quals(rng, len(ob.bases))
+    off = np.asarray(b.base_off)
+    for rd in rng.choice(b.n_reads, size=40, replace=False):
+        lo, hi = int(off[rd]), int(off[rd + 1])
+        quals[rng.integers(lo, hi, size=3)] = rng.integers(0, 128, size=3).astype(np.uint8)
+    with api.Context(0) as c:
+        R = c.pack(ob)
+        rec, aux, coff = c.overlap_batch(R)
+        got = c.score_records(R, quals, rec, aux["cluster"])
+        R.free()
+    want = orc.score_records(ob, quals, rec, aux["cluster"], 0.0, 0)
+    assert np.array_equal(got["mismatch_rate"], want[:, 1])
+    fin = np.isfinite(want[:, 0])
+    assert np.array_equal(np.isfinite(got["score"]), fin)
+    assert np.allclose(got["score"][fin], want[fin, 0], rtol=REL_TOL, atol=0.0)
+
+
 def test_scores_mismatch_threshold_and_min_read_len():
     b = small_cluster(64, err_rate=0.01)
     got = check(b, mismatch_prob=1e-3, seed=4)       # a low-quality mismatch has p < 1e-3 -> score 0
