@@ -254,7 +254,19 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # rank 0's stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") on stdout when the
+        # communicator comes up, so file descriptor 1 points at stderr until the first collective is through
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     C = args.clusters
     seeds = rank_cluster_seeds(rank, C)
     batch = synth.cluster_batch(C, seed0=seeds[0], **CLUSTER_KW)

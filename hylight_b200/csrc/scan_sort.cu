@@ -193,6 +193,15 @@ __global__ void rs_segments_kernel(const uint32_t *__restrict__ elem_off, const 
         seg_tile[n_seg] = t;
     }
 }
+// the same for many segments: starts and tile counts in parallel (seg_tile[n_seg] = 0), then an exclusive scan
+__global__ void rs_segments_wide_kernel(const uint32_t *__restrict__ elem_off, const uint32_t *__restrict__ seg_off, uint32_t n_seg,
+                                        uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_tile) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_seg) return;
+    const uint32_t a = elem_off[seg_off[c]];
+    seg_start[c] = a;
+    seg_tile[c] = c < n_seg ? (elem_off[seg_off[c + 1]] - a + RS_TILE - 1) / RS_TILE : 0u;
+}
 
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift,
                                                              uint32_t n_tiles, uint32_t *__restrict__ hist, RsSeg seg) {
@@ -489,7 +498,12 @@ int launch_radix_sort_segmented(uint64_t *keys[2], uint32_t *vals[2], uint64_t n
     uint32_t *scan_tmp = tmp + ((hist_n + 63) & ~63ull);
     uint32_t *seg_start = scan_tmp + scan_tmp_words(hist_n);
     uint32_t *seg_tile = seg_start + (((uint64_t)n_seg + 64) & ~63ull);
-    rs_segments_kernel<<<1, 256, 0, s>>>(elem_off, seg_off, n_seg, seg_start, seg_tile);
+    if (n_seg <= 2048) {
+        rs_segments_kernel<<<1, 256, 0, s>>>(elem_off, seg_off, n_seg, seg_start, seg_tile);
+    } else {  // (the histogram area is free until the first pass and large enough for the scan's partial sums)
+        rs_segments_wide_kernel<<<(n_seg + 1 + 255) / 256, 256, 0, s>>>(elem_off, seg_off, n_seg, seg_start, seg_tile);
+        launch_exclusive_scan(seg_tile, seg_tile, (uint64_t)n_seg + 1, hist, nullptr, s, lc);
+    }
     if (lc) lc->total++;
     RsSeg g;
     g.seg_start = seg_start, g.seg_tile = seg_tile, g.n_seg = n_seg;

@@ -616,3 +616,17 @@ def test_full_path_contigs_variable_length():
         with pytest.raises(api.HloError) as ei:
             c.pack(to_orc_batch(synth.ReadBatch.from_seqs([_contig_cluster(9, 3, 2600, 2700, genome_len=9000)])))
         assert "ungapped" in str(ei.value)
+
+
+def test_full_path_many_small_clusters(ctx):
+    """3000 clusters of a few reads each, empty ones in between: the segment table of the sort is built by the parallel
+    path (> 2048 segments)"""
+    rng = np.random.default_rng(31)
+    base = [bytes(s_) for s_ in small_cluster(76, n_fragments=400).cluster_reads(0)]
+    clusters, i = [], 0
+    for c in range(3000):
+        k = int(rng.integers(0, 7)) if c % 50 else 0
+        clusters.append([base[(i + j) % len(base)] for j in range(k)])
+        i += k
+    rec, coff, tm = check_full(ctx, synth.ReadBatch.from_seqs(clusters))
+    assert tm["sort_fallback"] == 0 and len(coff) == 3001
