@@ -218,6 +218,8 @@ class Context:
         return _copy_out(p.value, n.value, CAND_DT)
 
     def _recs(self, r, copy=True):
+        if not r.rec and not r.rec16:  # option "d2h" = 0: only the count came back
+            return None, None, None
         rec = _copy_out(r.rec16, r.n, REC16_DT) if (r.rec16 and not r.rec) else _copy_out(r.rec, r.n, REC_DT)
         aux = _copy_out(r.aux, r.n, AUX_DT) if r.aux else None
         coff = _copy_out(r.cluster_off, r.n_clusters + 1, np.dtype("<u8")) if r.cluster_off else None

@@ -93,6 +93,7 @@ struct hlo_ctx {
     LaunchCounter lc;
     hlo_timing tm;
     int pairgen_slots_log2 = 8;
+    int pairgen_slots_auto = 0;  // raised by batches whose reads overflowed the tables
     int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0, sort_prefix = 1, sort_hash_bits = 0, sort_segmented = 1;
     bool prefix_used = false, prefix_failed = false;
     int sorted_buf = 0;  // which of b_keys / b_vals holds the grouped pairs of the last run_index
@@ -105,7 +106,7 @@ struct hlo_ctx {
     VerifyTables tab{};
     // workspaces
     DevBuf b_cnt, b_mzoff, b_mzx, b_mzrr, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
-    DevBuf b_cands, b_counters, b_ovf, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
+    DevBuf b_cands, b_counters, b_ovf, b_ovf2, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
     DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp, b_qual, b_screc, b_scclu, b_scout, b_prob;
     PinBuf h_score;
     bool prob_ready = false;
@@ -279,7 +280,7 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->b_tab, &ctx->b_cnt, &ctx->b_mzoff, &ctx->b_mzx, &ctx->b_mzrr, &ctx->b_keys[0],
                       &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_bstart,
-                      &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovfcnt, &ctx->b_gkeys,
+                      &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovf2, &ctx->b_ovfcnt, &ctx->b_gkeys,
                       &ctx->b_gmn, &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos,
                       &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx, &ctx->b_sx, &ctx->b_srp, &ctx->b_qual, &ctx->b_screc, &ctx->b_scclu, &ctx->b_scout, &ctx->b_prob};
     for (DevBuf *b : bufs) b->release();
@@ -656,6 +657,8 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
     return HLO_OK;
 }
 
+constexpr int PAIRGEN_WIDE_SLOTS_LOG2 = 11;
+
 static uint32_t next_pow2_u32(uint32_t v) {
     uint32_t p = 1;
     while (p < v) p <<= 1;
@@ -680,6 +683,8 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
     a.overflow_reads = ctx->b_ovf.as<uint32_t>(), a.overflow_cap = d.n_reads;
     const bool fast = pairgen_fast_supported(d, &a.dg_bits) && !ctx->pairgen_generic;
     unsigned long long hc[13];
+    bool wide_pass = false;
+    const int slots0 = std::max(ctx->pairgen_slots_log2, ctx->pairgen_slots_auto);
     ctx->prefix_failed = false;
     if (ctx->prefix_used && !fast) {  // the fast path reads the prefix sort's flag with its own counters below
         unsigned long long flag = 0;
@@ -697,7 +702,7 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
         uint32_t n_list = d.n_reads;        // reads the generic kernel has to do
         const uint32_t *list = nullptr;     // nullptr = all of them
         if (fast) {
-            launch_pairgen(a, ctx->pairgen_slots_log2, s, &ctx->lc);
+            launch_pairgen(a, slots0, s, &ctx->lc);
             CK(cudaGetLastError());
             FETCH(hc, ctx->b_counters.p, sizeof hc);
             if (ctx->prefix_used && (hc[12] >> 32)) {  // a mixed prefix group was too large to repair: the caller redoes the index
@@ -706,6 +711,31 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
                 return HLO_OK;
             }
             n_list = (uint32_t)hc[2], list = a.overflow_reads;
+            const uint32_t first_overflow = n_list;
+            // reads with more (target, strand, diagonal) chains than the table holds (deep coverage, longer reads) go through
+            // the same kernel again with tables twice the size, up to 2048 slots, before the HBM-table kernel gets what is
+            // left.  (Straight to the largest tables is slow: one block per SM and a 16 KB table to clear per read.)
+            uint32_t *lists[2] = {ctx->b_ovf.as<uint32_t>(), nullptr};
+            int from = 0;
+            for (int sl = slots0 + 1; n_list && sl <= PAIRGEN_WIDE_SLOTS_LOG2; ++sl) {
+                if (!lists[1]) {
+                    CK(ctx->b_ovf2.ensure((size_t)d.n_reads * 4 + 4));
+                    lists[1] = ctx->b_ovf2.as<uint32_t>();
+                }
+                PairgenArgs a2 = a;
+                a2.work = lists[from], a2.n_work = n_list;
+                a2.overflow_reads = lists[from ^ 1];
+                CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 2, 0, 16, s));  // overflow count, work counter
+                launch_pairgen(a2, sl, s, &ctx->lc);
+                CK(cudaGetLastError());
+                FETCH(hc, ctx->b_counters.p, sizeof hc);
+                n_list = (uint32_t)hc[2], list = lists[from ^ 1];
+                from ^= 1;
+                wide_pass = true;
+            }
+            if (wide_pass) ctx->tm.n_overflow_reads = first_overflow;  // (reads that left the first table size)
+            // a batch that overflowed a lot: the following ones start with larger tables
+            if (attempt == 0 && first_overflow > d.n_reads / 16 && ctx->pairgen_slots_auto < 10) ctx->pairgen_slots_auto = slots0 + 1;
         }
         if (n_list) {  // exact path with tables in HBM, in chunks that bound the table memory
             CK(ctx->b_ovfcnt.ensure((size_t)n_list * 4 + 4));
@@ -751,7 +781,7 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
             }
             FETCH(hc, ctx->b_counters.p, sizeof hc);
         }
-        ctx->tm.n_overflow_reads = fast ? n_list : 0;
+        if (!wide_pass) ctx->tm.n_overflow_reads = fast ? n_list : 0;
         ctx->tm.n_seed_hits = hc[1];
         if (hc[0] <= cap) {
             *n_out = hc[0];
@@ -1119,6 +1149,7 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "pairgen_slots_log2")) {
         if (value < 5 || value > 10) FAIL(HLO_ERANGE, "pairgen_slots_log2=%lld outside [5,10]", (long long)value);
         ctx->pairgen_slots_log2 = (int)value;
+        ctx->pairgen_slots_auto = 0;
         return HLO_OK;
     }
     FAIL(HLO_EINVAL, "unknown option %s", name);

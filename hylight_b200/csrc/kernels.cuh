@@ -91,6 +91,8 @@ struct PairgenArgs {
     void *cands;             // output, 16 B per candidate
     uint64_t cand_cap;
     unsigned long long *counters;  // [0] candidates, [1] seed hits, [2] overflow reads, [3] work counter
+    const uint32_t *work = nullptr;  // fast path only: x indices of the reads to do (nullptr: all reads)
+    uint32_t n_work = 0;
     uint32_t *overflow_reads;      // x indices of the reads whose shared-memory table overflowed
     uint32_t overflow_cap;
 };

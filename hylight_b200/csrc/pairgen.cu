@@ -213,16 +213,17 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     const unsigned lt8 = (1u << l) - 1u;
     const int kshift = a.dg_bits + 1;
     const uint32_t max_len = a.reads.max_len;
-    const uint32_t n_reads = a.reads.n_reads;
+    const uint32_t n_work = a.work ? a.n_work : a.reads.n_reads;  // the listed reads (x indices), or all of them
     const int gap_min = a.gap_min;
     unsigned long long nh_total = 0;
     for (;;) {
         unsigned long long qq = 0;
         if (lane == 0) qq = atomicAdd(&a.counters[3], (unsigned long long)PG_RPW);
         qq = __shfl_sync(FULL, qq, 0);
-        if (qq >= n_reads) break;
-        const uint32_t xq = (uint32_t)qq + lane / PG_G;
-        const bool have_read = xq < n_reads;
+        if (qq >= n_work) break;
+        const uint32_t wi = (uint32_t)qq + lane / PG_G;
+        const bool have_read = wi < n_work;
+        const uint32_t xq = !have_read ? 0u : a.work ? __ldg(a.work + wi) : wi;
         uint32_t m0 = 0, m1 = 0, q = 0, lq = 0, cb = 0;
         if (have_read) {
             m0 = __ldg(a.mz_off + xq), m1 = __ldg(a.mz_off + xq + 1);
@@ -407,7 +408,8 @@ bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out) {
 }
 
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc) {
-    if (a.reads.n_reads == 0) return;
+    const uint32_t n_work = a.work ? a.n_work : a.reads.n_reads;
+    if (n_work == 0) return;
     const bool narrow = pairgen_narrow(a.reads, slots_log2);
     const size_t smem = pairgen_smem_bytes(slots_log2, narrow);
     void (*kern)(PairgenArgs, int) = narrow ? pairgen_group_kernel<true> : pairgen_group_kernel<false>;
@@ -417,7 +419,7 @@ void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, Launch
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PG_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = ((uint64_t)a.reads.n_reads + PG_GROUPS - 1) / PG_GROUPS;  // 4 reads per warp, 4 warps per block
+    uint64_t want = ((uint64_t)n_work + PG_GROUPS - 1) / PG_GROUPS;
     uint64_t grid = (uint64_t)sms * per_sm;
     if (grid > want) grid = want;
     kern<<<(unsigned)grid, PG_THREADS, smem, s>>>(a, slots_log2);
