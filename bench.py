@@ -335,7 +335,7 @@ def run_ours(args):
                 "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": vbytes,
                 "ms_per_launch": stages["verify_fast_ms"], "mean_overlap_len": mean_ol, "peak_source": peak_src,
                 "note": "traffic < algorithmic bytes: the rows of a cluster (1.4 MB per strand) are re-read from L2; the kernel is "
-                        "bound by the integer (ALU) pipe, 63% utilised (profiles/r1h_verify.md)"}
+                        "bound by the integer (ALU) pipe, 72% utilised (profiles/r1k_final.md)"}
 
     # ---- end-to-end leg: pinned host buffers -> hlo_overlap_host -> records on the host
     pb = api.PinnedArray(batch.bases.nbytes)
