@@ -148,13 +148,15 @@ def test_candidates_multi_cluster_and_ids(ctx):
 
 
 def test_candidates_table_overflow_path(ctx):
-    # 64 slots per warp force most reads through the exact global-memory table
-    ctx.set_option("pairgen_slots_log2", 6)
-    try:
-        _, tm = check_candidates(ctx, small_cluster(25, n_fragments=300, n_strains=1, strain_cov=40.0))
-        assert tm["n_overflow_reads"] > 0
-    finally:
-        ctx.set_option("pairgen_slots_log2", 10)
+    """64-slot tables overflow for most reads: they go through the kernel again with 128 ... 2048 slots"""
+    b = small_cluster(25, n_fragments=300, n_strains=1, strain_cov=40.0)
+    for slots in (6, 5):
+        ctx.set_option("pairgen_slots_log2", slots)
+        try:
+            _, tm = check_candidates(ctx, b)
+            assert tm["n_overflow_reads"] > 0
+        finally:
+            ctx.set_option("pairgen_slots_log2", 8)
 
 
 def test_candidates_mid_occ_and_params(ctx):
