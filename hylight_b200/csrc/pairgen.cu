@@ -13,16 +13,18 @@
 // the bucket entries AFTER its own entry (minus further entries of the same read).  No name comparison
 // and no wasted half of the bucket.
 //
-// pairgen_group_kernel: 8 lanes per query read (4 reads per warp, 16 per block).  The lanes stream the
-// suffix of each of the read's buckets from the hash-ordered hit array (coalesced 8-byte entries) and fold
-// every hit into the group's shared-memory hash table keyed by a 32-bit (t - cluster base, strand,
-// diagonal) that keeps min/max anchor position — the warp-level dedup of the north star.  Within one
-// query minimizer all keys are distinct, so only the key claim is an atomic (ATOMS.CAS; a claim by plain
-// store + read-back after __syncwarp was measured slower); min/max are plain read-modify-writes ordered
-// by a __syncwarp per minimizer.  Claimed slots go to a per-read list and the number of qualifying chains
-// is counted while inserting, so the emission is one pass over ~100 list entries instead of two over the
-// table.  Bucket ranges and hits are loaded one step ahead of their use.
-// A read whose table overflows, or a batch whose keys do not fit 32 bits, is done exactly by
+// pairgen_group_kernel: 16 lanes per query read (2 reads per warp, 8 per block).  The non-empty bucket suffixes
+// of the read are staged in shared memory and walked as one flat sequence of chunks (16 hits of one minimizer):
+// the lanes stream the hits from the hash-ordered hit array (coalesced 8-byte entries, loaded one chunk ahead) and
+// fold each into the group's shared-memory hash table keyed by a 32-bit (t - cluster base, strand, diagonal) that
+// keeps min/max anchor position — the warp-level dedup of the north star.  Within one chunk all keys are
+// distinct, so only the key claim is an atomic (ATOMS.CAS; a claim by plain store + read-back after __syncwarp,
+// and a plain load before the CAS, were measured slower); min/max are plain read-modify-writes ordered by a
+// __syncwarp per chunk.  Claimed slots go to a per-read list and the number of qualifying chains is counted
+// while inserting, so the emission is one pass over ~100 list entries instead of two over the table.  Lane use is
+// set by the chunk granularity (a bucket suffix holds ~12 hits): ~53 % (profiles/r1k_final.md).
+// Reads whose table overflows run again with tables of twice the size (ctx.cu:run_pairgen).
+// A read that overflows even 2048 slots, or a batch whose keys do not fit 32 bits, is done exactly by
 // pairgen_generic_kernel with a 64-bit-keyed table in HBM.
 // Algorithmic bytes: 8 B per seed hit in + 16 B per candidate out.
 #include <type_traits>
@@ -246,97 +248,104 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         __syncwarp();
         uint32_t nh = 0, nq = 0, list_n = 0;
         bool ovf = false;
-        // The minimizers are taken PG_STAGE at a time.  Their bucket ranges are staged in shared memory without the empty
-        // ones and with the long ones (more than one chunk of PG_G hits) first: the two reads of the warp run in
-        // lockstep, so pairing long with long and short with short wastes fewer chunks, steps without hits vanish, and
-        // a step reads its range with one broadcast LDS instead of address arithmetic + two global loads.
+        // The minimizers are taken PG_STAGE at a time: their non-empty bucket ranges are staged in shared memory, and the
+        // read then walks ONE flat sequence of chunks (PG_G hits of one minimizer each).  The two reads of the warp run
+        // in lockstep chunk by chunk, not minimizer by minimizer: a short range of one read no longer idles while the
+        // other read finishes a long one, steps without hits vanish, and there is no per-minimizer prologue — moving on
+        // to the next range is a few predicated instructions inside the chunk loop.
         for (uint32_t mb = 0; mb < nm_max; mb += PG_STAGE) {
-            uint32_t n_eff = 0;
+            uint32_t n_eff = 0, n_chunks = 0;
             {
                 uint2 rg_r[PG_STAGE / PG_G];
                 uint32_t qrp_r[PG_STAGE / PG_G];
-                unsigned big_b[PG_STAGE / PG_G], small_b[PG_STAGE / PG_G];
-                uint32_t n_big = 0, n_small = 0;
+                unsigned has_b[PG_STAGE / PG_G];
+                uint32_t my_chunks = 0;
 #pragma unroll
                 for (int rr = 0; rr < PG_STAGE / PG_G; ++rr) {
                     const uint32_t idx = mb + rr * PG_G + l;
                     rg_r[rr] = make_uint2(0u, 0u), qrp_r[rr] = 0u;
                     if (idx < nm) rg_r[rr] = __ldg(a.range + m0 + idx), qrp_r[rr] = __ldg(&a.mz_rr[m0 + idx].y);
                     const uint32_t sz = rg_r[rr].y - rg_r[rr].x;
-                    big_b[rr] = (__ballot_sync(FULL, sz > (uint32_t)PG_G) >> gshift) & PG_GMASK;
-                    small_b[rr] = (__ballot_sync(FULL, sz != 0u && sz <= (uint32_t)PG_G) >> gshift) & PG_GMASK;
-                    n_big += __popc(big_b[rr]), n_small += __popc(small_b[rr]);
+                    has_b[rr] = (__ballot_sync(FULL, sz != 0u) >> gshift) & PG_GMASK;
+                    my_chunks += (sz + PG_G - 1) / PG_G;
                 }
-                uint32_t pb = 0, ps = n_big;
+                uint32_t pos = 0;
 #pragma unroll
                 for (int rr = 0; rr < PG_STAGE / PG_G; ++rr) {
-                    const uint32_t sz = rg_r[rr].y - rg_r[rr].x;
-                    if (sz > (uint32_t)PG_G) stg[pb + __popc(big_b[rr] & lt8)] = make_uint4(rg_r[rr].x, rg_r[rr].y, qrp_r[rr], 0u);
-                    else if (sz != 0u) stg[ps + __popc(small_b[rr] & lt8)] = make_uint4(rg_r[rr].x, rg_r[rr].y, qrp_r[rr], 0u);
-                    pb += __popc(big_b[rr]), ps += __popc(small_b[rr]);
+                    if (rg_r[rr].y != rg_r[rr].x) stg[pos + __popc(has_b[rr] & lt8)] = make_uint4(rg_r[rr].x, rg_r[rr].y, qrp_r[rr], 0u);
+                    pos += __popc(has_b[rr]);
                 }
-                n_eff = n_big + n_small;
+                n_eff = pos;
+                // chunks of this read = sum over its lanes
+#pragma unroll
+                for (int dd = PG_G / 2; dd > 0; dd >>= 1) my_chunks += __shfl_xor_sync(FULL, my_chunks, dd);
+                n_chunks = my_chunks;
             }
             __syncwarp();
-            const uint32_t steps = __reduce_max_sync(FULL, n_eff);
-            // the range of a step and the first chunk of its hits are loaded one step ahead, later chunks one chunk ahead
+            const uint32_t trips = __reduce_max_sync(FULL, n_chunks);
+            // current chunk = hits [i0, min(i0 + PG_G, end)) of the range with query position qrp; next staged entry in e_n
+            uint32_t i0 = 0, end = 0, qrp = 0, sidx = 0;
             uint4 e_n = make_uint4(0u, 0u, 0u, 0u);
-            if (n_eff) e_n = stg[0];
-            uint2 h_first = make_uint2(q, 0u);
-            if (e_n.x + l < e_n.y) h_first = __ldg(a.hits + e_n.x + l);
-            for (uint32_t s = 0; s < steps; ++s) {
-                const uint2 rg = make_uint2(e_n.x, e_n.y);
-                const uint32_t qrp = e_n.z;
-                e_n = make_uint4(0u, 0u, 0u, 0u);
-                if (s + 1 < n_eff) e_n = stg[s + 1];
-                const int qpos = (int)(qrp >> 1);
-                const uint32_t nchunk_max = __reduce_max_sync(FULL, (rg.y - rg.x + PG_G - 1) / PG_G);
-                uint32_t i = rg.x + l;
-                uint2 h_n = h_first;
-                h_first = make_uint2(q, 0u);
-                if (e_n.x + l < e_n.y) h_first = __ldg(a.hits + e_n.x + l);
-                for (uint32_t c = 0; c < nchunk_max; ++c, i += PG_G) {
-                    const uint2 h = h_n;
-                    const bool in_range = i < rg.y;
-                    if (i + PG_G < rg.y) h_n = __ldg(a.hits + i + PG_G);
-                    int newslot = -1;
-                    if (in_range && h.x != q) {  // h.x == q: another minimizer of the query itself (-X: no self hits)
-                        const uint32_t t = h.x;
-                        ++nh;
-                        const uint32_t strand = (h.y ^ qrp) & 1u;
-                        const int tp = (int)((h.y >> 1) & 0x7fffu);
-                        const int qpi = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
-                        const int diag = tp - qpi;
-                        const uint32_t qp = (uint32_t)qpi;
-                        const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
-                        uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
-                        // claim-or-find, then ONE update path for both outcomes: a fresh slot holds (min = all ones, max = 0),
-                        // so "min/max with qp" initialises it and its old span (negative) is below any threshold
-                        bool done = false;
-                        uint32_t old = 0;
-                        for (uint32_t probe = 0; probe < S; ++probe) {
-                            old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
-                            if (old == HLO_EMPTY32 || old == key) {
-                                done = true;
-                                break;
-                            }
-                            slot = (slot + 1u) & smask;
-                        }
-                        if (done) {  // no other lane of the group holds this key in this step: plain read-modify-write
-                            const uint32_t v = vals[slot];
-                            const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
-                            vals[slot] = (val_t)(mn | mx << VSH);
-                            nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
-                            if (old == HLO_EMPTY32) newslot = (int)slot;
-                        }
-                        if (!done) ovf = true;
-                    }
-                    // remember the claimed slots (per-group list, positions from a ballot: no atomics)
-                    const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & PG_GMASK;
-                    if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
-                    list_n += __popc(gb);
+            if (n_eff) {
+                const uint4 e0 = stg[0];
+                i0 = e0.x, end = e0.y, qrp = e0.z;
+                if (n_eff > 1) e_n = stg[1];
+            }
+            uint2 h_n = make_uint2(q, 0u);
+            if (i0 + l < end) h_n = __ldg(a.hits + i0 + l);
+            for (uint32_t c = 0; c < trips; ++c) {
+                const uint2 h = h_n;
+                const bool in_range = i0 + l < end;
+                const uint32_t qrp_c = qrp;
+                // the chunk after this one: the rest of the range, or the start of the next staged range
+                if (i0 + PG_G < end) {
+                    i0 += PG_G;
+                } else {
+                    i0 = e_n.x, end = e_n.y, qrp = e_n.z;
+                    ++sidx;
+                    e_n = make_uint4(0u, 0u, 0u, 0u);
+                    if (sidx + 1 < n_eff) e_n = stg[sidx + 1];
                 }
-                __syncwarp();  // orders the plain min/max updates of consecutive minimizers
+                h_n = make_uint2(q, 0u);
+                if (i0 + l < end) h_n = __ldg(a.hits + i0 + l);
+                int newslot = -1;
+                if (in_range && h.x != q) {  // h.x == q: another minimizer of the query itself (-X: no self hits)
+                    const uint32_t t = h.x;
+                    ++nh;
+                    const int qpos = (int)(qrp_c >> 1);
+                    const uint32_t strand = (h.y ^ qrp_c) & 1u;
+                    const int tp = (int)((h.y >> 1) & 0x7fffu);
+                    const int qpi = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
+                    const int diag = tp - qpi;
+                    const uint32_t qp = (uint32_t)qpi;
+                    const uint32_t key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
+                    uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
+                    // claim-or-find, then ONE update path for both outcomes: a fresh slot holds (min = all ones, max = 0),
+                    // so "min/max with qp" initialises it and its old span (negative) is below any threshold
+                    bool done = false;
+                    uint32_t old = 0;
+                    for (uint32_t probe = 0; probe < S; ++probe) {
+                        old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
+                        if (old == HLO_EMPTY32 || old == key) {
+                            done = true;
+                            break;
+                        }
+                        slot = (slot + 1u) & smask;
+                    }
+                    if (done) {  // no other lane of the group holds this key in this chunk: plain read-modify-write
+                        const uint32_t v = vals[slot];
+                        const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
+                        vals[slot] = (val_t)(mn | mx << VSH);
+                        nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
+                        if (old == HLO_EMPTY32) newslot = (int)slot;
+                    }
+                    if (!done) ovf = true;
+                }
+                // remember the claimed slots (per-group list, positions from a ballot: no atomics)
+                const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & PG_GMASK;
+                if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
+                list_n += __popc(gb);
+                __syncwarp();  // orders the plain min/max updates of consecutive chunks (they may belong to different minimizers)
             }
             __syncwarp();  // the staging area is rewritten by the next batch
         }
