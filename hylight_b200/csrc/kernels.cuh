@@ -67,7 +67,6 @@ void launch_unpermute_pairs(const uint64_t *keys, const uint32_t *vals, uint64_t
 
 // up to 64 words from device memory to (mapped) host memory: the read-back path for counters
 void launch_copy_words(const uint32_t *src, uint32_t *dst, uint32_t n, cudaStream_t s, LaunchCounter *lc);
-void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, LaunchCounter *lc);
 
 // ---- pairgen.cu -----------------------------------------------------------------------------
 // index build on the hash-sorted minimizers

@@ -527,15 +527,6 @@ void launch_copy_words(const uint32_t *src, uint32_t *dst, uint32_t n, cudaStrea
     copy_words_kernel<<<1, 64, 0, s>>>(src, dst, n);
     if (lc) lc->total++;
 }
-__global__ void fill_kernel(uint32_t *v, uint32_t value, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = value;
-}
-void launch_fill_u32(uint32_t *v, uint32_t value, uint64_t n, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(v, value, n);
-    if (lc) lc->total++;
-}
 
 // ---- grouping by a PREFIX of the key -------------------------------------------------------------------------
 // The index only needs equal keys adjacent, in stable order — not the order between different keys.  Sorting on
