@@ -18,6 +18,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/hlovlp.h"
@@ -311,7 +312,9 @@ struct Shared {
 void worker(Shared *S, int device) {
     Options &o = *S->o;
     hlo_ctx *ctx = nullptr;
+    const auto tc0 = std::chrono::steady_clock::now();
     int rc = hlo_ctx_create(device, &o.P, &ctx);
+    double ctx_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
     if (rc) {
         std::lock_guard<std::mutex> g(S->log_mu);
         fprintf(stderr, "hylight-ovlp: device %d: %s\n", device, hlo_strerror(rc));
@@ -352,6 +355,7 @@ void worker(Shared *S, int device) {
                 std::vector<uint32_t>().swap(c.ids);
             }
         }
+        const auto t_parsed = std::chrono::steady_clock::now();
         hlo_reads *R = nullptr;
         const hlo_score *scores = nullptr;
         hlo_recs out{};
@@ -370,6 +374,7 @@ void worker(Shared *S, int device) {
             }
             if (rc) err = std::string(hlo_strerror(rc)) + ": " + hlo_last_error(ctx);
         }
+        const auto t_computed = std::chrono::steady_clock::now();
         if (err.empty()) {  // per-cluster files, written in parallel
             std::mutex emu;
             parallel_for(idx.size(), S->helpers, [&](size_t j) {
@@ -390,7 +395,11 @@ void worker(Shared *S, int device) {
         hlo_timing tm{};
         hlo_get_timing(ctx, &tm);
         if (R) hlo_reads_free(R);
-        const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        const auto t_end = std::chrono::steady_clock::now();
+        const double wall = std::chrono::duration<double, std::milli>(t_end - t0).count();
+        const double parse_ms = std::chrono::duration<double, std::milli>(t_parsed - t0).count();
+        const double call_ms = std::chrono::duration<double, std::milli>(t_computed - t_parsed).count();
+        const double write_ms = std::chrono::duration<double, std::milli>(t_end - t_computed).count();
         std::lock_guard<std::mutex> g(S->log_mu);
         if (!err.empty()) {
             fprintf(stderr, "hylight-ovlp: batch %zu on device %d failed: %s\n", b, device, err.c_str());
@@ -403,14 +412,19 @@ void worker(Shared *S, int device) {
                     "\"seed_hits\": %llu, \"candidates\": %llu, \"accepted\": %llu, \"records\": %llu, \"deferred\": %llu, "
                     "\"overflow_reads\": %llu, \"launches\": %llu, \"ms\": {\"h2d\": %.3f, \"pack\": %.3f, \"sketch\": %.3f, "
                     "\"sort\": %.3f, \"index\": %.3f, \"pairgen\": %.3f, \"verify\": %.3f, \"dedup\": %.3f, \"d2h\": %.3f, "
-                    "\"device_total\": %.3f, \"wall\": %.3f}}\n",
+                    "\"device_total\": %.3f, \"wall\": %.3f, \"host_parse\": %.3f, \"host_call\": %.3f, \"host_write\": %.3f, "
+                    "\"ctx_create\": %.3f}}\n",
                     b, device, idx.size(), (unsigned long long)tm.n_reads, (unsigned long long)tm.n_bases,
                     (unsigned long long)tm.n_minimizers, (unsigned long long)tm.n_seed_hits, (unsigned long long)tm.n_candidates,
                     (unsigned long long)tm.n_accepted, (unsigned long long)tm.n_records, (unsigned long long)tm.n_deferred,
                     (unsigned long long)tm.n_overflow_reads, (unsigned long long)tm.total_launches, tm.h2d_ms, tm.pack_ms,
-                    tm.sketch_ms, tm.sort_ms, tm.index_ms, tm.pairgen_ms, tm.verify_ms, tm.dedup_ms, tm.d2h_ms, tm.total_ms, wall);
+                    tm.sketch_ms, tm.sort_ms, tm.index_ms, tm.pairgen_ms, tm.verify_ms, tm.dedup_ms, tm.d2h_ms, tm.total_ms, wall, parse_ms,
+                    call_ms, write_ms, ctx_ms);
+        ctx_ms = 0.0;  // (reported with the worker's first batch)
     }
-    hlo_ctx_destroy(ctx);
+    // no hlo_ctx_destroy: the process is about to end, and releasing gigabytes of device and pinned memory buffer by
+    // buffer (then the CUDA context) costs about a second that the operating system does not need
+    (void)ctx;
 }
 
 uint64_t file_size(const std::string &p) {
@@ -462,5 +476,6 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < n_workers; ++i) th.emplace_back(worker, &S, o.devices[i % o.devices.size()]);
     for (auto &t : th) t.join();
     if (S.stats && S.stats != stderr) fclose(S.stats);
-    return S.failed ? 1 : 0;
+    fflush(nullptr);
+    _exit(S.failed ? 1 : 0);  // every output file is closed (and renamed into place) by now; skip the CUDA teardown
 }
