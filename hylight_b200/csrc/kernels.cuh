@@ -95,7 +95,7 @@ struct PairgenArgs {
     uint32_t *overflow_reads;      // x indices of the reads whose shared-memory table overflowed
     uint32_t overflow_cap;
 };
-// fast path: 8 lanes per query read, seed table in shared memory (2^slots_log2 slots per read)
+// fast path: 16 lanes per query read, seed table in shared memory (2^slots_log2 slots per read)
 bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out);
 size_t pairgen_smem_bytes(int slots_log2, bool narrow);
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc);

@@ -178,8 +178,8 @@ __device__ __forceinline__ void emit_cand(const PairgenArgs &a, unsigned long lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast path: 8 lanes per query read, 4 reads per warp in LOCKSTEP (every loop bound is the maximum over
-// the warp's 4 reads, so the warp never diverges into per-read paths), table in shared memory
+// fast path: PG_G lanes per query read, PG_RPW reads per warp in LOCKSTEP (every loop bound is the maximum over
+// the warp's reads, so the warp never diverges into per-read paths), table in shared memory
 constexpr int PG_THREADS = 128;
 constexpr int PG_G = 16;                       // lanes per read (8 and 16 measured; 16: fewer, fuller chunks and less smem per block)
 constexpr unsigned PG_GMASK = PG_G == 32 ? 0xffffffffu : ((1u << PG_G) - 1u);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
             }
             __syncwarp();  // the staging area is rewritten by the next batch
         }
-        // per-read reductions inside the 8-lane groups (uniform across the warp)
+        // per-read reductions inside the lane groups (uniform across the warp)
         const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & PG_GMASK) != 0u;
         if (ovf_any) {  // redo this read exactly in the generic kernel (its hits are counted there)
             if (l == 0 && have_read) {
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         } else {
             nh_total += nh;
         }
-        // candidates of the read = group sum of nq; reserve space for the warp's 4 reads with one atomic
+        // candidates of the read = group sum of nq; reserve space for the warp's reads with one atomic
         uint32_t inc = nq;  // inclusive scan over the whole warp: groups are laid out consecutively
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
