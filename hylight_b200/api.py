@@ -15,6 +15,8 @@ CAND_DT = np.dtype([("q", "<u4"), ("t", "<u4"), ("diag", "<i4"), ("strand_anchor
 REC_DT = np.dtype([("idA", "<u4"), ("idB", "<u4"), ("OHA", "<i4"), ("OHB", "<i4"), ("OLA", "<u4"), ("OLB", "<u4"),
                    ("K", "<u4"), ("ori", "<u4")])
 REC16_DT = np.dtype([("idA", "<u4"), ("idB", "<u4"), ("OHA", "<i2"), ("OHB", "<i2"), ("OLA", "<u2"), ("K_ori", "<u2")])
+REC8_DT = np.dtype([("idA", "<u2"), ("idB", "<u2"), ("OHA", "<i2"), ("K_ori", "<u2")])
+SCORE_DT = np.dtype([("score", "<f8"), ("mismatch_rate", "<f8")])
 AUX_DT = np.dtype([("cluster", "<u4"), ("blocklen", "<u4")])
 MZ_DT = np.dtype([("x", "<u8"), ("y", "<u8")])
 
@@ -23,7 +25,9 @@ ABI_SYMBOLS = [
     "hlo_params_default", "hlo_abi_version", "hlo_strerror", "hlo_last_error", "hlo_device_count",
     "hlo_ctx_create", "hlo_ctx_destroy", "hlo_host_alloc", "hlo_host_free", "hlo_pack_reads", "hlo_reads_free",
     "hlo_sketch", "hlo_candidates", "hlo_verify", "hlo_overlap_batch", "hlo_overlap_host", "hlo_get_timing",
-    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records", "hlo_write_overlaps_scored", "hlo_write_overlaps16", "hlo_write_sfo16",
+    "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records",
+    "hlo_write_overlaps_scored", "hlo_write_overlaps16", "hlo_write_sfo16", "hlo_submit", "hlo_wait", "hlo_set_score_params",
+    "hlo_write_overlaps8", "hlo_write_sfo8", "hlo_write_binary16",
 ]
 
 
@@ -43,7 +47,13 @@ class Params(C.Structure):
 
 class Recs(C.Structure):
     _fields_ = [("rec", C.c_void_p), ("aux", C.c_void_p), ("n", C.c_uint64), ("cluster_off", C.c_void_p),
-                ("n_clusters", C.c_uint32), ("rec16", C.c_void_p)]
+                ("n_clusters", C.c_uint32), ("rec16", C.c_void_p), ("rec8", C.c_void_p), ("score", C.c_void_p)]
+
+
+class Batch(C.Structure):
+    """hlo_batch: the input of hlo_submit"""
+    _fields_ = [("bases", C.c_void_p), ("quals", C.c_void_p), ("base_off", C.c_void_p), ("n_reads", C.c_uint32),
+                ("cluster_off", C.c_void_p), ("n_clusters", C.c_uint32), ("ids", C.c_void_p)]
 
 
 class Timing(C.Structure):
@@ -51,7 +61,8 @@ class Timing(C.Structure):
                                          "verify_ms", "dedup_ms", "d2h_ms", "total_ms", "verify_fast_ms", "sort_fallback")] + \
                [(n, C.c_uint64) for n in ("n_reads", "n_bases", "n_minimizers", "n_seed_hits", "n_candidates",
                                           "n_accepted", "n_records", "n_deferred", "n_overflow_reads",
-                                          "verify_launches", "total_launches")]
+                                          "verify_launches", "total_launches", "digest", "n_reruns", "n_syncs")] + \
+               [("mid_occ_lo", C.c_uint32), ("mid_occ_hi", C.c_uint32), ("score_ms", C.c_float), ("reserved_", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -95,6 +106,15 @@ def lib():
                                         C.c_uint32, C.POINTER(C.c_void_p)]
         L.hlo_stream.restype = C.c_void_p
         L.hlo_stream.argtypes = [C.c_void_p]
+        L.hlo_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
+        L.hlo_wait.argtypes = [C.c_void_p, C.POINTER(Recs)]
+        L.hlo_set_score_params.argtypes = [C.c_void_p, C.c_double, C.c_uint32]
+        L.hlo_write_overlaps16.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p]
+        L.hlo_write_sfo16.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p]
+        L.hlo_write_overlaps8.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_char_p]
+        L.hlo_write_sfo8.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_char_p]
+        L.hlo_write_binary16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]
+        L.hlo_write_overlaps_scored.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]
         _lib = L
     return _lib
 
@@ -218,11 +238,17 @@ class Context:
         return _copy_out(p.value, n.value, CAND_DT)
 
     def _recs(self, r, copy=True):
-        if not r.rec and not r.rec16:  # option "d2h" = 0: only the count came back
+        if not r.rec and not r.rec16 and not r.rec8:  # option "d2h" = 0: only the count came back
             return None, None, None
-        rec = _copy_out(r.rec16, r.n, REC16_DT) if (r.rec16 and not r.rec) else _copy_out(r.rec, r.n, REC_DT)
+        if r.rec8:
+            rec = _copy_out(r.rec8, r.n, REC8_DT)
+        elif r.rec16:
+            rec = _copy_out(r.rec16, r.n, REC16_DT)
+        else:
+            rec = _copy_out(r.rec, r.n, REC_DT)
         aux = _copy_out(r.aux, r.n, AUX_DT) if r.aux else None
         coff = _copy_out(r.cluster_off, r.n_clusters + 1, np.dtype("<u8")) if r.cluster_off else None
+        self.last_score = _copy_out(r.score, r.n, SCORE_DT) if r.score else None
         return rec, aux, coff
 
     def verify(self, reads, cands):
@@ -248,6 +274,34 @@ class Context:
         coff = np.ascontiguousarray(batch.cluster_off, dtype=np.uint32)
         r = self.overlap_host_raw(_ptr(bases), _ptr(off), len(off) - 1, _ptr(coff), len(coff) - 1)
         return self._recs(r)
+
+    def submit(self, batch, quals=None, ids=None):
+        """hlo_submit: enqueue upload + the whole chain, return at once.  The arrays are kept alive until wait()."""
+        keep = [np.ascontiguousarray(batch.bases, dtype=np.uint8), np.ascontiguousarray(batch.base_off, dtype=np.uint64),
+                np.ascontiguousarray(batch.cluster_off, dtype=np.uint32),
+                None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8),
+                None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)]
+        b = Batch(_ptr(keep[0]), _ptr(keep[3]), _ptr(keep[1]), len(keep[1]) - 1, _ptr(keep[2]), len(keep[2]) - 1, _ptr(keep[4]))
+        self._inflight = keep
+        self._check(lib().hlo_submit(self.h, C.byref(b)))
+
+    def submit_raw(self, bases_ptr, off_ptr, n_reads, coff_ptr, n_clusters, quals_ptr=None):
+        b = Batch(bases_ptr, quals_ptr, off_ptr, n_reads, coff_ptr, n_clusters, None)
+        self._check(lib().hlo_submit(self.h, C.byref(b)))
+
+    def wait_raw(self):
+        r = Recs()
+        self._check(lib().hlo_wait(self.h, C.byref(r)))
+        return r
+
+    def wait(self):
+        """hlo_wait: (records, aux, cluster offsets); fused scores, when asked for, in self.last_score"""
+        r = self.wait_raw()
+        self._inflight = None
+        return self._recs(r)
+
+    def set_score_params(self, mismatch_prob=0.0, min_read_len=0):
+        self._check(lib().hlo_set_score_params(self.h, float(mismatch_prob), int(min_read_len)))
 
     def score_records(self, reads, quals, rec, rec_cluster=None, mismatch_prob=0.0, min_read_len=0):
         """HaploConduct's overlap_score per record (EdgeCalculator.cpp:67-139): array (n, 2) of (score, mismatch_rate)."""
@@ -280,13 +334,80 @@ def expand_rec16(rec16):
     return out
 
 
+def expand_rec8(rec8, len_by_id):
+    """hlo_rec8 array + read lengths by name -> hlo_rec array (hlo_rec8_expand of the header)"""
+    len_by_id = np.asarray(len_by_id, dtype=np.int64)
+    out = np.zeros(len(rec8), dtype=REC_DT)
+    a = rec8["OHA"].astype(np.int64)
+    la, lb = len_by_id[rec8["idA"]], len_by_id[rec8["idB"]]
+    out["idA"], out["idB"], out["OHA"], out["OHB"] = rec8["idA"], rec8["idB"], a, a + lb - la
+    ol = np.where(a >= 0, np.minimum(la - a, lb), np.minimum(lb + a, la))
+    out["OLA"], out["OLB"] = ol, ol
+    out["K"] = rec8["K_ori"] & 0x7fff
+    out["ori"] = rec8["K_ori"] >> 15
+    return out
+
+
+def _wr(fn, *args):
+    rc = fn(*args)
+    if rc:
+        raise HloError(rc, lib().hlo_strerror(rc).decode())
+
+
 def write_overlaps16(rec16, path):
     rec16 = np.ascontiguousarray(rec16, dtype=REC16_DT)
-    L = lib()
-    L.hlo_write_overlaps16.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p]
-    rc = L.hlo_write_overlaps16(_ptr(rec16), len(rec16), os.fsencode(path))
-    if rc:
-        raise HloError(rc, L.hlo_strerror(rc).decode())
+    _wr(lib().hlo_write_overlaps16, _ptr(rec16), len(rec16), os.fsencode(path))
+
+
+def write_overlaps8(rec8, len_by_id, path):
+    rec8 = np.ascontiguousarray(rec8, dtype=REC8_DT)
+    lens = np.ascontiguousarray(len_by_id, dtype=np.uint32)
+    _wr(lib().hlo_write_overlaps8, _ptr(rec8), len(rec8), _ptr(lens), len(lens), os.fsencode(path))
+
+
+def write_sfo8(rec8, len_by_id, path):
+    rec8 = np.ascontiguousarray(rec8, dtype=REC8_DT)
+    lens = np.ascontiguousarray(len_by_id, dtype=np.uint32)
+    _wr(lib().hlo_write_sfo8, _ptr(rec8), len(rec8), _ptr(lens), len(lens), os.fsencode(path))
+
+
+def write_binary16(rec16, path, score=None):
+    rec16 = np.ascontiguousarray(rec16, dtype=REC16_DT)
+    sc = None if score is None else np.ascontiguousarray(score, dtype=SCORE_DT)
+    _wr(lib().hlo_write_binary16, _ptr(rec16), _ptr(sc), len(rec16), os.fsencode(path))
+
+
+def read_binary16(path):
+    """reader of the binary hand-off file (the Python twin of the EdgeCalculator patch in INTEGRATION.md §5)"""
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"HLOB", "not a hylight-ovlp binary overlaps file"
+    version, rec_bytes, flags = np.frombuffer(raw, dtype="<u4", count=3, offset=4)
+    n = int(np.frombuffer(raw, dtype="<u8", count=1, offset=16)[0])
+    assert version == 1 and rec_bytes == REC16_DT.itemsize
+    rec = np.frombuffer(raw, dtype=REC16_DT, count=n, offset=32).copy()
+    score = np.frombuffer(raw, dtype=SCORE_DT, count=n, offset=32 + 16 * n).copy() if flags & 1 else None
+    return rec, score
+
+
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z):
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9))
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb))
+    return z ^ (z >> np.uint64(31))
+
+
+def records_digest(rec):
+    """hlo_timing.digest recomputed on the host from hlo_rec records (records.cu:rec_digest): order-independent sum"""
+    rec = np.ascontiguousarray(rec, dtype=REC_DT)
+    with np.errstate(over="ignore"):
+        w0 = rec["idA"].astype(np.uint64) | (rec["idB"].astype(np.uint64) << np.uint64(32))
+        w1 = rec["OHA"].astype(np.int64).astype(np.uint64) & np.uint64(0xffffffff) | \
+            ((rec["OHB"].astype(np.int64).astype(np.uint64) & np.uint64(0xffffffff)) << np.uint64(32))
+        w2 = rec["OLA"].astype(np.uint64) | (rec["K"].astype(np.uint64) << np.uint64(32)) | (rec["ori"].astype(np.uint64) << np.uint64(63))
+        h = _mix64(w0 ^ _mix64(w1 ^ _mix64(w2 + np.uint64(0x9e3779b97f4a7c15))))
+        return int(h.sum(dtype=np.uint64))
 
 
 def write_sfo(rec, path):

@@ -40,6 +40,29 @@ struct DevReads {
 };
 #define HLO_PAD_WORDS 64
 
+// One block of 64-bit device counters per context, zeroed once per batch and read back ONCE at its end: every stage
+// sizes its work from the counts its predecessor left here, so the host never waits between stages.
+enum Ctr : int {
+    C_AMB = 0,      // ambiguous bases in the batch (pack)
+    C_SK_OVF,       // reads the single-pass sketch kernel handed to the generic one
+    C_MZ,           // minimizers (low word written by the scan)
+    C_COLL,         // low word: mixed prefix groups repaired; high word: 1 when one was too large (full sort needed)
+    C_CAND,         // candidates (may exceed the buffer: then only counted)
+    C_HITS,         // seed hits
+    C_PG_OVF,       // [PG_PASSES] reads whose table overflowed in pass p
+    C_PG_WORK = C_PG_OVF + 5,  // [PG_PASSES] work-stealing counters of the pair generator passes
+    C_ACC = C_PG_WORK + 5,     // accepted records
+    C_DEF,          // candidates deferred to the exact verify kernel
+    C_NOUT,         // records after the per-pair dedup (low word written by the scan)
+    C_FLAGS,        // HLO_FLAG_*
+    C_DIGEST,       // order-independent sum of a 64-bit mix of every output record
+    C_MIDOCC_LO,    // smallest / largest per-cluster occurrence cut-off of the batch
+    C_MIDOCC_HI,
+    C_COUNT = 32
+};
+#define HLO_PG_PASSES 5
+#define HLO_FLAG_MIDOCC_AMBIGUOUS 1ull  // a cluster's occurrence quantile fell into the clamp bin of the histogram
+
 #define HLO_MAX_W_PUBLIC 32  // window sizes the sketch kernel keeps in its per-thread ring
 #define HLO_LEN_MASK 0x7fffffffu
 #define HLO_AMB_FLAG 0x80000000u

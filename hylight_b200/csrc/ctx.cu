@@ -1,9 +1,15 @@
 // ctx.cu — C ABI of libhlovlp (include/hlovlp.h): context, packing, stage orchestration, timing.
 //
-// One ctx = one CUDA device + one stream.  All device work of a call is enqueued on the ctx stream;
-// stage boundaries are marked with CUDA events so that hlo_get_timing reports device time per stage.
-// There is deliberately no CPU code path for any stage: every entry point fails with HLO_ENODEV /
-// HLO_ECUDA when the device is missing.
+// One ctx = one CUDA device + one stream.  A batch is ENQUEUED as a whole — upload, 2-bit packing, sketch, segmented
+// radix sort, bucket index, pair generation (all table sizes), verify, records tail, optional score — without the host
+// waiting for the device in between: every stage takes its element count from a block of device counters (common.cuh:
+// Ctr) its predecessor left there, grids are sized from upper bounds and stride, and buffers are sized from estimates
+// learned from earlier batches.  hlo_wait reads the counter block once; a buffer that turned out too small makes it
+// grow the estimate and enqueue the batch again (hlo_timing.n_reruns: first batches of a new workload only).  The
+// one thing that needs a host decision inside a batch is the size of the record download.
+// Stage boundaries are marked with CUDA events so that hlo_get_timing reports device time per stage.
+// There is deliberately no CPU code path for any stage: every entry point fails with HLO_ENODEV / HLO_ECUDA when the
+// device is missing.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -67,7 +73,7 @@ struct PinBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum Stage { ST_BEGIN = 0, ST_H2D, ST_PACK, ST_SKETCH, ST_SORT, ST_INDEX, ST_PAIRGEN, ST_VERIFY, ST_DEDUP, ST_D2H, ST_COUNT };
+enum Stage { ST_BEGIN = 0, ST_H2D, ST_PACK, ST_SKETCH, ST_SORT, ST_INDEX, ST_PAIRGEN, ST_VERIFY, ST_DEDUP, ST_SCORE, ST_D2H, ST_COUNT };
 
 }  // namespace
 
@@ -75,12 +81,14 @@ struct hlo_reads {
     hlo_ctx *ctx = nullptr;
     int device = -1;
     DevReads d;
-    DevBuf b_ascii, b_off, b_coff, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_meta, b_bases, b_amb, b_ambcount;
+    DevBuf b_ascii, b_off, b_coff, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_meta, b_bases, b_amb, b_qual, b_ambcount;
     std::vector<uint32_t> h_len, h_ids, h_cidx, h_cluster_off, h_perm;
+    uint32_t max_id = 0;       // largest read name of the batch (decides whether 8-byte records can hold the names)
+    bool has_quals = false;    // b_qual holds the phred strings (32 bytes of padding in front, then a flag byte per read)
     float h2d_ms = 0.f, pack_ms = 0.f;
     void release() {
         b_ascii.release(), b_off.release(), b_coff.release(), b_len.release(), b_cbase.release(), b_cidx.release(), b_ids.release();
-        b_nrank.release(), b_perm.release(), b_meta.release(), b_bases.release(), b_amb.release(), b_ambcount.release();
+        b_nrank.release(), b_perm.release(), b_meta.release(), b_bases.release(), b_amb.release(), b_qual.release(), b_ambcount.release();
     }
 };
 
@@ -89,32 +97,46 @@ struct hlo_ctx {
     hlo_params P;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaEvent_t ev_vf[2] = {}, ev_compute_done = nullptr;
     std::string err;
     LaunchCounter lc;
     hlo_timing tm;
+    // options
     int pairgen_slots_log2 = 8;
     int pairgen_slots_auto = 0;  // raised by batches whose reads overflowed the tables
-    int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0, sort_prefix = 1, sort_hash_bits = 0, sort_segmented = 1;
-    bool prefix_used = false, prefix_failed = false;
-    int sorted_buf = 0;  // which of b_keys / b_vals holds the grouped pairs of the last run_index
-    bool keys_ready = false;
-    uint32_t *mapped_host = nullptr, *mapped_dev = nullptr;  // 256 B of mapped pinned memory (fetch_small)
-    cudaEvent_t ev_vf[2] = {};
+    int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0, sort_prefix = 1,
+        sort_hash_bits = 0, sort_segmented = 1, scores = 0, digest = 0, cap_scale_pct = 100, serialize_compute = 1;
+    double score_mismatch_prob = 0.0;
+    uint32_t score_min_read_len = 0;
+    // what earlier batches needed, per unit of the quantity the estimate scales with (0 = nothing learned yet)
+    double need_mz_per_base = 0.0, need_c_per_mz = 0.0, need_a_per_mz = 0.0;
+    // the batch in flight
+    uint64_t cap_mz = 0, cap_c = 0, cap_a = 0;   // entries the minimizer / candidate / record arrays of this enqueue hold
+    uint64_t min_mz = 0, min_c = 0, min_a = 0;   // lower bounds a rerun imposes
+    bool force_full_sort = false;                // rerun after a hash-prefix group was too large to repair
+    bool prefix_used = false;
+    int n_pg_passes = 0;                         // shared-memory pair generator passes enqueued (table sizes slots0 ..)
+    bool fast_pairgen = false;
+    bool inflight = false;
+    int rec_form = 0;                            // 0 hlo_rec, 1 hlo_rec16, 2 hlo_rec8: what this batch downloads
+    bool want_score = false;
+    unsigned long long *mapped_host = nullptr, *mapped_dev = nullptr;  // the counter block as the host sees it (mapped pinned memory)
+    unsigned long long hc[C_COUNT] = {};         // ... copied out after the wait
     // verify tables
     DevBuf b_tab;
     int tab_len = -1;
     VerifyTables tab{};
     // workspaces
-    DevBuf b_cnt, b_mzoff, b_mzx, b_mzrr, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_bstart, b_range, b_hits;
+    DevBuf b_cnt, b_mzoff, b_mzx, b_mzrr, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_range, b_hits, b_midocc, b_hist, b_seg1;
     DevBuf b_cands, b_counters, b_ovf, b_ovf2, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
-    DevBuf b_rec16, b_deferred, b_best, b_pos, b_out, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp, b_qual, b_screc, b_scclu, b_scout, b_prob;
+    DevBuf b_rec16, b_deferred, b_best, b_pos, b_slot, b_ent, b_entg, b_out, b_outc, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp;
+    DevBuf b_qual, b_screc, b_scclu, b_scout, b_prob;
     PinBuf h_score;
     bool prob_ready = false;
+    double prob_thr = -1.0;  // mismatch threshold the log-p table on the device was built for
     PinBuf h_out, h_aux, h_coff, h_mz, h_roff, h_cands, h_rec16, h_small;
-    std::vector<uint64_t> v_coff;
     hlo_reads scratch_reads;
-    // sketch state of the last run (device)
-    uint64_t n_mz = 0;
+    uint64_t n_mz = 0;  // minimizers of the last finished run
 };
 
 #define CK(call)                                                                                      \
@@ -129,15 +151,6 @@ struct hlo_ctx {
         }                                                                                             \
     } while (0)
 
-// Small device -> host read-backs (counters) go through a kernel that stores into mapped pinned memory, not
-// through the copy engine: a 4-byte cudaMemcpy queues behind another context's multi-hundred-MB record
-// download on the same engine and stalls the whole pipeline for milliseconds.
-#define FETCH(dst, dev_src, nbytes)                                              \
-    do {                                                                         \
-        int rc__ = fetch_small(ctx, (dst), (dev_src), (nbytes));                 \
-        if (rc__) return rc__;                                                   \
-    } while (0)
-
 #define FAIL(code, ...)                              \
     do {                                             \
         char buf__[512];                             \
@@ -146,21 +159,25 @@ struct hlo_ctx {
         return (code);                               \
     } while (0)
 
-// Kernels of different contexts on one device are serialised (one compute section at a time), so that with
-// two or more host workers per GPU one worker's uploads/downloads overlap another's kernels instead of every
-// worker sharing the SMs and then the PCIe link in lockstep (measured: 18.5 -> ~11 ms per 32-cluster step).
-static std::mutex g_compute_mutex[64];
+// The compute sections of the contexts of one device run one after the other, in submission order, without any host
+// lock: a submit makes its stream wait for the event the previous submit on that device recorded behind its last
+// kernel.  Uploads (before the wait) and record downloads (after the event) of one context then overlap another's
+// kernels, instead of three batches sharing the SMs kernel by kernel and reaching the PCIe link together.
+static std::mutex g_order_mutex[64];
+static cudaEvent_t g_last_compute[64] = {};
 
-// copies nbytes (multiple of 4, <= 256) from device memory to host memory and waits for it
-static int fetch_small(hlo_ctx *ctx, void *dst, const void *dev_src, size_t nbytes) {
-    if (nbytes > 256 || (nbytes & 3)) {
-        ctx->err = "fetch_small: bad size";
-        return HLO_EINVAL;
-    }
-    launch_copy_words(reinterpret_cast<const uint32_t *>(dev_src), ctx->mapped_dev, (uint32_t)(nbytes / 4), ctx->stream, &ctx->lc);
-    CK(cudaGetLastError());
+static inline unsigned long long *ctr(hlo_ctx *ctx, int i) { return ctx->b_counters.as<unsigned long long>() + i; }
+
+// waits for the stream and copies the counter block out of the mapped page
+static int sync_counters(hlo_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
-    memcpy(dst, ctx->mapped_host, nbytes);
+    ctx->tm.n_syncs++;
+    memcpy(ctx->hc, ctx->mapped_host, sizeof ctx->hc);
+    return HLO_OK;
+}
+static int enqueue_counter_readback(hlo_ctx *ctx) {
+    launch_copy_words(ctx->b_counters.as<uint32_t>(), reinterpret_cast<uint32_t *>(ctx->mapped_dev), 2 * C_COUNT, ctx->stream, &ctx->lc);
+    CK(cudaGetLastError());
     return HLO_OK;
 }
 
@@ -168,7 +185,7 @@ extern "C" {
 
 void hlo_params_default(hlo_params *p) {
     if (!p) return;
-    p->k = 21, p->w = 11, p->min_seeds = 2, p->min_chain_score = 30, p->mid_occ = 1000;
+    p->k = 21, p->w = 11, p->min_seeds = 2, p->min_chain_score = 30, p->mid_occ = 0;
     p->match_score = 4, p->mismatch_pen = 2, p->ambi_pen = 1, p->end_bonus = 100, p->min_dp_score = 60;
     p->min_ovlp_len = 60, p->max_overhang = 1, p->min_identity = 0.98, p->overhang_ratio = 0.8;
 }
@@ -224,7 +241,7 @@ static int check_params(const hlo_params &P, std::string &why) {
     if (P.w < 1 || P.w > HLO_MAX_W_PUBLIC) BAD("w=%d outside [1,%d]", P.w, HLO_MAX_W_PUBLIC);
     if (P.min_seeds < 1 || P.min_seeds > 2) BAD("min_seeds=%d: only 1 or 2 reduce to the min/max anchor test", P.min_seeds);
     if (P.min_chain_score > 2 * P.k) BAD("min_chain_score=%d > 2k: chain score no longer equals the anchor span", P.min_chain_score);
-    if (P.mid_occ < 1) BAD("mid_occ must be >= 1");
+    if (P.mid_occ < 0) BAD("mid_occ must be >= 0 (0 = minimap2's data-derived cut-off)");
     if (P.match_score < 1 || P.mismatch_pen < 0 || P.ambi_pen < 0) BAD("scores must be A>=1, B>=0, N>=0");
     if (P.min_ovlp_len < 1 || P.min_ovlp_len > 32767) BAD("min_ovlp_len=%d outside [1,32767]", P.min_ovlp_len);
     if (P.max_overhang < 0 || P.max_overhang > 15) BAD("max_overhang=%d outside [0,15]", P.max_overhang);
@@ -262,8 +279,10 @@ int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out) {
     }
     for (int i = 0; i <= ST_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaEventCreate(&ctx->ev_vf[0]), cudaEventCreate(&ctx->ev_vf[1]);
-    if (cudaHostAlloc((void **)&ctx->mapped_host, 256, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer((void **)&ctx->mapped_dev, ctx->mapped_host, 0) != cudaSuccess) {
+    cudaEventCreateWithFlags(&ctx->ev_compute_done, cudaEventDisableTiming);
+    if (cudaHostAlloc((void **)&ctx->mapped_host, sizeof(unsigned long long) * C_COUNT, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&ctx->mapped_dev, ctx->mapped_host, 0) != cudaSuccess ||
+        ctx->b_counters.ensure(sizeof(unsigned long long) * C_COUNT) != cudaSuccess) {
         cudaGetLastError();
         hlo_ctx_destroy(ctx);
         return HLO_ENOMEM;
@@ -278,11 +297,16 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->b_tab, &ctx->b_cnt, &ctx->b_mzoff, &ctx->b_mzx, &ctx->b_mzrr, &ctx->b_keys[0],
-                      &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_bstart,
-                      &ctx->b_range, &ctx->b_hits, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovf2, &ctx->b_ovfcnt, &ctx->b_gkeys,
-                      &ctx->b_gmn, &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos,
-                      &ctx->b_out, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx, &ctx->b_sx, &ctx->b_srp, &ctx->b_qual, &ctx->b_screc, &ctx->b_scclu, &ctx->b_scout, &ctx->b_prob};
+    {
+        std::lock_guard<std::mutex> g(g_order_mutex[ctx->device & 63]);
+        if (g_last_compute[ctx->device & 63] == ctx->ev_compute_done) g_last_compute[ctx->device & 63] = nullptr;
+    }
+    DevBuf *bufs[] = {&ctx->b_tab, &ctx->b_cnt, &ctx->b_mzoff, &ctx->b_mzx, &ctx->b_mzrr, &ctx->b_keys[0], &ctx->b_keys[1], &ctx->b_vals[0],
+                      &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_range, &ctx->b_hits, &ctx->b_midocc, &ctx->b_hist,
+                      &ctx->b_seg1, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovf2, &ctx->b_ovfcnt, &ctx->b_gkeys, &ctx->b_gmn,
+                      &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos, &ctx->b_slot, &ctx->b_ent,
+                      &ctx->b_entg, &ctx->b_out, &ctx->b_outc, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx, &ctx->b_sx, &ctx->b_srp,
+                      &ctx->b_qual, &ctx->b_screc, &ctx->b_scclu, &ctx->b_scout, &ctx->b_prob};
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&ctx->h_score, &ctx->h_out, &ctx->h_aux, &ctx->h_coff, &ctx->h_mz, &ctx->h_roff, &ctx->h_cands, &ctx->h_rec16, &ctx->h_small};
     for (PinBuf *b : pins) b->release();
@@ -291,6 +315,7 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i)
         if (ctx->ev_vf[i]) cudaEventDestroy(ctx->ev_vf[i]);
+    if (ctx->ev_compute_done) cudaEventDestroy(ctx->ev_compute_done);
     if (ctx->mapped_host) cudaFreeHost(ctx->mapped_host);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -330,7 +355,7 @@ static int build_tables(hlo_ctx *ctx, int max_len) {
     }
     CK(ctx->b_tab.ensure(h.size() * sizeof(uint16_t)));
     CK(cudaMemcpyAsync(ctx->b_tab.p, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // (h is a local; happens when a ctx first meets a longer read, not per batch)
     ctx->tab.min_matches = ctx->b_tab.as<uint16_t>();
     ctx->tab.max_clip = ctx->tab.min_matches + (L + 1);
     ctx->tab.max_k_upto = ctx->tab.max_clip + (L + 1);
@@ -371,8 +396,15 @@ static int ensure_host_meta(hlo_ctx *ctx, const hlo_reads *Rc) {
     return HLO_OK;
 }
 
-static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64_t *base_off, uint32_t n_reads,
-                     const uint32_t *cluster_off, uint32_t n_clusters, const uint32_t *ids) {
+// Upload + 2-bit packing of a batch, enqueued on the ctx stream; nothing here waits for the device (names other than
+// 0..N-1 go through pageable host vectors, whose copies are staged before cudaMemcpyAsync returns).
+static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
+    const char *bases = B.bases;
+    const uint64_t *base_off = B.base_off;
+    const uint32_t n_reads = B.n_reads;
+    const uint32_t *cluster_off = B.cluster_off;
+    uint32_t n_clusters = B.n_clusters;
+    const uint32_t *ids = B.ids;
     if (!bases || !base_off) FAIL(HLO_EINVAL, "hlo_pack_reads: null input");
     uint32_t one[2] = {0, n_reads};
     if (!cluster_off) cluster_off = one, n_clusters = 1;
@@ -406,14 +438,16 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     if (ids)
         for (uint32_t c = 0; c < n_clusters && plain; ++c)
             for (uint32_t i = cluster_off[c]; i < cluster_off[c + 1] && plain; ++i) plain = ids[i] == i - cluster_off[c];
+    R->max_id = max_cluster ? max_cluster - 1 : 0;
     std::vector<uint32_t> cbase, nrank;
     if (!plain) {
         R->h_len.resize(n_reads), R->h_ids.resize(n_reads), R->h_cidx.resize(n_reads), R->h_perm.resize(n_reads);
         cbase.resize(n_reads), nrank.resize(n_reads);
         for (uint32_t i = 0; i < n_reads; ++i) R->h_len[i] = (uint32_t)(base_off[i + 1] - base_off[i]);
+        uint32_t mx = 0;
         for (uint32_t c = 0; c < n_clusters; ++c) {
             const uint32_t r0 = cluster_off[c], r1 = cluster_off[c + 1], N = r1 - r0;
-            for (uint32_t i = r0; i < r1; ++i) cbase[i] = r0, R->h_cidx[i] = c, R->h_ids[i] = ids[i];
+            for (uint32_t i = r0; i < r1; ++i) cbase[i] = r0, R->h_cidx[i] = c, R->h_ids[i] = ids[i], mx = std::max(mx, ids[i]);
             std::vector<uint32_t> ord(N);
             for (uint32_t i = 0; i < N; ++i) ord[i] = r0 + i;
             std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b] || (ids[a] == ids[b] && a < b); });
@@ -424,6 +458,7 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
             std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return name_less(ids[a], ids[b]); });
             for (uint32_t x = 0; x < N; ++x) R->h_perm[r0 + x] = ord[x];
         }
+        R->max_id = mx;
     }
     // the ungapped model equals minimap2's banded extension only while an accepted overlap cannot hold a
     // stretch that triggers z-drop / loses the end bonus
@@ -433,6 +468,8 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
             FAIL(HLO_EUNSUPPORTED, "reads of %u bp at min_identity %.3f leave the domain where the ungapped end rule is exact", max_len,
                  ctx->P.min_identity);
     }
+    int rc = build_tables(ctx, (int)max_len);
+    if (rc) return rc;
     const uint64_t n_bases = base_off[n_reads];
     const uint32_t words = (max_len + 15) / 16;
     const uint32_t nv = std::max(1u, (words + 3u) / 4u);
@@ -454,16 +491,25 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
     CK(R->b_perm.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_bases.ensure((plane_words * 2 + 2 * HLO_PAD_WORDS) * 4));
     CK(R->b_amb.ensure((plane_words * 2 + 2 * HLO_PAD_WORDS) * 4));
-    CK(R->b_ambcount.ensure(16));
+    CK(R->b_ambcount.ensure(16));  // ambiguous bases of THIS read set: picks the sketch kernel's variant on the device
     d.len = R->b_len.as<uint32_t>(), d.cbase = R->b_cbase.as<uint32_t>(), d.cidx = R->b_cidx.as<uint32_t>();
     d.ids = R->b_ids.as<uint32_t>(), d.nrank = R->b_nrank.as<uint32_t>(), d.perm = R->b_perm.as<uint32_t>();
     d.meta = R->b_meta.as<uint4>();
     d.bases = R->b_bases.as<uint32_t>() + HLO_PAD_WORDS, d.amb = R->b_amb.as<uint32_t>() + HLO_PAD_WORDS;
+    R->has_quals = false;
+    if (B.quals) CK(R->b_qual.ensure(n_bases + 64 + (size_t)n_reads + 32));  // 32 bytes of padding on both sides, then a flag per read
     CK(cudaEventRecord(ctx->ev[ST_BEGIN], s));
     if (n_reads) {
         CK(cudaMemcpyAsync(R->b_ascii.p, bases, n_bases, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(R->b_off.p, base_off, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(R->b_coff.p, cluster_off, ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(R->b_coff.p, R->h_cluster_off.data(), ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
+        if (B.quals) {
+            uint8_t *dq = R->b_qual.as<uint8_t>() + 32;
+            CK(cudaMemsetAsync(R->b_qual.p, 0, 32, s));
+            CK(cudaMemsetAsync(dq + n_bases, 0, 32, s));
+            CK(cudaMemcpyAsync(dq, B.quals, n_bases, cudaMemcpyHostToDevice, s));
+            R->has_quals = true;
+        }
         if (!plain) {
             CK(cudaMemcpyAsync(d.len, R->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(d.cbase, cbase.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
@@ -473,23 +519,22 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const char *bases, const uint64
             std::vector<uint4> meta(n_reads);
             for (uint32_t i = 0; i < n_reads; ++i) meta[i] = make_uint4(R->h_len[i], R->h_ids[i], R->h_cidx[i], cbase[i]);
             CK(cudaMemcpyAsync(d.meta, meta.data(), (size_t)n_reads * 16, cudaMemcpyHostToDevice, s));
-            CK(cudaStreamSynchronize(s));  // (meta is a local)
             CK(cudaMemcpyAsync(d.perm, R->h_perm.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));  // (locals; only batches whose names are not 0..N-1 come here)
         }
     }
+    CK(cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long) * C_COUNT, s));
+    CK(cudaMemsetAsync(ctr(ctx, C_MIDOCC_LO), 0xff, sizeof(unsigned long long), s));
     CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));
     CK(cudaEventRecord(ctx->ev[ST_H2D], s));
     if (plain && n_reads) launch_read_meta(R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), d, s, &ctx->lc);
     launch_pack(R->b_ascii.as<uint8_t>(), R->b_off.as<uint64_t>(), d, R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
+    if (R->has_quals)
+        launch_qual_flags(R->b_qual.as<uint8_t>() + 32, R->b_off.as<uint64_t>(), n_reads,
+                          R->b_qual.as<uint8_t>() + 32 + ((n_bases + 32 + 15) & ~(uint64_t)15), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_PACK], s));
-    uint32_t amb = 0;
-    FETCH(&amb, R->b_ambcount.p, 4);  // the wait also keeps the caller's host buffers alive until the copies are done
-    d.has_amb = amb != 0;
-    CK(cudaEventElapsedTime(&R->h2d_ms, ctx->ev[ST_BEGIN], ctx->ev[ST_H2D]));
-    CK(cudaEventElapsedTime(&R->pack_ms, ctx->ev[ST_H2D], ctx->ev[ST_PACK]));
-    int rc = build_tables(ctx, (int)max_len);
-    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_COUNT], s));  // (ST_PACK is recorded again when a batch is rerun; this one stays)
     return HLO_OK;
 }
 
@@ -497,9 +542,23 @@ extern "C" int hlo_pack_reads(hlo_ctx *ctx, const char *bases, const uint64_t *b
                               const uint32_t *cluster_off, uint32_t n_clusters, const uint32_t *ids, hlo_reads **out) {
     if (!ctx || !out) return HLO_EINVAL;
     *out = nullptr;
+    if (ctx->inflight) FAIL(HLO_EINVAL, "a submitted batch is in flight on this ctx: call hlo_wait first");
     hlo_reads *R = new (std::nothrow) hlo_reads();
     if (!R) return HLO_ENOMEM;
-    int rc = pack_into(ctx, R, bases, base_off, n_reads, cluster_off, n_clusters, ids);
+    hlo_batch B{};
+    B.bases = bases, B.base_off = base_off, B.n_reads = n_reads, B.cluster_off = cluster_off, B.n_clusters = n_clusters, B.ids = ids;
+    ctx->lc = LaunchCounter();
+    int rc = pack_into(ctx, R, B);
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {  // the caller's buffers are free again when this returns
+        cudaGetLastError();
+        ctx->err = "hlo_pack_reads: device error while packing";
+        rc = HLO_ECUDA;
+    }
+    if (!rc) {
+        cudaEventElapsedTime(&R->h2d_ms, ctx->ev[ST_BEGIN], ctx->ev[ST_H2D]);
+        cudaEventElapsedTime(&R->pack_ms, ctx->ev[ST_H2D], ctx->ev[ST_COUNT]);
+        cudaGetLastError();
+    }
     if (rc) {
         R->release();
         delete R;
@@ -517,80 +576,7 @@ extern "C" void hlo_reads_free(hlo_reads *R) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stages
-
-// sketch.  Leaves mz_off (n_reads+1, name order), mz_x, mz_rp, mz_rid on the device; with the single-pass
-// fast kernel also the radix sort's input pairs (keys_ready).
-static int run_sketch(hlo_ctx *ctx, const hlo_reads *R, bool want_x) {
-    const DevReads &d = R->d;
-    cudaStream_t s = ctx->stream;
-    const uint32_t n = d.n_reads;
-    if ((uint64_t)d.n_bases > 0xffffffffull) FAIL(HLO_ERANGE, "batch of %llu bases exceeds the 2^32 minimizer index range", (unsigned long long)d.n_bases);
-    CK(ctx->b_cnt.ensure(((size_t)n + 1) * 4));
-    CK(ctx->b_mzoff.ensure(((size_t)n + 2) * 4));
-    CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)n + 1) * 4));
-    CK(ctx->b_counters.ensure(16 * 8));
-    ctx->keys_ready = false;
-    const bool fast = sketch_fast_supported(ctx->P.w, ctx->P.k) && !ctx->sketch_generic && n > 0;
-    uint32_t cap = 0;
-    if (fast) {
-        // strip capacity: 3.5x the expected density 2/(w+1) plus slack, never more than one per k-mer
-        // (sized for reads of at most 1024 bp: in a batch that mixes short reads with a few contigs the long ones overflow
-        // their strip and take the generic kernel, instead of every read paying for a contig-sized strip)
-        const uint32_t cap_len = std::min<uint32_t>(d.max_len, 1024u);
-        const uint32_t kmers = cap_len >= (uint32_t)ctx->P.k ? cap_len - (uint32_t)ctx->P.k + 1 : 0;
-        cap = std::min<uint32_t>(std::max<uint32_t>(kmers, 1u), (uint32_t)(7.0 * kmers / (ctx->P.w + 1)) + 8u);
-        CK(ctx->b_sx.ensure((size_t)n * cap * 8 + 8));
-        CK(ctx->b_srp.ensure((size_t)n * cap * 4 + 4));
-        CK(ctx->b_ovf.ensure((size_t)n * 4 + 4));
-        CK(cudaMemsetAsync(ctx->b_cnt.as<uint32_t>() + n, 0, 4, s));
-        CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 10, 0, 16, s));
-        launch_sketch_fast(d, ctx->P.w, ctx->P.k, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
-                           ctx->b_ovf.as<uint32_t>(), ctx->b_counters.as<unsigned long long>() + 10, s, &ctx->lc);
-    } else {
-        CK(cudaMemsetAsync(ctx->b_cnt.p, 0, ((size_t)n + 1) * 4, s));
-        launch_sketch_count(d, ctx->P.w, ctx->P.k, ctx->b_cnt.as<uint32_t>(), s, &ctx->lc);
-    }
-    // scanning n+1 counts (the last is 0) puts the total at mz_off[n]
-    launch_exclusive_scan(ctx->b_cnt.as<uint32_t>(), ctx->b_mzoff.as<uint32_t>(), (uint64_t)n + 1, ctx->b_tmp.as<uint32_t>(),
-                          ctx->b_counters.as<uint32_t>() + 22, s, &ctx->lc);  // grand total -> low word of counters[11]
-    CK(cudaGetLastError());
-    uint32_t total = 0;
-    unsigned long long n_ovf = 0;
-    if (fast) {  // one fetch for both: the scan leaves the total right behind the sketch overflow counter
-        unsigned long long two[2] = {0, 0};
-        FETCH(two, ctx->b_counters.as<unsigned long long>() + 10, 16);
-        n_ovf = two[0], total = (uint32_t)two[1];
-    } else {
-        FETCH(&total, ctx->b_counters.as<uint32_t>() + 22, 4);
-    }
-    ctx->n_mz = total;
-    // the hash words themselves are only wanted by hlo_sketch: the index is built from the sort keys
-    uint64_t *mz_x = nullptr;
-    if (want_x || !fast) {
-        CK(ctx->b_mzx.ensure((size_t)total * 8 + 8));
-        mz_x = ctx->b_mzx.as<uint64_t>();
-    }
-    CK(ctx->b_mzrr.ensure((size_t)total * 8 + 8));
-    if (fast) {
-        for (int i = 0; i < 2; ++i) {
-            CK(ctx->b_keys[i].ensure((size_t)total * 8 + 8));
-            CK(ctx->b_vals[i].ensure((size_t)total * 4 + 4));
-        }
-        launch_sketch_compact(d, cap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
-                              ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), ctx->b_keys[0].as<uint64_t>(),
-                              ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, s, &ctx->lc);
-        ctx->keys_ready = true;
-        if (n_ovf)  // reads with more minimizers than a strip holds, or low-complexity reads: the generic kernel writes them in place
-            launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), ctx->b_keys[0].as<uint64_t>(),
-                                ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, ctx->b_ovf.as<uint32_t>(), (uint32_t)n_ovf, s, &ctx->lc);
-    } else {
-        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), nullptr, nullptr, 0, nullptr, 0, s,
-                            &ctx->lc);
-    }
-    CK(cudaGetLastError());
-    return HLO_OK;
-}
+// stages (all enqueue-only)
 
 static int bits_for(uint64_t v) {
     int b = 1;
@@ -598,60 +584,153 @@ static int bits_for(uint64_t v) {
     return b;
 }
 
-// hash sort + bucket index.  Leaves range[] (per minimizer, read order) and hits[] (hash order).
-static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
+static uint32_t next_pow2_u32(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// buffer sizes of this enqueue: estimates (first batches) or what earlier batches needed plus slack, never below
+// what a rerun found out
+static void plan_caps(hlo_ctx *ctx, const hlo_reads *R) {
+    const DevReads &d = R->d;
+    const double scale = std::max(ctx->cap_scale_pct, 1) / 100.0;
+    const double dens = std::max(2.6 / (ctx->P.w + 1) * scale, ctx->need_mz_per_base * 1.1);
+    uint64_t mz = (uint64_t)((double)d.n_bases * dens) + d.n_reads + 1024;
+    mz = std::max(mz, ctx->min_mz);
+    mz = std::min<uint64_t>(mz, 0xfffffff0ull);
+    uint64_t c = (uint64_t)((double)mz * std::max(2.0 * scale, ctx->need_c_per_mz * 1.15)) + (1 << 16);
+    uint64_t a = (uint64_t)((double)mz * std::max(1.0 * scale, ctx->need_a_per_mz * 1.15)) + (1 << 16);
+    c = std::max(c, ctx->min_c), a = std::max(a, ctx->min_a);
+    a = std::min(a, c);  // every record comes from a candidate
+    a = std::min<uint64_t>(a, 0x7ffffff0ull);  // records.cu keeps a mark in bit 31 of a record index
+    ctx->cap_mz = mz, ctx->cap_c = c, ctx->cap_a = a;
+}
+
+__global__ void mz_clear_kernel(uint32_t *mz_off, uint32_t n_off, const unsigned long long *counters, uint64_t cap_mz) {
+    if ((uint32_t)counters[C_MZ] <= cap_mz) return;  // (low word: the scan writes 32 bits)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_off; i += gridDim.x * blockDim.x) mz_off[i] = 0u;
+}
+
+// sketch.  Leaves mz_off (n_reads+1, name order), mz_rr (+ mz_x when wanted) on the device; with the single-pass
+// fast kernel also the radix sort's input pairs.  A batch with more minimizers than cap_mz leaves an EMPTY sketch
+// (all offsets zero) behind, so that every later stage is a no-op; C_MZ keeps the true count for the rerun.
+static int enqueue_sketch(hlo_ctx *ctx, const hlo_reads *R, bool want_x, bool *keys_ready) {
+    const DevReads &d = R->d;
     cudaStream_t s = ctx->stream;
-    const uint64_t n = ctx->n_mz;
-    for (int i = 0; i < 2; ++i) {
-        CK(ctx->b_keys[i].ensure(n * 8 + 8));
-        CK(ctx->b_vals[i].ensure(n * 4 + 4));
+    const uint32_t n = d.n_reads;
+    if ((uint64_t)d.n_bases > 0xffffffffull) FAIL(HLO_ERANGE, "batch of %llu bases exceeds the 2^32 minimizer index range", (unsigned long long)d.n_bases);
+    const uint64_t cap = ctx->cap_mz;
+    CK(ctx->b_cnt.ensure(((size_t)n + 1) * 4));
+    CK(ctx->b_mzoff.ensure(((size_t)n + 2) * 4));
+    CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)n + 1) * 4));
+    CK(ctx->b_ovf.ensure((size_t)n * 4 + 4));
+    uint64_t *mz_x = nullptr;
+    const bool fast = sketch_fast_supported(ctx->P.w, ctx->P.k) && !ctx->sketch_generic && n > 0;
+    if (want_x || !fast) {
+        CK(ctx->b_mzx.ensure(cap * 8 + 8));
+        mz_x = ctx->b_mzx.as<uint64_t>();
     }
-    CK(ctx->b_tmp.ensure(std::max(std::max(sort_tmp_words(n), sort_segmented_tmp_words(n, R->d.n_clusters)), scan_tmp_words(n + 1)) * 4));
-    CK(ctx->b_flags.ensure(n * 4 + 4));
-    CK(ctx->b_range.ensure(n * 8 + 8));
-    CK(ctx->b_hits.ensure(n * 8 + 8));
+    CK(ctx->b_mzrr.ensure(cap * 8 + 8));
+    for (int i = 0; i < 2; ++i) {
+        CK(ctx->b_keys[i].ensure(cap * 8 + 8));
+        CK(ctx->b_vals[i].ensure(cap * 4 + 4));
+    }
+    *keys_ready = false;
+    uint32_t scap = 0;
+    if (fast) {
+        // strip capacity: 3.5x the expected density 2/(w+1) plus slack, never more than one per k-mer
+        // (sized for reads of at most 1024 bp: in a batch that mixes short reads with a few contigs the long ones overflow
+        // their strip and take the generic kernel, instead of every read paying for a contig-sized strip)
+        const uint32_t cap_len = std::min<uint32_t>(d.max_len, 1024u);
+        const uint32_t kmers = cap_len >= (uint32_t)ctx->P.k ? cap_len - (uint32_t)ctx->P.k + 1 : 0;
+        scap = std::min<uint32_t>(std::max<uint32_t>(kmers, 1u), (uint32_t)(7.0 * kmers / (ctx->P.w + 1)) + 8u);
+        CK(ctx->b_sx.ensure((size_t)n * scap * 8 + 8));
+        CK(ctx->b_srp.ensure((size_t)n * scap * 4 + 4));
+        CK(cudaMemsetAsync(ctx->b_cnt.as<uint32_t>() + n, 0, 4, s));
+        launch_sketch_fast(d, ctx->P.w, ctx->P.k, scap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
+                           ctx->b_ovf.as<uint32_t>(), ctr(ctx, C_SK_OVF), R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
+    } else {
+        CK(cudaMemsetAsync(ctx->b_cnt.p, 0, ((size_t)n + 1) * 4, s));
+        launch_sketch_count(d, ctx->P.w, ctx->P.k, ctx->b_cnt.as<uint32_t>(), s, &ctx->lc);
+    }
+    // scanning n+1 counts (the last is 0) puts the total at mz_off[n] (and into the counter block)
+    launch_exclusive_scan(ctx->b_cnt.as<uint32_t>(), ctx->b_mzoff.as<uint32_t>(), (uint64_t)n + 1, ctx->b_tmp.as<uint32_t>(),
+                          reinterpret_cast<uint32_t *>(ctr(ctx, C_MZ)), s, &ctx->lc);
+    if (fast) {
+        launch_sketch_compact(d, scap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
+                              ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), ctx->b_keys[0].as<uint64_t>(),
+                              ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, (uint32_t)cap, s, &ctx->lc);
+        *keys_ready = true;
+        // reads with more minimizers than a strip holds: the generic kernel writes them in place (the list is usually empty)
+        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), ctx->b_keys[0].as<uint64_t>(),
+                            ctx->b_vals[0].as<uint32_t>(), 2 * ctx->P.k, ctx->b_ovf.as<uint32_t>(), ctr(ctx, C_SK_OVF), (uint32_t)cap, s, &ctx->lc);
+    } else if (n) {
+        launch_sketch_write(d, ctx->P.w, ctx->P.k, ctx->b_mzoff.as<uint32_t>(), mz_x, ctx->b_mzrr.as<uint2>(), nullptr, nullptr, 0, nullptr, nullptr,
+                            (uint32_t)cap, s, &ctx->lc);
+    }
+    if (n) {
+        mz_clear_kernel<<<64, 256, 0, s>>>(ctx->b_mzoff.as<uint32_t>(), n + 1, ctr(ctx, 0), cap);
+        ctx->lc.total++;
+    }
+    CK(cudaGetLastError());
+    return HLO_OK;
+}
+
+// hash sort + bucket index.  Leaves range[] (per minimizer, read order) and hits[] (hash order).
+static int enqueue_index(hlo_ctx *ctx, const hlo_reads *R, bool keys_ready) {
+    cudaStream_t s = ctx->stream;
+    const DevReads &d = R->d;
+    const uint64_t cap = ctx->cap_mz;
+    const uint32_t *n_ptr = ctx->b_mzoff.as<uint32_t>() + d.n_reads;  // the minimizer count, on the device
+    // key = cluster index << 2k | hash: 2k hash bits + the bits of the cluster count
+    const int hash_bits = 2 * ctx->P.k;
+    const int key_bits = hash_bits + (d.n_clusters > 1 ? bits_for(d.n_clusters) : 0);
+    if (key_bits > 64) FAIL(HLO_ERANGE, "%u clusters with k=%d need a %d-bit sort key (limit 64): use smaller batches", d.n_clusters, ctx->P.k, key_bits);
+    const bool segmented = ctx->sort_segmented != 0;
+    const uint32_t n_seg = segmented ? d.n_clusters : 1u;
+    CK(ctx->b_tmp.ensure(std::max(sort_segmented_tmp_words(cap, n_seg), scan_tmp_words(cap + 1)) * 4));
+    CK(ctx->b_flags.ensure(cap * 4 + 8));
+    CK(ctx->b_range.ensure(cap * 8 + 8));
+    CK(ctx->b_hits.ensure(cap * 8 + 8));
+    CK(ctx->b_midocc.ensure((size_t)d.n_clusters * 4 + 4));
+    // occurrence histogram: a bucket can hold at most as many entries as its cluster has minimizers; sizes past the
+    // clamp bin only matter when the cut-off quantile itself lands there (then the batch is refused)
+    const uint32_t bins = next_pow2_u32((uint32_t)std::min<uint64_t>(65536ull, (uint64_t)d.max_cluster * 4 + 64));
+    if (ctx->P.mid_occ <= 0) CK(ctx->b_hist.ensure((size_t)d.n_clusters * bins * 4));
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
-    if (!allow_prefix) {
-        // a redo after a prefix attempt: the (key, index) pairs are intact but permuted — put every pair back at its
-        // index, into the other buffer, and sort from there
-        const int from = ctx->sorted_buf;
-        launch_unpermute_pairs(keys[from], vals[from], n, keys[from ^ 1], vals[from ^ 1], s, &ctx->lc);
-        if (from == 0) std::swap(keys[0], keys[1]), std::swap(vals[0], vals[1]);
-    } else if (!ctx->keys_ready) {
-        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(), R->d.cidx, 2 * ctx->P.k, n, keys[0], vals[0], s, &ctx->lc);
-    }
-    // key = cluster index << 2k | hash: 2k hash bits + the bits of the cluster count
-    const int key_bits = 2 * ctx->P.k + (R->d.n_clusters > 1 ? bits_for(R->d.n_clusters) : 0);
-    if (key_bits > 64) FAIL(HLO_ERANGE, "%u clusters with k=%d need a %d-bit sort key (limit 64): use smaller batches", R->d.n_clusters, ctx->P.k, key_bits);
+    if (!keys_ready)
+        launch_hash_keys(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(), d.cidx, hash_bits, cap, n_ptr, keys[0], vals[0], s, &ctx->lc);
     // (1) The minimizer array is cluster-major already, so every cluster is sorted as its own segment: the cluster bits
     //     of the key cost no pass.  (2) Grouping needs equal keys adjacent and stable, not a total order: only the top
     //     24 hash bits are sorted (3 passes instead of 6) and the rare groups in which two hashes share that prefix are
-    //     repaired afterwards.
-    const int hash_bits = 2 * ctx->P.k;
-    const bool segmented = ctx->sort_segmented && n < (1ull << 32);
-    const int top = segmented ? hash_bits : key_bits;          // sorted bits end here
-    const int avail = segmented ? hash_bits : key_bits;        // ... and this many exist below
-    int sort_bits = ctx->sort_hash_bits > 0 ? (segmented ? 0 : key_bits - hash_bits) + ctx->sort_hash_bits : (segmented ? 24 : ((key_bits - hash_bits + 19 + 7) / 8) * 8);
-    const bool prefix = allow_prefix && ctx->sort_prefix && sort_bits < avail && n > 1;
-    ctx->prefix_used = prefix;
-    if (!prefix) sort_bits = avail;
-    int cur;
-    if (segmented)
-        cur = launch_radix_sort_segmented(keys, vals, n, top - sort_bits, top, ctx->b_mzoff.as<uint32_t>(), R->b_coff.as<uint32_t>(), R->d.n_clusters,
-                                          ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
-    else
-        cur = launch_radix_sort(keys, vals, n, top - sort_bits, top, ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
-    if (prefix) {  // counters[12] = (groups repaired, 1 if one was too large: run_pairgen's fetch sees it and the index is redone)
-        CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 12, 0, 8, s));
-        launch_collision_fix(keys[cur], vals[cur], n, top - sort_bits, ctx->b_flags.as<uint32_t>(), ctx->b_counters.as<uint32_t>() + 24, s,
-                             &ctx->lc);
+    //     repaired afterwards.  Option sort_segmented = 0: one segment, the cluster index is part of the sorted key.
+    const uint32_t *seg_off = R->b_coff.as<uint32_t>();
+    if (!segmented) {
+        CK(ctx->b_seg1.ensure(8));
+        CK(ctx->h_small.ensure(64));
+        uint32_t *hs = ctx->h_small.as<uint32_t>();
+        hs[0] = 0, hs[1] = d.n_reads;
+        CK(cudaMemcpyAsync(ctx->b_seg1.p, hs, 8, cudaMemcpyHostToDevice, s));
+        seg_off = ctx->b_seg1.as<uint32_t>();
     }
+    const int top = segmented ? hash_bits : key_bits;  // sorted bits end here, and this many exist below
+    int sort_bits = ctx->sort_hash_bits > 0 ? (segmented ? 0 : key_bits - hash_bits) + ctx->sort_hash_bits
+                                            : (segmented ? 24 : ((key_bits - hash_bits + 19 + 7) / 8) * 8);
+    const bool prefix = !ctx->force_full_sort && ctx->sort_prefix && sort_bits < top;
+    ctx->prefix_used = prefix;
+    if (!prefix) sort_bits = top;
+    const int cur = launch_radix_sort_segmented(keys, vals, cap, top - sort_bits, top, ctx->b_mzoff.as<uint32_t>(), seg_off, n_seg,
+                                                ctx->b_tmp.as<uint32_t>(), s, &ctx->lc);
+    if (prefix)
+        launch_collision_fix(keys[cur], vals[cur], cap, n_ptr, top - sort_bits, ctx->b_flags.as<uint32_t>(),
+                             reinterpret_cast<uint32_t *>(ctr(ctx, C_COLL)), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SORT], s));
-    ctx->sorted_buf = keys[cur] == ctx->b_keys[0].as<uint64_t>() ? 0 : 1;
-    launch_bucket_index(keys[cur], vals[cur], ctx->b_mzrr.as<uint2>(), n, ctx->P.mid_occ, ctx->b_hits.as<uint2>(), ctx->b_range.as<uint2>(), s,
-                        &ctx->lc);
+    launch_bucket_index(keys[cur], vals[cur], ctx->b_mzrr.as<uint2>(), cap, n_ptr, hash_bits, ctx->P.mid_occ, d.n_clusters,
+                        ctx->b_midocc.as<uint32_t>(), ctx->b_hist.as<uint32_t>(), bins, ctr(ctx, 0), ctx->b_hits.as<uint2>(),
+                        ctx->b_range.as<uint2>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_INDEX], s));
     return HLO_OK;
@@ -659,19 +738,8 @@ static int run_index(hlo_ctx *ctx, const hlo_reads *R, bool allow_prefix) {
 
 constexpr int PAIRGEN_WIDE_SLOTS_LOG2 = 11;
 
-static uint32_t next_pow2_u32(uint32_t v) {
-    uint32_t p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
-
-// candidates into b_cands (CandI, or hlo_cand when external); *n_out = their number
-static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t *n_out) {
-    cudaStream_t s = ctx->stream;
+static PairgenArgs pairgen_args(hlo_ctx *ctx, const hlo_reads *R, int external) {
     const DevReads &d = R->d;
-    CK(ctx->b_counters.ensure(16 * 8));
-    CK(ctx->b_ovf.ensure((size_t)d.n_reads * 4 + 4));
-    uint64_t cap = std::max<uint64_t>(ctx->b_cands.cap / 16, std::max<uint64_t>(ctx->n_mz * 3, 1 << 16));
     PairgenArgs a;
     a.reads = d;
     a.mz_off = ctx->b_mzoff.as<uint32_t>(), a.mz_rr = ctx->b_mzrr.as<uint2>();
@@ -679,154 +747,292 @@ static int run_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t 
     a.k = ctx->P.k;
     a.gap_min = std::max(std::max(ctx->P.min_chain_score - ctx->P.k, ctx->P.min_seeds - 1), 0);
     a.external = external;
-    a.counters = ctx->b_counters.as<unsigned long long>();
+    a.cands = ctx->b_cands.p, a.cand_cap = ctx->cap_c;
+    a.cand_counter = ctr(ctx, C_CAND), a.hit_counter = ctr(ctx, C_HITS);
+    a.ovf_counter = ctr(ctx, C_PG_OVF), a.work_counter = ctr(ctx, C_PG_WORK);
     a.overflow_reads = ctx->b_ovf.as<uint32_t>(), a.overflow_cap = d.n_reads;
-    const bool fast = pairgen_fast_supported(d, &a.dg_bits) && !ctx->pairgen_generic;
-    unsigned long long hc[13];
-    bool wide_pass = false;
-    const int slots0 = std::max(ctx->pairgen_slots_log2, ctx->pairgen_slots_auto);
-    ctx->prefix_failed = false;
-    if (ctx->prefix_used && !fast) {  // the fast path reads the prefix sort's flag with its own counters below
-        unsigned long long flag = 0;
-        FETCH(&flag, ctx->b_counters.as<unsigned long long>() + 12, 8);
-        if (flag >> 32) {
-            ctx->prefix_failed = true;
-            *n_out = 0;
-            return HLO_OK;
-        }
-    }
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        CK(ctx->b_cands.ensure(cap * 16));
-        a.cands = ctx->b_cands.p, a.cand_cap = cap;
-        CK(cudaMemsetAsync(ctx->b_counters.p, 0, 64, s));
-        uint32_t n_list = d.n_reads;        // reads the generic kernel has to do
-        const uint32_t *list = nullptr;     // nullptr = all of them
-        if (fast) {
-            launch_pairgen(a, slots0, s, &ctx->lc);
-            CK(cudaGetLastError());
-            FETCH(hc, ctx->b_counters.p, sizeof hc);
-            if (ctx->prefix_used && (hc[12] >> 32)) {  // a mixed prefix group was too large to repair: the caller redoes the index
-                ctx->prefix_failed = true;
-                *n_out = 0;
-                return HLO_OK;
-            }
-            n_list = (uint32_t)hc[2], list = a.overflow_reads;
-            const uint32_t first_overflow = n_list;
-            // reads with more (target, strand, diagonal) chains than the table holds (deep coverage, longer reads) go through
-            // the same kernel again with tables twice the size, up to 2048 slots, before the HBM-table kernel gets what is
-            // left.  (Straight to the largest tables is slow: one block per SM and a 16 KB table to clear per read.)
-            uint32_t *lists[2] = {ctx->b_ovf.as<uint32_t>(), nullptr};
-            int from = 0;
-            for (int sl = slots0 + 1; n_list && sl <= PAIRGEN_WIDE_SLOTS_LOG2; ++sl) {
-                if (!lists[1]) {
-                    CK(ctx->b_ovf2.ensure((size_t)d.n_reads * 4 + 4));
-                    lists[1] = ctx->b_ovf2.as<uint32_t>();
-                }
-                PairgenArgs a2 = a;
-                a2.work = lists[from], a2.n_work = n_list;
-                a2.overflow_reads = lists[from ^ 1];
-                CK(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 2, 0, 16, s));  // overflow count, work counter
-                launch_pairgen(a2, sl, s, &ctx->lc);
-                CK(cudaGetLastError());
-                FETCH(hc, ctx->b_counters.p, sizeof hc);
-                n_list = (uint32_t)hc[2], list = lists[from ^ 1];
-                from ^= 1;
-                wide_pass = true;
-            }
-            if (wide_pass) ctx->tm.n_overflow_reads = first_overflow;  // (reads that left the first table size)
-            // a batch that overflowed a lot: the following ones start with larger tables
-            if (attempt == 0 && first_overflow > d.n_reads / 16 && ctx->pairgen_slots_auto < 10) ctx->pairgen_slots_auto = slots0 + 1;
-        }
-        if (n_list) {  // exact path with tables in HBM, in chunks that bound the table memory
-            CK(ctx->b_ovfcnt.ensure((size_t)n_list * 4 + 4));
-            launch_generic_hit_counts(a, list, n_list, ctx->b_ovfcnt.as<uint32_t>(), s, &ctx->lc);
-            std::vector<uint32_t> cnt(n_list);
-            CK(cudaMemcpyAsync(cnt.data(), ctx->b_ovfcnt.p, (size_t)n_list * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            const uint64_t slot_budget = 1ull << 28;  // 4 GiB of tables per chunk
-            uint32_t i0 = 0;
-            std::vector<uint64_t> off;
-            while (i0 < n_list) {
-                off.assign(1, 0);
-                uint32_t i1 = i0;
-                while (i1 < n_list) {
-                    const uint64_t sl = next_pow2_u32(std::max(2u * cnt[i1], 64u));
-                    if (i1 > i0 && off.back() + sl > slot_budget) break;
-                    off.push_back(off.back() + sl);
-                    ++i1;
-                }
-                const uint64_t tot = off.back();
-                CK(ctx->b_gkeys.ensure(tot * 8 + 8));
-                CK(ctx->b_gmn.ensure(tot * 4 + 4));
-                CK(ctx->b_gmx.ensure(tot * 4 + 4));
-                CK(ctx->b_goff.ensure(off.size() * 8));
-                CK(cudaMemcpyAsync(ctx->b_goff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
-                CK(cudaMemsetAsync(ctx->b_gkeys.p, 0xff, tot * 8, s));
-                CK(cudaMemsetAsync(ctx->b_gmn.p, 0xff, tot * 4, s));
-                CK(cudaMemsetAsync(ctx->b_gmx.p, 0, tot * 4, s));
-                // a chunk is addressed by offsetting the list (or, without a list, by a list of x indices)
-                const uint32_t *chunk_list = list ? list + i0 : nullptr;
-                if (!list && i0 > 0) {
-                    std::vector<uint32_t> xs(i1 - i0);
-                    for (uint32_t i = i0; i < i1; ++i) xs[i - i0] = i;
-                    CK(cudaMemcpyAsync(ctx->b_ovf.p, xs.data(), xs.size() * 4, cudaMemcpyHostToDevice, s));
-                    CK(cudaStreamSynchronize(s));
-                    chunk_list = ctx->b_ovf.as<uint32_t>();
-                }
-                launch_pairgen_generic(a, chunk_list, i1 - i0, ctx->b_gkeys.as<unsigned long long>(), ctx->b_gmn.as<uint32_t>(),
-                                       ctx->b_gmx.as<uint32_t>(), ctx->b_goff.as<uint64_t>(), s, &ctx->lc);
-                CK(cudaGetLastError());
-                CK(cudaStreamSynchronize(s));
-                i0 = i1;
-            }
-            FETCH(hc, ctx->b_counters.p, sizeof hc);
-        }
-        if (!wide_pass) ctx->tm.n_overflow_reads = fast ? n_list : 0;
-        ctx->tm.n_seed_hits = hc[1];
-        if (hc[0] <= cap) {
-            *n_out = hc[0];
-            return HLO_OK;
-        }
-        cap = hc[0] + hc[0] / 16 + 1024;  // buffer was too small: the kernels only counted past the end; redo
-    }
-    FAIL(HLO_ECUDA, "candidate buffer sizing did not converge");
+    a.dg_bits = 0;
+    return a;
 }
 
-// verify candidates (device) -> Rec16 in b_rec16; *n_acc = accepted
-static int run_verify(hlo_ctx *ctx, const hlo_reads *R, const CandI *d_cands, uint64_t n, uint64_t *n_acc) {
+// candidates into b_cands (CandI, or hlo_cand when external).  The shared-memory pair generator runs once for every
+// read and then once per larger table size for the reads whose table overflowed — every pass takes its work list
+// and its length from the device, so the later passes usually start, find nothing to do, and end.  What overflows
+// even 2048 slots (and every batch whose keys do not fit 32 bits) is left to the HBM-table kernel, which needs
+// host-side sizing and therefore runs from hlo_wait.
+static int enqueue_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external) {
     cudaStream_t s = ctx->stream;
-    *n_acc = 0;
-    CK(ctx->b_counters.ensure(8 * 8));
-    CK(ctx->b_rec16.ensure(n * sizeof(Rec16) + 16));
-    CK(ctx->b_deferred.ensure(n * 4 + 4));
-    CK(cudaMemsetAsync(ctx->b_counters.p, 0, 64, s));
-    VerifyArgs a;
-    a.reads = R->d, a.tab = ctx->tab, a.prm = verify_params(ctx);
-    a.cands = d_cands, a.n = n;
-    a.out = ctx->b_rec16.as<Rec16>();
-    a.counters = ctx->b_counters.as<unsigned long long>();
-    a.deferred = ctx->b_deferred.as<uint32_t>();
-    const bool force_exact = ctx->verify_exact != 0 || !verify_fast_supported(R->d, ctx->tab);
-    unsigned long long hc[2] = {0, 0};
-    if (force_exact) {
-        launch_verify_exact(a, nullptr, n, s, &ctx->lc);
-    } else {
-        CK(cudaEventRecord(ctx->ev_vf[0], s));
-        launch_verify_fast(a, s, &ctx->lc);
-        CK(cudaEventRecord(ctx->ev_vf[1], s));
-        CK(cudaGetLastError());
-        FETCH(hc, ctx->b_counters.p, sizeof hc);
-        if (n && cudaEventElapsedTime(&ctx->tm.verify_fast_ms, ctx->ev_vf[0], ctx->ev_vf[1]) != cudaSuccess) cudaGetLastError();
-        if (hc[1]) launch_verify_exact(a, a.deferred, hc[1], s, &ctx->lc);
+    const DevReads &d = R->d;
+    CK(ctx->b_ovf.ensure((size_t)d.n_reads * 4 + 4));
+    CK(ctx->b_ovf2.ensure((size_t)d.n_reads * 4 + 4));
+    CK(ctx->b_cands.ensure(ctx->cap_c * 16 + 16));
+    PairgenArgs a = pairgen_args(ctx, R, external);
+    ctx->fast_pairgen = pairgen_fast_supported(d, &a.dg_bits) && !ctx->pairgen_generic && d.n_reads > 0;
+    ctx->n_pg_passes = 0;
+    if (!ctx->fast_pairgen) return HLO_OK;
+    const int slots0 = std::min(std::max(ctx->pairgen_slots_log2, ctx->pairgen_slots_auto), PAIRGEN_WIDE_SLOTS_LOG2);
+    uint32_t *lists[2] = {ctx->b_ovf.as<uint32_t>(), ctx->b_ovf2.as<uint32_t>()};
+    int p = 0;
+    for (int sl = slots0; sl <= PAIRGEN_WIDE_SLOTS_LOG2 && p < HLO_PG_PASSES; ++sl, ++p) {
+        PairgenArgs ap = a;
+        ap.ovf_counter = ctr(ctx, C_PG_OVF + p), ap.work_counter = ctr(ctx, C_PG_WORK + p);
+        ap.overflow_reads = lists[p & 1];
+        if (p > 0) ap.work = lists[(p - 1) & 1], ap.n_work_ptr = ctr(ctx, C_PG_OVF + p - 1);
+        launch_pairgen(ap, sl, s, &ctx->lc);
     }
+    ctx->n_pg_passes = p;
     CK(cudaGetLastError());
-    const unsigned long long n_def = hc[1];
-    if (force_exact || n_def) FETCH(hc, ctx->b_counters.p, sizeof hc);  // else the count fetched after the fast kernel is final
-    ctx->tm.n_deferred = force_exact ? n : n_def;
-    *n_acc = hc[0];
     return HLO_OK;
 }
 
+// The HBM-table pair generator for the reads listed on the device (n_list of them; list == nullptr: every read).
+// Host-sized tables: this is the slow, synchronous path of batches with extremely deep reads.
+static int run_pairgen_generic(hlo_ctx *ctx, const hlo_reads *R, int external, const uint32_t *list, uint32_t n_list) {
+    cudaStream_t s = ctx->stream;
+    PairgenArgs a = pairgen_args(ctx, R, external);
+    if (!n_list) return HLO_OK;
+    CK(ctx->b_ovfcnt.ensure((size_t)n_list * 4 + 4));
+    launch_generic_hit_counts(a, list, n_list, ctx->b_ovfcnt.as<uint32_t>(), s, &ctx->lc);
+    std::vector<uint32_t> cnt(n_list);
+    CK(cudaMemcpyAsync(cnt.data(), ctx->b_ovfcnt.p, (size_t)n_list * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->tm.n_syncs++;
+    const uint64_t slot_budget = 1ull << 28;  // 4 GiB of tables per chunk
+    uint32_t i0 = 0;
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> xs;
+    while (i0 < n_list) {
+        off.assign(1, 0);
+        uint32_t i1 = i0;
+        while (i1 < n_list) {
+            const uint64_t sl = next_pow2_u32(std::max(2u * cnt[i1], 64u));
+            if (i1 > i0 && off.back() + sl > slot_budget) break;
+            off.push_back(off.back() + sl);
+            ++i1;
+        }
+        const uint64_t tot = off.back();
+        CK(ctx->b_gkeys.ensure(tot * 8 + 8));
+        CK(ctx->b_gmn.ensure(tot * 4 + 4));
+        CK(ctx->b_gmx.ensure(tot * 4 + 4));
+        CK(ctx->b_goff.ensure(off.size() * 8));
+        CK(cudaMemcpyAsync(ctx->b_goff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(ctx->b_gkeys.p, 0xff, tot * 8, s));
+        CK(cudaMemsetAsync(ctx->b_gmn.p, 0xff, tot * 4, s));
+        CK(cudaMemsetAsync(ctx->b_gmx.p, 0, tot * 4, s));
+        // a chunk is addressed by offsetting the list (or, without a list, by a list of x indices)
+        const uint32_t *chunk_list = list ? list + i0 : nullptr;
+        if (!list && i0 > 0) {
+            xs.resize(i1 - i0);
+            for (uint32_t i = i0; i < i1; ++i) xs[i - i0] = i;
+            CK(ctx->b_ovfcnt.ensure((size_t)xs.size() * 4 + 4));
+            CK(cudaMemcpyAsync(ctx->b_ovfcnt.p, xs.data(), xs.size() * 4, cudaMemcpyHostToDevice, s));
+            chunk_list = ctx->b_ovfcnt.as<uint32_t>();
+        }
+        launch_pairgen_generic(a, chunk_list, i1 - i0, ctx->b_gkeys.as<unsigned long long>(), ctx->b_gmn.as<uint32_t>(),
+                               ctx->b_gmx.as<uint32_t>(), ctx->b_goff.as<uint64_t>(), s, &ctx->lc);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s));
+        ctx->tm.n_syncs++;
+        i0 = i1;
+    }
+    return HLO_OK;
+}
+
+// verify the candidates in b_cands (their count: the device counter, clamped to n_cap) -> Rec16 in b_rec16
+static int enqueue_verify(hlo_ctx *ctx, const hlo_reads *R, uint64_t n_cap) {
+    cudaStream_t s = ctx->stream;
+    CK(ctx->b_rec16.ensure(ctx->cap_a * sizeof(Rec16) + 16));
+    CK(ctx->b_deferred.ensure(n_cap * 4 + 4));
+    CK(cudaMemsetAsync(ctr(ctx, C_ACC), 0, 2 * sizeof(unsigned long long), s));  // C_ACC, C_DEF (a second verify after the generic pair generator starts over)
+    VerifyArgs a;
+    a.reads = R->d, a.tab = ctx->tab, a.prm = verify_params(ctx);
+    a.cands = ctx->b_cands.as<CandI>();
+    a.n_ptr = ctr(ctx, C_CAND), a.n_cap = n_cap;
+    a.out = ctx->b_rec16.as<Rec16>(), a.out_cap = ctx->cap_a;
+    a.acc_counter = ctr(ctx, C_ACC), a.def_counter = ctr(ctx, C_DEF);
+    a.deferred = ctx->b_deferred.as<uint32_t>();
+    // the shared-memory threshold tables of the fast kernel hold 1023 entries: decided by THIS batch's longest read,
+    // not by the longest read the ctx ever saw (the tables only grow)
+    VerifyTables tab_batch = ctx->tab;
+    tab_batch.max_len = std::max<int32_t>((int32_t)R->d.max_len, 1);
+    const bool force_exact = ctx->verify_exact != 0 || !verify_fast_supported(R->d, tab_batch);
+    if (force_exact) {
+        launch_verify_exact(a, true, s, &ctx->lc);
+    } else {
+        VerifyArgs af = a;
+        af.tab.max_len = tab_batch.max_len;  // the kernel stages max_len + 1 entries of each of the three tables
+        CK(cudaEventRecord(ctx->ev_vf[0], s));
+        launch_verify_fast(af, s, &ctx->lc);
+        CK(cudaEventRecord(ctx->ev_vf[1], s));
+        launch_verify_exact(a, false, s, &ctx->lc);  // the deferred candidates (a device-side count, usually a handful)
+    }
+    CK(cudaGetLastError());
+    return HLO_OK;
+}
+
+// per-pair keep-longest + (idA, idB) order + expansion: group by idA, sort the small groups (records.cu)
+static int enqueue_tail(hlo_ctx *ctx, const hlo_reads *R) {
+    cudaStream_t s = ctx->stream;
+    const DevReads &d = R->d;
+    const uint32_t ng = d.n_reads;
+    const uint64_t cap = ctx->cap_a;
+    const unsigned long long *n_ptr = ctr(ctx, C_ACC);
+    CK(ctx->b_bid.ensure(((size_t)ng + 2) * 4 * 4));  // records per idA | group offsets | distinct idB per idA | output offsets
+    CK(ctx->b_slot.ensure(cap * 4 + 4));              // slot of a record inside its group, then "entries with a smaller idB"
+    CK(ctx->b_ent.ensure(cap * 8 + 8));               // (rank of idB, record index) entries
+    CK(ctx->b_entg.ensure(cap * 4 + 4));              // group of an entry
+    CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)ng + 1) * 4));
+    CK(ctx->b_coff.ensure(((size_t)d.n_clusters + 2) * 8));
+    const bool need_rec = ctx->rec_form == 0 || ctx->want_score;
+    if (need_rec) CK(ctx->b_out.ensure(cap * sizeof(hlo_rec) + 32));
+    if (ctx->rec_form != 0) CK(ctx->b_outc.ensure(cap * (ctx->rec_form == 1 ? sizeof(hlo_rec16) : sizeof(hlo_rec8)) + 32));
+    const bool need_aux = ctx->aux_out || ctx->want_score;
+    if (need_aux) CK(ctx->b_aux.ensure(cap * sizeof(hlo_rec_aux) + 32));
+    uint32_t *g_cnt = ctx->b_bid.as<uint32_t>(), *g_off = g_cnt + (ng + 2), *g_uniq = g_off + (ng + 2), *g_uoff = g_uniq + (ng + 2);
+    uint2 *g_ent = ctx->b_ent.as<uint2>();
+    uint32_t *g_entg = ctx->b_entg.as<uint32_t>(), *g_slot = ctx->b_slot.as<uint32_t>();
+    const Rec16 *rec = ctx->b_rec16.as<Rec16>();
+    CK(cudaMemsetAsync(g_cnt, 0, ((size_t)ng + 2) * 4, s));
+    CK(cudaMemsetAsync(g_uniq, 0, ((size_t)ng + 2) * 4, s));
+    launch_group_count(rec, n_ptr, cap, d, g_cnt, g_slot, s, &ctx->lc);
+    launch_exclusive_scan(g_cnt, g_off, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
+    launch_group_scatter(rec, n_ptr, cap, d, g_off, g_slot, g_ent, g_entg, s, &ctx->lc);
+    uint32_t *g_lt = g_slot;  // (the slots are consumed by the scatter)
+    launch_group_mark(rec, n_ptr, cap, g_off, g_entg, 1, g_ent, g_uniq, g_lt, s, &ctx->lc);
+    launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), reinterpret_cast<uint32_t *>(ctr(ctx, C_NOUT)), s, &ctx->lc);
+    ExpandOut eo;
+    if (need_rec) eo.out = ctx->b_out.as<hlo_rec>();
+    if (ctx->rec_form == 1) eo.out16 = ctx->b_outc.as<hlo_rec16>();
+    if (ctx->rec_form == 2) eo.out8 = ctx->b_outc.as<hlo_rec8>();
+    if (need_aux) eo.aux = ctx->b_aux.as<hlo_rec_aux>();
+    if (ctx->digest) {
+        CK(cudaMemsetAsync(ctr(ctx, C_DIGEST), 0, sizeof(unsigned long long), s));  // (the tail runs twice after the HBM-table pair generator)
+        eo.digest = ctr(ctx, C_DIGEST);
+    }
+    launch_group_expand(rec, n_ptr, cap, d, g_off, g_uoff, g_entg, g_ent, g_lt, eo, s, &ctx->lc);
+    if (d.n_reads) launch_cluster_offsets(g_uoff, R->b_coff.as<uint32_t>(), d.n_clusters, ctx->b_coff.as<unsigned long long>(), s, &ctx->lc);
+    else CK(cudaMemsetAsync(ctx->b_coff.p, 0, ((size_t)d.n_clusters + 1) * 8, s));
+    CK(cudaGetLastError());
+    return HLO_OK;
+}
+
+static int ensure_score_table(hlo_ctx *ctx, double mismatch_prob) {
+    cudaStream_t s = ctx->stream;
+    if (!ctx->prob_ready) {  // phred_to_prob (EdgeCalculator.cpp:59-63) for every byte value, the reference's own expression
+        CK(ctx->h_small.ensure(128 * sizeof(double)));
+        double *tab = ctx->h_small.as<double>();
+        for (int b = 0; b < 128; ++b) tab[b] = pow(10, -(b - 33) / 10.0);
+        CK(ctx->b_prob.ensure(128 * sizeof(double) + 2 * 128 * 128 * sizeof(double)));
+        CK(cudaMemcpyAsync(ctx->b_prob.p, tab, 128 * sizeof(double), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));  // (once per ctx)
+        ctx->prob_ready = true;
+        ctx->prob_thr = -1.0;
+    }
+    if (ctx->prob_thr != mismatch_prob) {
+        launch_score_table(ctx->b_prob.as<double>(), mismatch_prob, ctx->b_prob.as<double>() + 128, s, &ctx->lc);
+        ctx->prob_thr = mismatch_prob;
+    }
+    return HLO_OK;
+}
+
+// the consumer's overlap score (score.cu) on the records the tail just left in HBM
+static int enqueue_score(hlo_ctx *ctx, const hlo_reads *R) {
+    cudaStream_t s = ctx->stream;
+    const DevReads &d = R->d;
+    int rc = ensure_score_table(ctx, ctx->score_mismatch_prob);
+    if (rc) return rc;
+    CK(ctx->b_scout.ensure(ctx->cap_a * sizeof(hlo_score) + 16));
+    const uint8_t *dq = R->b_qual.as<uint8_t>() + 32;
+    const uint8_t *qflag = dq + ((d.n_bases + 32 + 15) & ~(uint64_t)15);
+    launch_score_records(d, dq, qflag, R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), ctx->b_out.as<hlo_rec>(),
+                         reinterpret_cast<const uint32_t *>(ctx->b_aux.p), 2, reinterpret_cast<const uint32_t *>(ctr(ctx, C_NOUT)), ctx->cap_a,
+                         ctx->b_prob.as<double>() + 128, ctx->score_min_read_len, ctx->b_scout.as<hlo_score>(), s, &ctx->lc);
+    CK(cudaGetLastError());
+    return HLO_OK;
+}
+
+// sketch -> index -> pair generation
+static int enqueue_front(hlo_ctx *ctx, const hlo_reads *R, int external) {
+    cudaStream_t s = ctx->stream;
+    bool keys_ready = false;
+    int rc = enqueue_sketch(ctx, R, false, &keys_ready);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
+    rc = enqueue_index(ctx, R, keys_ready);
+    if (rc) return rc;
+    rc = enqueue_pairgen(ctx, R, external);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
+    return HLO_OK;
+}
+
+// verify -> tail -> score -> counter block to the host page
+static int enqueue_back(hlo_ctx *ctx, const hlo_reads *R) {
+    cudaStream_t s = ctx->stream;
+    int rc = enqueue_verify(ctx, R, ctx->cap_c);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
+    rc = enqueue_tail(ctx, R);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[ST_DEDUP], s));
+    if (ctx->want_score) {
+        rc = enqueue_score(ctx, R);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev[ST_SCORE], s));
+    return enqueue_counter_readback(ctx);
+}
+
+static void reset_counters_for_rerun(hlo_ctx *ctx) {
+    cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long) * C_COUNT, ctx->stream);
+    cudaMemsetAsync(ctr(ctx, C_MIDOCC_LO), 0xff, sizeof(unsigned long long), ctx->stream);
+}
+
+// After a wait: did an estimate-sized buffer overflow?  Updates the learned needs; returns true when the front must
+// be enqueued again.
+static bool front_needs_rerun(hlo_ctx *ctx, const hlo_reads *R) {
+    const unsigned long long *hc = ctx->hc;
+    const uint64_t mz = (uint32_t)hc[C_MZ];
+    bool rerun = false;
+    if (R->d.n_bases) ctx->need_mz_per_base = std::max(ctx->need_mz_per_base, (double)mz / (double)R->d.n_bases);
+    if (mz > ctx->cap_mz) {
+        ctx->min_mz = mz + mz / 16 + 1024;
+        return true;  // (nothing behind the sketch ran on real data)
+    }
+    if (ctx->prefix_used && (hc[C_COLL] >> 32)) {  // rare: heavily repeated minimizers share a hash prefix — sort on all bits instead
+        ctx->force_full_sort = true;
+        ctx->tm.sort_fallback = 1.0f;
+        return true;
+    }
+    if (mz) ctx->need_c_per_mz = std::max(ctx->need_c_per_mz, (double)hc[C_CAND] / (double)mz);
+    if (hc[C_CAND] > ctx->cap_c) {
+        ctx->min_c = hc[C_CAND] + hc[C_CAND] / 16 + 1024;
+        rerun = true;
+    }
+    return rerun;
+}
+
+static void start_compute_section(hlo_ctx *ctx) {
+    if (!ctx->serialize_compute) return;
+    std::lock_guard<std::mutex> g(g_order_mutex[ctx->device & 63]);
+    cudaEvent_t prev = g_last_compute[ctx->device & 63];
+    if (prev && prev != ctx->ev_compute_done) cudaStreamWaitEvent(ctx->stream, prev, 0);
+}
+static void end_compute_section(hlo_ctx *ctx) {
+    cudaEventRecord(ctx->ev_compute_done, ctx->stream);
+    if (!ctx->serialize_compute) return;
+    std::lock_guard<std::mutex> g(g_order_mutex[ctx->device & 63]);
+    g_last_compute[ctx->device & 63] = ctx->ev_compute_done;
+}
+
+static void begin_batch(hlo_ctx *ctx, const hlo_reads *R) {
+    ctx->min_mz = ctx->min_c = ctx->min_a = 0;
+    ctx->force_full_sort = false;
+    // 8-byte records need every read name below 2^16; else the 16-byte form
+    ctx->rec_form = ctx->compact == 2 ? (R->max_id < 65536u ? 2 : 1) : (ctx->compact ? 1 : 0);
+    ctx->want_score = ctx->scores && R->has_quals && R->d.plain_names;
+    plan_caps(ctx, R);
+}
 
 static void finish_timing(hlo_ctx *ctx, const hlo_reads *R, int last_stage) {
     auto el = [&](int a, int b) {
@@ -845,10 +1051,16 @@ static void finish_timing(hlo_ctx *ctx, const hlo_reads *R, int last_stage) {
     if (last_stage >= ST_PAIRGEN) t.pairgen_ms = el(ST_INDEX, ST_PAIRGEN);
     if (last_stage >= ST_VERIFY) t.verify_ms = el(ST_PAIRGEN, ST_VERIFY);
     if (last_stage >= ST_DEDUP) t.dedup_ms = el(ST_VERIFY, ST_DEDUP);
-    if (last_stage >= ST_D2H) t.d2h_ms = el(ST_DEDUP, ST_D2H);
-    t.total_ms = t.h2d_ms + t.pack_ms + t.sketch_ms + t.sort_ms + t.index_ms + t.pairgen_ms + t.verify_ms + t.dedup_ms + t.d2h_ms;
+    if (last_stage >= ST_SCORE) t.score_ms = el(ST_DEDUP, ST_SCORE);
+    if (last_stage >= ST_D2H) t.d2h_ms = el(ST_SCORE, ST_D2H);
+    t.total_ms = t.h2d_ms + t.pack_ms + t.sketch_ms + t.sort_ms + t.index_ms + t.pairgen_ms + t.verify_ms + t.dedup_ms + t.score_ms + t.d2h_ms;
     t.n_reads = R->d.n_reads, t.n_bases = R->d.n_bases, t.n_minimizers = ctx->n_mz;
     t.total_launches = ctx->lc.total, t.verify_launches = ctx->lc.verify;
+    if (last_stage >= ST_VERIFY && ctx->lc.verify) {
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, ctx->ev_vf[0], ctx->ev_vf[1]) == cudaSuccess) t.verify_fast_ms = v;
+        else cudaGetLastError();
+    }
 }
 
 static void reset_timing(hlo_ctx *ctx) {
@@ -856,24 +1068,173 @@ static void reset_timing(hlo_ctx *ctx) {
     ctx->lc = LaunchCounter();
 }
 
+// Runs the front (sketch .. pair generation) to completion, rerunning when a buffer was too small and handing
+// overflowing reads to the HBM-table kernel.  On return hc[] holds the counters and b_cands every candidate.
+// with_back: also enqueue verify + tail behind the front, so that the usual batch needs ONE wait.
+static int complete_front(hlo_ctx *ctx, const hlo_reads *R, int external, bool with_back, bool already_enqueued) {
+    cudaStream_t s = ctx->stream;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        if (!(already_enqueued && attempt == 0)) {
+            if (attempt > 0) {
+                ctx->tm.n_reruns++;
+                plan_caps(ctx, R);
+                reset_counters_for_rerun(ctx);
+                CK(cudaEventRecord(ctx->ev[ST_PACK], s));
+            }
+            int rc = enqueue_front(ctx, R, external);
+            if (rc) return rc;
+            if (with_back) rc = enqueue_back(ctx, R);
+            else rc = enqueue_counter_readback(ctx);
+            if (rc) return rc;
+            end_compute_section(ctx);
+        }
+        int rc = sync_counters(ctx);
+        if (rc) return rc;
+        const unsigned long long *hc = ctx->hc;
+        if (hc[C_FLAGS] & HLO_FLAG_MIDOCC_AMBIGUOUS)
+            FAIL(HLO_EUNSUPPORTED, "a cluster's minimizer occurrences are too extreme for the automatic occurrence cut-off "
+                                   "(the quantile fell into the histogram's clamp bin): set mid_occ explicitly");
+        if (front_needs_rerun(ctx, R)) continue;
+        // reads the shared-memory tables could not hold (or all of them, when the fast kernel does not apply)
+        uint32_t n_list = R->d.n_reads;
+        const uint32_t *list = nullptr;
+        uint64_t first_overflow = 0;
+        if (ctx->fast_pairgen) {
+            const int last = ctx->n_pg_passes - 1;
+            n_list = (uint32_t)std::min<unsigned long long>(hc[C_PG_OVF + last], R->d.n_reads);
+            list = (last & 1) ? ctx->b_ovf2.as<uint32_t>() : ctx->b_ovf.as<uint32_t>();
+            first_overflow = hc[C_PG_OVF];
+            // a batch that overflowed a lot: the following ones start with larger tables
+            const int slots0 = std::min(std::max(ctx->pairgen_slots_log2, ctx->pairgen_slots_auto), PAIRGEN_WIDE_SLOTS_LOG2);
+            if (first_overflow > R->d.n_reads / 16 && ctx->pairgen_slots_auto < 10) ctx->pairgen_slots_auto = std::min(slots0 + 1, 10);
+        }
+        ctx->tm.n_overflow_reads = ctx->fast_pairgen ? first_overflow : 0;
+        if (n_list) {
+            rc = run_pairgen_generic(ctx, R, external, list, n_list);
+            if (rc) return rc;
+            rc = enqueue_counter_readback(ctx);
+            if (rc) return rc;
+            rc = sync_counters(ctx);
+            if (rc) return rc;
+            if (front_needs_rerun(ctx, R)) continue;
+            if (with_back) {  // the records behind the first verify missed the candidates just added: once more
+                rc = enqueue_back(ctx, R);
+                if (rc) return rc;
+                end_compute_section(ctx);
+                rc = sync_counters(ctx);
+                if (rc) return rc;
+            }
+        }
+        ctx->n_mz = (uint32_t)ctx->hc[C_MZ];
+        ctx->tm.n_seed_hits = ctx->hc[C_HITS];
+        ctx->tm.n_candidates = ctx->hc[C_CAND];
+        ctx->tm.mid_occ_lo = ctx->hc[C_MIDOCC_LO] > 0xffffffffull ? 0u : (uint32_t)ctx->hc[C_MIDOCC_LO];
+        ctx->tm.mid_occ_hi = (uint32_t)ctx->hc[C_MIDOCC_HI];
+        return HLO_OK;
+    }
+    FAIL(HLO_ECUDA, "buffer sizing did not converge");
+}
+
+// the whole chain on packed reads; out may be nullptr with option d2h = 0
+static int run_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out, bool already_enqueued) {
+    cudaStream_t s = ctx->stream;
+    const DevReads &d = R->d;
+    bool enqueued = already_enqueued;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        int rc = complete_front(ctx, R, 0, true, enqueued);
+        enqueued = false;
+        if (rc) return rc;
+        const unsigned long long *hc = ctx->hc;
+        const uint64_t mz = ctx->n_mz;
+        if (mz) ctx->need_a_per_mz = std::max(ctx->need_a_per_mz, (double)hc[C_ACC] / (double)mz);
+        if (hc[C_ACC] > ctx->cap_a) {  // more records than the estimate: grow, and the next pass enqueues front and back again
+            if (hc[C_ACC] >= 0x7ffffff0ull) FAIL(HLO_ERANGE, "more than 2^31 accepted overlaps in one batch: use smaller batches");
+            ctx->min_a = hc[C_ACC] + hc[C_ACC] / 16 + 1024;
+            ctx->min_c = std::max(ctx->min_c, ctx->min_a);
+            ctx->tm.n_reruns++;
+            plan_caps(ctx, R);
+            reset_counters_for_rerun(ctx);
+            CK(cudaEventRecord(ctx->ev[ST_PACK], s));
+            continue;
+        }
+        ctx->tm.n_accepted = hc[C_ACC];
+        ctx->tm.n_deferred = ctx->verify_exact ? hc[C_CAND] : hc[C_DEF];
+        ctx->tm.digest = hc[C_DIGEST];
+        const uint64_t n_out = (uint32_t)hc[C_NOUT];
+        ctx->tm.n_records = n_out;
+        if (ctx->d2h && out) {
+            const size_t rb = ctx->rec_form == 0 ? sizeof(hlo_rec) : ctx->rec_form == 1 ? sizeof(hlo_rec16) : sizeof(hlo_rec8);
+            CK(ctx->h_out.ensure(n_out * rb + 32));
+            CK(ctx->h_coff.ensure(((size_t)d.n_clusters + 2) * 8));
+            CK(cudaMemcpyAsync(ctx->h_out.p, ctx->rec_form == 0 ? ctx->b_out.p : ctx->b_outc.p, n_out * rb, cudaMemcpyDeviceToHost, s));
+            if (ctx->aux_out) {
+                CK(ctx->h_aux.ensure(n_out * sizeof(hlo_rec_aux) + 32));
+                CK(cudaMemcpyAsync(ctx->h_aux.p, ctx->b_aux.p, n_out * sizeof(hlo_rec_aux), cudaMemcpyDeviceToHost, s));
+            }
+            if (ctx->want_score) {
+                CK(ctx->h_score.ensure(n_out * sizeof(hlo_score) + 32));
+                CK(cudaMemcpyAsync(ctx->h_score.p, ctx->b_scout.p, n_out * sizeof(hlo_score), cudaMemcpyDeviceToHost, s));
+            }
+            CK(cudaMemcpyAsync(ctx->h_coff.p, ctx->b_coff.p, ((size_t)d.n_clusters + 1) * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(ctx->ev[ST_D2H], s));
+            CK(cudaStreamSynchronize(s));
+            ctx->tm.n_syncs++;
+        } else {
+            CK(cudaEventRecord(ctx->ev[ST_D2H], s));
+            CK(cudaEventSynchronize(ctx->ev[ST_D2H]));
+        }
+        if (out) {
+            memset(out, 0, sizeof *out);
+            if (ctx->d2h) {
+                if (ctx->rec_form == 0) out->rec = ctx->h_out.as<hlo_rec>();
+                else if (ctx->rec_form == 1) out->rec16 = ctx->h_out.as<hlo_rec16>();
+                else out->rec8 = ctx->h_out.as<hlo_rec8>();
+                out->aux = ctx->aux_out ? ctx->h_aux.as<hlo_rec_aux>() : nullptr;
+                out->score = ctx->want_score ? ctx->h_score.as<hlo_score>() : nullptr;
+                out->cluster_off = ctx->h_coff.as<uint64_t>();
+            }
+            out->n = n_out, out->n_clusters = d.n_clusters;
+        }
+        finish_timing(ctx, R, ST_D2H);
+        return HLO_OK;
+    }
+    FAIL(HLO_ECUDA, "buffer sizing did not converge");
+}
+
 extern "C" {
 
 int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64_t **read_off, uint64_t *n) {
     if (!ctx || !R || !mz || !read_off || !n) return HLO_EINVAL;
+    if (ctx->inflight) FAIL(HLO_EINVAL, "a submitted batch is in flight on this ctx: call hlo_wait first");
     CK(cudaSetDevice(ctx->device));
     reset_timing(ctx);
     cudaStream_t s = ctx->stream;
-    CK(cudaEventRecord(ctx->ev[ST_PACK], s));
-    int rc = run_sketch(ctx, R, true);
-    if (rc) return rc;
-    const uint64_t tot = ctx->n_mz;
+    begin_batch(ctx, R);
+    uint64_t tot = 0;
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 4) FAIL(HLO_ECUDA, "buffer sizing did not converge");
+        if (attempt) plan_caps(ctx, R), ctx->tm.n_reruns++;
+        reset_counters_for_rerun(ctx);
+        CK(cudaEventRecord(ctx->ev[ST_PACK], s));
+        bool keys_ready = false;
+        int rc = enqueue_sketch(ctx, R, true, &keys_ready);
+        if (rc) return rc;
+        rc = enqueue_counter_readback(ctx);
+        if (rc) return rc;
+        rc = sync_counters(ctx);
+        if (rc) return rc;
+        tot = (uint32_t)ctx->hc[C_MZ];
+        if (tot <= ctx->cap_mz) break;
+        ctx->min_mz = tot + 1024;
+    }
+    ctx->n_mz = tot;
     CK(ctx->b_mz.ensure(tot * sizeof(hlo_mz) + 16));
     launch_mz_assemble(ctx->b_mzx.as<uint64_t>(), ctx->b_mzrr.as<uint2>(), tot, ctx->b_mz.as<hlo_mz>(), s,
                        &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
     // the device arrays are in name order (sketch.cu); hand them back in the caller's read order
-    rc = ensure_host_meta(ctx, R);
+    int rc = ensure_host_meta(ctx, R);
     if (rc) return rc;
     CK(ctx->h_mz.ensure(tot * sizeof(hlo_mz) + 16));
     CK(ctx->h_roff.ensure(((size_t)R->d.n_reads + 1) * 8));
@@ -901,35 +1262,17 @@ int hlo_sketch(hlo_ctx *ctx, const hlo_reads *R, const hlo_mz **mz, const uint64
     return HLO_OK;
 }
 
-static int stages_to_candidates(hlo_ctx *ctx, const hlo_reads *R, int external, uint64_t *n_c, bool mark_start = true) {
-    cudaStream_t s = ctx->stream;
-    if (mark_start) CK(cudaEventRecord(ctx->ev[ST_PACK], s));
-    int rc = run_sketch(ctx, R, false);
-    if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[ST_SKETCH], s));
-    rc = run_index(ctx, R, true);
-    if (rc) return rc;
-    rc = run_pairgen(ctx, R, external, n_c);
-    if (rc) return rc;
-    if (ctx->prefix_failed) {  // rare: two heavily repeated minimizers share a hash prefix — sort on all bits instead
-        ctx->tm.sort_fallback = 1.0f;
-        rc = run_index(ctx, R, false);
-        if (rc) return rc;
-        rc = run_pairgen(ctx, R, external, n_c);
-        if (rc) return rc;
-    }
-    CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
-    ctx->tm.n_candidates = *n_c;
-    return HLO_OK;
-}
-
 int hlo_candidates(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand **cands, uint64_t *n) {
     if (!ctx || !R || !cands || !n) return HLO_EINVAL;
+    if (ctx->inflight) FAIL(HLO_EINVAL, "a submitted batch is in flight on this ctx: call hlo_wait first");
     CK(cudaSetDevice(ctx->device));
     reset_timing(ctx);
-    uint64_t n_c = 0;
-    int rc = stages_to_candidates(ctx, R, 1, &n_c);
+    begin_batch(ctx, R);
+    reset_counters_for_rerun(ctx);
+    CK(cudaEventRecord(ctx->ev[ST_PACK], ctx->stream));
+    int rc = complete_front(ctx, R, 1, false, false);
     if (rc) return rc;
+    const uint64_t n_c = ctx->hc[C_CAND];
     CK(ctx->h_cands.ensure(n_c * sizeof(hlo_cand) + 16));
     CK(cudaMemcpyAsync(ctx->h_cands.p, ctx->b_cands.p, n_c * sizeof(hlo_cand), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -948,6 +1291,7 @@ int hlo_candidates(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand **cands, uin
 
 int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t n, hlo_recs *out) {
     if (!ctx || !R || (!cands && n) || !out) return HLO_EINVAL;
+    if (ctx->inflight) FAIL(HLO_EINVAL, "a submitted batch is in flight on this ctx: call hlo_wait first");
     CK(cudaSetDevice(ctx->device));
     reset_timing(ctx);
     cudaStream_t s = ctx->stream;
@@ -955,18 +1299,39 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
         const int rcm = ensure_host_meta(ctx, R);
         if (rcm) return rcm;
     }
-    for (uint64_t i = 0; i < n; ++i)
-        if (cands[i].q >= R->d.n_reads || cands[i].t >= R->d.n_reads) FAIL(HLO_EINVAL, "candidate %llu names a read outside the batch", (unsigned long long)i);
+    // A candidate is trusted by the kernels (its diagonal and anchors are packed next to the read lengths and steer row
+    // reads): everything is checked here
+    for (uint64_t i = 0; i < n; ++i) {
+        const hlo_cand &c = cands[i];
+        if (c.q >= R->d.n_reads || c.t >= R->d.n_reads) FAIL(HLO_EINVAL, "candidate %llu names a read outside the batch", (unsigned long long)i);
+        const int ql = (int)R->h_len[c.q], tl = (int)R->h_len[c.t];
+        if (!(c.diag > -ql && c.diag < tl) && !(ql == 0 || tl == 0))
+            FAIL(HLO_EINVAL, "candidate %llu: diagonal %d leaves no overlap between reads of %d and %d bases", (unsigned long long)i, c.diag, ql, tl);
+        if ((ql == 0 || tl == 0) && (c.diag <= -32768 || c.diag >= 32768)) FAIL(HLO_EINVAL, "candidate %llu: diagonal out of range", (unsigned long long)i);
+        const int a_start = (int)((c.strand_anchor >> 1) & 0x7fffu), a_end = (int)(c.strand_anchor >> 16);
+        if (a_end != 0 && (a_start > a_end || a_end > ql))
+            FAIL(HLO_EINVAL, "candidate %llu: anchor span [%d, %d) outside the query (%d bases)", (unsigned long long)i, a_start, a_end, ql);
+    }
+    ctx->rec_form = 0, ctx->want_score = false;
+    ctx->cap_c = n, ctx->cap_a = n;
     CK(ctx->b_candx.ensure(n * sizeof(hlo_cand) + 16));
     CK(ctx->b_cands.ensure(n * sizeof(CandI) + 16));
+    CK(ctx->h_small.ensure(64));
+    CK(cudaMemsetAsync(ctr(ctx, 1), 0, sizeof(unsigned long long) * (C_COUNT - 1), s));
+    *ctx->h_small.as<unsigned long long>() = n;
+    CK(cudaMemcpyAsync(ctr(ctx, C_CAND), ctx->h_small.p, 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->b_candx.p, cands, n * sizeof(hlo_cand), cudaMemcpyHostToDevice, s));
     launch_cands_to_internal(ctx->b_candx.as<hlo_cand>(), n, R->d, ctx->b_cands.as<CandI>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
-    uint64_t n_acc = 0;
-    int rc = run_verify(ctx, R, ctx->b_cands.as<CandI>(), n, &n_acc);
+    int rc = enqueue_verify(ctx, R, n);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
+    rc = enqueue_counter_readback(ctx);
+    if (rc) return rc;
+    rc = sync_counters(ctx);
+    if (rc) return rc;
+    const uint64_t n_acc = ctx->hc[C_ACC];
     CK(ctx->h_rec16.ensure(n_acc * sizeof(Rec16) + 16));
     CK(cudaMemcpyAsync(ctx->h_rec16.p, ctx->b_rec16.p, n_acc * sizeof(Rec16), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -988,11 +1353,15 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
                       (int)(x.ds & 1u), x.kb & 0xffffu, &ro[i]);
         ao[i].cluster = R->h_cidx[x.q], ao[i].blocklen = x.kb >> 16;
     }
-    out->rec = ro, out->rec16 = nullptr, out->aux = ao, out->n = n_acc, out->cluster_off = nullptr, out->n_clusters = R->d.n_clusters;
+    memset(out, 0, sizeof *out);
+    out->rec = ro, out->aux = ao, out->n = n_acc, out->n_clusters = R->d.n_clusters;
     ctx->tm.n_candidates = n, ctx->tm.n_accepted = n_acc, ctx->tm.n_records = n_acc;
+    ctx->tm.n_deferred = ctx->verify_exact ? n : ctx->hc[C_DEF];
     {
         float v = 0.f;
         if (cudaEventElapsedTime(&v, ctx->ev[ST_PAIRGEN], ctx->ev[ST_VERIFY]) == cudaSuccess) ctx->tm.verify_ms = v;
+        else cudaGetLastError();
+        if (ctx->lc.verify && cudaEventElapsedTime(&v, ctx->ev_vf[0], ctx->ev_vf[1]) == cudaSuccess) ctx->tm.verify_fast_ms = v;
         else cudaGetLastError();
         ctx->tm.total_ms = ctx->tm.verify_ms;
         ctx->tm.n_reads = R->d.n_reads, ctx->tm.n_bases = R->d.n_bases;
@@ -1003,86 +1372,28 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
 
 int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     if (!ctx || !R || !out) return HLO_EINVAL;
+    if (ctx->inflight) FAIL(HLO_EINVAL, "a submitted batch is in flight on this ctx: call hlo_wait first");
     CK(cudaSetDevice(ctx->device));
     reset_timing(ctx);
     cudaStream_t s = ctx->stream;
     const DevReads &d = R->d;
-    uint64_t n_c = 0, n_acc = 0;
-    float repack_ms = -1.f;
-    std::unique_lock<std::mutex> compute_lock(g_compute_mutex[ctx->device & 63]);
+    begin_batch(ctx, R);
+    start_compute_section(ctx);
+    reset_counters_for_rerun(ctx);
+    bool repacked = false;
     if (ctx->repack && d.n_reads) {
         // the packer again, from the ASCII bases still resident in HBM (results are identical; the
         // ambiguity flags it ORs into len[] are idempotent)
+        CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));
         CK(cudaEventRecord(ctx->ev[ST_H2D], s));
         launch_pack(R->b_ascii.as<uint8_t>(), R->b_off.as<uint64_t>(), d, R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[ST_PACK], s));
-        repack_ms = 0.f;
+        repacked = true;
     }
-    int rc = stages_to_candidates(ctx, R, 0, &n_c, repack_ms < 0.f);
+    CK(cudaEventRecord(ctx->ev[ST_PACK], s));
+    int rc = run_batch(ctx, R, out, false);
     if (rc) return rc;
-    rc = run_verify(ctx, R, ctx->b_cands.as<CandI>(), n_c, &n_acc);
-    if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));
-    ctx->tm.n_accepted = n_acc;
-    if (n_acc > 0xfffffff0ull) FAIL(HLO_ERANGE, "more than 2^32 accepted overlaps in one batch");
-    // per-pair keep-longest + (idA, idB) order + expansion: group by idA, sort the small groups (records.cu)
-    const uint32_t ng = d.n_reads;
-    CK(ctx->b_flags.ensure(((size_t)ng + 2) * 4));   // records per idA
-    CK(ctx->b_bid.ensure(((size_t)ng + 2) * 4));     // group offsets
-    CK(ctx->b_best.ensure(((size_t)ng + 2) * 4));    // distinct idB per idA
-    CK(ctx->b_pos.ensure(((size_t)ng + 2) * 4));     // output offsets
-    CK(ctx->b_vals[0].ensure(n_acc * 4 + 4));        // slot of a record inside its group
-    CK(ctx->b_keys[0].ensure(n_acc * 8 + 8));        // (rank of idB, record index) entries
-    CK(ctx->b_vals[1].ensure(n_acc * 4 + 4));        // group of an entry
-    CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)ng + 1) * 4));
-    CK(ctx->b_out.ensure(n_acc * sizeof(hlo_rec) + 32));
-    CK(ctx->b_aux.ensure(n_acc * sizeof(hlo_rec_aux) + 32));
-    CK(ctx->b_coff.ensure(((size_t)d.n_clusters + 2) * 8));
-    uint32_t *g_cnt = ctx->b_flags.as<uint32_t>(), *g_off = ctx->b_bid.as<uint32_t>();
-    uint32_t *g_uniq = ctx->b_best.as<uint32_t>(), *g_uoff = ctx->b_pos.as<uint32_t>();
-    uint2 *g_ent = ctx->b_keys[0].as<uint2>();
-    CK(cudaMemsetAsync(g_cnt, 0, ((size_t)ng + 1) * 4, s));
-    CK(cudaMemsetAsync(g_uniq, 0, ((size_t)ng + 1) * 4, s));
-    launch_group_count(ctx->b_rec16.as<Rec16>(), n_acc, d, g_cnt, ctx->b_vals[0].as<uint32_t>(), s, &ctx->lc);
-    launch_exclusive_scan(g_cnt, g_off, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
-    uint32_t *g_entg = ctx->b_vals[1].as<uint32_t>();
-    launch_group_scatter(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, ctx->b_vals[0].as<uint32_t>(), g_ent, g_entg, s, &ctx->lc);
-    uint32_t *g_lt = ctx->b_vals[0].as<uint32_t>();  // (the slots are consumed by the scatter)
-    launch_group_mark(ctx->b_rec16.as<Rec16>(), n_acc, g_off, g_entg, 1, g_ent, g_uniq, g_lt, s, &ctx->lc);
-    uint32_t n_out32 = 0;
-    launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), ctx->b_counters.as<uint32_t>() + 8, s, &ctx->lc);
-    launch_group_expand(ctx->b_rec16.as<Rec16>(), n_acc, d, g_off, g_uoff, g_entg, g_ent, g_lt, ctx->b_out.as<hlo_rec>(),
-                        ctx->compact ? ctx->b_out.as<hlo_rec16>() : nullptr, ctx->aux_out ? ctx->b_aux.as<hlo_rec_aux>() : nullptr, s, &ctx->lc);
-    if (d.n_reads) launch_cluster_offsets(g_uoff, R->b_coff.as<uint32_t>(), d.n_clusters, ctx->b_coff.as<unsigned long long>(), s, &ctx->lc);
-    else CK(cudaMemsetAsync(ctx->b_coff.p, 0, ((size_t)d.n_clusters + 1) * 8, s));
-    CK(cudaGetLastError());
-    FETCH(&n_out32, ctx->b_counters.as<uint32_t>() + 8, 4);
-    const uint64_t n_out = n_out32;
-    CK(cudaEventRecord(ctx->ev[ST_DEDUP], s));
-    compute_lock.unlock();  // the download below overlaps the next worker's kernels
-    if (ctx->d2h) {
-        CK(ctx->h_out.ensure(n_out * sizeof(hlo_rec) + 32));
-        CK(ctx->h_aux.ensure(n_out * sizeof(hlo_rec_aux) + 32));
-        CK(ctx->h_coff.ensure(((size_t)d.n_clusters + 2) * 8));
-        CK(cudaMemcpyAsync(ctx->h_out.p, ctx->b_out.p, n_out * (ctx->compact ? sizeof(hlo_rec16) : sizeof(hlo_rec)), cudaMemcpyDeviceToHost, s));
-        if (ctx->aux_out) CK(cudaMemcpyAsync(ctx->h_aux.p, ctx->b_aux.p, n_out * sizeof(hlo_rec_aux), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_coff.p, ctx->b_coff.p, ((size_t)d.n_clusters + 1) * 8, cudaMemcpyDeviceToHost, s));
-    }
-    CK(cudaEventRecord(ctx->ev[ST_D2H], s));
-    CK(cudaStreamSynchronize(s));
-    if (ctx->d2h) {
-        out->rec = ctx->compact ? nullptr : ctx->h_out.as<hlo_rec>();
-        out->rec16 = ctx->compact ? ctx->h_out.as<hlo_rec16>() : nullptr;
-        out->aux = ctx->aux_out ? ctx->h_aux.as<hlo_rec_aux>() : nullptr;
-        out->cluster_off = ctx->h_coff.as<uint64_t>();
-    } else {
-        out->rec = nullptr, out->rec16 = nullptr, out->aux = nullptr, out->cluster_off = nullptr;
-    }
-    out->n = n_out, out->n_clusters = d.n_clusters;
-    ctx->tm.n_records = n_out;
-    finish_timing(ctx, R, ST_D2H);
-    if (repack_ms >= 0.f) {  // this call ran the packer itself: report its time instead of the upload's
+    if (repacked) {  // this call ran the packer itself: report its time instead of the upload's
         float v = 0.f;
         if (cudaEventElapsedTime(&v, ctx->ev[ST_H2D], ctx->ev[ST_PACK]) != cudaSuccess) cudaGetLastError(), v = 0.f;
         ctx->tm.total_ms += v - ctx->tm.pack_ms - ctx->tm.h2d_ms;
@@ -1091,65 +1402,86 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     return HLO_OK;
 }
 
+int hlo_submit(hlo_ctx *ctx, const hlo_batch *batch) {
+    if (!ctx || !batch) return HLO_EINVAL;
+    if (ctx->inflight) FAIL(HLO_EINVAL, "a submitted batch is already in flight on this ctx: call hlo_wait first");
+    CK(cudaSetDevice(ctx->device));
+    reset_timing(ctx);
+    hlo_reads *R = &ctx->scratch_reads;
+    if (ctx->scores && !batch->quals) FAIL(HLO_EINVAL, "option scores is set but the batch carries no qualities");
+    int rc = pack_into(ctx, R, *batch);
+    if (rc) return rc;
+    if (ctx->scores && !R->d.plain_names) FAIL(HLO_EUNSUPPORTED, "the fused score needs read names 0..N-1 in file order");
+    begin_batch(ctx, R);
+    start_compute_section(ctx);  // (the uploads above are already enqueued: they overlap the previous batch's kernels)
+    rc = enqueue_front(ctx, R, 0);
+    if (!rc) rc = enqueue_back(ctx, R);
+    if (rc) return rc;
+    end_compute_section(ctx);
+    ctx->inflight = true;
+    return HLO_OK;
+}
+
+int hlo_wait(hlo_ctx *ctx, hlo_recs *out) {
+    if (!ctx || !out) return HLO_EINVAL;
+    if (!ctx->inflight) FAIL(HLO_EINVAL, "hlo_wait without hlo_submit");
+    CK(cudaSetDevice(ctx->device));
+    ctx->inflight = false;
+    hlo_reads *R = &ctx->scratch_reads;
+    int rc = run_batch(ctx, R, out, true);
+    if (rc) return rc;
+    cudaEventElapsedTime(&R->h2d_ms, ctx->ev[ST_BEGIN], ctx->ev[ST_H2D]);
+    cudaEventElapsedTime(&R->pack_ms, ctx->ev[ST_H2D], ctx->ev[ST_COUNT]);
+    cudaGetLastError();
+    ctx->tm.total_ms += R->h2d_ms + R->pack_ms - ctx->tm.h2d_ms - ctx->tm.pack_ms;
+    ctx->tm.h2d_ms = R->h2d_ms, ctx->tm.pack_ms = R->pack_ms;
+    return HLO_OK;
+}
+
 int hlo_overlap_host(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, uint32_t n_reads, const uint32_t *cluster_off,
                      uint32_t n_clusters, hlo_recs *out) {
     if (!ctx || !out) return HLO_EINVAL;
-    int rc = pack_into(ctx, &ctx->scratch_reads, bases, base_off, n_reads, cluster_off, n_clusters, nullptr);
+    hlo_batch B{};
+    B.bases = bases, B.base_off = base_off, B.n_reads = n_reads, B.cluster_off = cluster_off, B.n_clusters = n_clusters;
+    int rc = hlo_submit(ctx, &B);
     if (rc) return rc;
-    return hlo_overlap_batch(ctx, &ctx->scratch_reads, out);
+    return hlo_wait(ctx, out);
+}
+
+int hlo_set_score_params(hlo_ctx *ctx, double mismatch_prob, uint32_t min_read_len) {
+    if (!ctx) return HLO_EINVAL;
+    ctx->score_mismatch_prob = mismatch_prob, ctx->score_min_read_len = min_read_len;
+    return HLO_OK;
 }
 
 int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return HLO_EINVAL;
-    if (!strcmp(name, "verify_exact")) {
-        ctx->verify_exact = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "sort_onesweep")) {
-        radix_sort_use_onesweep(value != 0);
-        return HLO_OK;
-    }
-    if (!strcmp(name, "sketch_generic")) {
-        ctx->sketch_generic = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "sort_segmented")) {
-        ctx->sort_segmented = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "sort_prefix")) {
-        ctx->sort_prefix = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "sort_hash_bits")) {  // 0 = automatic
-        if (value < 0 || value > 64) return HLO_EINVAL;
-        ctx->sort_hash_bits = (int)value;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "pairgen_generic")) {
-        ctx->pairgen_generic = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "repack")) {
-        ctx->repack = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "compact")) {
-        ctx->compact = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "aux")) {
-        ctx->aux_out = value != 0;
-        return HLO_OK;
-    }
-    if (!strcmp(name, "d2h")) {
-        ctx->d2h = value != 0;
-        return HLO_OK;
-    }
+    struct Opt {
+        const char *name;
+        int *field;
+        int64_t lo, hi;
+    };
+    const Opt opts[] = {{"verify_exact", &ctx->verify_exact, 0, 1},       {"sketch_generic", &ctx->sketch_generic, 0, 1},
+                        {"sort_segmented", &ctx->sort_segmented, 0, 1},   {"sort_prefix", &ctx->sort_prefix, 0, 1},
+                        {"sort_hash_bits", &ctx->sort_hash_bits, 0, 64},  {"pairgen_generic", &ctx->pairgen_generic, 0, 1},
+                        {"repack", &ctx->repack, 0, 1},                   {"compact", &ctx->compact, 0, 2},
+                        {"aux", &ctx->aux_out, 0, 1},                     {"d2h", &ctx->d2h, 0, 1},
+                        {"scores", &ctx->scores, 0, 1},                   {"digest", &ctx->digest, 0, 1},
+                        {"cap_scale_pct", &ctx->cap_scale_pct, 1, 100000}, {"serialize_compute", &ctx->serialize_compute, 0, 1}};
+    for (const Opt &o : opts)
+        if (!strcmp(name, o.name)) {
+            if (value < o.lo || value > o.hi) FAIL(HLO_ERANGE, "%s=%lld outside [%lld,%lld]", name, (long long)value, (long long)o.lo, (long long)o.hi);
+            *o.field = (int)value;
+            return HLO_OK;
+        }
     if (!strcmp(name, "pairgen_slots_log2")) {
         if (value < 5 || value > 10) FAIL(HLO_ERANGE, "pairgen_slots_log2=%lld outside [5,10]", (long long)value);
         ctx->pairgen_slots_log2 = (int)value;
         ctx->pairgen_slots_auto = 0;
+        return HLO_OK;
+    }
+    if (!strcmp(name, "forget_sizes")) {  // drop what earlier batches taught the buffer estimates
+        ctx->need_mz_per_base = ctx->need_c_per_mz = ctx->need_a_per_mz = 0.0;
         return HLO_OK;
     }
     FAIL(HLO_EINVAL, "unknown option %s", name);
@@ -1158,6 +1490,7 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
 int hlo_score_records(hlo_ctx *ctx, const hlo_reads *R, const char *quals, const hlo_rec *rec, const uint32_t *rec_cluster, uint64_t n,
                       double mismatch_prob, uint32_t min_read_len, const hlo_score **out) {
     if (!ctx || !R || !quals || (!rec && n) || !out) return HLO_EINVAL;
+    if (ctx->inflight) FAIL(HLO_EINVAL, "a submitted batch is in flight on this ctx: call hlo_wait first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const DevReads &d = R->d;
@@ -1169,23 +1502,15 @@ int hlo_score_records(hlo_ctx *ctx, const hlo_reads *R, const char *quals, const
             for (uint32_t i = R->h_cluster_off[c]; i < R->h_cluster_off[c + 1]; ++i)
                 if (R->h_ids[i] != i - R->h_cluster_off[c]) FAIL(HLO_EUNSUPPORTED, "hlo_score_records needs read names 0..N-1 in file order");
     }
-    if (!ctx->prob_ready) {  // phred_to_prob (EdgeCalculator.cpp:59-63) for every byte value, the reference's own expression
-        double tab[128];
-        for (int b = 0; b < 128; ++b) tab[b] = pow(10, -(b - 33) / 10.0);
-        CK(ctx->b_prob.ensure(sizeof tab + 2 * 128 * 128 * sizeof(double)));
-        CK(cudaMemcpyAsync(ctx->b_prob.p, tab, sizeof tab, cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));
-        ctx->prob_ready = true;
-    }
-    CK(ctx->b_qual.ensure(d.n_bases + 64 + (size_t)d.n_reads + 16));  // 32 bytes of padding on both sides, then a flag per read
+    reset_timing(ctx);
+    int rc = ensure_score_table(ctx, mismatch_prob);
+    if (rc) return rc;
+    CK(ctx->b_qual.ensure(d.n_bases + 64 + (size_t)d.n_reads + 32));  // 32 bytes of padding on both sides, then a flag per read
     CK(ctx->b_screc.ensure(n * sizeof(hlo_rec) + 32));
     CK(ctx->b_scclu.ensure(n * 4 + 4));
     CK(ctx->b_scout.ensure(n * sizeof(hlo_score) + 16));
     CK(ctx->h_score.ensure(n * sizeof(hlo_score) + 16));
-    CK(const_cast<hlo_reads *>(R)->b_coff.ensure(((size_t)d.n_clusters + 1) * 4));
-    reset_timing(ctx);
     CK(cudaEventRecord(ctx->ev[ST_BEGIN], s));
-    CK(cudaMemcpyAsync(R->b_coff.p, R->h_cluster_off.data(), ((size_t)d.n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
     uint8_t *d_qual = ctx->b_qual.as<uint8_t>() + 32, *d_qflag = d_qual + ((d.n_bases + 32 + 15) & ~(uint64_t)15);
     CK(cudaMemsetAsync(ctx->b_qual.p, 0, 32, s));
     CK(cudaMemsetAsync(d_qual + d.n_bases, 0, 32, s));
@@ -1193,10 +1518,9 @@ int hlo_score_records(hlo_ctx *ctx, const hlo_reads *R, const char *quals, const
     if (n) CK(cudaMemcpyAsync(ctx->b_screc.p, rec, n * sizeof(hlo_rec), cudaMemcpyHostToDevice, s));
     if (n && rec_cluster) CK(cudaMemcpyAsync(ctx->b_scclu.p, rec_cluster, n * 4, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(ctx->ev[ST_H2D], s));
-    launch_score_table(ctx->b_prob.as<double>(), mismatch_prob, ctx->b_prob.as<double>() + 128, s, &ctx->lc);
     launch_qual_flags(d_qual, R->b_off.as<uint64_t>(), d.n_reads, d_qflag, s, &ctx->lc);
     launch_score_records(d, d_qual, d_qflag, R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), ctx->b_screc.as<hlo_rec>(),
-                         rec_cluster ? ctx->b_scclu.as<uint32_t>() : nullptr, n, ctx->b_prob.as<double>() + 128, min_read_len,
+                         rec_cluster ? ctx->b_scclu.as<uint32_t>() : nullptr, 1, nullptr, n, ctx->b_prob.as<double>() + 128, min_read_len,
                          ctx->b_scout.as<hlo_score>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_VERIFY], s));

@@ -40,16 +40,22 @@ int format_overlap(const hlo_rec *r, char *buf, size_t cap) {
     return snprintf(buf, cap, "%u\t%u\t%lld\t-\t-\t%c\t%c\t%lld\t-\t%lld\t-\ts\ts", id1, id2, pos1, ori1, ori2, perc, ovlen);
 }
 
-// decimal digits of v at p; returns the end
+// decimal digits of v at p; returns the end (two digits per division: the files hold hundreds of millions of numbers)
+static const char DIGIT_PAIRS[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960"
+    "616263646566676869707172737475767778798081828384858687888990919293949596979899";
 inline char *put_u64(char *p, unsigned long long v) {
     char tmp[24];
-    int n = 0;
-    do {
-        tmp[n++] = (char)('0' + v % 10);
-        v /= 10;
-    } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
+    int n = 24;
+    while (v >= 100) {
+        const unsigned r = (unsigned)(v % 100) * 2;
+        v /= 100;
+        tmp[--n] = DIGIT_PAIRS[r + 1], tmp[--n] = DIGIT_PAIRS[r];
+    }
+    if (v >= 10) tmp[--n] = DIGIT_PAIRS[v * 2 + 1], tmp[--n] = DIGIT_PAIRS[v * 2];
+    else tmp[--n] = (char)('0' + v);
+    memcpy(p, tmp + n, (size_t)(24 - n));
+    return p + (24 - n);
 }
 
 // the same 13 fields as format_overlap, without snprintf (the files hold millions of lines); returns the length or -1
@@ -88,6 +94,49 @@ int format_overlap_fast(const hlo_rec *r, char *buf) {
     memcpy(p, "\t-\ts\ts", 6), p += 6;
     *p = 0;
     return (int)(p - buf);
+}
+
+// the 13-column file from any record form: get(i, r) yields record i (false: malformed input).  Lines are formatted
+// into one buffer and leave with a single write; the file appears under its name only when it is complete.
+template <class Get>
+int write_overlaps_from(uint64_t n, const hlo_score *score, const char *path, Get get) {
+    if (!path) return HLO_EINVAL;
+    std::string tmp = std::string(path) + ".tmp";
+    std::vector<char> out;
+    out.resize((size_t)n * (score ? 120 : 72) + 64);  // ids < 2^32: a line is at most 10+10+5+5+3+5 digits + 25 fixed characters
+    char *w = out.data();
+    char prev[160];
+    int prev_len = -1;
+    hlo_rec r;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!get(i, r)) return HLO_EINVAL;
+        char *line = w;
+        const int len = format_overlap_fast(&r, line);
+        if (len < 0) return HLO_EINVAL;
+        if (len == prev_len && memcmp(line, prev, (size_t)len) == 0) continue;  // `uniq` (sfo2overlaps.py:107)
+        memcpy(prev, line, (size_t)len), prev_len = len;
+        w += len;
+        if (score) w += snprintf(w, 64, "\t%.17g\t%.17g", score[i].score, score[i].mismatch_rate);  // round-trip precision
+        *w++ = '\n';
+    }
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return HLO_EIO;
+    const size_t bytes = (size_t)(w - out.data());
+    bool ok = bytes == 0 || fwrite(out.data(), 1, bytes, f) == bytes;
+    if (fclose(f) != 0) ok = false;
+    if (!ok || rename(tmp.c_str(), path) != 0) {  // never leave a partial file behind
+        remove(tmp.c_str());
+        return HLO_EIO;
+    }
+    return HLO_OK;
+}
+
+int write_overlaps_impl(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path) {
+    if (!rec && n) return HLO_EINVAL;
+    return write_overlaps_from(n, score, path, [&](uint64_t i, hlo_rec &r) {
+        r = rec[i];
+        return true;
+    });
 }
 
 }  // namespace
@@ -129,64 +178,67 @@ int hlo_write_sfo(const hlo_rec *rec, uint64_t n, const char *path) {
     return HLO_OK;
 }
 
-static int write_overlaps_impl(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path);
-
-// 16-byte records are expanded block-wise and written through the 32-byte code
-static int write16_blocks(const hlo_rec16 *rec, uint64_t n, const char *path, bool sfo) {
+int hlo_write_overlaps16(const hlo_rec16 *rec, uint64_t n, const char *path) {
+    if (!rec && n) return HLO_EINVAL;
+    return write_overlaps_from(n, nullptr, path, [&](uint64_t i, hlo_rec &r) {
+        hlo_rec16_expand(&rec[i], &r);
+        return true;
+    });
+}
+int hlo_write_sfo16(const hlo_rec16 *rec, uint64_t n, const char *path) {
     if ((!rec && n) || !path) return HLO_EINVAL;
-    std::string all;
     std::vector<hlo_rec> tmp((size_t)n);
     for (uint64_t i = 0; i < n; ++i) hlo_rec16_expand(&rec[i], &tmp[(size_t)i]);
-    return sfo ? hlo_write_sfo(tmp.data(), n, path) : write_overlaps_impl(tmp.data(), nullptr, n, path);
+    return hlo_write_sfo(tmp.data(), n, path);
 }
-int hlo_write_overlaps16(const hlo_rec16 *rec, uint64_t n, const char *path) { return write16_blocks(rec, n, path, false); }
-int hlo_write_sfo16(const hlo_rec16 *rec, uint64_t n, const char *path) { return write16_blocks(rec, n, path, true); }
+
+// 8-byte records carry (idA, idB, OHA, K, ori); the other fields follow from the two read lengths (hlo_rec8_expand)
+int hlo_write_overlaps8(const hlo_rec8 *rec, uint64_t n, const uint32_t *len_by_id, uint32_t n_ids, const char *path) {
+    if ((!rec && n) || (!len_by_id && n)) return HLO_EINVAL;
+    return write_overlaps_from(n, nullptr, path, [&](uint64_t i, hlo_rec &r) {
+        if (rec[i].idA >= n_ids || rec[i].idB >= n_ids) return false;
+        hlo_rec8_expand(&rec[i], len_by_id[rec[i].idA], len_by_id[rec[i].idB], &r);
+        return true;
+    });
+}
+int hlo_write_sfo8(const hlo_rec8 *rec, uint64_t n, const uint32_t *len_by_id, uint32_t n_ids, const char *path) {
+    if ((!rec && n) || !path || (!len_by_id && n)) return HLO_EINVAL;
+    std::vector<hlo_rec> tmp((size_t)n);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (rec[i].idA >= n_ids || rec[i].idB >= n_ids) return HLO_EINVAL;
+        hlo_rec8_expand(&rec[i], len_by_id[rec[i].idA], len_by_id[rec[i].idB], &tmp[(size_t)i]);
+    }
+    return hlo_write_sfo(tmp.data(), n, path);
+}
+
+// binary hand-off (include/hlovlp.h; the reader patch for EdgeCalculator.cpp:569-604 is in INTEGRATION.md §5)
+int hlo_write_binary16(const hlo_rec16 *rec, const hlo_score *score, uint64_t n, const char *path) {
+    if ((!rec && n) || !path) return HLO_EINVAL;
+    std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return HLO_EIO;
+    struct {
+        char magic[4];
+        uint32_t version, rec_bytes, flags;
+        uint64_t n, reserved;
+    } h = {{'H', 'L', 'O', 'B'}, 1u, (uint32_t)sizeof(hlo_rec16), score ? 1u : 0u, n, 0ull};
+    static_assert(sizeof h == 32, "header is 32 bytes");
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    if (ok && n) ok = fwrite(rec, sizeof(hlo_rec16), (size_t)n, f) == (size_t)n;
+    if (ok && n && score) ok = fwrite(score, sizeof(hlo_score), (size_t)n, f) == (size_t)n;
+    if (fclose(f) != 0) ok = false;
+    if (!ok || rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        return HLO_EIO;
+    }
+    return HLO_OK;
+}
 
 int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path) { return write_overlaps_impl(rec, nullptr, n, path); }
 
 int hlo_write_overlaps_scored(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path) {
     if (!score && n) return HLO_EINVAL;
     return write_overlaps_impl(rec, score, n, path);
-}
-
-static int write_overlaps_impl(const hlo_rec *rec, const hlo_score *score, uint64_t n, const char *path) {
-    if ((!rec && n) || !path) return HLO_EINVAL;
-    std::string tmp = std::string(path) + ".tmp";
-    FILE *f = fopen(tmp.c_str(), "w");
-    if (!f) return HLO_EIO;
-    static const size_t BUF = 4 << 20;
-    std::string out;
-    out.reserve(BUF + 256);
-    char line[160], prev[160];
-    prev[0] = 0;
-    bool ok = true;
-    for (uint64_t i = 0; i < n && ok; ++i) {
-        const int len = format_overlap_fast(&rec[i], line);
-        if (len < 0) {
-            ok = false;
-            break;
-        }
-        if (i && strcmp(line, prev) == 0) continue;  // `uniq`
-        out.append(line, (size_t)len);
-        if (score) {  // two more columns: overlap score and mismatch rate, round-trip precision
-            char sc[64];
-            const int sl = snprintf(sc, sizeof sc, "\t%.17g\t%.17g", score[i].score, score[i].mismatch_rate);
-            out.append(sc, (size_t)sl);
-        }
-        out.push_back('\n');
-        memcpy(prev, line, (size_t)len + 1);
-        if (out.size() >= BUF) {
-            ok = fwrite(out.data(), 1, out.size(), f) == out.size();
-            out.clear();
-        }
-    }
-    if (ok && !out.empty()) ok = fwrite(out.data(), 1, out.size(), f) == out.size();
-    if (fclose(f) != 0) ok = false;
-    if (!ok || rename(tmp.c_str(), path) != 0) {  // never leave a partial file behind
-        remove(tmp.c_str());
-        return HLO_EIO;
-    }
-    return HLO_OK;
 }
 
 }  // extern "C"

@@ -5,10 +5,13 @@
 //     fastq2fasta.py ; minimap2 --sr -X -c -k 21 -w 11 -s 60 -m 30 -n 2 -r 0 -A 4 -B 2 --end-bonus 100 F F
 //       | cut -f 1-12 | filter_ovlp_inline.py L 0.98 1 0.8 ; minimap22sfo.py ; sfo2overlaps.py
 // and writes the same 13-column `.overlaps` file (and optionally the 8-column SFO file) that
-// tools/HaploConduct/src/EdgeCalculator.cpp:561-666 parses.  All arithmetic runs in libhlovlp's CUDA
-// kernels through the C ABI of include/hlovlp.h; this file only parses text, batches clusters, drives
-// one worker thread per GPU (clusters are independent: dynamic queue, host-side gather, no NCCL) and
-// writes text.  There is no CPU code path for the overlap computation.
+// tools/HaploConduct/src/EdgeCalculator.cpp:561-666 parses — or, with --binary_out, the records themselves
+// (hlo_write_binary16; reader patch in INTEGRATION.md §5).  All arithmetic runs in libhlovlp's CUDA kernels through
+// the C ABI of include/hlovlp.h; this file only parses text, batches clusters (largest first), drives a
+// few worker threads per GPU (clusters are independent: dynamic queue, host-side gather, no NCCL) and writes files.
+// A worker owns one context and one set of page-locked input buffers for its whole life: per batch it parses into
+// them, calls hlo_submit / hlo_wait (nothing is allocated, and the device is never waited for between stages), and
+// writes the cluster files.  There is no CPU code path for the overlap computation.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -27,24 +30,45 @@ namespace {
 
 struct Cluster {
     std::string in1, in2, out, sfo;
-    std::string bases, quals;
-    std::vector<uint64_t> off{0};
-    std::vector<uint32_t> ids;
+    uint64_t bytes = 0;  // size of the input files: an upper bound of the bases, and the batching weight
     std::string err;
     uint64_t n_records = 0;
+};
+
+// one cluster's reads as parsed from its files
+struct Parsed {
+    std::string bases, quals;
+    std::vector<uint32_t> lens, ids;
+    void clear() { bases.clear(), quals.clear(), lens.clear(), ids.clear(); }
 };
 
 struct Options {
     hlo_params P;
     std::vector<int> devices;
-    uint64_t batch_bases = 256ull << 20;
+    uint64_t batch_bases = 96ull << 20;
     int workers_per_device = 3;
     bool rename = false;
     bool scores = false;          // also write <out>.scored: 13 columns + HaploConduct's overlap score and mismatch rate
+    bool binary_out = false;      // <out> holds the records (hlo_write_binary16) instead of text
     double mismatch_prob = 0.0;   // ViralQuasispecies --mismatch
     uint32_t min_read_len = 0;    // ViralQuasispecies --min_read_len
     std::string stats;
     std::vector<Cluster> clusters;
+};
+
+// page-locked host array that only grows (hlo_host_alloc)
+template <class T>
+struct PinVec {
+    T *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) hlo_host_free(p);
+        cap = n + n / 4 + 1024;
+        p = (T *)hlo_host_alloc(cap * sizeof(T));
+        if (!p) cap = 0;
+        return p != nullptr;
+    }
 };
 
 bool read_file(const std::string &path, std::string &data, std::string &err) {
@@ -53,9 +77,15 @@ bool read_file(const std::string &path, std::string &data, std::string &err) {
         err = "cannot open " + path;
         return false;
     }
-    char buf[1 << 16];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    const size_t old = data.size();
+    if (sz > 0) {
+        data.resize(old + (size_t)sz);
+        const size_t got = fread(&data[old], 1, (size_t)sz, f);
+        data.resize(old + got);
+    }
     const bool ok = !ferror(f);
     fclose(f);
     if (!ok) err = "read error on " + path;
@@ -79,9 +109,9 @@ bool parse_id(const char *s, const char *e, uint32_t &id) {
 }
 
 // FASTA (multi-line) or FASTQ (4-line records, fastq2fasta.py:32-40) -> appended to c
-bool parse_reads(const std::string &path, Cluster &c, bool rename, bool want_quals = false) {
-    std::string data;
-    if (!read_file(path, data, c.err)) return false;
+bool parse_reads(const std::string &path, Parsed &c, std::string &err, bool rename, bool want_quals, std::string &data) {
+    data.clear();
+    if (!read_file(path, data, err)) return false;
     const char *p = data.data(), *end = p + data.size();
     auto line_end = [&](const char *q) {
         const char *e = (const char *)memchr(q, '\n', (size_t)(end - q));
@@ -91,11 +121,11 @@ bool parse_reads(const std::string &path, Cluster &c, bool rename, bool want_qua
     if (p == end) return true;
     const bool fq = *p == '@';
     if (!fq && *p != '>') {
-        c.err = path + ": neither FASTA nor FASTQ";
+        err = path + ": neither FASTA nor FASTQ";
         return false;
     }
     if (!fq && want_quals) {
-        c.err = path + ": --scores needs FASTQ input (phred qualities)";
+        err = path + ": --scores needs FASTQ input (phred qualities)";
         return false;
     }
     while (p < end) {
@@ -105,16 +135,17 @@ bool parse_reads(const std::string &path, Cluster &c, bool rename, bool want_qua
         }
         const char *le = line_end(p);
         if (*p != (fq ? '@' : '>')) {
-            c.err = path + ": malformed record header";
+            err = path + ": malformed record header";
             return false;
         }
         uint32_t id = (uint32_t)c.ids.size();
         if (!rename && !parse_id(p + 1, le, id)) {
-            c.err = path + ": read name '" + std::string(p + 1, le) + "' is not a plain decimal integer (use --rename)";
+            err = path + ": read name '" + std::string(p + 1, le) + "' is not a plain decimal integer (use --rename)";
             return false;
         }
         c.ids.push_back(id);
         p = le < end ? le + 1 : end;
+        const size_t b0 = c.bases.size();
         if (fq) {
             const char *se = line_end(p);
             const char *s_end = se;
@@ -128,7 +159,7 @@ bool parse_reads(const std::string &path, Cluster &c, bool rename, bool want_qua
                     const char *q_end = e2;
                     while (q_end > p && q_end[-1] == '\r') --q_end;
                     if ((size_t)(q_end - p) != slen) {
-                        c.err = path + ": quality string and sequence differ in length";
+                        err = path + ": quality string and sequence differ in length";
                         return false;
                     }
                     c.quals.append(p, q_end);
@@ -144,7 +175,7 @@ bool parse_reads(const std::string &path, Cluster &c, bool rename, bool want_qua
                 p = se < end ? se + 1 : end;
             }
         }
-        c.off.push_back(c.bases.size());
+        c.lens.push_back((uint32_t)(c.bases.size() - b0));
     }
     return true;
 }
@@ -156,14 +187,21 @@ void usage() {
             "       hylight-ovlp --clusters list.tsv [options]      (lines: in<TAB>out[<TAB>sfo]; in may be 'a.1.fq,a.2.fq')\n"
             "options (defaults = polyte.tune_params.py:500-510):\n"
             "  --min_ovlp_len 60  --min_identity 0.98  --max_overhang 1  --overhang_ratio 0.8\n"
-            "  -k 21  -w 11  --min_seeds 2  --min_chain_score 30  --mid_occ 1000\n"
+            "  -k 21  -w 11  --min_seeds 2  --min_chain_score 30\n"
+            "  --mid_occ 0         occurrence cut-off; 0 = minimap2's default, derived from every cluster's index\n"
+            "  --stage_b           the thresholds of HyLight's contig stage (HyLight.py:309-311): --min_ovlp_len 90\n"
+            "                      --min_identity 0.99 --max_overhang 2\n"
             "  --rename            name reads 0..N-1 in file order (what rename_fas.py does)\n"
             "  --devices 0,1,..|all   GPUs to use (default all)\n"
-            "  --batch_bases N     bases per device batch (default 268435456)\n"
-            "  --workers_per_device N  host workers (context + stream each) per GPU; one computes while the others\n"
-            "                      upload, download and write text (default 3)\n"
-            "  --scores            also write <out>.scored = the 13 columns + HaploConduct's phred-weighted overlap score and\n"
-            "                      mismatch rate (EdgeCalculator.cpp:67-139); FASTQ input; [--mismatch_prob P] [--min_read_len L]\n"
+            "  --batch_bases N     input bytes per device batch (default 100663296)\n"
+            "  --workers_per_device N  host workers (context + stream + pinned buffers each) per GPU; one's kernels run\n"
+            "                      while the others parse, upload, download and write files (default 3)\n"
+            "  --binary_out        write the records themselves (32-byte header + 16-byte records, include/hlovlp.h\n"
+            "                      hlo_write_binary16) instead of text: the hand-off for a HaploConduct with the reader\n"
+            "                      patch of INTEGRATION.md\n"
+            "  --scores            also compute HaploConduct's phred-weighted overlap score and mismatch rate\n"
+            "                      (EdgeCalculator.cpp:67-139) on the device: <out>.scored = 13 columns + the two (text), or\n"
+            "                      appended to the binary file; FASTQ input; [--mismatch_prob P] [--min_read_len L]\n"
             "  --stats FILE        JSON-lines per batch\n");
 }
 
@@ -182,6 +220,8 @@ bool parse_args(int argc, char **argv, Options &o, std::string &err) {
         const char *v = nullptr;
         if (a == "--rename") o.rename = true;
         else if (a == "--scores") o.scores = true;
+        else if (a == "--binary_out") o.binary_out = true;
+        else if (a == "--stage_b") o.P.min_ovlp_len = 90, o.P.min_identity = 0.99, o.P.max_overhang = 2;
         else if (a == "-h" || a == "--help") return false;
         else if (!val(v)) {
             err = "missing value for " + a;
@@ -302,104 +342,173 @@ void parallel_for(size_t n, size_t threads, F fn) {
 struct Shared {
     Options *o;
     size_t helpers = 1;  // host threads a worker may use to parse and to write the clusters of its batch
-    std::vector<std::vector<size_t>> batches;  // cluster indices per batch
+    std::vector<std::vector<size_t>> batches;  // cluster indices per batch, largest batch first
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
     std::mutex log_mu;
     FILE *stats = nullptr;
 };
 
+double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
 void worker(Shared *S, int device) {
     Options &o = *S->o;
+    // the context (CUDA start-up: a few hundred ms on a cold process) comes up while the first batch is parsed
     hlo_ctx *ctx = nullptr;
-    const auto tc0 = std::chrono::steady_clock::now();
-    int rc = hlo_ctx_create(device, &o.P, &ctx);
-    double ctx_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
-    if (rc) {
-        std::lock_guard<std::mutex> g(S->log_mu);
-        fprintf(stderr, "hylight-ovlp: device %d: %s\n", device, hlo_strerror(rc));
-        S->failed = 1;
-        return;
-    }
-    hlo_set_option(ctx, "aux", 0);  // the files need the records and the per-cluster offsets only
-    const bool compact = !o.scores;  // 16-byte records: half the download (the scorer takes the 32-byte form)
-    hlo_set_option(ctx, "compact", compact ? 1 : 0);
+    int ctx_rc = 0;
+    double ctx_ms = 0.0;
+    std::thread ctx_thread([&] {
+        const auto tc0 = std::chrono::steady_clock::now();
+        ctx_rc = hlo_ctx_create(device, &o.P, &ctx);
+        if (!ctx_rc) {
+            hlo_set_option(ctx, "aux", 0);  // the files need the records and the per-cluster offsets only
+            // text: 8-byte records (OHB and the overlap length follow from the read lengths parsed here);
+            // binary hand-off: the self-contained 16-byte form
+            hlo_set_option(ctx, "compact", o.binary_out ? 1 : 2);
+            if (o.scores) {
+                hlo_set_option(ctx, "scores", 1);
+                hlo_set_score_params(ctx, o.mismatch_prob, o.min_read_len);
+            }
+        }
+        ctx_ms = ms_since(tc0);
+    });
+    bool ctx_joined = false;
+    PinVec<char> p_bases, p_quals;
+    PinVec<uint64_t> p_off;
+    PinVec<uint32_t> p_coff, p_ids;
+    std::vector<Parsed> parsed;
+    std::vector<std::string> file_buf;  // one per helper slot: the raw text of the file being parsed
     for (;;) {
         const size_t b = S->next.fetch_add(1);
         if (b >= S->batches.size() || S->failed) break;
         const auto t0 = std::chrono::steady_clock::now();
         const std::vector<size_t> &idx = S->batches[b];
-        // parse the clusters of the batch (in parallel), then concatenate
-        std::string bases, quals;
-        std::vector<uint64_t> off{0};
-        std::vector<uint32_t> ids, coff{0};
+        const size_t nc = idx.size();
+        if (parsed.size() < nc) parsed.resize(nc);
+        if (file_buf.size() < nc) file_buf.resize(nc);
+        // parse the clusters of the batch (in parallel), then lay them out back to back in the pinned buffers
         std::atomic<bool> parse_ok{true};
-        parallel_for(idx.size(), S->helpers, [&](size_t j) {
+        parallel_for(nc, S->helpers, [&](size_t j) {
             Cluster &c = o.clusters[idx[j]];
-            if (!(parse_reads(c.in1, c, o.rename, o.scores) && (c.in2.empty() || parse_reads(c.in2, c, o.rename, o.scores)))) parse_ok = false;
+            Parsed &P = parsed[j];
+            P.clear();
+            if (!(parse_reads(c.in1, P, c.err, o.rename, o.scores, file_buf[j]) &&
+                  (c.in2.empty() || parse_reads(c.in2, P, c.err, o.rename, o.scores, file_buf[j]))))
+                parse_ok = false;
         });
-        bool ok = parse_ok;
-        if (ok) {
-            size_t nb = 0, nr = 0;
-            for (size_t ci : idx) nb += o.clusters[ci].bases.size(), nr += o.clusters[ci].ids.size();
-            bases.reserve(nb), off.reserve(nr + 1), ids.reserve(nr);
-            for (size_t ci : idx) {
-                Cluster &c = o.clusters[ci];
-                for (size_t r = 1; r < c.off.size(); ++r) off.push_back(bases.size() + c.off[r]);
-                bases += c.bases;
-                if (o.scores) quals += c.quals, std::string().swap(c.quals);
-                ids.insert(ids.end(), c.ids.begin(), c.ids.end());
-                coff.push_back((uint32_t)ids.size());
-                std::string().swap(c.bases);
-                std::vector<uint64_t>().swap(c.off);
-                std::vector<uint32_t>().swap(c.ids);
-            }
-        }
-        const auto t_parsed = std::chrono::steady_clock::now();
-        hlo_reads *R = nullptr;
-        const hlo_score *scores = nullptr;
-        hlo_recs out{};
         std::string err;
-        if (!ok) {
+        bool ok = parse_ok;
+        size_t nb = 0, nr = 0;
+        std::vector<size_t> b_start(nc + 1, 0), r_start(nc + 1, 0);
+        if (ok) {
+            for (size_t j = 0; j < nc; ++j) {
+                b_start[j] = nb, r_start[j] = nr;
+                nb += parsed[j].bases.size(), nr += parsed[j].ids.size();
+            }
+            b_start[nc] = nb, r_start[nc] = nr;
+            if (nr > 0xfffffff0ull) ok = false, err = "more than 2^32 reads in one batch: lower --batch_bases";
+        } else {
             for (size_t ci : idx)
                 if (!o.clusters[ci].err.empty()) err = o.clusters[ci].err;
-        } else {
-            rc = hlo_pack_reads(ctx, bases.data(), off.data(), (uint32_t)ids.size(), coff.data(), (uint32_t)idx.size(), ids.data(), &R);
-            if (!rc) rc = hlo_overlap_batch(ctx, R, &out);
-            if (!rc && o.scores) {
-                std::vector<uint32_t> rc_of(out.n);  // cluster of every record, from the per-cluster offsets
-                for (size_t j = 0; j < idx.size(); ++j)
-                    for (uint64_t k = out.cluster_off[j]; k < out.cluster_off[j + 1]; ++k) rc_of[k] = (uint32_t)j;
-                rc = hlo_score_records(ctx, R, quals.data(), out.rec, rc_of.data(), out.n, o.mismatch_prob, o.min_read_len, &scores);
+        }
+        if (ok && !(p_bases.ensure(nb + 16) && p_off.ensure(nr + 1) && p_coff.ensure(nc + 1) && p_ids.ensure(nr + 1) &&
+                    (!o.scores || p_quals.ensure(nb + 16))))
+            ok = false, err = "out of page-locked host memory";
+        if (ok) {
+            parallel_for(nc, S->helpers, [&](size_t j) {
+                const Parsed &P = parsed[j];
+                memcpy(p_bases.p + b_start[j], P.bases.data(), P.bases.size());
+                if (o.scores) memcpy(p_quals.p + b_start[j], P.quals.data(), P.quals.size());
+                uint64_t off = b_start[j];
+                for (size_t r = 0; r < P.lens.size(); ++r) {
+                    p_off.p[r_start[j] + r] = off;
+                    p_ids.p[r_start[j] + r] = P.ids[r];
+                    off += P.lens[r];
+                }
+                p_coff.p[j] = (uint32_t)r_start[j];
+            });
+            p_off.p[nr] = nb, p_coff.p[nc] = (uint32_t)nr;
+        }
+        const double parse_ms = ms_since(t0);
+        if (!ctx_joined) {
+            ctx_thread.join();
+            ctx_joined = true;
+            if (ctx_rc) {
+                std::lock_guard<std::mutex> g(S->log_mu);
+                fprintf(stderr, "hylight-ovlp: device %d: %s\n", device, hlo_strerror(ctx_rc));
+                S->failed = 1;
+                return;
             }
+        }
+        const auto t_call = std::chrono::steady_clock::now();
+        hlo_recs out{};
+        int rc = 0;
+        if (ok) {
+            hlo_batch B{};
+            B.bases = p_bases.p, B.quals = o.scores ? p_quals.p : nullptr, B.base_off = p_off.p, B.n_reads = (uint32_t)nr;
+            B.cluster_off = p_coff.p, B.n_clusters = (uint32_t)nc, B.ids = o.rename ? nullptr : p_ids.p;
+            rc = hlo_submit(ctx, &B);
+            if (!rc) rc = hlo_wait(ctx, &out);
             if (rc) err = std::string(hlo_strerror(rc)) + ": " + hlo_last_error(ctx);
         }
-        const auto t_computed = std::chrono::steady_clock::now();
+        const double call_ms = ms_since(t_call);
+        const auto t_write = std::chrono::steady_clock::now();
         if (err.empty()) {  // per-cluster files, written in parallel
             std::mutex emu;
-            parallel_for(idx.size(), S->helpers, [&](size_t j) {
+            parallel_for(nc, S->helpers, [&](size_t j) {
                 Cluster &c = o.clusters[idx[j]];
-                const uint64_t n = out.cluster_off[j + 1] - out.cluster_off[j];
+                const uint64_t r0 = out.cluster_off[j], n = out.cluster_off[j + 1] - r0;
                 c.n_records = n;
-                const hlo_rec *r0 = compact ? nullptr : out.rec + out.cluster_off[j];
-                const hlo_rec16 *c0 = compact ? out.rec16 + out.cluster_off[j] : nullptr;
-                int wrc = compact ? hlo_write_overlaps16(c0, n, c.out.c_str()) : hlo_write_overlaps(r0, n, c.out.c_str());
-                if (!wrc && !c.sfo.empty()) wrc = compact ? hlo_write_sfo16(c0, n, c.sfo.c_str()) : hlo_write_sfo(r0, n, c.sfo.c_str());
-                if (!wrc && scores) wrc = hlo_write_overlaps_scored(r0, scores + out.cluster_off[j], n, (c.out + ".scored").c_str());
+                const hlo_score *sc = out.score ? out.score + r0 : nullptr;
+                int wrc = 0;
+                std::vector<hlo_rec> full;   // the 32-byte form, only where a writer needs it
+                std::vector<hlo_rec16> r16;  // the 16-byte form for the binary file when the library sent 8-byte records
+                std::vector<uint32_t> len_by_id;
+                if (out.rec8) {  // names -> lengths (a name is the read's position unless the file carried its own)
+                    const Parsed &P = parsed[j];
+                    uint32_t mx = 0;
+                    for (uint32_t id : P.ids) mx = std::max(mx, id);
+                    len_by_id.assign((size_t)mx + 1, 0u);
+                    for (size_t r = 0; r < P.ids.size(); ++r) len_by_id[P.ids[r]] = P.lens[r];
+                }
+                auto need_full = [&]() {
+                    if (!full.empty() || !n) return;
+                    full.resize(n);
+                    for (uint64_t i = 0; i < n; ++i) {
+                        if (out.rec8) hlo_rec8_expand(&out.rec8[r0 + i], len_by_id[out.rec8[r0 + i].idA], len_by_id[out.rec8[r0 + i].idB], &full[i]);
+                        else if (out.rec16) hlo_rec16_expand(&out.rec16[r0 + i], &full[i]);
+                        else full[i] = out.rec[r0 + i];
+                    }
+                };
+                if (o.binary_out) {
+                    wrc = hlo_write_binary16(out.rec16 ? out.rec16 + r0 : nullptr, sc, n, c.out.c_str());
+                } else if (out.rec8) {
+                    wrc = hlo_write_overlaps8(out.rec8 + r0, n, len_by_id.data(), (uint32_t)len_by_id.size(), c.out.c_str());
+                } else if (out.rec16) {
+                    wrc = hlo_write_overlaps16(out.rec16 + r0, n, c.out.c_str());
+                } else {
+                    wrc = hlo_write_overlaps(out.rec + r0, n, c.out.c_str());
+                }
+                if (!wrc && !c.sfo.empty()) {
+                    need_full();
+                    wrc = hlo_write_sfo(full.data(), n, c.sfo.c_str());
+                }
+                if (!wrc && sc && !o.binary_out) {
+                    need_full();
+                    wrc = hlo_write_overlaps_scored(full.data(), sc, n, (c.out + ".scored").c_str());
+                }
                 if (wrc) {
                     std::lock_guard<std::mutex> g(emu);
                     err = std::string(hlo_strerror(wrc)) + " writing " + c.out;
                 }
             });
         }
+        const double write_ms = ms_since(t_write);
         hlo_timing tm{};
         hlo_get_timing(ctx, &tm);
-        if (R) hlo_reads_free(R);
-        const auto t_end = std::chrono::steady_clock::now();
-        const double wall = std::chrono::duration<double, std::milli>(t_end - t0).count();
-        const double parse_ms = std::chrono::duration<double, std::milli>(t_parsed - t0).count();
-        const double call_ms = std::chrono::duration<double, std::milli>(t_computed - t_parsed).count();
-        const double write_ms = std::chrono::duration<double, std::milli>(t_end - t_computed).count();
+        const double wall = ms_since(t0);
         std::lock_guard<std::mutex> g(S->log_mu);
         if (!err.empty()) {
             fprintf(stderr, "hylight-ovlp: batch %zu on device %d failed: %s\n", b, device, err.c_str());
@@ -410,18 +519,21 @@ void worker(Shared *S, int device) {
             fprintf(S->stats,
                     "{\"batch\": %zu, \"device\": %d, \"clusters\": %zu, \"reads\": %llu, \"bases\": %llu, \"minimizers\": %llu, "
                     "\"seed_hits\": %llu, \"candidates\": %llu, \"accepted\": %llu, \"records\": %llu, \"deferred\": %llu, "
-                    "\"overflow_reads\": %llu, \"launches\": %llu, \"ms\": {\"h2d\": %.3f, \"pack\": %.3f, \"sketch\": %.3f, "
-                    "\"sort\": %.3f, \"index\": %.3f, \"pairgen\": %.3f, \"verify\": %.3f, \"dedup\": %.3f, \"d2h\": %.3f, "
+                    "\"overflow_reads\": %llu, \"launches\": %llu, \"reruns\": %llu, \"syncs\": %llu, \"mid_occ\": [%u, %u], "
+                    "\"ms\": {\"h2d\": %.3f, \"pack\": %.3f, \"sketch\": %.3f, "
+                    "\"sort\": %.3f, \"index\": %.3f, \"pairgen\": %.3f, \"verify\": %.3f, \"dedup\": %.3f, \"score\": %.3f, \"d2h\": %.3f, "
                     "\"device_total\": %.3f, \"wall\": %.3f, \"host_parse\": %.3f, \"host_call\": %.3f, \"host_write\": %.3f, "
                     "\"ctx_create\": %.3f}}\n",
-                    b, device, idx.size(), (unsigned long long)tm.n_reads, (unsigned long long)tm.n_bases,
+                    b, device, nc, (unsigned long long)tm.n_reads, (unsigned long long)tm.n_bases,
                     (unsigned long long)tm.n_minimizers, (unsigned long long)tm.n_seed_hits, (unsigned long long)tm.n_candidates,
                     (unsigned long long)tm.n_accepted, (unsigned long long)tm.n_records, (unsigned long long)tm.n_deferred,
-                    (unsigned long long)tm.n_overflow_reads, (unsigned long long)tm.total_launches, tm.h2d_ms, tm.pack_ms,
-                    tm.sketch_ms, tm.sort_ms, tm.index_ms, tm.pairgen_ms, tm.verify_ms, tm.dedup_ms, tm.d2h_ms, tm.total_ms, wall, parse_ms,
-                    call_ms, write_ms, ctx_ms);
+                    (unsigned long long)tm.n_overflow_reads, (unsigned long long)tm.total_launches, (unsigned long long)tm.n_reruns,
+                    (unsigned long long)tm.n_syncs, tm.mid_occ_lo, tm.mid_occ_hi, tm.h2d_ms, tm.pack_ms,
+                    tm.sketch_ms, tm.sort_ms, tm.index_ms, tm.pairgen_ms, tm.verify_ms, tm.dedup_ms, tm.score_ms, tm.d2h_ms, tm.total_ms, wall,
+                    parse_ms, call_ms, write_ms, ctx_ms);
         ctx_ms = 0.0;  // (reported with the worker's first batch)
     }
+    if (!ctx_joined) ctx_thread.join();
     // no hlo_ctx_destroy: the process is about to end, and releasing gigabytes of device and pinned memory buffer by
     // buffer (then the CUDA context) costs about a second that the operating system does not need
     (void)ctx;
@@ -448,13 +560,18 @@ int main(int argc, char **argv) {
     }
     Shared S;
     S.o = &o;
-    // batches: consecutive clusters until ~batch_bases (file size is an upper bound of the base count);
-    // largest batches are not reordered so that output files appear in list order
+    // batches: clusters largest first (the long jobs start early, the short ones fill the tail), packed
+    // until ~batch_bases (file size is an upper bound of the base count); every cluster has its own output file, so
+    // the order of the list does not matter
     {
+        for (Cluster &c : o.clusters) c.bytes = file_size(c.in1) + (c.in2.empty() ? 0 : file_size(c.in2));
+        std::vector<size_t> order(o.clusters.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return o.clusters[a].bytes > o.clusters[b].bytes; });
         std::vector<size_t> cur;
         uint64_t acc = 0;
-        for (size_t i = 0; i < o.clusters.size(); ++i) {
-            const uint64_t sz = file_size(o.clusters[i].in1) + (o.clusters[i].in2.empty() ? 0 : file_size(o.clusters[i].in2));
+        for (size_t i : order) {
+            const uint64_t sz = o.clusters[i].bytes;
             if (!cur.empty() && acc + sz > o.batch_bases) {
                 S.batches.push_back(cur);
                 cur.clear(), acc = 0;

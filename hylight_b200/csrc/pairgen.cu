@@ -37,55 +37,67 @@ namespace hlo {
 #define HLO_EMPTY32 0xffffffffu
 
 __global__ void hash_keys_kernel(const uint64_t *__restrict__ x, const uint2 *__restrict__ mz_rr,
-                                 const uint32_t *__restrict__ cidx, int hash_bits, uint64_t n, uint64_t *__restrict__ keys,
-                                 uint32_t *__restrict__ vals) {
+                                 const uint32_t *__restrict__ cidx, int hash_bits, const uint32_t *__restrict__ n_ptr,
+                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = (x[i] >> 8) | (uint64_t)cidx[mz_rr[i].x] << hash_bits, vals[i] = (uint32_t)i;
+    if (i < *n_ptr) keys[i] = (x[i] >> 8) | (uint64_t)cidx[mz_rr[i].x] << hash_bits, vals[i] = (uint32_t)i;
 }
-void launch_hash_keys(const uint64_t *mz_x, const uint2 *mz_rr, const uint32_t *cidx, int hash_bits, uint64_t n, uint64_t *keys,
-                      uint32_t *vals, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    hash_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mz_x, mz_rr, cidx, hash_bits, n, keys, vals);
+void launch_hash_keys(const uint64_t *mz_x, const uint2 *mz_rr, const uint32_t *cidx, int hash_bits, uint64_t n_cap, const uint32_t *n_ptr,
+                      uint64_t *keys, uint32_t *vals, cudaStream_t s, LaunchCounter *lc) {
+    if (n_cap == 0) return;
+    hash_keys_kernel<<<(unsigned)((n_cap + 255) / 256), 256, 0, s>>>(mz_x, mz_rr, cidx, hash_bits, n_ptr, keys, vals);
     if (lc) lc->total++;
 }
 
-// The whole bucket index in one pass over the (cluster, hash)-grouped minimizers:
-//   hits[i]  = (read, pos<<1|strand) of the i-th entry (one 8-byte gather from the read-order array);
-//   range[m] = the hits minimizer m seeds: the part of its bucket behind its own entry (i + 1 .. bucket end),
-//              or nothing when the bucket holds more than mid_occ entries (scatter to read order).
+// The bucket index over the (cluster, hash)-grouped minimizers, in two modes of one tile kernel:
+//   EMIT = false: occurrence histogram.  The first entry of every bucket adds one to hist[cluster][min(size, bins - 1)]:
+//              the input of minimap2's data-derived occurrence cut-off (mm_idx_cal_max_occ: the (1 - 2e-4) quantile of the
+//              occurrences of the distinct minimizers, + 1, clamped to [10, 10^6]; midocc_kernel below).  Skipped when the
+//              caller fixes mid_occ.
+//   EMIT = true:  hits[i]  = (read, pos<<1|strand) of the i-th entry (one 8-byte gather from the read-order array);
+//              range[m] = the hits minimizer m seeds: the part of its bucket behind its own entry (i + 1 .. bucket end),
+//              or nothing when the bucket holds more than the cluster's cut-off (scatter to read order).
 // A tile of 1024 entries finds its bucket boundaries from warp ballots of "key differs from the previous key";
 // only the two buckets that stick out of the tile need a look at the neighbouring tiles' keys, and that search
-// stops after mid_occ entries (a longer bucket is dropped anyway).  The keys are cluster-major, so the gather
-// and the scatter stay inside one cluster's few MB.
+// stops after `reach` entries (EMIT: the cut-off, a longer bucket is dropped anyway; histogram: the clamp bin).
+// The keys are cluster-major, so the gather and the scatter stay inside one cluster's few MB.
 constexpr int IX_THREADS = 256;
 constexpr int IX_ITEMS = 4;
 constexpr int IX_TILE = IX_THREADS * IX_ITEMS;
 constexpr int IX_RUNS = IX_TILE / 32;
 
+template <bool EMIT>
 __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
-                                                                  const uint2 *__restrict__ mz_rr, uint64_t n, int mid_occ,
-                                                                  uint2 *__restrict__ hits, uint2 *__restrict__ range) {
+                                                                  const uint2 *__restrict__ mz_rr, const uint32_t *__restrict__ n_ptr,
+                                                                  int hash_bits, const uint32_t *__restrict__ midocc, uint32_t *__restrict__ hist,
+                                                                  uint32_t bins, uint2 *__restrict__ hits, uint2 *__restrict__ range) {
     __shared__ int run_first[IX_RUNS], run_last[IX_RUNS];     // first / last bucket start inside a run of 32 entries (tile-relative)
     __shared__ int next_after[IX_RUNS], last_before[IX_RUNS]; // first start in a later run / last start in an earlier run
     __shared__ uint32_t tile_prev, tile_next;                 // start of the tile's first bucket, end of its last (global)
+    const uint64_t n = *n_ptr;
     const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     const uint64_t base = (uint64_t)blockIdx.x * IX_TILE;
+    if (base >= n) return;
     const uint32_t tn = (uint32_t)((n - base) < (uint64_t)IX_TILE ? (n - base) : (uint64_t)IX_TILE);
     unsigned bal[IX_ITEMS];
     uint32_t idx[IX_ITEMS];
+    uint32_t clu[IX_ITEMS];
 #pragma unroll
     for (int j = 0; j < IX_ITEMS; ++j) {
         const uint32_t r = (uint32_t)j * (IX_THREADS / 32) + wp, e = r * 32 + lane;
         const uint64_t i = base + e;
         const bool ok = e < tn;
         bool flag = false;
-        idx[j] = 0;
+        idx[j] = 0, clu[j] = 0;
         if (ok) {
             const uint64_t kx = skeys[i];
             flag = i == 0 || kx != skeys[i - 1];
-            idx[j] = svals[i];
-            hits[i] = mz_rr[idx[j]];
+            clu[j] = (uint32_t)(kx >> hash_bits);
+            if (EMIT) {
+                idx[j] = svals[i];
+                hits[i] = mz_rr[idx[j]];
+            }
         }
         bal[j] = __ballot_sync(FULL, flag);
         if (lane == 0) {
@@ -110,6 +122,7 @@ __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t
         uint64_t end = base + tn;
         if (end < n) {
             const uint64_t key_last = skeys[end - 1];
+            const uint64_t reach = EMIT ? (uint64_t)midocc[(uint32_t)(key_last >> hash_bits)] : (uint64_t)bins;
             for (;;) {
                 const uint64_t i = end + lane;
                 const bool differs = i >= n || skeys[i] != key_last;
@@ -119,14 +132,15 @@ __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t
                     break;
                 }
                 end += 32;
-                if (end - (base + tn) > (uint64_t)max(mid_occ, 0)) break;  // already larger than mid_occ: dropped anyway
+                if (end - (base + tn) > reach) break;  // already larger than the cut-off (or the clamp bin): no need to know more
             }
         }
         if (lane == 0) tile_next = (uint32_t)end;
-    } else if (wp == 2) {  // start of the bucket the tile's first entry belongs to
+    } else if (wp == 2 && EMIT) {  // start of the bucket the tile's first entry belongs to
         uint64_t start = base;
         if (base > 0 && tn > 0) {
             const uint64_t key_first = skeys[base];
+            const uint64_t reach = (uint64_t)midocc[(uint32_t)(key_first >> hash_bits)];
             for (;;) {
                 // lane l looks at entry start - 1 - l
                 const bool differs = start < (uint64_t)lane + 1 || skeys[start - 1 - lane] != key_first;
@@ -136,7 +150,7 @@ __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t
                     break;
                 }
                 start -= 32;
-                if (base - start > (uint64_t)max(mid_occ, 0)) break;
+                if (base - start > reach) break;
             }
         }
         if (lane == 0) tile_prev = (uint32_t)start;
@@ -147,19 +161,81 @@ __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t
         const uint32_t r = (uint32_t)j * (IX_THREADS / 32) + wp, e = r * 32 + lane;
         if (e >= tn) continue;
         const unsigned above = lane == 31 ? 0u : bal[j] >> (lane + 1);
-        const unsigned upto = bal[j] & (0xffffffffu >> (31 - lane));
         const int nb = above ? (int)e + __ffs(above) : next_after[r];
-        const int pb = upto ? (int)(r * 32) + 31 - __clz(upto) : last_before[r];
         const uint32_t en = nb == INT_MAX ? tile_next : (uint32_t)(base + (uint32_t)nb);
-        const uint32_t st = pb < 0 ? tile_prev : (uint32_t)(base + (uint32_t)pb);
-        range[idx[j]] = (int)(en - st) > mid_occ ? make_uint2(0u, 0u) : make_uint2((uint32_t)(base + e) + 1u, en);
+        if (EMIT) {
+            const unsigned upto = bal[j] & (0xffffffffu >> (31 - lane));
+            const int pb = upto ? (int)(r * 32) + 31 - __clz(upto) : last_before[r];
+            const uint32_t st = pb < 0 ? tile_prev : (uint32_t)(base + (uint32_t)pb);
+            range[idx[j]] = (en - st) > midocc[clu[j]] ? make_uint2(0u, 0u) : make_uint2((uint32_t)(base + e) + 1u, en);
+        } else if ((bal[j] >> lane) & 1u) {  // first entry of its bucket: one count for the bucket's size
+            const uint32_t sz = en - (uint32_t)(base + e);
+            atomicAdd(&hist[(size_t)clu[j] * bins + (sz < bins - 1u ? sz : bins - 1u)], 1u);
+        }
     }
 }
-void launch_bucket_index(const uint64_t *skeys, const uint32_t *svals, const uint2 *mz_rr, uint64_t n, int mid_occ, uint2 *hits,
-                         uint2 *range, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    bucket_index_kernel<<<(unsigned)((n + IX_TILE - 1) / IX_TILE), IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n, mid_occ, hits, range);
-    if (lc) lc->total++;
+
+// one block per cluster: mid_occ = clamp(k-th smallest occurrence + 1, 10, 10^6), k = (uint32_t)((1 - 2e-4f) * distinct)
+// (minimap2 mm_idx_cal_max_occ / mm_mapopt_update; the float constant is promoted to double there as here)
+__global__ void __launch_bounds__(256) midocc_kernel(const uint32_t *__restrict__ hist, uint32_t bins, uint32_t n_clusters, int fixed,
+                                                     uint32_t *__restrict__ midocc, unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t s_thr;
+    const uint32_t c = blockIdx.x;
+    if (c >= n_clusters) return;
+    uint32_t thr;
+    if (fixed > 0) {
+        thr = (uint32_t)fixed;
+    } else {
+        const uint32_t *h = hist + (size_t)c * bins;
+        const uint32_t per = (bins + 255u) / 256u, b0 = threadIdx.x * per, b1 = min(bins, b0 + per);
+        uint32_t sum = 0;
+        for (uint32_t b = b0; b < b1; ++b) sum += h[b];
+        part[threadIdx.x] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t n = 0;
+            for (int t = 0; t < 256; ++t) n += part[t];
+            uint32_t v = 0;
+            if (n) {
+                const uint32_t k = (uint32_t)((1. - (double)2e-4f) * (double)n);
+                uint32_t cum = 0;
+                int t = 0;
+                while (t < 255 && cum + part[t] <= k) cum += part[t], ++t;
+                uint32_t b = (uint32_t)t * per;
+                const uint32_t be = min(bins, b + per);
+                while (b + 1 < be && cum + h[b] <= k) cum += h[b], ++b;
+                v = b;
+                if (v == bins - 1u) atomicOr(&counters[C_FLAGS], HLO_FLAG_MIDOCC_AMBIGUOUS);  // the true occurrence is not known
+            }
+            long long m = (long long)v + 1;
+            if (m < 10) m = 10;
+            if (m > 1000000) m = 1000000;
+            s_thr = (uint32_t)m;
+        }
+        __syncthreads();
+        thr = s_thr;
+    }
+    if (threadIdx.x == 0) {
+        midocc[c] = thr;
+        atomicMin(&counters[C_MIDOCC_LO], (unsigned long long)thr);
+        atomicMax(&counters[C_MIDOCC_HI], (unsigned long long)thr);
+    }
+}
+
+void launch_bucket_index(const uint64_t *skeys, const uint32_t *svals, const uint2 *mz_rr, uint64_t n_cap, const uint32_t *n_ptr, int hash_bits,
+                         int fixed_mid_occ, uint32_t n_clusters, uint32_t *midocc, uint32_t *hist, uint32_t bins, unsigned long long *counters,
+                         uint2 *hits, uint2 *range, cudaStream_t s, LaunchCounter *lc) {
+    if (n_cap == 0 || n_clusters == 0) return;
+    const unsigned grid = (unsigned)((n_cap + IX_TILE - 1) / IX_TILE);
+    if (fixed_mid_occ <= 0) {
+        cudaMemsetAsync(hist, 0, (size_t)n_clusters * bins * sizeof(uint32_t), s);
+        bucket_index_kernel<false><<<grid, IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n_ptr, hash_bits, nullptr, hist, bins, hits, range);
+        if (lc) lc->total++;
+    }
+    midocc_kernel<<<n_clusters, 256, 0, s>>>(hist, bins, n_clusters, fixed_mid_occ, midocc, counters);
+    bucket_index_kernel<true><<<grid, IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n_ptr, hash_bits, midocc, hist, bins, hits, range);
+    if (lc) lc->total += 2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -215,12 +291,17 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     const unsigned lt8 = (1u << l) - 1u;
     const int kshift = a.dg_bits + 1;
     const uint32_t max_len = a.reads.max_len;
-    const uint32_t n_work = a.work ? a.n_work : a.reads.n_reads;  // the listed reads (x indices), or all of them
+    // the listed reads (x indices; their number is a device counter left by the previous pass), or all of them
+    uint32_t n_work = a.reads.n_reads;
+    if (a.work) {
+        const unsigned long long nw = *a.n_work_ptr;
+        n_work = nw < (unsigned long long)a.overflow_cap ? (uint32_t)nw : a.overflow_cap;
+    }
     const int gap_min = a.gap_min;
     unsigned long long nh_total = 0;
     for (;;) {
         unsigned long long qq = 0;
-        if (lane == 0) qq = atomicAdd(&a.counters[3], (unsigned long long)PG_RPW);
+        if (lane == 0) qq = atomicAdd(a.work_counter, (unsigned long long)PG_RPW);
         qq = __shfl_sync(FULL, qq, 0);
         if (qq >= n_work) break;
         const uint32_t wi = (uint32_t)qq + lane / PG_G;
@@ -353,7 +434,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & PG_GMASK) != 0u;
         if (ovf_any) {  // redo this read exactly in the generic kernel (its hits are counted there)
             if (l == 0 && have_read) {
-                const unsigned long long p = atomicAdd(&a.counters[2], 1ULL);
+                const unsigned long long p = atomicAdd(a.ovf_counter, 1ULL);
                 if (p < a.overflow_cap) a.overflow_reads[p] = xq;
             }
             nq = 0, list_n = 0;
@@ -369,7 +450,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
         }
         const uint32_t total = __shfl_sync(FULL, inc, 31);
         unsigned long long base = 0;
-        if (lane == 0 && total) base = atomicAdd(&a.counters[0], (unsigned long long)total);
+        if (lane == 0 && total) base = atomicAdd(a.cand_counter, (unsigned long long)total);
         base = __shfl_sync(FULL, base, 0);
         // exclusive prefix of my group = inclusive prefix of the last lane of the previous group
         const uint32_t gprev = __shfl_sync(FULL, inc, (gshift + 31u) & 31u);
@@ -399,7 +480,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     // seed-hit statistic: one atomic per warp
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nh_total += __shfl_xor_sync(FULL, nh_total, d);
-    if (lane == 0 && nh_total) atomicAdd(&a.counters[1], nh_total);
+    if (lane == 0 && nh_total) atomicAdd(a.hit_counter, nh_total);
 }
 
 static bool pairgen_narrow(const DevReads &r, int slots_log2) { return r.max_len <= 255 && slots_log2 <= 8; }
@@ -417,7 +498,7 @@ bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out) {
 }
 
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc) {
-    const uint32_t n_work = a.work ? a.n_work : a.reads.n_reads;
+    const uint32_t n_work = a.reads.n_reads;  // (a listed pass usually finds its device-side count at zero and leaves at once)
     if (n_work == 0) return;
     const bool narrow = pairgen_narrow(a.reads, slots_log2);
     const size_t smem = pairgen_smem_bytes(slots_log2, narrow);
@@ -506,12 +587,12 @@ __global__ void __launch_bounds__(256) pairgen_generic_kernel(PairgenArgs a, con
     }
     if (nh) atomicAdd(&nh_tot, (unsigned long long)nh);
     __syncthreads();
-    if (threadIdx.x == 0 && nh_tot) atomicAdd(&a.counters[1], nh_tot);
+    if (threadIdx.x == 0 && nh_tot) atomicAdd(a.hit_counter, nh_tot);
     for (uint32_t j = threadIdx.x; j < S; j += blockDim.x) {
         const unsigned long long key = keys[j];
         const uint32_t lo = mn[j], hi = mx[j];
         if (key != HLO_EMPTY_KEY && (int)(hi - lo) >= a.gap_min) {
-            const unsigned long long p = atomicAdd(&a.counters[0], 1ULL);
+            const unsigned long long p = atomicAdd(a.cand_counter, 1ULL);
             const uint32_t t = (uint32_t)(key >> 32), low = (uint32_t)key;
             const uint32_t lt = a.reads.len[t];
             emit_cand(a, p, q, t, low >> 31, (int)(low & 0x7fffffffu) - HLO_DIAG_BIAS, lo, hi, ql, lt & 0x7fffu, (lt | lq) >> 31);

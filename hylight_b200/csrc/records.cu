@@ -29,123 +29,168 @@ __device__ __forceinline__ bool rec_better(const Rec16 &x, const Rec16 &y) {
     return (x.ds >> 1) < (y.ds >> 1);
 }
 
-// group = numeric rank (batch-global) of the record's idA; slot[i] = position of record i inside its group
-__global__ void __launch_bounds__(256) group_count_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
-                                                          uint32_t *__restrict__ cnt, uint32_t *__restrict__ slot) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
-    const uint32_t nq = r.plain_names ? qt.x : __ldg(r.nrank + qt.x), nt = r.plain_names ? qt.y : __ldg(r.nrank + qt.y);
-    slot[i] = atomicAdd(&cnt[min(nq, nt)], 1u);
+// Every pass takes the number of accepted records from the verify kernels' device counter (clamped to the buffer) and
+// runs on a resident grid that strides: the host sizes nothing from a count it would have to wait for.
+constexpr int RT_THREADS = 256;
+static unsigned tail_grid(uint64_t n_cap) {
+    const uint64_t want = (n_cap + RT_THREADS - 1) / RT_THREADS;
+    return (unsigned)(want < 148ull * 8 ? (want ? want : 1) : 148ull * 8);
 }
-void launch_group_count(const Rec16 *rec, uint64_t n, DevReads r, uint32_t *cnt, uint32_t *slot, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    group_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, cnt, slot);
+__device__ __forceinline__ uint64_t tail_n(const unsigned long long *n_ptr, uint64_t n_cap) {
+    const unsigned long long n = *n_ptr;
+    return n < n_cap ? n : n_cap;
+}
+
+// group = numeric rank (batch-global) of the record's idA; slot[i] = position of record i inside its group
+__global__ void __launch_bounds__(RT_THREADS) group_count_kernel(const Rec16 *__restrict__ rec, const unsigned long long *__restrict__ n_ptr,
+                                                                 uint64_t n_cap, DevReads r, uint32_t *__restrict__ cnt,
+                                                                 uint32_t *__restrict__ slot) {
+    const uint64_t n = tail_n(n_ptr, n_cap);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
+        const uint32_t nq = r.plain_names ? qt.x : __ldg(r.nrank + qt.x), nt = r.plain_names ? qt.y : __ldg(r.nrank + qt.y);
+        slot[i] = atomicAdd(&cnt[min(nq, nt)], 1u);
+    }
+}
+void launch_group_count(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, uint32_t *cnt, uint32_t *slot,
+                        cudaStream_t s, LaunchCounter *lc) {
+    if (n_cap == 0) return;
+    group_count_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, r, cnt, slot);
     if (lc) lc->total++;
 }
 
 // entry = (rank of idB, record index) at off[group] + slot; entg = its group
-__global__ void __launch_bounds__(256) group_scatter_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
-                                                            const uint32_t *__restrict__ off, const uint32_t *__restrict__ slot,
-                                                            uint2 *__restrict__ ent, uint32_t *__restrict__ entg) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
-    const uint32_t nq = r.plain_names ? qt.x : __ldg(r.nrank + qt.x), nt = r.plain_names ? qt.y : __ldg(r.nrank + qt.y);
-    const uint32_t g = min(nq, nt), p = off[g] + slot[i];
-    ent[p] = make_uint2(max(nq, nt), (uint32_t)i);
-    entg[p] = g;
+__global__ void __launch_bounds__(RT_THREADS) group_scatter_kernel(const Rec16 *__restrict__ rec, const unsigned long long *__restrict__ n_ptr,
+                                                                   uint64_t n_cap, DevReads r, const uint32_t *__restrict__ off,
+                                                                   const uint32_t *__restrict__ slot, uint2 *__restrict__ ent,
+                                                                   uint32_t *__restrict__ entg) {
+    const uint64_t n = tail_n(n_ptr, n_cap);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
+        const uint32_t nq = r.plain_names ? qt.x : __ldg(r.nrank + qt.x), nt = r.plain_names ? qt.y : __ldg(r.nrank + qt.y);
+        const uint32_t g = min(nq, nt), p = off[g] + slot[i];
+        ent[p] = make_uint2(max(nq, nt), (uint32_t)i);
+        entg[p] = g;
+    }
 }
-void launch_group_scatter(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *slot, uint2 *ent,
-                          uint32_t *entg, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    group_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, slot, ent, entg);
+void launch_group_scatter(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *off,
+                          const uint32_t *slot, uint2 *ent, uint32_t *entg, cudaStream_t s, LaunchCounter *lc) {
+    if (n_cap == 0) return;
+    group_scatter_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, r, off, slot, ent, entg);
     if (lc) lc->total++;
 }
 
 // Pass A, one thread per ENTRY (entries are laid out group by group, so the lanes of a warp walk the same one
 // or two groups and their loads coalesce): is my record the one to keep for its pair?  (No other entry of the
 // group with the same idB is better.)  The answer goes to the top bit of the entry and is counted per group.
-__global__ void __launch_bounds__(256) group_mark_kernel(const Rec16 *__restrict__ rec, uint64_t n, const uint32_t *__restrict__ off,
-                                                         const uint32_t *__restrict__ entg, int dedup, uint2 *ent,
-                                                         uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const uint2 me = ent[p];
-    const uint32_t g = entg[p];
-    bool keep = true;
-    uint32_t lt = 0;  // entries of the group with a smaller idB: my place in the group when it holds no duplicate pair
-    const uint32_t b = off[g], e = off[g + 1];
-    for (uint32_t j = b; j < e; ++j) {
-        const uint2 y = ent[j];
-        lt += y.x < me.x;
-        if (dedup && y.x == me.x && j != p && rec_better(rec[y.y & 0x7fffffffu], rec[me.y])) keep = false;  // same pair, better record
-    }
-    lt_out[p] = lt;
-    if (keep) {
-        ent[p].y = me.y | 0x80000000u;
-        atomicAdd(&uniq[g], 1u);
+__global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__restrict__ rec, const unsigned long long *__restrict__ n_ptr,
+                                                                uint64_t n_cap, const uint32_t *__restrict__ off,
+                                                                const uint32_t *__restrict__ entg, int dedup, uint2 *ent,
+                                                                uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out) {
+    const uint64_t n = tail_n(n_ptr, n_cap);
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 me = ent[p];
+        const uint32_t g = entg[p];
+        bool keep = true;
+        uint32_t lt = 0;  // entries of the group with a smaller idB: my place in the group when it holds no duplicate pair
+        const uint32_t b = off[g], e = off[g + 1];
+        for (uint32_t j = b; j < e; ++j) {
+            const uint2 y = ent[j];
+            lt += y.x < me.x;
+            // same pair, better record (the mark bit another thread may have set meanwhile is masked off)
+            if (dedup && y.x == me.x && j != p && rec_better(rec[y.y & 0x7fffffffu], rec[me.y & 0x7fffffffu])) keep = false;
+        }
+        lt_out[p] = lt;
+        if (keep) {
+            ent[p].y = me.y | 0x80000000u;
+            atomicAdd(&uniq[g], 1u);
+        }
     }
 }
-void launch_group_mark(const Rec16 *rec, uint64_t n, const uint32_t *off, const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq,
-                       uint32_t *lt, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    group_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, off, entg, dedup, ent, uniq, lt);
+void launch_group_mark(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, const uint32_t *off, const uint32_t *entg, int dedup,
+                       uint2 *ent, uint32_t *uniq, uint32_t *lt, cudaStream_t s, LaunchCounter *lc) {
+    if (n_cap == 0) return;
+    group_mark_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, off, entg, dedup, ent, uniq, lt);
     if (lc) lc->total++;
+}
+
+// order-independent digest term of one output record (bench.py recomputes it on the host from the downloaded records)
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t rec_digest(const hlo_rec &o) {
+    const uint64_t w0 = (uint64_t)o.idA | (uint64_t)o.idB << 32;
+    const uint64_t w1 = (uint64_t)(uint32_t)o.OHA | (uint64_t)(uint32_t)o.OHB << 32;
+    const uint64_t w2 = (uint64_t)o.OLA | (uint64_t)o.K << 32 | (uint64_t)o.ori << 63;
+    return mix64(w0 ^ mix64(w1 ^ mix64(w2 + 0x9e3779b97f4a7c15ULL)));
 }
 
 // Pass B, one thread per kept entry: its place inside the group = number of kept entries with a smaller idB
 // (= the count pass A left when the group has no duplicate pair; otherwise counted here)
-// (ties between kept entries cannot occur with dedup; without dedup the better record goes first); expand it there.
-__global__ void __launch_bounds__(256) group_expand_kernel(const Rec16 *__restrict__ rec, uint64_t n, DevReads r,
-                                                           const uint32_t *__restrict__ off, const uint32_t *__restrict__ uoff,
-                                                           const uint32_t *__restrict__ entg, const uint2 *__restrict__ ent,
-                                                           const uint32_t *__restrict__ lt, hlo_rec *__restrict__ out, hlo_rec16 *__restrict__ out16,
-                                                           hlo_rec_aux *__restrict__ aux) {
-    const uint64_t pe = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pe >= n) return;
-    const uint2 me = ent[pe];
-    if (!(me.y >> 31)) return;
-    const uint32_t g = entg[pe];
-    const uint32_t b = off[g], e = off[g + 1];
-    const Rec16 x = rec[me.y & 0x7fffffffu];
-    uint32_t rank = lt[pe];  // exact when every entry of the group was kept (no duplicate pair: the usual case)
-    if (uoff[g + 1] - uoff[g] != e - b) {
-        rank = 0;
-        for (uint32_t j = b; j < e; ++j) {
-            const uint2 y = ent[j];
-            if (!(y.y >> 31) || j == pe) continue;
-            rank += y.x < me.x || (y.x == me.x && rec_better(rec[y.y & 0x7fffffffu], x));
+// (ties between kept entries cannot occur with dedup; without dedup the better record goes first); expand it there,
+// in every form the caller asked for: hlo_rec (32 B), hlo_rec16, hlo_rec8, hlo_rec_aux.
+__global__ void __launch_bounds__(RT_THREADS) group_expand_kernel(const Rec16 *__restrict__ rec, const unsigned long long *__restrict__ n_ptr,
+                                                                  uint64_t n_cap, DevReads r, const uint32_t *__restrict__ off,
+                                                                  const uint32_t *__restrict__ uoff, const uint32_t *__restrict__ entg,
+                                                                  const uint2 *__restrict__ ent, const uint32_t *__restrict__ lt,
+                                                                  ExpandOut o_) {
+    const uint64_t n = tail_n(n_ptr, n_cap);
+    uint64_t dg = 0;
+    for (uint64_t pe = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pe < n; pe += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 me = ent[pe];
+        if (!(me.y >> 31)) continue;
+        const uint32_t g = entg[pe];
+        const uint32_t b = off[g], e = off[g + 1];
+        const Rec16 x = rec[me.y & 0x7fffffffu];
+        uint32_t rank = lt[pe];  // exact when every entry of the group was kept (no duplicate pair: the usual case)
+        if (uoff[g + 1] - uoff[g] != e - b) {
+            rank = 0;
+            for (uint32_t j = b; j < e; ++j) {
+                const uint2 y = ent[j];
+                if (!(y.y >> 31) || j == pe) continue;
+                rank += y.x < me.x || (y.x == me.x && rec_better(rec[y.y & 0x7fffffffu], x));
+            }
         }
+        const uint32_t p = uoff[g] + rank;
+        const uint4 mq = __ldg(r.meta + x.q), mt = __ldg(r.meta + x.t);  // (length, name, cluster, cluster base)
+        const int ql = (int)mq.x, tl = (int)mt.x;
+        const int diag = (int)(x.ds >> 1) - HLO_DIAG_BIAS;
+        hlo_rec o;
+        expand_record(mq.y, mt.y, ql, tl, diag, (int)(x.ds & 1u), x.kb & 0xffffu, &o);
+        if (o_.out8)  // 8-byte form (hlo_rec8): ids below 2^16; OHB and OLA follow from OHA and the two read lengths
+            reinterpret_cast<uint2 *>(o_.out8)[p] = make_uint2(o.idA | o.idB << 16, ((uint32_t)o.OHA & 0xffffu) | (o.K | o.ori << 15) << 16);
+        if (o_.out16)  // 16-byte form (hlo_rec16): OLB == OLA, 16-bit overhangs and lengths
+            reinterpret_cast<uint4 *>(o_.out16)[p] = make_uint4(o.idA, o.idB, ((uint32_t)o.OHA & 0xffffu) | (uint32_t)o.OHB << 16,
+                                                                o.OLA | (o.K | o.ori << 15) << 16);
+        if (o_.out) {
+            uint4 *dst = reinterpret_cast<uint4 *>(o_.out + p);
+            dst[0] = make_uint4(o.idA, o.idB, (uint32_t)o.OHA, (uint32_t)o.OHB);
+            dst[1] = make_uint4(o.OLA, o.OLB, o.K, o.ori);
+        }
+        if (o_.aux) {
+            hlo_rec_aux ax;
+            ax.cluster = mq.z;
+            ax.blocklen = x.kb >> 16;
+            o_.aux[p] = ax;
+        }
+        if (o_.digest) dg += rec_digest(o);
     }
-    const uint32_t p = uoff[g] + rank;
-    const uint4 mq = __ldg(r.meta + x.q), mt = __ldg(r.meta + x.t);  // (length, name, cluster, cluster base)
-    const int ql = (int)mq.x, tl = (int)mt.x;
-    const int diag = (int)(x.ds >> 1) - HLO_DIAG_BIAS;
-    hlo_rec o;
-    expand_record(mq.y, mt.y, ql, tl, diag, (int)(x.ds & 1u), x.kb & 0xffffu, &o);
-    if (out16) {  // 16-byte form (hlo_rec16): OLB == OLA, 16-bit overhangs and lengths
-        reinterpret_cast<uint4 *>(out16)[p] = make_uint4(o.idA, o.idB, ((uint32_t)o.OHA & 0xffffu) | (uint32_t)o.OHB << 16,
-                                                          o.OLA | (o.K | o.ori << 15) << 16);
-    } else {
-        uint4 *dst = reinterpret_cast<uint4 *>(out + p);
-        dst[0] = make_uint4(o.idA, o.idB, (uint32_t)o.OHA, (uint32_t)o.OHB);
-        dst[1] = make_uint4(o.OLA, o.OLB, o.K, o.ori);
-    }
-    if (aux) {
-        hlo_rec_aux ax;
-        ax.cluster = mq.z;
-        ax.blocklen = x.kb >> 16;
-        aux[p] = ax;
+    if (o_.digest) {  // (sums commute: any order gives the same value)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) dg += __shfl_xor_sync(0xffffffffu, dg, d);
+        if ((threadIdx.x & 31) == 0 && dg) atomicAdd(o_.digest, (unsigned long long)dg);
     }
 }
-void launch_group_expand(const Rec16 *rec, uint64_t n, DevReads r, const uint32_t *off, const uint32_t *uoff, const uint32_t *entg,
-                         const uint2 *ent, const uint32_t *lt, hlo_rec *out, hlo_rec16 *out16, hlo_rec_aux *aux, cudaStream_t s,
-                         LaunchCounter *lc) {
-    if (n == 0) return;
-    group_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rec, n, r, off, uoff, entg, ent, lt, out, out16, aux);
+void launch_group_expand(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *off, const uint32_t *uoff,
+                         const uint32_t *entg, const uint2 *ent, const uint32_t *lt, const ExpandOut &o, cudaStream_t s, LaunchCounter *lc) {
+    if (n_cap == 0) return;
+    group_expand_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, r, off, uoff, entg, ent, lt, o);
     if (lc) lc->total++;
 }
+
+uint64_t host_rec_digest(const hlo_rec &o) { return rec_digest(o); }
 
 // coff[c] = index of the first output record of cluster c = output offset of the cluster's first group (groups are
 // numbered cluster by cluster: cluster base + numeric rank of idA); coff[n_clusters] = number of records

@@ -80,9 +80,13 @@ __device__ __forceinline__ void load16(const uint8_t *quals, long long A, uint32
 __global__ void __launch_bounds__(SC_THREADS, 1) score_records_kernel(DevReads r, const uint8_t *__restrict__ quals,
                                                                       const uint8_t *__restrict__ qflag, const uint64_t *__restrict__ base_off,
                                                                       const uint32_t *__restrict__ cluster_off, const hlo_rec *__restrict__ rec,
-                                                                      const uint32_t *__restrict__ rec_cluster, uint64_t n,
+                                                                      const uint32_t *__restrict__ rec_cluster, int cluster_stride,
+                                                                      const uint32_t *__restrict__ n_ptr, uint64_t n_cap,
                                                                       const double *__restrict__ tab, uint32_t min_read_len,
                                                                       hlo_score *__restrict__ out) {
+    // n_ptr: the record count on the device (the fused path never brings it to the host first); else n_cap is the count
+    uint64_t n = n_cap;
+    if (n_ptr) n = *n_ptr < n_cap ? *n_ptr : n_cap;
     extern __shared__ double s_tab[];  // [2][SC_NQ][SC_NQ]
     for (uint32_t e = threadIdx.x; e < 2u * SC_NQ * SC_NQ; e += blockDim.x) {
         const uint32_t m = e / (SC_NQ * SC_NQ), rem = e % (SC_NQ * SC_NQ);
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_records_kernel(DevReads r
     const double *t_match = s_tab - (SC_Q0 * SC_NQ + SC_Q0);  // indexed by phred byte 1 * SC_NQ + phred byte 2
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const hlo_rec x = rec[i];
-        const uint32_t cb = rec_cluster ? cluster_off[rec_cluster[i]] : 0u;
+        const uint32_t cb = rec_cluster ? cluster_off[rec_cluster[i * cluster_stride]] : 0u;  // (stride 2: the cluster field of hlo_rec_aux)
         // the 13-column fields of sfo2overlaps.py:150-200
         uint32_t id1, id2;
         int pos1;
@@ -168,8 +172,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_records_kernel(DevReads r
 }
 
 void launch_score_records(const DevReads &r, const uint8_t *quals, const uint8_t *qflag, const uint64_t *base_off, const uint32_t *cluster_off,
-                          const hlo_rec *rec, const uint32_t *rec_cluster, uint64_t n, const double *tab, uint32_t min_read_len, hlo_score *out,
-                          cudaStream_t s, LaunchCounter *lc) {
+                          const hlo_rec *rec, const uint32_t *rec_cluster, int cluster_stride, const uint32_t *n_ptr, uint64_t n,
+                          const double *tab, uint32_t min_read_len, hlo_score *out, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
     const size_t smem = (size_t)2 * SC_NQ * SC_NQ * sizeof(double);
     cudaFuncSetAttribute(score_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -178,7 +182,8 @@ void launch_score_records(const DevReads &r, const uint8_t *quals, const uint8_t
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint64_t want = (n + SC_THREADS - 1) / SC_THREADS;
     const unsigned grid = (unsigned)(want < (uint64_t)sms ? want : (uint64_t)sms);
-    score_records_kernel<<<grid, SC_THREADS, smem, s>>>(r, quals, qflag, base_off, cluster_off, rec, rec_cluster, n, tab, min_read_len, out);
+    score_records_kernel<<<grid, SC_THREADS, smem, s>>>(r, quals, qflag, base_off, cluster_off, rec, rec_cluster, cluster_stride, n_ptr, n, tab,
+                                                        min_read_len, out);
     if (lc) lc->total++;
 }
 

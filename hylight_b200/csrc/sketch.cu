@@ -129,28 +129,39 @@ __device__ __forceinline__ void sketch_read(const DevReads &r, int w, int k, uin
     if (!WRITE) count[xi] = n;
 }
 
+// list != nullptr: the reads listed there (x indices); their number is *n_list_ptr (a device counter, clamped to the
+// batch size).  cap_mz: entries the output arrays hold — a batch with more minimizers writes nothing (the host sees the
+// count and reruns with larger arrays).
 template <bool WRITE>
 __global__ void __launch_bounds__(128) sketch_kernel(DevReads r, int w, int k, uint32_t *__restrict__ count,
                                                      const uint32_t *__restrict__ off, MzOut o,
-                                                     const uint32_t *__restrict__ list, uint32_t n_list) {
-    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ti >= (list ? n_list : r.n_reads)) return;
-    sketch_read<WRITE>(r, w, k, count, off, o, list ? list[ti] : ti);
+                                                     const uint32_t *__restrict__ list, const unsigned long long *__restrict__ n_list_ptr,
+                                                     uint32_t cap_mz) {
+    uint32_t n = r.n_reads;
+    if (list) {
+        const unsigned long long nl = *n_list_ptr;
+        n = nl < (unsigned long long)r.n_reads ? (uint32_t)nl : r.n_reads;
+    }
+    if (WRITE && off[r.n_reads] > cap_mz) return;
+    for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < n; ti += gridDim.x * blockDim.x)
+        sketch_read<WRITE>(r, w, k, count, off, o, list ? list[ti] : ti);
 }
 
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc) {
     if (r.n_reads == 0) return;
     MzOut o{nullptr, nullptr, nullptr, nullptr, 0};
-    sketch_kernel<false><<<(r.n_reads + 127) / 128, 128, 0, s>>>(r, w, k, count, nullptr, o, nullptr, 0);
+    sketch_kernel<false><<<(r.n_reads + 127) / 128, 128, 0, s>>>(r, w, k, count, nullptr, o, nullptr, nullptr, 0u);
     if (lc) lc->total++;
 }
 
 void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, uint64_t *keys, uint32_t *vals,
-                         int hash_bits, const uint32_t *list, uint32_t n_list, cudaStream_t s, LaunchCounter *lc) {
-    const uint32_t n = list ? n_list : r.n_reads;
-    if (n == 0) return;
+                         int hash_bits, const uint32_t *list, const unsigned long long *n_list_ptr, uint32_t cap_mz, cudaStream_t s,
+                         LaunchCounter *lc) {
+    if (r.n_reads == 0) return;
     MzOut o{mz_x, mz_rr, keys, vals, hash_bits};
-    sketch_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(r, w, k, nullptr, off, o, list, n_list);
+    // a listed launch usually has nothing to do (no read overflowed its strip): a small grid that strides
+    const unsigned grid = list ? 148u : (r.n_reads + 127) / 128;
+    sketch_kernel<true><<<grid, 128, 0, s>>>(r, w, k, nullptr, off, o, list, n_list_ptr, cap_mz);
     if (lc) lc->total++;
 }
 
@@ -305,9 +316,9 @@ __device__ __noinline__ uint32_t sketch_strip_exact(const DevReads &r, int k, ui
 // against a valid entry and keep mm_sketch's "rightmost" choice among themselves.
 
 template <int WW, bool AMB>
-__global__ void __launch_bounds__(128, WW <= 11 ? 5 : 2) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
-                                                             uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
-                                                             uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt) {
+__device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+                                                 uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
+                                                 uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt) {
     const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
     if (xi >= r.n_reads) return;
     const uint32_t read = __ldg(r.perm + xi);
@@ -408,22 +419,27 @@ __global__ void __launch_bounds__(128, WW <= 11 ? 5 : 2) sketch_fast_kernel(DevR
     }
 }
 
-bool sketch_fast_supported(int w, int k) { return (k & 1) && k >= 1 && k <= 28 && (w == 11 || w == 5 || w == 19); }
-
+// A batch without ambiguous bases (the packer's device counter says so; the host never looks) runs the body that
+// does not touch the ambiguity plane.  The branch is uniform over the grid.
 template <int WW>
-static void launch_sketch_fast_w(const DevReads &r, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count, uint32_t *ovf_list,
-                                 unsigned long long *ovf_cnt, cudaStream_t s) {
-    const unsigned grid = (r.n_reads + 127) / 128;
-    if (r.has_amb) sketch_fast_kernel<WW, true><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
-    else sketch_fast_kernel<WW, false><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
+__global__ void __launch_bounds__(128, WW <= 11 ? 5 : 2) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+                                                             uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
+                                                             uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt,
+                                                             const uint32_t *__restrict__ amb_count) {
+    if (*amb_count) sketch_fast_body<WW, true>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
+    else sketch_fast_body<WW, false>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
 }
 
+bool sketch_fast_supported(int w, int k) { return (k & 1) && k >= 1 && k <= 28 && (w == 11 || w == 5 || w == 19); }
+
 void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
-                        uint32_t *ovf_list, unsigned long long *ovf_cnt, cudaStream_t s, LaunchCounter *lc) {
+                        uint32_t *ovf_list, unsigned long long *ovf_cnt, const uint32_t *amb_count, cudaStream_t s,
+                        LaunchCounter *lc) {
     if (r.n_reads == 0) return;
-    if (w == 11) launch_sketch_fast_w<11>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, s);
-    else if (w == 5) launch_sketch_fast_w<5>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, s);
-    else launch_sketch_fast_w<19>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, s);
+    const unsigned grid = (r.n_reads + 127) / 128;
+    if (w == 11) sketch_fast_kernel<11><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, amb_count);
+    else if (w == 5) sketch_fast_kernel<5><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, amb_count);
+    else sketch_fast_kernel<19><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, amb_count);
     if (lc) lc->total++;
 }
 
@@ -434,10 +450,12 @@ __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_
                                                              const uint32_t *__restrict__ srp, const uint32_t *__restrict__ count,
                                                              const uint32_t *__restrict__ off, uint64_t *__restrict__ mz_x,
                                                              uint2 *__restrict__ mz_rr,
-                                                             uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int hash_bits) {
+                                                             uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int hash_bits,
+                                                             uint32_t cap_mz) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t xi = (uint32_t)(gid >> 3), l = (uint32_t)(gid & 7);
     if (xi >= r.n_reads) return;
+    if (off[r.n_reads] > cap_mz) return;  // more minimizers than the arrays hold: the host reruns the batch with larger ones
     const uint32_t n = count[xi];
     if (n > cap) return;  // written by the generic kernel
     const uint32_t read = r.perm[xi];
@@ -456,10 +474,11 @@ __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_
 
 void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
                            const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, uint64_t *keys, uint32_t *vals,
-                           int hash_bits, cudaStream_t s, LaunchCounter *lc) {
+                           int hash_bits, uint32_t cap_mz, cudaStream_t s, LaunchCounter *lc) {
     const uint64_t total = (uint64_t)r.n_reads * 8;
     if (total == 0) return;
-    sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rr, keys, vals, hash_bits);
+    sketch_compact_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r, cap, sx, srp, count, off, mz_x, mz_rr, keys, vals, hash_bits,
+                                                                          cap_mz);
     if (lc) lc->total++;
 }
 

@@ -21,9 +21,12 @@
 //      NV LDG.128 per row (Y from the 16-byte vector that holds base S), a two-stage word select,
 //      funnel shifts for the residual 2-bit offset, XOR, (x|x>>1)&0x5555.. fold, popcount;
 //   4. thresholds from the host-built integer tables (shared memory), end rule on the outermost 32
-//      bases; accepted 16-byte records are staged per block in shared memory and leave with one global
-//      atomicAdd per ~400 records and coalesced stores (a per-warp global atomic on one address was the
-//      top stall of the first version: profiles/r1b).  The next candidate is loaded one iteration ahead.
+//      bases; accepted 16-byte records are staged PER WARP in shared memory (positions from a ballot) and
+//      leave with one global atomicAdd per ~100 records and coalesced stores (a global atomic per warp
+//      iteration on one address was the top stall of the first version: profiles/r1b; a per-block stage
+//      cost a barrier per iteration).  The next candidate is loaded one iteration ahead.
+// (The north star sketches a warp per pair; one thread per candidate measured 3x faster — a 150-base row is
+// three 16-byte vectors, too little for 32 lanes — and is what this file does.  DESIGN.md §0.)
 // Bound: integer (ALU) pipe and L1 wavefronts (one per 16-byte vector of the randomly addressed row);
 // rows are L2-resident.  Algorithmic bytes per candidate = 16 + 2*ceil(OL/4) (when OL >= min_len) + 16
 // per accepted record (SURVEY.md §8d counts 32 B for the expanded record; the expansion is records.cu).
@@ -77,9 +80,10 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     constexpr int NV = (W + 3) / 4, NW = 4 * NV;
     __shared__ uint16_t s_tab[3 * 1024];
     __shared__ uint4 s_out[VF_WARPS][VF_STAGE];
-    // thresholds into shared memory (3 tables of max_len + 1 <= 1024 entries)
+    // thresholds into shared memory (3 tables, max_len + 1 <= 1024 entries of each; max_len = this batch's longest read)
     const int tl1 = a.tab.max_len + 1;
-    for (int i = threadIdx.x; i < 3 * tl1; i += VF_THREADS) s_tab[i] = a.tab.min_matches[i];
+    for (int i = threadIdx.x; i < tl1; i += VF_THREADS)
+        s_tab[i] = a.tab.min_matches[i], s_tab[tl1 + i] = a.tab.max_clip[i], s_tab[2 * tl1 + i] = a.tab.max_k_upto[i];
     __syncthreads();
     const uint16_t *t_min_matches = s_tab, *t_max_clip = s_tab + tl1, *t_max_k = s_tab + 2 * tl1;
     uint4 *w_out = s_out[threadIdx.x >> 5];
@@ -91,18 +95,21 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     const uint64_t plane4 = (uint64_t)a.reads.n_reads * NV;  // uint4 per plane
     const uint4 *rows = reinterpret_cast<const uint4 *>(a.reads.bases);
     const uint4 *cands = reinterpret_cast<const uint4 *>(a.cands);
-    const uint64_t n_round = (a.n + 31) & ~31ull;  // whole warps iterate together
+    // the candidate count is the pair generator's device counter (it may exceed the buffer: then the host reruns)
+    const unsigned long long n_dev = *a.n_ptr;
+    const uint64_t a_n = n_dev < a.n_cap ? n_dev : a.n_cap;
+    const uint64_t n_round = (a_n + 31) & ~31ull;  // whole warps iterate together
     const int o = a.prm.max_overhang, min_len = a.prm.min_len;
     uint64_t c = (uint64_t)blockIdx.x * VF_THREADS + threadIdx.x;
     if (c >= n_round) return;  // (after the only block barrier)
     uint4 cv_next = make_uint4(0u, 0u, 0u, 0u);
-    if (c < a.n) cv_next = __ldg(cands + c);
+    if (c < a_n) cv_next = __ldg(cands + c);
     for (; c < n_round; c += n_threads) {
         bool accept = false, defer = false;
         uint4 rec = make_uint4(0u, 0u, 0u, 0u);
         const uint4 cv = cv_next;
-        const bool live = c < a.n;
-        if (c + n_threads < a.n) cv_next = __ldg(cands + c + n_threads);  // next iteration's candidate, in flight early
+        const bool live = c < a_n;
+        if (c + n_threads < a_n) cv_next = __ldg(cands + c + n_threads);  // next iteration's candidate, in flight early
         if (live) {
             const uint32_t q = cv.x, t = cv.y;
             const int D = (int)(cv.z & 0xffffu) - 32768;
@@ -189,17 +196,18 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
         const unsigned def_b = __ballot_sync(0xffffffffu, defer);
         if (def_b) {  // rare
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&a.counters[1], (unsigned long long)__popc(def_b));
+            if (lane == 0) base = atomicAdd(a.def_counter, (unsigned long long)__popc(def_b));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (defer) a.deferred[base + __popc(def_b & lt_mask)] = (uint32_t)c;
+            if (defer) a.deferred[base + __popc(def_b & lt_mask)] = (uint32_t)c;  // (one slot per candidate: cannot overflow)
         }
         const bool last = c + n_threads >= n_round;
         if (w_cnt > VF_STAGE - 32 || (last && w_cnt)) {  // the next iteration might not fit
             __syncwarp();
             unsigned long long gb = 0;
-            if (lane == 0) gb = atomicAdd(&a.counters[0], (unsigned long long)w_cnt);
+            if (lane == 0) gb = atomicAdd(a.acc_counter, (unsigned long long)w_cnt);
             gb = __shfl_sync(0xffffffffu, gb, 0);
-            for (uint32_t i = lane; i < w_cnt; i += 32) reinterpret_cast<uint4 *>(a.out)[gb + i] = w_out[i];
+            for (uint32_t i = lane; i < w_cnt; i += 32)
+                if (gb + i < a.out_cap) reinterpret_cast<uint4 *>(a.out)[gb + i] = w_out[i];  // past the end: counted only
             __syncwarp();
             w_cnt = 0;
         }
@@ -214,7 +222,7 @@ template <int W, int F>
 static void launch_vf2(const VerifyArgs &a, int sms, cudaStream_t s) {
     int per_sm = 8;  // persistent grid: as many blocks as are resident at once (each builds its tables once)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, verify_fast_kernel<W, F>, VF_THREADS, 0);
-    const uint64_t want = (a.n + VF_THREADS - 1) / VF_THREADS;
+    const uint64_t want = (a.n_cap + VF_THREADS - 1) / VF_THREADS;
     const uint64_t grid = std::min<uint64_t>(want, (uint64_t)sms * (per_sm > 0 ? per_sm : 1));
     verify_fast_kernel<W, F><<<(unsigned)grid, VF_THREADS, 0, s>>>(a);
 }
@@ -226,7 +234,7 @@ static void launch_vf(const VerifyArgs &a, int sms, cudaStream_t s) {
 }
 
 void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) {
-    if (a.n == 0) return;
+    if (a.n_cap == 0) return;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -247,10 +255,7 @@ void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc) 
 
 __device__ __forceinline__ int get_base(const uint32_t *row, int j) { return (int)((row[j >> 4] >> ((j & 15) * 2)) & 3u); }
 
-__global__ void __launch_bounds__(128) verify_exact_kernel(VerifyArgs a, const uint32_t *__restrict__ idx, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t c = idx ? idx[i] : i;
+__device__ __forceinline__ void verify_exact_one(const VerifyArgs &a, uint64_t c) {
     const CandI cd = a.cands[c];
     const uint32_t q = cd.q, t = cd.t;
     const int D = (int)(cd.z & 0xffffu) - 32768;
@@ -303,7 +308,8 @@ __global__ void __launch_bounds__(128) verify_exact_kernel(VerifyArgs a, const u
     if (maplen > a.tab.max_len) return;
     if (blocklen - K < (int)a.tab.min_matches[blocklen]) return;
     if (cl + cr > (int)a.tab.max_clip[maplen]) return;
-    const unsigned long long p = atomicAdd(&a.counters[0], 1ULL);
+    const unsigned long long p = atomicAdd(a.acc_counter, 1ULL);
+    if (p >= a.out_cap) return;  // counted only
     Rec16 rec;
     rec.q = q, rec.t = t;
     rec.ds = ((uint32_t)(D + HLO_DIAG_BIAS) << 1) | strand;
@@ -311,9 +317,21 @@ __global__ void __launch_bounds__(128) verify_exact_kernel(VerifyArgs a, const u
     a.out[p] = rec;
 }
 
-void launch_verify_exact(const VerifyArgs &a, const uint32_t *idx, uint64_t n, cudaStream_t s, LaunchCounter *lc) {
-    if (n == 0) return;
-    verify_exact_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a, idx, n);
+// idx == nullptr: candidates [0, min(*a.n_ptr, a.n_cap)); else the *a.def_counter candidates listed in idx
+__global__ void __launch_bounds__(128) verify_exact_kernel(VerifyArgs a, const uint32_t *__restrict__ idx) {
+    unsigned long long n = idx ? *a.def_counter : *a.n_ptr;
+    if (n > a.n_cap) n = a.n_cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        verify_exact_one(a, idx ? idx[i] : i);
+}
+
+// all_cands: every candidate (option "verify_exact", long reads); else the deferred list of the fast kernel (usually a
+// handful: a small grid that strides)
+void launch_verify_exact(const VerifyArgs &a, bool all_cands, cudaStream_t s, LaunchCounter *lc) {
+    if (a.n_cap == 0) return;
+    const uint64_t want = all_cands ? (a.n_cap + 127) / 128 : 148 * 4;
+    const unsigned grid = (unsigned)std::min<uint64_t>(want, 148 * 64);
+    verify_exact_kernel<<<grid, 128, 0, s>>>(a, all_cands ? nullptr : a.deferred);
     if (lc) lc->total++, lc->verify++;
 }
 

@@ -9,8 +9,9 @@
  * polyte.tune_params.py:510-517 and :549-557).
  *
  * Conventions: every function returns 0 or a negative hlo_status; nothing throws or exits.
- * Inputs are caller-owned plain host pointers, only read during the call.  Outputs are
- * ctx-owned host buffers valid until the next call on the same ctx (or hlo_ctx_destroy).
+ * Inputs are caller-owned plain host pointers, only read during the call (hlo_submit: until the
+ * matching hlo_wait returns).  Outputs are ctx-owned host buffers valid until the next call on the
+ * same ctx (or hlo_ctx_destroy).
  * A ctx is bound to one CUDA device and is single-threaded; distinct ctxs are independent.
  * There is no CPU fallback: without a CUDA device hlo_ctx_create fails with HLO_ENODEV.
  */
@@ -24,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HLO_ABI_VERSION 1
+#define HLO_ABI_VERSION 2
 
 typedef enum hlo_status {
     HLO_OK = 0,
@@ -48,7 +49,10 @@ typedef struct hlo_params {
     int32_t w;               /* -w 11 */
     int32_t min_seeds;       /* -n 2   (1 or 2 supported) */
     int32_t min_chain_score; /* -m 30  (must be <= 2k) */
-    int32_t mid_occ;         /* 1000: --sr preset; minimizers occurring more often seed nothing */
+    int32_t mid_occ;         /* 0 = minimap2's default: per index (= per cluster) the (1 - 2e-4) quantile of the occurrences of
+                                the distinct minimizers, + 1, clamped to [10, 10^6] (mm_idx_cal_max_occ; the reference command
+                                passes the flag --sr, not the preset -x sr, so nothing fixes it); > 0 = that cut-off (-f INT).
+                                Minimizers occurring more often seed nothing. */
     int32_t match_score;     /* -A 4 */
     int32_t mismatch_pen;    /* -B 2 */
     int32_t ambi_pen;        /* --score-N default 1 */
@@ -109,20 +113,52 @@ static inline void hlo_rec16_expand(const hlo_rec16 *c, hlo_rec *r) {
     r->OLA = c->OLA, r->OLB = c->OLA, r->K = c->K_ori & 0x7fffu, r->ori = c->K_ori >> 15;
 }
 
+/* The same record in 8 bytes (option "compact" = 2): a quarter of hlo_rec's device->host traffic.  Valid when every
+ * read name of the batch is below 65536 (a cluster of HyLight's --size 15000 has 30000 reads).  OHB and OLA are
+ * not stored: with the two read lengths, which the caller has, minimap22sfo.py:51-59 gives
+ *   OHB = OHA + len(idB) - len(idA)      OLA = OLB = OHA >= 0 ? min(len(idA) - OHA, len(idB)) : min(len(idB) + OHA, len(idA))
+ * (both hold before and after the flips of sfo2overlaps.py:112-122, which swap the reads together with the fields). */
+typedef struct hlo_rec8 {
+    uint16_t idA, idB;
+    int16_t OHA;
+    uint16_t K_ori; /* K | ori << 15 */
+} hlo_rec8; /* 8 bytes */
+
+static inline void hlo_rec8_expand(const hlo_rec8 *c, uint32_t lenA, uint32_t lenB, hlo_rec *r) {
+    const int32_t a = c->OHA, la = (int32_t)lenA, lb = (int32_t)lenB;
+    const int32_t ol = a >= 0 ? ((la - a) < lb ? (la - a) : lb) : ((lb + a) < la ? (lb + a) : la);
+    r->idA = c->idA, r->idB = c->idB, r->OHA = a, r->OHB = a + lb - la;
+    r->OLA = (uint32_t)ol, r->OLB = (uint32_t)ol, r->K = c->K_ori & 0x7fffu, r->ori = c->K_ori >> 15;
+}
+
 /* Extra per-record facts the reference computes on the way (PAF columns 10/11) */
 typedef struct hlo_rec_aux {
     uint32_t cluster; /* cluster index inside the batch */
     uint32_t blocklen; /* PAF col 11 */
 } hlo_rec_aux;
 
+struct hlo_score;
 typedef struct hlo_recs {
     const hlo_rec *rec;         /* n records, sorted by (cluster, idA, idB, ...) */
     const hlo_rec_aux *aux;     /* n entries, parallel to rec */
     uint64_t n;
     const uint64_t *cluster_off; /* n_clusters + 1 offsets into rec (NULL for hlo_verify) */
     uint32_t n_clusters;
-    const hlo_rec16 *rec16;     /* with option "compact" = 1: the n records in 16-byte form, and rec == NULL */
+    const hlo_rec16 *rec16;     /* with option "compact" = 1 (or 2 when a name of the batch is >= 65536): the n records in 16-byte form, rec == NULL */
+    const hlo_rec8 *rec8;       /* with option "compact" = 2: the n records in 8-byte form, rec == rec16 == NULL */
+    const struct hlo_score *score; /* with option "scores" = 1 and qualities in the batch: n entries parallel to the records, else NULL */
 } hlo_recs;
+
+/* One batch of clusters on the host, the input of hlo_submit (and of hlo_overlap_host through its arguments). */
+typedef struct hlo_batch {
+    const char *bases;           /* all sequences concatenated, ASCII (ACGTUN, any case; other letters are ambiguous) */
+    const char *quals;           /* phred+33, same offsets as bases; NULL unless option "scores" is set */
+    const uint64_t *base_off;    /* n_reads + 1 offsets into bases */
+    uint32_t n_reads;
+    const uint32_t *cluster_off; /* n_clusters + 1 offsets into the read list (NULL = one cluster) */
+    uint32_t n_clusters;
+    const uint32_t *ids;         /* n_reads decimal names (NULL = position inside the cluster, what rename_fas.py writes) */
+} hlo_batch;
 
 /* minimizer tuple, same two words as minimap2's mm128_t: x = hash<<8 | span, y = rid<<32 | pos<<1 | strand */
 typedef struct hlo_mz {
@@ -132,12 +168,18 @@ typedef struct hlo_mz {
 /* per-stage device timings of the last hlo_overlap_batch / hlo_verify call, milliseconds (CUDA events) */
 typedef struct hlo_timing {
     float h2d_ms, pack_ms, sketch_ms, sort_ms, index_ms, pairgen_ms, verify_ms, dedup_ms, d2h_ms, total_ms;
-    float verify_fast_ms;  /* the warp-per-pair verify kernel alone (one launch) */
-    float sort_fallback;   /* 1 = the in-shared-memory bucket sort overflowed and the plain radix passes redid the index */
+    float verify_fast_ms;  /* the one-thread-per-candidate verify kernel alone (one launch) */
+    float sort_fallback;   /* 1 = a mixed hash-prefix group was too large to repair and the index was redone on all hash bits */
     uint64_t n_reads, n_bases, n_minimizers, n_seed_hits, n_candidates, n_accepted, n_records;
     uint64_t n_deferred;     /* candidates that took the exact slow verify path */
     uint64_t n_overflow_reads; /* query reads whose seed table overflowed shared memory */
     uint64_t verify_launches, total_launches;
+    uint64_t digest;         /* option "digest": sum over the output records of a 64-bit mix of their fields (order independent) */
+    uint64_t n_reruns;       /* times the batch was enqueued again because a device buffer sized from an estimate was too small */
+    uint64_t n_syncs;        /* host waits on the device during the call */
+    uint32_t mid_occ_lo, mid_occ_hi; /* smallest / largest per-cluster occurrence cut-off used */
+    float score_ms;          /* the fused score kernel (option "scores") */
+    float reserved_;
 } hlo_timing;
 
 typedef struct hlo_ctx hlo_ctx;
@@ -193,9 +235,20 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *reads, const hlo_cand *cands, uint
 /* sketch -> sort -> seed/chain -> verify -> per-pair keep-longest -> sorted records, per cluster. */
 int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *reads, hlo_recs *out);
 
-/* pack + overlap in one call from host buffers (the e2e entry the bench times). */
+/* pack + overlap in one call from host buffers (the e2e entry the bench times) = hlo_submit + hlo_wait. */
 int hlo_overlap_host(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, uint32_t n_reads,
                      const uint32_t *cluster_off, uint32_t n_clusters, hlo_recs *out);
+
+/*
+ * The same, asynchronous: hlo_submit enqueues the upload and every kernel of the chain on the ctx
+ * stream and returns without waiting for the device; hlo_wait blocks until the records are on the host.  No stage
+ * waits for the host in between: buffers are sized from estimates learned from earlier batches, counts stay in a
+ * device counter block, and hlo_wait reruns the batch with larger buffers in the rare case one was too small
+ * (hlo_timing.n_reruns).  One batch in flight per ctx; a caller overlaps batches by cycling over two or three
+ * contexts.  The input buffers must stay valid and unchanged until hlo_wait returns.
+ */
+int hlo_submit(hlo_ctx *ctx, const hlo_batch *batch);
+int hlo_wait(hlo_ctx *ctx, hlo_recs *out);
 
 int hlo_get_timing(const hlo_ctx *ctx, hlo_timing *t);
 
@@ -215,6 +268,9 @@ typedef struct hlo_score {
 } hlo_score;
 int hlo_score_records(hlo_ctx *ctx, const hlo_reads *reads, const char *quals, const hlo_rec *rec, const uint32_t *rec_cluster,
                       uint64_t n, double mismatch_prob, uint32_t min_read_len, const hlo_score **out);
+/* ViralQuasispecies --mismatch / --min_read_len for the fused score of hlo_submit (option "scores"): the score kernel
+ * then runs on the device-resident records before they are downloaded, and hlo_recs.score comes back with them. */
+int hlo_set_score_params(hlo_ctx *ctx, double mismatch_prob, uint32_t min_read_len);
 
 /* Tuning / test knobs.  "verify_exact" (0|1): route every candidate through the base-by-base verify
  * kernel; "pairgen_slots_log2" (5..10): slots of the per-read shared-memory seed table;
@@ -222,12 +278,14 @@ int hlo_score_records(hlo_ctx *ctx, const hlo_reads *reads, const char *quals, c
  * device-resident measurement covers the packer); "d2h" (0|1): copy the records back to the host
  * (with 0 hlo_overlap_batch returns n only; rec/aux/cluster_off are NULL); "aux" (0|1): also copy the
  * hlo_rec_aux array back (with 0 hlo_recs.aux is NULL: a caller that only writes the files needs rec and
- * cluster_off); "compact" (0|1): hlo_overlap_batch / hlo_overlap_host return hlo_recs.rec16
- * (16-byte records) instead of rec; "sketch_generic" / "pairgen_generic" (0|1): force the generic (any w, k / 64-bit keyed)
- * kernels instead of the specialised ones; "sort_segmented" (1|0): sort every cluster's minimizers as its own segment
- * (0: one sort with the cluster index in the key); "sort_prefix" (1|0): sort only a prefix of the hash and repair the
- * groups in which two hashes share it (0: all hash bits); "sort_hash_bits" (0 = automatic): length of that prefix;
- * "sort_onesweep" (0|1, process-wide, unsegmented sort only): one-sweep radix passes.  None of them changes a result. */
+ * cluster_off); "compact" (0|1|2): hlo_overlap_batch / hlo_overlap_host / hlo_wait return hlo_recs.rec16
+ * (16-byte records) or hlo_recs.rec8 (8-byte records) instead of rec; "scores" (0|1): fused overlap score (see
+ * hlo_set_score_params); "digest" (0|1): hlo_timing.digest; "sketch_generic" / "pairgen_generic" (0|1): force the
+ * generic (any w, k / 64-bit keyed) kernels instead of the specialised ones; "sort_segmented" (1|0): sort every
+ * cluster's minimizers as its own segment (0: one segment with the cluster index in the key); "sort_prefix" (1|0):
+ * sort only a prefix of the hash and repair the groups in which two hashes share it (0: all hash bits);
+ * "sort_hash_bits" (0 = automatic): length of that prefix; "cap_scale_pct" (default 100): scales the first-batch
+ * buffer estimates (tests use a small value to force the rerun path).  None of them changes a result. */
 int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value);
 
 /* The CUDA stream (cudaStream_t) every call on this ctx enqueues its work on, so that a caller can
@@ -243,6 +301,16 @@ int hlo_write_overlaps(const hlo_rec *rec, uint64_t n, const char *path);
 /* hlo_write_overlaps / hlo_write_sfo for 16-byte records */
 int hlo_write_overlaps16(const hlo_rec16 *rec, uint64_t n, const char *path);
 int hlo_write_sfo16(const hlo_rec16 *rec, uint64_t n, const char *path);
+/* ... and for 8-byte records: len_by_id[id] = length of the read named id (n_ids entries) */
+int hlo_write_overlaps8(const hlo_rec8 *rec, uint64_t n, const uint32_t *len_by_id, uint32_t n_ids, const char *path);
+int hlo_write_sfo8(const hlo_rec8 *rec, uint64_t n, const uint32_t *len_by_id, uint32_t n_ids, const char *path);
+/*
+ * Binary hand-off past the text reader of the consumer (tools/HaploConduct/src/EdgeCalculator.cpp:569-604;
+ * SURVEY.md §8f row 4): a 32-byte header {"HLOB", u32 version = 1, u32 record bytes = 16, u32 flags (bit 0: scores
+ * follow), u64 n, u64 reserved} then n hlo_rec16, then (flag bit 0) n hlo_score.  INTEGRATION.md §5 holds the reader
+ * patch.  score may be NULL.  Written to a temp file, then renamed.
+ */
+int hlo_write_binary16(const hlo_rec16 *rec, const struct hlo_score *score, uint64_t n, const char *path);
 /* The same lines with two more columns, hlo_score.score and .mismatch_rate (%.17g): the file a HaploConduct whose
  * reader takes the precomputed score would consume (15 fields; the stock reader wants exactly 13). */
 int hlo_write_overlaps_scored(const hlo_rec *rec, const struct hlo_score *score, uint64_t n, const char *path);

@@ -55,7 +55,7 @@ void orc_params_default(hlo_params *p) {
     p->w = 11;
     p->min_seeds = 2;
     p->min_chain_score = 30;
-    p->mid_occ = 1000;
+    p->mid_occ = 0; /* minimap2's default: derived from the index (orc_mid_occ) */
     p->match_score = 4;
     p->mismatch_pen = 2;
     p->ambi_pen = 1;
@@ -196,6 +196,42 @@ static int idx_cmp(const void *a, const void *b) {
     return p->y < q->y ? -1 : (p->y > q->y ? 1 : 0);
 }
 
+static int u32_cmp(const void *a, const void *b) {
+    const uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/*
+ * The occurrence cut-off minimap2 derives from an index when -f / --mid-occ is not given (options.c
+ * mm_mapopt_update + index.c mm_idx_cal_max_occ, defaults mid_occ_frac = 2e-4f, min_mid_occ = 10,
+ * max_mid_occ = 1000000): with a[] = the occurrence counts of the n DISTINCT minimizers,
+ *     thres = ks_ksmall(n, a, (uint32_t)((1. - f) * n)) + 1        (k-th smallest, k counted from 0)
+ * then raised to min_mid_occ and capped at max_mid_occ.  The reference command line
+ * (polyte.tune_params.py:510) passes the long flag --sr, which sets MM_F_SR only — not the preset
+ * "-x sr" — so nothing fixes mid_occ and every cluster (one index per minimap2 process) gets its own.
+ * idx: the cluster's (hash, y) entries sorted by hash.
+ */
+static int orc_mid_occ_sorted(const idx_ent *idx, uint64_t nm) {
+    if (nm == 0) return 10;
+    uint32_t *a = (uint32_t *)malloc(nm * sizeof *a);
+    uint64_t n = 0;
+    if (!a) return 10;
+    for (uint64_t i = 0; i < nm;) {
+        uint64_t j = i + 1;
+        while (j < nm && idx[j].h == idx[i].h) ++j;
+        a[n++] = (uint32_t)(j - i);
+        i = j;
+    }
+    qsort(a, n, sizeof *a, u32_cmp);
+    const float f = 2e-4f;
+    const uint32_t k = (uint32_t)((1. - f) * n);
+    long long thres = (long long)a[k < n ? k : n - 1] + 1;
+    free(a);
+    if (thres < 10) thres = 10;
+    if (thres > 1000000) thres = 1000000;
+    return (int)thres;
+}
+
 typedef struct {
     uint32_t t;
     uint32_t strand;
@@ -213,16 +249,17 @@ static int anchor_cmp(const void *a, const void *b) {
 
 /*
  * Candidates of a batch of clusters.  For every query read (file order) collect the seed hits of its
- * minimizers inside its own cluster, drop minimizers with more than mid_occ occurrences (--sr sets
- * mid_occ=1000; the high-occurrence rescue selects round(span/500)=0 seeds for reads <= 250 bp), apply
+ * minimizers inside its own cluster, drop minimizers with more than mid_occ occurrences (P->mid_occ > 0:
+ * that value; else minimap2's data-derived cut-off of the cluster, orc_mid_occ_sorted; the
+ * high-occurrence rescue selects round(span/500)=0 seeds for reads <= 250 bp), apply
  * -X (no self hits; a seed is skipped when strcmp(qname,tname) > 0), convert to anchors, and chain the
  * anchors of one (target, strand, diagonal) — the only chains "-r 0" (bw = 0) admits.  Chain score =
  * k + sum(min(k, gap)); kept iff #anchors >= -n and score >= -m.
  * Output sorted by (q, t, strand, diag); q/t are batch-global read indices.
  */
-int orc_candidates(const char *bases, const uint64_t *base_off, uint32_t n_reads, const uint32_t *cluster_off,
-                   uint32_t n_clusters, const uint32_t *ids, const hlo_params *P, hlo_cand **out, uint64_t *n_out,
-                   uint64_t *n_seed_hits) {
+int orc_candidates2(const char *bases, const uint64_t *base_off, uint32_t n_reads, const uint32_t *cluster_off,
+                    uint32_t n_clusters, const uint32_t *ids, const hlo_params *P, hlo_cand **out, uint64_t *n_out,
+                    uint64_t *n_seed_hits, uint32_t *mid_occ_out /* n_clusters entries, or NULL */) {
     uint32_t oc[2];
     if (!cluster_off) {
         oc[0] = 0, oc[1] = n_reads;
@@ -253,6 +290,8 @@ int orc_candidates(const char *bases, const uint64_t *base_off, uint32_t n_reads
         }
         for (uint64_t i = 0; i < nm; ++i) idx[i].h = mz[m0 + i].x >> 8, idx[i].y = mz[m0 + i].y;
         qsort(idx, nm, sizeof *idx, idx_cmp);
+        const int mid_occ = P->mid_occ > 0 ? P->mid_occ : orc_mid_occ_sorted(idx, nm);
+        if (mid_occ_out) mid_occ_out[c] = (uint32_t)mid_occ;
         for (uint32_t q = r0; q < r1 && rc == HLO_OK; ++q) {
             const int ql = (int)(base_off[q + 1] - base_off[q]);
             const uint32_t qid = ids ? ids[q] : q - r0;
@@ -274,7 +313,7 @@ int orc_candidates(const char *bases, const uint64_t *base_off, uint32_t n_reads
                     if (idx[mid].h <= h) lo = mid + 1; else hi = mid;
                 }
                 uint64_t e = lo;
-                if ((int64_t)(e - s) > (int64_t)P->mid_occ) continue;
+                if ((int64_t)(e - s) > (int64_t)mid_occ) continue;
                 for (uint64_t j = s; j < e; ++j) {
                     const uint32_t t = (uint32_t)(idx[j].y >> 32);
                     if (t == q) continue; /* -X: no self hits (self chains would be dropped at filter_ovlp_inline.py:26) */
@@ -344,6 +383,22 @@ int orc_candidates(const char *bases, const uint64_t *base_off, uint32_t n_reads
     *n_out = n_c;
     if (n_seed_hits) *n_seed_hits = hits_total;
     return HLO_OK;
+}
+
+int orc_candidates(const char *bases, const uint64_t *base_off, uint32_t n_reads, const uint32_t *cluster_off,
+                   uint32_t n_clusters, const uint32_t *ids, const hlo_params *P, hlo_cand **out, uint64_t *n_out,
+                   uint64_t *n_seed_hits) {
+    return orc_candidates2(bases, base_off, n_reads, cluster_off, n_clusters, ids, P, out, n_out, n_seed_hits, NULL);
+}
+
+/* the cut-off alone, per cluster (tests compare it with hlo_timing.mid_occ_lo / _hi) */
+int orc_mid_occ(const char *bases, const uint64_t *base_off, uint32_t n_reads, const uint32_t *cluster_off, uint32_t n_clusters,
+                const hlo_params *P, uint32_t *mid_occ_out) {
+    hlo_cand *c = NULL;
+    uint64_t n = 0, h = 0;
+    int rc = orc_candidates2(bases, base_off, n_reads, cluster_off, n_clusters, NULL, P, &c, &n, &h, mid_occ_out);
+    free(c);
+    return rc;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -41,6 +41,57 @@ def build(force=False):
     return so
 
 
+_ECREF = None
+
+
+def ecref():
+    """oracle/_ref/libecref.so: the reference's OWN EdgeCalculator::score / overlap_score
+    (tools/HaploConduct/src/EdgeCalculator.cpp:25-140), compiled by oracle/Makefile where /root/reference is present
+    (the build container; the file travels to the GPU box).  None when it was never built."""
+    global _ECREF
+    if _ECREF is None:
+        so = os.path.join(_HERE, "_ref", "libecref.so")
+        if not os.path.exists(so) and os.path.exists("/root/reference/tools/HaploConduct/src/EdgeCalculator.cpp"):
+            subprocess.call(["make", "-C", _HERE, "_ref/libecref.so"], stdout=subprocess.DEVNULL)
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ecref_overlap_score.restype = C.c_double
+        L.ecref_overlap_score.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_uint,
+                                          C.c_double, C.c_uint, C.POINTER(C.c_double)]
+        L.ecref_phred_to_prob.restype = C.c_double
+        L.ecref_phred_to_prob.argtypes = [C.c_int]
+        _ECREF = L
+    return _ECREF
+
+
+_COMP = bytes.maketrans(b"ACGTN", b"TGCAN")
+
+
+def ecref_score_record(b, quals, rec_row, cluster_base=0, mismatch_prob=0.0, min_read_len=0):
+    """One record through the reference's own overlap_score, with the S-S orientation handling of compute_overlap
+    (EdgeCalculator.cpp:199-221; Read.h:172-201 get_rev_comp / get_rev_phred) done here: (score, mismatch_rate)."""
+    L = ecref()
+    OHA = int(rec_row["OHA"])
+    if OHA >= 0:
+        id1, id2, pos1, fw1, fw2 = int(rec_row["idA"]), int(rec_row["idB"]), OHA, True, int(rec_row["ori"]) == 0
+    else:
+        id1, id2, pos1, fw1, fw2 = int(rec_row["idB"]), int(rec_row["idA"]), -OHA, int(rec_row["ori"]) == 0, True
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+
+    def oriented(i, fw):
+        lo, hi = int(b.base_off[cluster_base + i]), int(b.base_off[cluster_base + i + 1])
+        s = bytes(b.bases[lo:hi]).upper()          # FastqStorage.cpp:123 upper-cases on load
+        q = bytes(quals[lo:hi])
+        return (s, q) if fw else (s.translate(_COMP)[::-1], q[::-1])
+
+    s1, q1 = oriented(id1, fw1)
+    s2, q2 = oriented(id2, fw2)
+    mr = C.c_double()
+    sc = L.ecref_overlap_score(s1, len(s1), s2, len(s2), q1, q2, pos1, float(mismatch_prob), int(min_read_len), C.byref(mr))
+    return sc, mr.value
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -144,6 +195,16 @@ def candidates(b, p=None):
         arr = np.zeros(0, dtype=CAND_DT)
     lib().orc_free(out_p)
     return arr, hits.value
+
+
+def mid_occ(b, p=None):
+    """per-cluster occurrence cut-off (minimap2's data-derived mid_occ, or p.mid_occ when > 0)"""
+    p = p or default_params()
+    out = np.zeros(max(b.n_clusters, 1), dtype=np.uint32)
+    rc = lib().orc_mid_occ(_ptr(b.bases), _ptr(b.base_off), C.c_uint32(b.n_reads), _ptr(b.cluster_off), C.c_uint32(b.n_clusters),
+                           C.byref(p), _ptr(out))
+    assert rc == 0, rc
+    return out[:b.n_clusters]
 
 
 def verify(b, cands, p=None, want_paf=False):

@@ -296,7 +296,21 @@ def test_verify_empty_and_invalid(ctx):
     bad["q"] = 10 ** 6
     with pytest.raises(api.HloError):
         ctx.verify(R, bad)
+    # a diagonal that leaves no overlap, or an anchor span outside the query, would steer the kernels' row reads
+    for diag, sa in ((150, 0), (-150, 0), (40000, 0), (-40000, 0), (10, api_cand_pack(0, 100, 400)), (10, api_cand_pack(1, 90, 50))):
+        bad = np.zeros(1, dtype=api.CAND_DT)
+        bad["q"], bad["t"], bad["diag"], bad["strand_anchor"] = 0, 1, diag, sa
+        with pytest.raises(api.HloError):
+            ctx.verify(R, bad)
+    ok = np.zeros(1, dtype=api.CAND_DT)
+    ok["q"], ok["t"], ok["diag"] = 0, 1, 149
+    rec, aux = ctx.verify(R, ok)  # a 1-base overlap is a legal (rejected) candidate
+    assert len(rec) == 0
     R.free()
+
+
+def api_cand_pack(strand, a_start, a_end):
+    return (strand & 1) | (a_start << 1) | (a_end << 16)
 
 
 # ------------------------------------------------------------------------------------------------- full path
@@ -366,17 +380,13 @@ def test_full_path_longer_reads_take_the_wide_and_generic_kernels(ctx):
 
 
 def test_full_path_generic_kernels_forced(ctx):
-    """the generic pair generator (64-bit keys, table in HBM) and the classic / one-sweep sorts give the same records"""
+    """the generic pair generator (64-bit keys, table in HBM) gives the same records"""
     b = small_cluster(50, n_fragments=150)
-    for opts in (("pairgen_generic",), ("sort_onesweep", "sort_segmented")):
-        ctx.set_option(opts[0], 1)
-        if len(opts) > 1:
-            ctx.set_option(opts[1], 0)  # the one-sweep passes exist for the unsegmented sort only
-        try:
-            check_full(ctx, b)
-        finally:
-            ctx.set_option(opts[0], 0)
-            ctx.set_option("sort_segmented", 1)
+    ctx.set_option("pairgen_generic", 1)
+    try:
+        check_full(ctx, b)
+    finally:
+        ctx.set_option("pairgen_generic", 0)
 
 
 def test_full_path_sort_paths(ctx):
@@ -419,7 +429,7 @@ def test_full_path_random_parameters(seed):
     rb = synth.ReadBatch.from_seqs([seqs])
     pkw = dict(min_ovlp_len=int(rng.integers(30, 80)), min_identity=float(rng.choice([0.9, 0.95, 0.98, 0.99, 1.0])),
                max_overhang=int(rng.integers(0, 6)), overhang_ratio=float(rng.choice([0.0, 0.02, 0.8])),
-               mid_occ=int(rng.choice([30, 1000])), min_seeds=int(rng.integers(1, 3)))
+               mid_occ=int(rng.choice([0, 30, 1000])), min_seeds=int(rng.integers(1, 3)))
     if pkw["min_ovlp_len"] * pkw["min_identity"] < 30:
         pkw["min_ovlp_len"] = 40
     with api.Context(0) as c:
