@@ -156,7 +156,7 @@ def minimap2_chain_tuples(exe, fasta, params, workdir):
         if len(a) < 11:
             continue
         rows.append((0, 0, int(a[0]), int(a[5]), int(a[1]), int(a[2]), int(a[3]), 1 if a[4] == "-" else 0, int(a[6]), int(a[7]),
-                     int(a[8]), int(a[9]), int(a[10]), 0, 0, 0, 0, 1))
+                     int(a[8]), int(a[9]), int(a[10]), 0, 0, 0, 0, 1, 0))
     paf = np.array(rows, dtype=orc.PAF_DT) if rows else np.zeros(0, dtype=orc.PAF_DT)
     keep = orc.filter_chunked(paf, params)
     rec = orc.paf_rows_to_recs(paf, keep)

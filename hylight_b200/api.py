@@ -42,7 +42,7 @@ class Params(C.Structure):
                 ("mid_occ", C.c_int32), ("match_score", C.c_int32), ("mismatch_pen", C.c_int32),
                 ("ambi_pen", C.c_int32), ("end_bonus", C.c_int32), ("min_dp_score", C.c_int32),
                 ("min_ovlp_len", C.c_int32), ("max_overhang", C.c_int32), ("min_identity", C.c_double),
-                ("overhang_ratio", C.c_double)]
+                ("overhang_ratio", C.c_double), ("zdrop", C.c_int32), ("pair_rule", C.c_int32)]
 
 
 class Recs(C.Structure):

@@ -115,7 +115,12 @@ struct VerifyParams {
     int32_t k, a, b, n;  // k-mer, match, mismatch, ambiguous scores
     int32_t min_len, max_overhang;
     int32_t bad_limit;  // fast verify kernel: largest number of bad columns for which a 32-base end window is exact
+    int32_t end_bonus, zdrop;  // ksw2 extension: a query-limited end reaches the read end iff s_end + end_bonus > max; stop at max - s > zdrop
+    int32_t defer_mm;   // fast verify kernel: from this many mismatches on, a query-limited end might not reach the read end: exact kernel
+    int32_t pair_rule;  // 1: rows that pass length + identity but fail the overhang test are emitted with HLO_KB_OVERHANG_FAIL
 };
+#define HLO_KB_OVERHANG_FAIL 0x8000u  // bit 15 of Rec16.kb (K uses bits 0..14): the row failed the overhang test (pair_rule 1)
+#define HLO_KB_K_MASK 0x7fffu
 
 // ---------------------------------------------------------------------------------------------
 // decimal-string order of two unsigned integers == strcmp(str(a), str(b)) < 0  (minimap2 -X skips a

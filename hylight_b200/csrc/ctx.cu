@@ -117,6 +117,7 @@ struct hlo_ctx {
     bool prefix_used = false;
     int n_pg_passes = 0;                         // shared-memory pair generator passes enqueued (table sizes slots0 ..)
     bool fast_pairgen = false;
+    bool exact_all = false;                      // every candidate of this batch goes through the exact verify kernel
     bool inflight = false;
     int rec_form = 0;                            // 0 hlo_rec, 1 hlo_rec16, 2 hlo_rec8: what this batch downloads
     bool want_score = false;
@@ -188,6 +189,7 @@ void hlo_params_default(hlo_params *p) {
     p->k = 21, p->w = 11, p->min_seeds = 2, p->min_chain_score = 30, p->mid_occ = 0;
     p->match_score = 4, p->mismatch_pen = 2, p->ambi_pen = 1, p->end_bonus = 100, p->min_dp_score = 60;
     p->min_ovlp_len = 60, p->max_overhang = 1, p->min_identity = 0.98, p->overhang_ratio = 0.8;
+    p->zdrop = 400, p->pair_rule = 0;
 }
 
 int hlo_abi_version(void) { return HLO_ABI_VERSION; }
@@ -247,6 +249,8 @@ static int check_params(const hlo_params &P, std::string &why) {
     if (P.max_overhang < 0 || P.max_overhang > 15) BAD("max_overhang=%d outside [0,15]", P.max_overhang);
     if (!(P.min_identity > 0.0 && P.min_identity <= 1.0)) BAD("min_identity must be in (0,1]");
     if (!(P.overhang_ratio >= 0.0)) BAD("overhang_ratio must be >= 0");
+    if (P.zdrop < 0 || P.end_bonus < 0) BAD("zdrop and end_bonus must be >= 0");
+    if (P.pair_rule != 0 && P.pair_rule != 1) BAD("pair_rule must be 0 (filter_ovlp_inline.py) or 1 (filter_trans_ovlp_inline_v3.py)");
     // minimap2's own post-alignment filters (-s min_dp_max, mlen >= -m) must never bind on an accepted overlap
     const double worst = (double)P.min_ovlp_len * ((double)P.match_score - (double)(P.match_score + P.mismatch_pen) * (1.0 - P.min_identity));
     if (worst < (double)P.min_dp_score) BAD("-s %d could drop overlaps the filter accepts (min dp score %.1f)", P.min_dp_score, worst);
@@ -371,6 +375,12 @@ static VerifyParams verify_params(const hlo_ctx *ctx) {
     const int wmax = ctx->P.match_score + std::max(ctx->P.mismatch_pen, ctx->P.ambi_pen);
     v.bad_limit = (33 * ctx->P.match_score + wmax - 1) / wmax - 1;  // A*33 - wmax*m > 0
     if (v.bad_limit < 0) v.bad_limit = 0;
+    v.end_bonus = ctx->P.end_bonus, v.zdrop = ctx->P.zdrop, v.pair_rule = ctx->P.pair_rule;
+    // a query-limited end keeps its end bonus (and is not z-dropped) while the score cannot fall min(end_bonus, zdrop + 1)
+    // below its maximum: B per mismatch.  The fast kernel holds no ambiguous base.
+    const int room = std::min(ctx->P.end_bonus, ctx->P.zdrop + 1);
+    v.defer_mm = ctx->P.mismatch_pen > 0 ? (room + ctx->P.mismatch_pen - 1) / ctx->P.mismatch_pen : 0x7fffffff;
+    if (room <= 0) v.defer_mm = 0;
     return v;
 }
 
@@ -459,14 +469,6 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
             for (uint32_t x = 0; x < N; ++x) R->h_perm[r0 + x] = ord[x];
         }
         R->max_id = mx;
-    }
-    // the ungapped model equals minimap2's banded extension only while an accepted overlap cannot hold a
-    // stretch that triggers z-drop / loses the end bonus
-    {
-        const int lim = std::min(ctx->P.end_bonus, 100);
-        if ((1.0 - ctx->P.min_identity) * (double)max_len * (double)std::max(ctx->P.mismatch_pen, 1) >= (double)lim && max_len > 0)
-            FAIL(HLO_EUNSUPPORTED, "reads of %u bp at min_identity %.3f leave the domain where the ungapped end rule is exact", max_len,
-                 ctx->P.min_identity);
     }
     int rc = build_tables(ctx, (int)max_len);
     if (rc) return rc;
@@ -595,12 +597,15 @@ static uint32_t next_pow2_u32(uint32_t v) {
 static void plan_caps(hlo_ctx *ctx, const hlo_reads *R) {
     const DevReads &d = R->d;
     const double scale = std::max(ctx->cap_scale_pct, 1) / 100.0;
-    const double dens = std::max(2.6 / (ctx->P.w + 1) * scale, ctx->need_mz_per_base * 1.1);
-    uint64_t mz = (uint64_t)((double)d.n_bases * dens) + d.n_reads + 1024;
+    const uint64_t slack = std::max<uint64_t>(1024, (uint64_t)(65536 * std::min(scale, 1.0)));
+    // a priori: 1.3x the expected minimizer density 2/(w+1), 2 candidates and 1 record per minimizer; once a batch has
+    // been seen: what it needed + 15 % (grids and scans are sized by these bounds, so a tight one is also a fast one)
+    const double dens = ctx->need_mz_per_base > 0 ? ctx->need_mz_per_base * 1.15 : 2.6 / (ctx->P.w + 1) * scale;
+    uint64_t mz = (uint64_t)((double)d.n_bases * dens) + d.n_reads / 8 + slack;
     mz = std::max(mz, ctx->min_mz);
     mz = std::min<uint64_t>(mz, 0xfffffff0ull);
-    uint64_t c = (uint64_t)((double)mz * std::max(2.0 * scale, ctx->need_c_per_mz * 1.15)) + (1 << 16);
-    uint64_t a = (uint64_t)((double)mz * std::max(1.0 * scale, ctx->need_a_per_mz * 1.15)) + (1 << 16);
+    uint64_t c = (uint64_t)((double)mz * (ctx->need_c_per_mz > 0 ? ctx->need_c_per_mz * 1.15 : 2.0 * scale)) + slack;
+    uint64_t a = (uint64_t)((double)mz * (ctx->need_a_per_mz > 0 ? ctx->need_a_per_mz * 1.15 : 1.0 * scale)) + slack;
     c = std::max(c, ctx->min_c), a = std::max(a, ctx->min_a);
     a = std::min(a, c);  // every record comes from a candidate
     a = std::min<uint64_t>(a, 0x7ffffff0ull);  // records.cu keeps a mark in bit 31 of a record index
@@ -697,7 +702,7 @@ static int enqueue_index(hlo_ctx *ctx, const hlo_reads *R, bool keys_ready) {
     // occurrence histogram: a bucket can hold at most as many entries as its cluster has minimizers; sizes past the
     // clamp bin only matter when the cut-off quantile itself lands there (then the batch is refused)
     const uint32_t bins = next_pow2_u32((uint32_t)std::min<uint64_t>(65536ull, (uint64_t)d.max_cluster * 4 + 64));
-    if (ctx->P.mid_occ <= 0) CK(ctx->b_hist.ensure((size_t)d.n_clusters * bins * 4));
+    if (ctx->P.mid_occ <= 0) CK(ctx->b_hist.ensure(bucket_hist_words(d.n_clusters, bins) * 4));
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
     if (!keys_ready)
@@ -856,6 +861,7 @@ static int enqueue_verify(hlo_ctx *ctx, const hlo_reads *R, uint64_t n_cap) {
     VerifyTables tab_batch = ctx->tab;
     tab_batch.max_len = std::max<int32_t>((int32_t)R->d.max_len, 1);
     const bool force_exact = ctx->verify_exact != 0 || !verify_fast_supported(R->d, tab_batch);
+    ctx->exact_all = force_exact;
     if (force_exact) {
         launch_verify_exact(a, true, s, &ctx->lc);
     } else {
@@ -1106,7 +1112,10 @@ static int complete_front(hlo_ctx *ctx, const hlo_reads *R, int external, bool w
             first_overflow = hc[C_PG_OVF];
             // a batch that overflowed a lot: the following ones start with larger tables
             const int slots0 = std::min(std::max(ctx->pairgen_slots_log2, ctx->pairgen_slots_auto), PAIRGEN_WIDE_SLOTS_LOG2);
-            if (first_overflow > R->d.n_reads / 16 && ctx->pairgen_slots_auto < 10) ctx->pairgen_slots_auto = std::min(slots0 + 1, 10);
+            // ... and so do batches whose tables run full: a table holds at least one key per candidate of its read, and
+            // probe chains grow quickly past ~1/3 load (BASELINE configs[3]: 152 chains per read, 256 slots: 13.4 ms; 512: 11.6)
+            const bool crowded = R->d.n_reads && (double)hc[C_CAND] / (double)R->d.n_reads > 0.3 * (double)(1u << slots0);
+            if ((first_overflow > R->d.n_reads / 16 || crowded) && ctx->pairgen_slots_auto < 10) ctx->pairgen_slots_auto = std::min(slots0 + 1, 10);
         }
         ctx->tm.n_overflow_reads = ctx->fast_pairgen ? first_overflow : 0;
         if (n_list) {
@@ -1158,7 +1167,7 @@ static int run_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out, bool alrea
             continue;
         }
         ctx->tm.n_accepted = hc[C_ACC];
-        ctx->tm.n_deferred = ctx->verify_exact ? hc[C_CAND] : hc[C_DEF];
+        ctx->tm.n_deferred = ctx->exact_all ? hc[C_CAND] : hc[C_DEF];
         ctx->tm.digest = hc[C_DIGEST];
         const uint64_t n_out = (uint32_t)hc[C_NOUT];
         ctx->tm.n_records = n_out;
@@ -1347,16 +1356,19 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
     CK(ctx->h_aux.ensure(n_acc * sizeof(hlo_rec_aux) + 16));
     hlo_rec *ro = ctx->h_out.as<hlo_rec>();
     hlo_rec_aux *ao = ctx->h_aux.as<hlo_rec_aux>();
+    uint64_t n_keep = 0;
     for (uint64_t i = 0; i < n_acc; ++i) {
         const Rec16 &x = h[i];
+        if (x.kb & HLO_KB_OVERHANG_FAIL) continue;  // (pair_rule 1 keeps such rows for the pair decision; a verified record they are not)
         expand_record(R->h_ids[x.q], R->h_ids[x.t], (int)R->h_len[x.q], (int)R->h_len[x.t], (int)(x.ds >> 1) - HLO_DIAG_BIAS,
-                      (int)(x.ds & 1u), x.kb & 0xffffu, &ro[i]);
-        ao[i].cluster = R->h_cidx[x.q], ao[i].blocklen = x.kb >> 16;
+                      (int)(x.ds & 1u), x.kb & HLO_KB_K_MASK, &ro[n_keep]);
+        ao[n_keep].cluster = R->h_cidx[x.q], ao[n_keep].blocklen = x.kb >> 16;
+        ++n_keep;
     }
     memset(out, 0, sizeof *out);
-    out->rec = ro, out->aux = ao, out->n = n_acc, out->n_clusters = R->d.n_clusters;
-    ctx->tm.n_candidates = n, ctx->tm.n_accepted = n_acc, ctx->tm.n_records = n_acc;
-    ctx->tm.n_deferred = ctx->verify_exact ? n : ctx->hc[C_DEF];
+    out->rec = ro, out->aux = ao, out->n = n_keep, out->n_clusters = R->d.n_clusters;
+    ctx->tm.n_candidates = n, ctx->tm.n_accepted = n_keep, ctx->tm.n_records = n_keep;
+    ctx->tm.n_deferred = ctx->exact_all ? n : ctx->hc[C_DEF];
     {
         float v = 0.f;
         if (cudaEventElapsedTime(&v, ctx->ev[ST_PAIRGEN], ctx->ev[ST_VERIFY]) == cudaSuccess) ctx->tm.verify_ms = v;

@@ -76,6 +76,7 @@ void launch_hash_keys(const uint64_t *mz_x, const uint2 *mz_rr, const uint32_t *
 // when its bucket holds more than the cluster's occurrence cut-off midocc[cluster] — fixed_mid_occ when > 0, else
 // minimap2's data-derived value from the occurrence histogram hist[n_clusters][bins] (both filled here).
 // skeys: equal keys adjacent (the grouped order; cluster = key >> hash_bits), svals: their m.
+size_t bucket_hist_words(uint32_t n_clusters, uint32_t bins);  // u32 words of `hist`
 void launch_bucket_index(const uint64_t *skeys, const uint32_t *svals, const uint2 *mz_rr, uint64_t n_cap, const uint32_t *n_ptr, int hash_bits,
                          int fixed_mid_occ, uint32_t n_clusters, uint32_t *midocc, uint32_t *hist, uint32_t bins, unsigned long long *counters,
                          uint2 *hits, uint2 *range, cudaStream_t s, LaunchCounter *lc);

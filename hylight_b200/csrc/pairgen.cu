@@ -65,12 +65,14 @@ constexpr int IX_THREADS = 256;
 constexpr int IX_ITEMS = 4;
 constexpr int IX_TILE = IX_THREADS * IX_ITEMS;
 constexpr int IX_RUNS = IX_TILE / 32;
+constexpr uint32_t IX_LO = 1024, IX_REP = 8;  // occurrence histogram: [cluster][IX_REP][IX_LO] below IX_LO, [cluster][bins] above
 
 template <bool EMIT>
 __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
                                                                   const uint2 *__restrict__ mz_rr, const uint32_t *__restrict__ n_ptr,
                                                                   int hash_bits, const uint32_t *__restrict__ midocc, uint32_t *__restrict__ hist,
-                                                                  uint32_t bins, uint2 *__restrict__ hits, uint2 *__restrict__ range) {
+                                                                  uint32_t *__restrict__ hist_hi, uint32_t *hist_max, uint32_t bins,
+                                                                  uint2 *__restrict__ hits, uint2 *__restrict__ range) {
     __shared__ int run_first[IX_RUNS], run_last[IX_RUNS];     // first / last bucket start inside a run of 32 entries (tile-relative)
     __shared__ int next_after[IX_RUNS], last_before[IX_RUNS]; // first start in a later run / last start in an earlier run
     __shared__ uint32_t tile_prev, tile_next;                 // start of the tile's first bucket, end of its last (global)
@@ -169,15 +171,23 @@ __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t
             const uint32_t st = pb < 0 ? tile_prev : (uint32_t)(base + (uint32_t)pb);
             range[idx[j]] = (en - st) > midocc[clu[j]] ? make_uint2(0u, 0u) : make_uint2((uint32_t)(base + e) + 1u, en);
         } else if ((bal[j] >> lane) & 1u) {  // first entry of its bucket: one count for the bucket's size
-            const uint32_t sz = en - (uint32_t)(base + e);
-            atomicAdd(&hist[(size_t)clu[j] * bins + (sz < bins - 1u ? sz : bins - 1u)], 1u);
+            // sizes below IX_LO (nearly all: a bucket holds about one entry per read covering the minimizer) go to one of
+            // IX_REP replicas of the low part of the histogram — a cluster's buckets crowd on a few dozen sizes, and the
+            // replicas spread what would be same-address atomics
+            uint32_t sz = en - (uint32_t)(base + e);
+            sz = sz < bins - 1u ? sz : bins - 1u;
+            const uint32_t lo = bins < IX_LO ? bins : IX_LO;
+            if (sz < lo) atomicAdd(&hist[((size_t)clu[j] * IX_REP + (blockIdx.x & (IX_REP - 1))) * lo + sz], 1u);
+            else atomicAdd(&hist_hi[(size_t)clu[j] * bins + sz], 1u);
+            if (sz > hist_max[clu[j]]) atomicMax(&hist_max[clu[j]], sz);  // (the plain read first: nearly every bucket is below the maximum already)
         }
     }
 }
 
 // one block per cluster: mid_occ = clamp(k-th smallest occurrence + 1, 10, 10^6), k = (uint32_t)((1 - 2e-4f) * distinct)
 // (minimap2 mm_idx_cal_max_occ / mm_mapopt_update; the float constant is promoted to double there as here)
-__global__ void __launch_bounds__(256) midocc_kernel(const uint32_t *__restrict__ hist, uint32_t bins, uint32_t n_clusters, int fixed,
+__global__ void __launch_bounds__(256) midocc_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ hist_hi,
+                                                     const uint32_t *__restrict__ hist_max, uint32_t bins_all, uint32_t n_clusters, int fixed,
                                                      uint32_t *__restrict__ midocc, unsigned long long *__restrict__ counters) {
     __shared__ uint32_t part[256];
     __shared__ uint32_t s_thr;
@@ -187,10 +197,19 @@ __global__ void __launch_bounds__(256) midocc_kernel(const uint32_t *__restrict_
     if (fixed > 0) {
         thr = (uint32_t)fixed;
     } else {
-        const uint32_t *h = hist + (size_t)c * bins;
+        // distinct minimizers of cluster c that occur v times
+        const uint32_t lo = bins_all < IX_LO ? bins_all : IX_LO;
+        // only sizes up to the cluster's largest bucket are occupied: the walk below covers those
+        const uint32_t bins = min(bins_all, hist_max[c] + 1u);
+        auto h = [&](uint32_t v) {
+            if (v >= lo) return hist_hi[(size_t)c * bins_all + v];
+            uint32_t t = 0;
+            for (uint32_t r = 0; r < IX_REP; ++r) t += hist[((size_t)c * IX_REP + r) * lo + v];
+            return t;
+        };
         const uint32_t per = (bins + 255u) / 256u, b0 = threadIdx.x * per, b1 = min(bins, b0 + per);
         uint32_t sum = 0;
-        for (uint32_t b = b0; b < b1; ++b) sum += h[b];
+        for (uint32_t b = b0; b < b1; ++b) sum += h(b);
         part[threadIdx.x] = sum;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -204,9 +223,9 @@ __global__ void __launch_bounds__(256) midocc_kernel(const uint32_t *__restrict_
                 while (t < 255 && cum + part[t] <= k) cum += part[t], ++t;
                 uint32_t b = (uint32_t)t * per;
                 const uint32_t be = min(bins, b + per);
-                while (b + 1 < be && cum + h[b] <= k) cum += h[b], ++b;
+                while (b + 1 < be && cum + h(b) <= k) cum += h(b), ++b;
                 v = b;
-                if (v == bins - 1u) atomicOr(&counters[C_FLAGS], HLO_FLAG_MIDOCC_AMBIGUOUS);  // the true occurrence is not known
+                if (v == bins_all - 1u) atomicOr(&counters[C_FLAGS], HLO_FLAG_MIDOCC_AMBIGUOUS);  // the true occurrence is not known
             }
             long long m = (long long)v + 1;
             if (m < 10) m = 10;
@@ -223,18 +242,25 @@ __global__ void __launch_bounds__(256) midocc_kernel(const uint32_t *__restrict_
     }
 }
 
+size_t bucket_hist_words(uint32_t n_clusters, uint32_t bins) {  // low replicas | high part | largest size per cluster
+    return (size_t)n_clusters * ((size_t)IX_REP * (bins < IX_LO ? bins : IX_LO) + bins + 1);
+}
+
 void launch_bucket_index(const uint64_t *skeys, const uint32_t *svals, const uint2 *mz_rr, uint64_t n_cap, const uint32_t *n_ptr, int hash_bits,
                          int fixed_mid_occ, uint32_t n_clusters, uint32_t *midocc, uint32_t *hist, uint32_t bins, unsigned long long *counters,
                          uint2 *hits, uint2 *range, cudaStream_t s, LaunchCounter *lc) {
     if (n_cap == 0 || n_clusters == 0) return;
     const unsigned grid = (unsigned)((n_cap + IX_TILE - 1) / IX_TILE);
+    uint32_t *hist_hi = hist ? hist + (size_t)n_clusters * IX_REP * (bins < IX_LO ? bins : IX_LO) : nullptr;
+    uint32_t *hist_max = hist ? hist_hi + (size_t)n_clusters * bins : nullptr;
     if (fixed_mid_occ <= 0) {
-        cudaMemsetAsync(hist, 0, (size_t)n_clusters * bins * sizeof(uint32_t), s);
-        bucket_index_kernel<false><<<grid, IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n_ptr, hash_bits, nullptr, hist, bins, hits, range);
+        cudaMemsetAsync(hist, 0, bucket_hist_words(n_clusters, bins) * sizeof(uint32_t), s);
+        bucket_index_kernel<false><<<grid, IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n_ptr, hash_bits, nullptr, hist, hist_hi, hist_max, bins, hits,
+                                                               range);
         if (lc) lc->total++;
     }
-    midocc_kernel<<<n_clusters, 256, 0, s>>>(hist, bins, n_clusters, fixed_mid_occ, midocc, counters);
-    bucket_index_kernel<true><<<grid, IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n_ptr, hash_bits, midocc, hist, bins, hits, range);
+    midocc_kernel<<<n_clusters, 256, 0, s>>>(hist, hist_hi, hist_max, bins, n_clusters, fixed_mid_occ, midocc, counters);
+    bucket_index_kernel<true><<<grid, IX_THREADS, 0, s>>>(skeys, svals, mz_rr, n_ptr, hash_bits, midocc, hist, hist_hi, hist_max, bins, hits, range);
     if (lc) lc->total += 2;
 }
 

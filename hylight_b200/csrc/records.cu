@@ -22,7 +22,7 @@ namespace hlo {
 __device__ __forceinline__ bool rec_better(const Rec16 &x, const Rec16 &y) {
     const uint32_t bx = x.kb >> 16, by = y.kb >> 16;
     if (bx != by) return bx > by;
-    const uint32_t kx = x.kb & 0xffffu, ky = y.kb & 0xffffu;
+    const uint32_t kx = x.kb & HLO_KB_K_MASK, ky = y.kb & HLO_KB_K_MASK;
     if (kx != ky) return kx < ky;
     const uint32_t sx = x.ds & 1u, sy = y.ds & 1u;
     if (sx != sy) return sx < sy;
@@ -101,6 +101,9 @@ __global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__r
             if (dedup && y.x == me.x && j != p && rec_better(rec[y.y & 0x7fffffffu], rec[me.y & 0x7fffffffu])) keep = false;
         }
         lt_out[p] = lt;
+        // pair_rule 1 (filter_trans_ovlp_inline_v3.py): the best row stands for its pair even when it failed the overhang
+        // test — and then the pair yields nothing
+        if (keep && (rec[me.y & 0x7fffffffu].kb & HLO_KB_OVERHANG_FAIL)) keep = false;
         if (keep) {
             ent[p].y = me.y | 0x80000000u;
             atomicAdd(&uniq[g], 1u);
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(RT_THREADS) group_expand_kernel(const Rec16 *_
         const int ql = (int)mq.x, tl = (int)mt.x;
         const int diag = (int)(x.ds >> 1) - HLO_DIAG_BIAS;
         hlo_rec o;
-        expand_record(mq.y, mt.y, ql, tl, diag, (int)(x.ds & 1u), x.kb & 0xffffu, &o);
+        expand_record(mq.y, mt.y, ql, tl, diag, (int)(x.ds & 1u), x.kb & HLO_KB_K_MASK, &o);
         if (o_.out8)  // 8-byte form (hlo_rec8): ids below 2^16; OHB and OLA follow from OHA and the two read lengths
             reinterpret_cast<uint2 *>(o_.out8)[p] = make_uint2(o.idA | o.idB << 16, ((uint32_t)o.OHA & 0xffffu) | (o.K | o.ori << 15) << 16);
         if (o_.out16)  // 16-byte form (hlo_rec16): OLB == OLA, 16-bit overhangs and lengths

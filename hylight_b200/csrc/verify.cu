@@ -160,11 +160,14 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
 #pragma unroll
                     for (int i = 0; i + 1 < W; i += 2) mm += __popc(f[i] | (f[i + 1] << 1));
                     if (W & 1) mm += __popc(f[W - 1]);
-                    // cheap exact reject: the block keeps at least mm - o mismatches and is at most OL long
-                    if (mm <= (int)t_max_k[OL] + o) {
+                    // cheap exact reject: the block keeps at least mm - o mismatches (pair_rule 1: a flagged row may lose up
+                    // to a window of them) and is at most OL long
+                    if (mm <= (int)t_max_k[OL] + (a.prm.pair_rule ? 33 : o)) {
                         int cl = 0, cmm = 0;
                         bool ok = true;
-                        if (mm > 0 && (left_t || right_t)) {
+                        if (mm >= a.prm.defer_mm) {
+                            ok = false, defer = true;  // enough bad columns to cost a query-limited end its end bonus: the exact rule decides
+                        } else if (mm > 0 && (left_t || right_t)) {
                             if (mm > a.prm.bad_limit) {
                                 ok = false, defer = true;  // a 32-base window no longer decides the end rule
                             } else {
@@ -175,13 +178,16 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
                                 cl = r.clip, cmm = r.mm;
                             }
                         }
-                        if (ok && cl <= o) {
+                        if (ok && (cl <= o || a.prm.pair_rule)) {
                             const int maplen = OL - cl;  // no ambiguous base on this path: blocklen = maplen
                             const int K = mm - cmm;
-                            if (maplen >= min_len && maplen >= 1 && maplen - K >= (int)t_min_matches[maplen] &&
-                                cl <= (int)t_max_clip[maplen]) {
-                                accept = true;
-                                rec = make_uint4(q, t, ((uint32_t)(D + HLO_DIAG_BIAS) << 1) | strand, (uint32_t)K | ((uint32_t)maplen << 16));
+                            if (maplen >= min_len && maplen >= 1 && maplen - K >= (int)t_min_matches[maplen]) {
+                                const bool oh_ok = cl <= o && cl <= (int)t_max_clip[maplen];
+                                if (oh_ok || a.prm.pair_rule) {
+                                    accept = true;
+                                    rec = make_uint4(q, t, ((uint32_t)(D + HLO_DIAG_BIAS) << 1) | strand,
+                                                     (uint32_t)K | (oh_ok ? 0u : HLO_KB_OVERHANG_FAIL) | ((uint32_t)maplen << 16));
+                                }
                             }
                         }
                     }
@@ -276,25 +282,41 @@ __device__ __forceinline__ void verify_exact_one(const VerifyArgs &a, uint64_t c
     int cl = 0, cr = 0;
     // column class: 0 match, 1 mismatch, 2 ambiguous
 #define COLCLASS(j) ((ambf && (get_base(QA, (j)) | get_base(TA, (j) + D))) ? 2 : (get_base(Q, (j)) != get_base(T, (j) + D)))
-    if (D < 0) {
+    // Each end is a ksw2 extension from the outermost anchor outward (oracle/hlo_oracle.c:orc_extend_end): s = cumulative
+    // score, best = its largest value so far (strict >: the earliest position), stop when best - s > zdrop.  An end where
+    // the QUERY ends first reaches the read end iff not z-dropped and s_end + end_bonus > best; every other end stops at
+    // the position of best.
+    {
         int s = 0, best = 0, best_n = 0, cnt = 0;
+        bool dropped = false;
         for (int j = aS - 1; j >= js; --j) {
             const int cc = COLCLASS(j);
             s += cc == 0 ? A : (cc == 1 ? -B : -N);
             ++cnt;
             if (s > best) best = s, best_n = cnt;
+            else if (best - s > a.prm.zdrop) {
+                dropped = true;
+                break;
+            }
         }
-        cl = (aS - js) - best_n;
+        const bool reach = D >= 0 && !dropped && s + a.prm.end_bonus > best;
+        cl = reach ? 0 : (aS - js) - best_n;
     }
-    if (tl - D < ql) {
+    {
         int s = 0, best = 0, best_n = 0, cnt = 0;
+        bool dropped = false;
         for (int j = aE; j < je; ++j) {
             const int cc = COLCLASS(j);
             s += cc == 0 ? A : (cc == 1 ? -B : -N);
             ++cnt;
             if (s > best) best = s, best_n = cnt;
+            else if (best - s > a.prm.zdrop) {
+                dropped = true;
+                break;
+            }
         }
-        cr = (je - aE) - best_n;
+        const bool reach = !(tl - D < ql) && !dropped && s + a.prm.end_bonus > best;
+        cr = reach ? 0 : (je - aE) - best_n;
     }
     const int bs = js + cl, be = je - cr;
     int K = 0, n_ambi = 0;
@@ -307,13 +329,14 @@ __device__ __forceinline__ void verify_exact_one(const VerifyArgs &a, uint64_t c
     if (maplen < 1 || blocklen < 1 || blocklen < a.prm.min_len) return;
     if (maplen > a.tab.max_len) return;
     if (blocklen - K < (int)a.tab.min_matches[blocklen]) return;
-    if (cl + cr > (int)a.tab.max_clip[maplen]) return;
+    const bool oh_ok = cl + cr <= (int)a.tab.max_clip[maplen];
+    if (!oh_ok && !a.prm.pair_rule) return;
     const unsigned long long p = atomicAdd(a.acc_counter, 1ULL);
     if (p >= a.out_cap) return;  // counted only
     Rec16 rec;
     rec.q = q, rec.t = t;
     rec.ds = ((uint32_t)(D + HLO_DIAG_BIAS) << 1) | strand;
-    rec.kb = (uint32_t)K | ((uint32_t)blocklen << 16);
+    rec.kb = (uint32_t)K | (oh_ok ? 0u : HLO_KB_OVERHANG_FAIL) | ((uint32_t)blocklen << 16);
     a.out[p] = rec;
 }
 

@@ -62,6 +62,16 @@ typedef struct hlo_params {
     int32_t max_overhang;    /* filter_ovlp_inline.py argv[3] = 1 (0..15) */
     double min_identity;     /* filter_ovlp_inline.py argv[2] = 0.98 */
     double overhang_ratio;   /* filter_ovlp_inline.py argv[4] = 0.8 */
+    int32_t zdrop;           /* -z 400 (minimap2 default): an end extension stops where the score has fallen this far below its
+                                maximum; only the exact verify kernel ever meets it */
+    int32_t pair_rule;       /* which row of a read pair survives:
+                                0 = filter_ovlp_inline.py:12-39,42-91 (short-read pass): rows failing the overhang test are dropped
+                                    first, then the longest row of the pair is kept;
+                                1 = filter_trans_ovlp_inline_v3.py:49-77 (HyLight.py:309-311, contig stage b): the first row of the
+                                    pair that passes length and identity stands for the pair, and the pair is dropped when THAT
+                                    row fails the overhang test.
+                                Both scripts work on 1000-line chunks of minimap2's output order; the library applies the rule
+                                per cluster with "first" / "longest" = the canonical best row. */
 } hlo_params;
 
 /*

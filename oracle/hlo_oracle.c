@@ -65,6 +65,8 @@ void orc_params_default(hlo_params *p) {
     p->max_overhang = 1;
     p->min_identity = 0.98;
     p->overhang_ratio = 0.8;
+    p->zdrop = 400;
+    p->pair_rule = 0;
 }
 
 /* strcmp() of the decimal spellings of a and b — the order minimap2 -X uses on read names
@@ -415,6 +417,8 @@ typedef struct orc_paf {
     int32_t dp_max;       /* peak local score over the block (mm_update_extra) */
     int32_t clip_l, clip_r, n_ambi;
     int32_t valid;        /* 0: geometry gives no overlap */
+    int32_t zdrop_mid;    /* 1: inside the block the score falls more than zdrop below an earlier maximum: minimap2 would
+                             split the alignment there (mm_align1's z-drop test); reported, not modelled */
 } orc_paf;
 
 static inline int comp_base(int c) { return c < 4 ? 3 - c : 4; }
@@ -422,12 +426,31 @@ static inline int comp_base(int c) { return c < 4 ? 3 - c : 4; }
 /*
  * Ungapped extension with minimap2's end rule (align.c mm_align1 in SR mode + ksw2 extension):
  *  - between first and last anchor: ungapped ("if (is_sr) perform ungapped alignment");
- *  - an end where the QUERY ends first: the +end_bonus makes the extension reach the query end;
- *  - an end where the TARGET ends first: the query end is unreachable, the extension stops at the
- *    earliest position (ksw2 updates max with strict >) attaining the maximum cumulative score
- *    (+A match, -B mismatch, -score_N ambiguous) counted outward from the outermost anchor.
+ *  - each end is a ksw2 EXTENSION from the outermost anchor outward: cumulative score s (+A match, -B mismatch,
+ *    -score_N ambiguous), max = its largest value so far (strict >: the earliest position wins), and the extension
+ *    stops early when max - s > zdrop (ksw_apply_zdrop; off the diagonal there is nothing: bw = 0);
+ *  - an end where the QUERY ends first reaches the query end iff it was not z-dropped and mqe + end_bonus > max
+ *    (mqe = s at the query end; ksw2 "reach_end"); otherwise, and always where the TARGET ends first (the query end is
+ *    never reached, mqe = -inf), the block ends at the position of max.
+ *    (For the reads of the short-read pass — 150-250 bp at >= 98 % — B * mismatches < end_bonus, so a query-limited end
+ *    always reaches the read end; the general rule matters for contigs)
  * matches/blocklen exclude ambiguous columns (mm_update_extra).
  */
+static int orc_extend_end(const int *sc, int n, int query_limited, int end_bonus, int zdrop) {
+    /* sc[0..n): column scores from the anchor outward; returns the number of columns kept */
+    int s = 0, best = 0, best_n = 0, dropped = 0;
+    for (int i = 0; i < n; ++i) {
+        s += sc[i];
+        if (s > best) best = s, best_n = i + 1;
+        else if (best - s > zdrop) {
+            dropped = 1;
+            break;
+        }
+    }
+    if (query_limited && !dropped && s + end_bonus > best) return n;
+    return best_n;
+}
+
 void orc_extend(const char *bases, const uint64_t *base_off, const hlo_params *P, const hlo_cand *cd, uint32_t qid,
                 uint32_t tid, orc_paf *o) {
     const uint8_t *nt4 = nt4_table();
@@ -446,28 +469,26 @@ void orc_extend(const char *bases, const uint64_t *base_off, const hlo_params *P
 #define TB(j) (nt4[(uint8_t)ts_[(j) + D]])
 #define SC(a, b) (((a) > 3 || (b) > 3) ? -P->ambi_pen : ((a) == (b) ? P->match_score : -P->mismatch_pen))
     int clip_l = 0, clip_r = 0;
-    if (D < 0) { /* left end is target-limited */
-        int s = 0, best = 0, best_n = 0, n = 0;
-        for (int j = a_start - 1; j >= js; --j) {
-            int a = QB(j), b = TB(j);
-            s += SC(a, b);
-            ++n;
-            if (s > best) best = s, best_n = n;
+    int *sc = (int *)malloc((size_t)(je - js + 1) * sizeof *sc);
+    {   /* left end: target-limited iff D < 0 (then js = -D > 0 = where the target starts), else the query starts at 0 */
+        const int n = a_start - js;
+        for (int i = 0; i < n; ++i) {
+            const int j = a_start - 1 - i, a = QB(j), b = TB(j);
+            sc[i] = SC(a, b);
         }
-        clip_l = (a_start - js) - best_n;
+        clip_l = n - orc_extend_end(sc, n, D >= 0, P->end_bonus, P->zdrop);
     }
-    if (tl - D < ql) { /* right end is target-limited */
-        int s = 0, best = 0, best_n = 0, n = 0;
-        for (int j = a_end; j < je; ++j) {
-            int a = QB(j), b = TB(j);
-            s += SC(a, b);
-            ++n;
-            if (s > best) best = s, best_n = n;
+    {   /* right end: target-limited iff tl - D < ql */
+        const int n = je - a_end;
+        for (int i = 0; i < n; ++i) {
+            const int j = a_end + i, a = QB(j), b = TB(j);
+            sc[i] = SC(a, b);
         }
-        clip_r = (je - a_end) - best_n;
+        clip_r = n - orc_extend_end(sc, n, !(tl - D < ql), P->end_bonus, P->zdrop);
     }
+    free(sc);
     const int bs = js + clip_l, be = je - clip_r;
-    int n_ambi = 0, n_diff = 0, s = 0, dp_max = 0;
+    int n_ambi = 0, n_diff = 0, s = 0, dp_max = 0, run_max = 0, run = 0, zmid = 0;
     for (int j = bs; j < be; ++j) {
         int a = QB(j), b = TB(j);
         if (a > 3 || b > 3) ++n_ambi;
@@ -475,6 +496,9 @@ void orc_extend(const char *bases, const uint64_t *base_off, const hlo_params *P
         s += SC(a, b);
         if (s < 0) s = 0;
         else if (s > dp_max) dp_max = s;
+        run += SC(a, b);
+        if (run > run_max) run_max = run;
+        else if (run_max - run > P->zdrop) zmid = 1;
     }
 #undef QB
 #undef TB
@@ -484,6 +508,7 @@ void orc_extend(const char *bases, const uint64_t *base_off, const hlo_params *P
     o->blocklen = (be - bs) - n_ambi;
     o->matches = o->blocklen - n_diff;
     o->dp_max = dp_max;
+    o->zdrop_mid = zmid;
     if (strand) o->qs = ql - be, o->qe = ql - bs;
     else o->qs = bs, o->qe = be;
     o->ts = bs + D, o->te = be + D;
@@ -503,8 +528,9 @@ int orc_extend_all(const char *bases, const uint64_t *base_off, const uint32_t *
 /* ------------------------------------------------------------------------------------------ */
 /* (2a) filter_ovlp_inline.py                                                                    */
 
-/* rm_intermatch, filter_ovlp_inline.py:42-91.  Returns 1 if the row is kept. */
-int orc_filter_row(const orc_paf *r, const hlo_params *P) {
+/* rm_intermatch, filter_ovlp_inline.py:42-91 (and the same two tests of filter_trans_ovlp_inline_v3.py:49-77).
+ * Returns bit 0: the row passes length and identity; bit 1: ... and the overhang test. */
+int orc_filter_row2(const orc_paf *r, const hlo_params *P) {
     if (!r->valid) return 0;
     const int l1 = r->ql, b1 = r->qs, e1 = r->qe, l2 = r->tl;
     if (r->blocklen < P->min_ovlp_len) return 0;
@@ -518,11 +544,14 @@ int orc_filter_row(const orc_paf *r, const hlo_params *P) {
     const double x = (double)maplen * P->overhang_ratio;
     /* python: overhang > min(o, maplen * r); min() returns x only when x < o */
     if (x < (double)P->max_overhang) {
-        if ((double)overhang > x) return 0;
+        if ((double)overhang > x) return 1;
     } else if (overhang > P->max_overhang)
-        return 0;
-    return 1;
+        return 1;
+    return 3;
 }
+
+/* Returns 1 if filter_ovlp_inline.py's rm_intermatch keeps the row. */
+int orc_filter_row(const orc_paf *r, const hlo_params *P) { return orc_filter_row2(r, P) == 3; }
 
 /* ------------------------------------------------------------------------------------------ */
 /* (2b) minimap22sfo.py:47-74 + sfo2overlaps.py:37-50 (flip_N :112-117, flip_I :119-122)          */
@@ -710,7 +739,11 @@ int orc_overlap_batch(const char *bases, const uint64_t *base_off, uint32_t n_re
         orc_paf row;
         uint32_t q = cands[i].q, t = cands[i].t;
         orc_extend(bases, base_off, P, &cands[i], ids ? ids[q] : q - rbase[q], ids ? ids[t] : t - rbase[t], &row);
-        if (!orc_filter_row(&row, P)) continue;
+        const int pass = orc_filter_row2(&row, P);
+        /* pair_rule 0: only rows that pass everything compete for their pair; pair_rule 1: every row that passes length
+         * and identity competes, and the winner's overhang test decides the pair (row.valid = 2 marks a failed test) */
+        if (P->pair_rule ? !(pass & 1) : pass != 3) continue;
+        if (pass != 3) row.valid = 2;
         rows[n_acc].row = row;
         rows[n_acc].order = i;
         ++n_acc;
@@ -726,9 +759,13 @@ int orc_overlap_batch(const char *bases, const uint64_t *base_off, uint32_t n_re
                 if (paf_better(&rows[j].row, cands[rows[j].order].diag, &rows[best].row, cands[rows[best].order].diag)) best = j;
                 ++j;
             }
-            rows[n_keep++] = rows[best];
+            if (rows[best].row.valid == 1) rows[n_keep++] = rows[best]; /* (pair_rule 1: the winner failed the overhang test) */
             i = j;
         }
+    } else if (P->pair_rule) {
+        n_keep = 0;
+        for (uint64_t i = 0; i < n_acc; ++i)
+            if (rows[i].row.valid == 1) rows[n_keep++] = rows[i];
     }
     hlo_rec *rec = (hlo_rec *)malloc((n_keep ? n_keep : 1) * sizeof *rec);
     uint32_t *blk = (uint32_t *)malloc((n_keep ? n_keep : 1) * sizeof *blk);
@@ -885,6 +922,55 @@ uint64_t orc_filter_chunked(const orc_paf *rows, uint64_t n, const hlo_params *P
     }
     free(sel);
     return n_out;
+}
+
+/*
+ * filter_trans_ovlp_inline_v3.py (HyLight.py:309-311 pipes minimap2 into it with "-len 90 -iden 0.99 -oh 2 -sfo") on a
+ * list of PAF rows in the GIVEN order: per chunk of 1000 input lines (:33-37), a row that fails length / identity or
+ * is a self hit is skipped (:49-50); the FIRST remaining row of an unordered pair registers the pair (:52-55) and
+ * later rows of the pair are skipped; the registered row is then dropped when overhang > min(o, maplen * 0.8)
+ * (:57-71; the ratio 0.8 is literal in the script).  keep_idx: surviving rows in output order.
+ */
+uint64_t orc_filter_chunked_v3(const orc_paf *rows, uint64_t n, const hlo_params *P, uint64_t *keep_idx) {
+    uint64_t n_out = 0;
+    uint64_t *seen = (uint64_t *)malloc(1000 * sizeof *seen);
+    hlo_params Q = *P;
+    Q.overhang_ratio = 0.8;
+    for (uint64_t c0 = 0; c0 < n; c0 += 1000) {
+        uint64_t c1 = c0 + 1000 < n ? c0 + 1000 : n, ns = 0;
+        for (uint64_t i = c0; i < c1; ++i) {
+            const int pass = orc_filter_row2(&rows[i], &Q);
+            if (!(pass & 1)) continue;
+            if (rows[i].qid == rows[i].tid) continue;
+            uint32_t a = rows[i].qid, b = rows[i].tid;
+            uint64_t j;
+            for (j = 0; j < ns; ++j) {
+                const orc_paf *o = &rows[seen[j]];
+                if ((o->qid == a && o->tid == b) || (o->qid == b && o->tid == a)) break;
+            }
+            if (j < ns) continue;
+            seen[ns++] = i;
+            if (pass == 3) keep_idx[n_out++] = i;
+        }
+    }
+    free(seen);
+    return n_out;
+}
+
+/* the SFO lines that script prints with -sfo (its own minimap22sfo(), :83-102): no swap of the ids */
+int orc_write_sfo_v3(const orc_paf *rows, const uint64_t *idx, uint64_t n, const char *path) {
+    FILE *f = fopen(path, "w");
+    if (!f) return HLO_EIO;
+    for (uint64_t i = 0; i < n; ++i) {
+        const orc_paf *r = &rows[idx ? idx[i] : i];
+        int OHA, OHB, OLA;
+        if (!r->strand) OHA = r->qs - r->ts, OHB = r->tl - r->ts - (r->ql - r->qs);
+        else OHA = r->qs - (r->tl - r->te), OHB = r->te - (r->ql - r->qs);
+        if (OHA >= 0) OLA = (r->ql - OHA) < r->tl ? (r->ql - OHA) : r->tl;
+        else OLA = (r->tl + OHA) < r->ql ? (r->tl + OHA) : r->ql;
+        fprintf(f, "%u\t%u\t%c\t%d\t%d\t%d\t%d\t%d\n", r->qid, r->tid, r->strand ? 'I' : 'N', OHA, OHB, OLA, OLA, r->blocklen - r->matches);
+    }
+    return fclose(f) ? HLO_EIO : HLO_OK;
 }
 
 /* Convert a list of PAF rows (already filtered) straight to sorted, uniq'd records: minimap22sfo.py +

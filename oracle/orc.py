@@ -19,7 +19,7 @@ MZ_DT = np.dtype([("x", "<u8"), ("y", "<u8")])
 PAF_DT = np.dtype([("q", "<u4"), ("t", "<u4"), ("qid", "<u4"), ("tid", "<u4"), ("ql", "<i4"), ("qs", "<i4"),
                    ("qe", "<i4"), ("strand", "<i4"), ("tl", "<i4"), ("ts", "<i4"), ("te", "<i4"), ("matches", "<i4"),
                    ("blocklen", "<i4"), ("dp_max", "<i4"), ("clip_l", "<i4"), ("clip_r", "<i4"), ("n_ambi", "<i4"),
-                   ("valid", "<i4")])
+                   ("valid", "<i4"), ("zdrop_mid", "<i4")])
 
 
 class Params(C.Structure):
@@ -27,7 +27,7 @@ class Params(C.Structure):
                 ("mid_occ", C.c_int32), ("match_score", C.c_int32), ("mismatch_pen", C.c_int32),
                 ("ambi_pen", C.c_int32), ("end_bonus", C.c_int32), ("min_dp_score", C.c_int32),
                 ("min_ovlp_len", C.c_int32), ("max_overhang", C.c_int32), ("min_identity", C.c_double),
-                ("overhang_ratio", C.c_double)]
+                ("overhang_ratio", C.c_double), ("zdrop", C.c_int32), ("pair_rule", C.c_int32)]
 
 
 def build(force=False):
@@ -98,6 +98,7 @@ def lib():
         _LIB = C.CDLL(build())
         _LIB.orc_sketch.restype = C.c_uint64
         _LIB.orc_filter_chunked.restype = C.c_uint64
+        _LIB.orc_filter_chunked_v3.restype = C.c_uint64
         _LIB.orc_paf_rows_to_recs.restype = C.c_uint64
         _LIB.orc_sort_uniq_recs.restype = C.c_uint64
         _LIB.orc_sizeof_paf.restype = C.c_size_t
@@ -264,6 +265,21 @@ def filter_chunked(paf, p=None):
     keep = np.zeros(max(len(paf), 1), dtype=np.uint64)
     n = lib().orc_filter_chunked(_ptr(paf), C.c_uint64(len(paf)), C.byref(p), _ptr(keep))
     return keep[:n].copy()
+
+
+def filter_chunked_v3(paf, p=None):
+    """filter_trans_ovlp_inline_v3.py on rows in the given order: indices of the surviving rows"""
+    p = p or default_params()
+    paf = np.ascontiguousarray(paf, dtype=PAF_DT)
+    keep = np.zeros(max(len(paf), 1), dtype=np.uint64)
+    n = lib().orc_filter_chunked_v3(_ptr(paf), C.c_uint64(len(paf)), C.byref(p), _ptr(keep))
+    return keep[:n].copy()
+
+
+def write_sfo_v3(paf, idx, path):
+    paf = np.ascontiguousarray(paf, dtype=PAF_DT)
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    assert lib().orc_write_sfo_v3(_ptr(paf), _ptr(idx), C.c_uint64(len(idx)), path.encode()) == 0
 
 
 def paf_rows_to_recs(paf, idx=None):

@@ -56,7 +56,7 @@ def test_rerun_path_when_the_estimates_are_too_small():
         c.submit(b)
         rec, aux, coff = c.wait()
         tm = c.timing()
-        assert tm["n_reruns"] >= 2, tm
+        assert tm["n_reruns"] >= 3, tm  # minimizers, then candidates, then records
         assert np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o)
         assert tm["digest"] == api.records_digest(rec)
         c.submit(b)
@@ -248,4 +248,3 @@ def test_config4_full_size_cluster_matches_the_oracle():
     assert len(rec) == len(rec_o) > 3_000_000
     assert np.array_equal(rec, rec_o) and np.array_equal(aux["blocklen"], blk_o)
     assert tm["digest"] == api.records_digest(rec)
-    assert tm["n_overflow_reads"] > 0  # reads with more chains than a 256-slot table

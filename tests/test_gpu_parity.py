@@ -614,9 +614,7 @@ def _contig_cluster(seed, n_contigs, lo, hi, genome_len=30000, n_strains=2, snp_
 
 def test_full_path_contigs_variable_length():
     """the same chain on contigs (min_overlap_len 50), alone and in one batch with clusters of
-    short reads (the long sequences take the generic sketch / pack kernels and the exact verify kernel).  The
-    ungapped extension model holds while (1 - min_identity) * length * B < end bonus, i.e. up to 2499 bp at 0.98;
-    longer sequences are refused (test below)"""
+    short reads (the long sequences take the generic sketch / pack kernels and the exact verify kernel)."""
     contigs = _contig_cluster(7, 120, 150, 2400, genome_len=9000)
     mid = _contig_cluster(8, 150, 200, 1500, genome_len=12000, n_strains=3)
     short = [bytes(s_) for s_ in small_cluster(75, n_fragments=150).cluster_reads(0)]
@@ -625,9 +623,69 @@ def test_full_path_contigs_variable_length():
         assert len(rec) > 50
         rec, coff, tm = check_full(c, synth.ReadBatch.from_seqs([short, contigs, mid, short[:50]]), min_ovlp_len=50)
         assert coff[1] > 0 and coff[2] > coff[1] and coff[3] > coff[2]
-        with pytest.raises(api.HloError) as ei:
-            c.pack(to_orc_batch(synth.ReadBatch.from_seqs([_contig_cluster(9, 3, 2600, 2700, genome_len=9000)])))
-        assert "ungapped" in str(ei.value)
+
+
+def test_full_path_long_contigs_general_end_rule():
+    """contigs of up to 30 kb (round 1 refused everything above 2499 bp): the exact verify kernel applies ksw2's extension
+    rule in full — a query-limited end reaches the read end only while s_end + end_bonus > max and the score never falls
+    zdrop below its maximum — so overlaps with hundreds of mismatches are decided like minimap2 decides them"""
+    contigs = _contig_cluster(11, 40, 3000, 30000, genome_len=60000, n_strains=3, snp_rate=0.004)
+    with api.Context(0, min_ovlp_len=50) as c:
+        rec, coff, tm = check_full(c, synth.ReadBatch.from_seqs([contigs]), min_ovlp_len=50)
+        assert len(rec) > 30 and int(rec["K"].max()) > 60  # more mismatches than the end bonus pays for (B * K >= 100)
+        assert tm["n_deferred"] == tm["n_candidates"]
+    # ends that LOSE the end bonus: a divergent tail right at a query-limited end (45 of the last 60 bases differ)
+    rng = np.random.default_rng(5)
+    g = rng.integers(0, 4, size=5000).astype(np.uint8)
+    A = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for i in range(30):
+        s0 = int(rng.integers(0, 2000))
+        r = g[s0:s0 + 2500].copy()
+        if i % 3 == 0:
+            bad = rng.choice(60, size=45, replace=False) + (2500 - 60)
+            r[bad] = (r[bad] + 1 + rng.integers(0, 3, size=45)) % 4
+        if i % 5 == 0:
+            bad = rng.choice(80, size=70, replace=False)
+            r[bad] = (r[bad] + 1) % 4
+        reads.append(A[r].tobytes())
+    for pkw in (dict(min_ovlp_len=50, min_identity=0.9, max_overhang=15, overhang_ratio=0.8), dict(min_ovlp_len=50, min_identity=0.9, max_overhang=0)):
+        with api.Context(0, **pkw) as c:
+            b = synth.ReadBatch.from_seqs([reads])
+            rec, coff, tm = check_full(c, b, **pkw)
+            ob = to_orc_batch(b)
+            oc, _ = orc.candidates(ob, orc.default_params(**pkw))
+            _, _, _, paf = orc.verify(ob, oc, orc.default_params(**pkw), want_paf=True)
+            assert max(int(paf["clip_l"].max()), int(paf["clip_r"].max())) >= 40  # whole divergent tails were clipped: ends that lost the bonus
+            check_verify(c, b, oc, **pkw)
+
+
+def test_stage_b_pair_rule(ctx):
+    """HyLight's contig stage (HyLight.py:309-311: -len 90 -iden 0.99 -oh 2, filter_trans_ovlp_inline_v3.py): the best row of a
+    pair stands for it, and the pair is dropped when that row fails the overhang test — unlike the short-read pass, where a
+    shorter row that passes could still represent the pair"""
+    rng = np.random.default_rng(12)
+    unit = "".join("ACGT"[i] for i in rng.integers(0, 4, size=37))
+    g = "".join("ACGT"[i] for i in rng.integers(0, 4, size=1500))
+    genome = g[:600] + unit * 14 + g[600:]  # a long tandem repeat: pairs of reads align on several diagonals at 100 %
+    seqs = []
+    for i in range(200):
+        s0 = int(rng.integers(400, 600 + 37 * 14 - 100))
+        r = bytearray(genome[s0:s0 + int(rng.integers(200, 260))].encode())
+        if i % 3 == 0:  # three terminal mismatches: where this end limits the overlap it is clipped by 3 > max_overhang, so the
+            for j in (0, 1, 2):  # longest row of such a pair fails the overhang test while a shifted, shorter row passes
+                r[j] = ord("ACGT"[("ACGT".index(chr(r[j])) + 1) % 4])
+        seqs.append(bytes(r))
+    b = synth.ReadBatch.from_seqs([seqs])
+    base = dict(min_ovlp_len=90, min_identity=0.99, max_overhang=2)
+    out = {}
+    for rule in (0, 1):
+        with api.Context(0, pair_rule=rule, **base) as c:
+            rec, coff, tm = check_full(c, b, pair_rule=rule, **base)
+            out[rule] = rec
+    assert len(out[0]) > 10000 and len(out[1]) > 10000
+    pairs = lambda r: set(zip(r["idA"].tolist(), r["idB"].tolist()))
+    assert pairs(out[1]) <= pairs(out[0]) and pairs(out[1]) != pairs(out[0])  # pairs whose best row fails the overhang test vanish
 
 
 def test_full_path_many_small_clusters(ctx):
