@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "hlo_sketch", "hlo_candidates", "hlo_verify", "hlo_overlap_batch", "hlo_overlap_host", "hlo_get_timing",
     "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records",
     "hlo_write_overlaps_scored", "hlo_write_overlaps16", "hlo_write_sfo16", "hlo_submit", "hlo_wait", "hlo_set_score_params",
-    "hlo_write_overlaps8", "hlo_write_sfo8", "hlo_write_binary16",
+    "hlo_write_overlaps8", "hlo_write_sfo8", "hlo_write_binary16", "hlo_pack2b",
 ]
 
 
@@ -53,7 +53,8 @@ class Recs(C.Structure):
 class Batch(C.Structure):
     """hlo_batch: the input of hlo_submit"""
     _fields_ = [("bases", C.c_void_p), ("quals", C.c_void_p), ("base_off", C.c_void_p), ("n_reads", C.c_uint32),
-                ("cluster_off", C.c_void_p), ("n_clusters", C.c_uint32), ("ids", C.c_void_p)]
+                ("cluster_off", C.c_void_p), ("n_clusters", C.c_uint32), ("ids", C.c_void_p),
+                ("packed", C.c_void_p), ("read_len", C.c_void_p), ("amb", C.c_void_p), ("n_amb", C.c_uint64)]
 
 
 class Timing(C.Structure):
@@ -281,12 +282,26 @@ class Context:
                 np.ascontiguousarray(batch.cluster_off, dtype=np.uint32),
                 None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8),
                 None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)]
-        b = Batch(_ptr(keep[0]), _ptr(keep[3]), _ptr(keep[1]), len(keep[1]) - 1, _ptr(keep[2]), len(keep[2]) - 1, _ptr(keep[4]))
+        b = Batch(_ptr(keep[0]), _ptr(keep[3]), _ptr(keep[1]), len(keep[1]) - 1, _ptr(keep[2]), len(keep[2]) - 1, _ptr(keep[4]),
+                  None, None, None, 0)
         self._inflight = keep
         self._check(lib().hlo_submit(self.h, C.byref(b)))
 
     def submit_raw(self, bases_ptr, off_ptr, n_reads, coff_ptr, n_clusters, quals_ptr=None):
-        b = Batch(bases_ptr, quals_ptr, off_ptr, n_reads, coff_ptr, n_clusters, None)
+        b = Batch(bases_ptr, quals_ptr, off_ptr, n_reads, coff_ptr, n_clusters, None, None, None, None, 0)
+        self._check(lib().hlo_submit(self.h, C.byref(b)))
+
+    def submit_packed(self, pk, cluster_off):
+        """hlo_submit of a batch in the 2-bit packed form (pk = pack2b(batch)): a quarter of the upload"""
+        words, lens, amb = pk
+        coff = np.ascontiguousarray(cluster_off, dtype=np.uint32)
+        self._inflight = [words, lens, amb, coff]
+        b = Batch(None, None, None, len(lens), _ptr(coff), len(coff) - 1, None, _ptr(words), _ptr(lens), _ptr(amb) if len(amb) else None,
+                  len(amb))
+        self._check(lib().hlo_submit(self.h, C.byref(b)))
+
+    def submit_packed_raw(self, words_ptr, len_ptr, n_reads, coff_ptr, n_clusters, amb_ptr=None, n_amb=0):
+        b = Batch(None, None, None, n_reads, coff_ptr, n_clusters, None, words_ptr, len_ptr, amb_ptr, n_amb)
         self._check(lib().hlo_submit(self.h, C.byref(b)))
 
     def wait_raw(self):
@@ -332,6 +347,24 @@ def expand_rec16(rec16):
     out["K"] = rec16["K_ori"] & 0x7fff
     out["ori"] = rec16["K_ori"] >> 15
     return out
+
+
+def pack2b(batch):
+    """hlo_pack2b: ASCII reads -> (packed words u32, read lengths u32, ambiguous positions u64 = read << 32 | pos)"""
+    bases = np.ascontiguousarray(batch.bases, dtype=np.uint8)
+    off = np.ascontiguousarray(batch.base_off, dtype=np.uint64)
+    n = len(off) - 1
+    lens = np.zeros(max(n, 1), dtype=np.uint32)
+    words = np.zeros(int(((np.diff(off).astype(np.int64) + 15) // 16).sum()) + 1, dtype=np.uint32)
+    amb = np.zeros(len(bases) + 1, dtype=np.uint64)
+    nw, na = C.c_uint64(), C.c_uint64()
+    L = lib()
+    L.hlo_pack2b.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_uint64,
+                             C.POINTER(C.c_uint64)]
+    rc = L.hlo_pack2b(_ptr(bases), _ptr(off), n, _ptr(words), C.byref(nw), _ptr(lens), _ptr(amb), len(amb), C.byref(na))
+    if rc:
+        raise HloError(rc, L.hlo_strerror(rc).decode())
+    return words[:nw.value].copy(), lens[:n].copy(), amb[:na.value].copy()
 
 
 def expand_rec8(rec8, len_by_id):

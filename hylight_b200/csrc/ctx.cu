@@ -83,12 +83,15 @@ struct hlo_reads {
     DevReads d;
     DevBuf b_ascii, b_off, b_coff, b_len, b_cbase, b_cidx, b_ids, b_nrank, b_perm, b_meta, b_bases, b_amb, b_qual, b_ambcount;
     std::vector<uint32_t> h_len, h_ids, h_cidx, h_cluster_off, h_perm;
+    bool packed_input = false; // the batch arrived 2-bit packed: b_ascii holds the packed words, b_off the words-per-read scan (no ASCII, no base offsets)
+    DevBuf b_rlen, b_amblist;
     uint32_t max_id = 0;       // largest read name of the batch (decides whether 8-byte records can hold the names)
     bool has_quals = false;    // b_qual holds the phred strings (32 bytes of padding in front, then a flag byte per read)
     float h2d_ms = 0.f, pack_ms = 0.f;
     void release() {
         b_ascii.release(), b_off.release(), b_coff.release(), b_len.release(), b_cbase.release(), b_cidx.release(), b_ids.release();
         b_nrank.release(), b_perm.release(), b_meta.release(), b_bases.release(), b_amb.release(), b_qual.release(), b_ambcount.release();
+        b_rlen.release(), b_amblist.release();
     }
 };
 
@@ -415,7 +418,13 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
     const uint32_t *cluster_off = B.cluster_off;
     uint32_t n_clusters = B.n_clusters;
     const uint32_t *ids = B.ids;
-    if (!bases || !base_off) FAIL(HLO_EINVAL, "hlo_pack_reads: null input");
+    const bool packed = B.packed != nullptr && !bases;
+    if (packed) {
+        if (!B.read_len && n_reads) FAIL(HLO_EINVAL, "packed batch without read_len");
+        if (B.quals) FAIL(HLO_EUNSUPPORTED, "qualities (fused score) need the ASCII form of the batch");
+        if (ids) FAIL(HLO_EUNSUPPORTED, "explicit read names need the ASCII form of the batch");
+        if (B.n_amb && !B.amb) FAIL(HLO_EINVAL, "n_amb without amb");
+    } else if (!bases || !base_off) FAIL(HLO_EINVAL, "hlo_pack_reads: null input");
     uint32_t one[2] = {0, n_reads};
     if (!cluster_off) cluster_off = one, n_clusters = 1;
     if (cluster_off[0] != 0 || cluster_off[n_clusters] != n_reads) FAIL(HLO_EINVAL, "cluster_off must span [0, n_reads]");
@@ -426,7 +435,18 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
     R->h_len.clear(), R->h_ids.clear(), R->h_cidx.clear(), R->h_perm.clear();
     // one lean pass over the offsets: monotone, length limit, longest read (sizes the rows)
     uint32_t max_len = 0;
-    {
+    uint64_t packed_words = 0, packed_bases = 0;
+    if (packed) {
+        uint32_t worst = 0;
+        for (uint32_t i = 0; i < n_reads; ++i) {
+            const uint32_t l = B.read_len[i];
+            worst = l > worst ? l : worst;
+            packed_words += (l + 15u) >> 4, packed_bases += l;
+        }
+        if (worst > 32767) FAIL(HLO_ERANGE, "a read of %u bp exceeds the limit of 32767 (anchor fields of hlo_cand)", worst);
+        if (packed_words > 0xfffffff0ull) FAIL(HLO_ERANGE, "packed batch too large");
+        max_len = worst;
+    } else {
         uint64_t worst = 0;
         bool mono = true;
         for (uint32_t i = 0; i < n_reads; ++i) {
@@ -472,7 +492,8 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
     }
     int rc = build_tables(ctx, (int)max_len);
     if (rc) return rc;
-    const uint64_t n_bases = base_off[n_reads];
+    const uint64_t n_bases = packed ? packed_bases : base_off[n_reads];
+    R->packed_input = packed;
     const uint32_t words = (max_len + 15) / 16;
     const uint32_t nv = std::max(1u, (words + 3u) / 4u);
     const uint32_t stride_w = 4u * nv;
@@ -481,8 +502,13 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
     d.max_cluster = max_cluster;
     d.plain_names = plain ? 1 : 0;
     const size_t plane_words = (size_t)n_reads * stride_w;
-    CK(R->b_ascii.ensure(n_bases + 16));
+    CK(R->b_ascii.ensure(packed ? packed_words * 4 + 16 : n_bases + 16));
     CK(R->b_off.ensure(((size_t)n_reads + 1) * 8));
+    if (packed) {
+        CK(R->b_rlen.ensure((size_t)n_reads * 4 + 4));
+        CK(R->b_amblist.ensure(B.n_amb * 8 + 8));
+        CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)n_reads + 1) * 4));
+    }
     CK(R->b_coff.ensure(((size_t)n_clusters + 1) * 4));
     CK(R->b_len.ensure((size_t)n_reads * 4 + 4));
     CK(R->b_cbase.ensure((size_t)n_reads * 4 + 4));
@@ -501,7 +527,12 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
     R->has_quals = false;
     if (B.quals) CK(R->b_qual.ensure(n_bases + 64 + (size_t)n_reads + 32));  // 32 bytes of padding on both sides, then a flag per read
     CK(cudaEventRecord(ctx->ev[ST_BEGIN], s));
-    if (n_reads) {
+    if (n_reads && packed) {
+        CK(cudaMemcpyAsync(R->b_ascii.p, B.packed, packed_words * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(R->b_rlen.p, B.read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s));
+        if (B.n_amb) CK(cudaMemcpyAsync(R->b_amblist.p, B.amb, B.n_amb * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(R->b_coff.p, R->h_cluster_off.data(), ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
+    } else if (n_reads) {
         CK(cudaMemcpyAsync(R->b_ascii.p, bases, n_bases, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(R->b_off.p, base_off, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(R->b_coff.p, R->h_cluster_off.data(), ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, s));
@@ -529,8 +560,17 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
     CK(cudaMemsetAsync(ctr(ctx, C_MIDOCC_LO), 0xff, sizeof(unsigned long long), s));
     CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));
     CK(cudaEventRecord(ctx->ev[ST_H2D], s));
-    if (plain && n_reads) launch_read_meta(R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), d, s, &ctx->lc);
-    launch_pack(R->b_ascii.as<uint8_t>(), R->b_off.as<uint64_t>(), d, R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
+    if (packed && n_reads) {
+        // words per read -> first word of every read (scan) -> rows of both strands; the listed ambiguous bases on top
+        uint32_t *wcount = R->b_off.as<uint32_t>(), *woff = wcount + (n_reads + 1);
+        launch_packed_meta(R->b_rlen.as<uint32_t>(), R->b_coff.as<uint32_t>(), d, wcount, s, &ctx->lc);
+        launch_exclusive_scan(wcount, woff, (uint64_t)n_reads + 1, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
+        launch_unpack2b(R->b_ascii.as<uint32_t>(), woff, R->b_amblist.as<unsigned long long>(), B.n_amb, d, R->b_ambcount.as<uint32_t>(), s,
+                        &ctx->lc);
+    } else {
+        if (plain && n_reads) launch_read_meta(R->b_off.as<uint64_t>(), R->b_coff.as<uint32_t>(), d, s, &ctx->lc);
+        launch_pack(R->b_ascii.as<uint8_t>(), R->b_off.as<uint64_t>(), d, R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
+    }
     if (R->has_quals)
         launch_qual_flags(R->b_qual.as<uint8_t>() + 32, R->b_off.as<uint64_t>(), n_reads,
                           R->b_qual.as<uint8_t>() + 32 + ((n_bases + 32 + 15) & ~(uint64_t)15), s, &ctx->lc);
@@ -1393,7 +1433,7 @@ int hlo_overlap_batch(hlo_ctx *ctx, const hlo_reads *R, hlo_recs *out) {
     start_compute_section(ctx);
     reset_counters_for_rerun(ctx);
     bool repacked = false;
-    if (ctx->repack && d.n_reads) {
+    if (ctx->repack && d.n_reads && !R->packed_input) {
         // the packer again, from the ASCII bases still resident in HBM (results are identical; the
         // ambiguity flags it ORs into len[] are idempotent)
         CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));

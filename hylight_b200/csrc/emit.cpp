@@ -143,6 +143,42 @@ int write_overlaps_impl(const hlo_rec *rec, const hlo_score *score, uint64_t n, 
 
 extern "C" {
 
+int hlo_pack2b(const char *bases, const uint64_t *base_off, uint32_t n_reads, uint32_t *words, uint64_t *n_words, uint32_t *read_len,
+               uint64_t *amb, uint64_t amb_cap, uint64_t *n_amb) {
+    if (!bases || !base_off || !words || !read_len || !n_words || !n_amb) return HLO_EINVAL;
+    static uint8_t lut[256];
+    static bool init = false;
+    if (!init) {  // (idempotent: concurrent first calls write the same bytes)
+        memset(lut, 4, sizeof lut);
+        lut['A'] = lut['a'] = 0, lut['C'] = lut['c'] = 1, lut['G'] = lut['g'] = 2, lut['T'] = lut['t'] = lut['U'] = lut['u'] = 3;
+        init = true;
+    }
+    uint64_t w = 0, na = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        if (base_off[r + 1] < base_off[r]) return HLO_EINVAL;
+        const uint64_t L = base_off[r + 1] - base_off[r];
+        if (L > 0xffffffffull) return HLO_ERANGE;
+        read_len[r] = (uint32_t)L;
+        const uint8_t *s = reinterpret_cast<const uint8_t *>(bases) + base_off[r];
+        for (uint64_t i0 = 0; i0 < L; i0 += 16) {
+            const uint64_t n = L - i0 < 16 ? L - i0 : 16;
+            uint32_t v = 0;
+            for (uint64_t i = 0; i < n; ++i) {
+                const uint32_t c = lut[s[i0 + i]];
+                if (c > 3) {
+                    if (amb && na < amb_cap) amb[na] = (uint64_t)r << 32 | (i0 + i);
+                    ++na;
+                } else {
+                    v |= c << (2 * i);
+                }
+            }
+            words[w++] = v;
+        }
+    }
+    *n_words = w, *n_amb = na;
+    return na > amb_cap ? HLO_ERANGE : HLO_OK;
+}
+
 int hlo_format_overlap_line(const hlo_rec *rec, char *buf, size_t cap) {
     if (!rec || !buf || cap < 128) return HLO_EINVAL;
     return format_overlap(rec, buf, cap);

@@ -17,6 +17,12 @@ void launch_pack(const uint8_t *ascii, const uint64_t *base_off, DevReads r, uin
 // per-read metadata (len, cbase, cidx, ids, nrank, perm) on the device for names 0..N-1 in file order
 void launch_read_meta(const uint64_t *base_off, const uint32_t *cluster_off, DevReads r, cudaStream_t s, LaunchCounter *lc);
 
+// packed input (hlo_batch.packed): per-read metadata + words per read (wcount, n_reads + 1 entries, the last 0); then,
+// with woff = their exclusive scan, the rows of both strands and the listed ambiguous bases
+void launch_packed_meta(const uint32_t *read_len, const uint32_t *cluster_off, DevReads r, uint32_t *wcount, cudaStream_t s, LaunchCounter *lc);
+void launch_unpack2b(const uint32_t *packed, const uint32_t *woff, const unsigned long long *amb, uint64_t n_amb, DevReads r,
+                     uint32_t *amb_count, cudaStream_t s, LaunchCounter *lc);
+
 // ---- sketch.cu ------------------------------------------------------------------------------
 // pass 0: count[r] = number of minimizers of read r;  pass 1: write them at off[r].
 void launch_sketch_count(const DevReads &r, int w, int k, uint32_t *count, cudaStream_t s, LaunchCounter *lc);

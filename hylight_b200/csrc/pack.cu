@@ -226,6 +226,94 @@ void launch_read_meta(const uint64_t *base_off, const uint32_t *cluster_off, Dev
     if (lc) lc->total++;
 }
 
+// ---- packed input (hlo_batch.packed): the reads arrive 2-bit packed, word aligned, back to back --------------------
+// words per read (for the scan that gives every read its first word) and the plain per-read metadata
+__global__ void __launch_bounds__(256) packed_meta_kernel(const uint32_t *__restrict__ read_len, const uint32_t *__restrict__ cluster_off,
+                                                          DevReads r, uint32_t *__restrict__ wcount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > r.n_reads) return;
+    if (i == r.n_reads) {
+        wcount[i] = 0;
+        return;
+    }
+    uint32_t lo = 0, hi = r.n_clusters;  // invariant: cluster_off[lo] <= i < cluster_off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(cluster_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t cb = __ldg(cluster_off + lo), N = __ldg(cluster_off + lo + 1) - cb, L = read_len[i];
+    wcount[i] = (L + 15u) >> 4;
+    r.len[i] = L;
+    r.cbase[i] = cb;
+    r.cidx[i] = lo;
+    r.ids[i] = i - cb;
+    r.nrank[i] = i;
+    r.meta[i] = make_uint4(L, i - cb, lo, cb);
+    r.perm[i] = cb + dec_order_kth(N, i - cb);
+}
+
+// rows of both strands from the packed stream: the forward row is a copy, the reverse-complement row is derived from
+// two forward words (bit reversal + complement), as pack_tile_kernel does from its staged rows
+__global__ void __launch_bounds__(256) unpack2b_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ woff, DevReads r) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sw = r.stride_w;
+    if (gid >= (uint64_t)r.n_reads * sw) return;
+    const uint32_t read = (uint32_t)(gid / sw), wi = (uint32_t)(gid % sw);
+    const int L = (int)(r.len[read] & HLO_LEN_MASK);
+    const uint32_t nw = ((uint32_t)L + 15u) >> 4;
+    const uint32_t *src = packed + woff[read];
+    uint32_t fw = 0, rw = 0;
+    const int n = L - (int)wi * 16;  // bases of this word inside the read
+    if (n > 0) {
+        const uint32_t m = n >= 16 ? 0xffffffffu : ((1u << (2 * n)) - 1u);
+        fw = __ldg(src + wi) & m;
+        // RC bases 16wi .. 16wi+15 = forward bases L-16wi-16 .. L-16wi-1, reversed and complemented
+        const int start = L - (int)wi * 16 - 16;
+        const int j = start >> 4;  // floor; -1 when the window starts before base 0
+        const uint32_t sh = (uint32_t)(start & 15) * 2u;
+        const uint32_t lo = j >= 0 ? __ldg(src + j) : 0u, hi = (uint32_t)(j + 1) < nw ? __ldg(src + j + 1) : 0u;
+        rw = ~rev_pairs(__funnelshift_r(lo, hi, sh)) & m;
+    }
+    const uint64_t plane = (uint64_t)r.n_reads * sw;
+    r.bases[gid] = fw, r.bases[plane + gid] = rw;
+    r.amb[gid] = 0u, r.amb[plane + gid] = 0u;
+}
+
+// the listed ambiguous bases: flag bits in both ambiguity planes, code 0 in both base planes
+__global__ void __launch_bounds__(256) packed_amb_kernel(const unsigned long long *__restrict__ amb, uint64_t n_amb, DevReads r,
+                                                         uint32_t *__restrict__ amb_count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_amb) return;
+    const uint32_t read = (uint32_t)(amb[i] >> 32), pos = (uint32_t)amb[i];
+    if (read >= r.n_reads) return;
+    const uint32_t L = r.len[read] & HLO_LEN_MASK;
+    if (pos >= L) return;
+    const uint64_t plane = (uint64_t)r.n_reads * r.stride_w, row = (uint64_t)read * r.stride_w;
+    const uint32_t rp = L - 1u - pos;
+    atomicOr(&r.amb[row + (pos >> 4)], 1u << ((pos & 15u) * 2u));
+    atomicOr(&r.amb[plane + row + (rp >> 4)], 1u << ((rp & 15u) * 2u));
+    atomicAnd(&r.bases[row + (pos >> 4)], ~(3u << ((pos & 15u) * 2u)));
+    atomicAnd(&r.bases[plane + row + (rp >> 4)], ~(3u << ((rp & 15u) * 2u)));
+    atomicOr(&r.len[read], HLO_AMB_FLAG);
+    atomicAdd(amb_count, 1u);
+}
+
+void launch_packed_meta(const uint32_t *read_len, const uint32_t *cluster_off, DevReads r, uint32_t *wcount, cudaStream_t s, LaunchCounter *lc) {
+    packed_meta_kernel<<<(r.n_reads + 1 + 255) / 256, 256, 0, s>>>(read_len, cluster_off, r, wcount);
+    if (lc) lc->total++;
+}
+void launch_unpack2b(const uint32_t *packed, const uint32_t *woff, const unsigned long long *amb, uint64_t n_amb, DevReads r,
+                     uint32_t *amb_count, cudaStream_t s, LaunchCounter *lc) {
+    const uint64_t total = (uint64_t)r.n_reads * r.stride_w;
+    if (total == 0) return;
+    unpack2b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(packed, woff, r);
+    if (lc) lc->total++;
+    if (n_amb) {
+        packed_amb_kernel<<<(unsigned)((n_amb + 255) / 256), 256, 0, s>>>(amb, n_amb, r, amb_count);
+        if (lc) lc->total++;
+    }
+}
+
 void launch_pack(const uint8_t *ascii, const uint64_t *base_off, DevReads r, uint32_t *amb_count, cudaStream_t s,
                  LaunchCounter *lc) {
     const uint64_t total = (uint64_t)r.n_reads * r.stride_w;

@@ -168,6 +168,15 @@ typedef struct hlo_batch {
     const uint32_t *cluster_off; /* n_clusters + 1 offsets into the read list (NULL = one cluster) */
     uint32_t n_clusters;
     const uint32_t *ids;         /* n_reads decimal names (NULL = position inside the cluster, what rename_fas.py writes) */
+    /* Alternative to bases / base_off for callers that keep their reads 2-bit packed (a quarter of the upload; hlo_pack2b
+     * produces this form): packed != NULL and bases == NULL.  Read r occupies ceil(read_len[r] / 16) consecutive 32-bit
+     * words, reads back to back in read order; base i of a read sits in bits [2(i % 16), 2(i % 16) + 2) of its word i / 16,
+     * A=0 C=1 G=2 T/U=3; an ambiguous base is stored as 0 and listed in amb as read << 32 | position (any order).
+     * quals must be NULL in this form. */
+    const uint32_t *packed;
+    const uint32_t *read_len;    /* n_reads lengths */
+    const uint64_t *amb;         /* n_amb entries, or NULL */
+    uint64_t n_amb;
 } hlo_batch;
 
 /* minimizer tuple, same two words as minimap2's mm128_t: x = hash<<8 | span, y = rid<<32 | pos<<1 | strand */
@@ -259,6 +268,13 @@ int hlo_overlap_host(hlo_ctx *ctx, const char *bases, const uint64_t *base_off, 
  */
 int hlo_submit(hlo_ctx *ctx, const hlo_batch *batch);
 int hlo_wait(hlo_ctx *ctx, hlo_recs *out);
+
+/* Host-side helper: ASCII reads -> the packed form of hlo_batch (plain C loop; a caller with many cores splits the
+ * read list).  words: sum over reads of ceil(len / 16) u32; read_len: n_reads; amb: room for amb_cap entries — the
+ * number of ambiguous bases found is returned in *n_amb, HLO_ERANGE when it exceeds amb_cap.  Returns the number of
+ * words written in *n_words. */
+int hlo_pack2b(const char *bases, const uint64_t *base_off, uint32_t n_reads, uint32_t *words, uint64_t *n_words, uint32_t *read_len,
+               uint64_t *amb, uint64_t amb_cap, uint64_t *n_amb);
 
 int hlo_get_timing(const hlo_ctx *ctx, hlo_timing *t);
 

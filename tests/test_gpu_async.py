@@ -248,3 +248,29 @@ def test_config4_full_size_cluster_matches_the_oracle():
     assert len(rec) == len(rec_o) > 3_000_000
     assert np.array_equal(rec, rec_o) and np.array_equal(aux["blocklen"], blk_o)
     assert tm["digest"] == api.records_digest(rec)
+
+
+def test_packed_2bit_input_gives_the_same_records():
+    """hlo_batch.packed: the reads arrive 2-bit packed (a quarter of the upload), ambiguous bases as a list"""
+    rng = np.random.default_rng(8)
+    b1 = small_cluster(281, n_fragments=150, n_rate=0.004)
+    ragged = []
+    for s_ in small_cluster(282, n_fragments=90, read_len=250).cluster_reads(0):
+        s_ = bytearray(s_[:int(rng.integers(100, 251))])
+        if rng.random() < 0.3:
+            s_[int(rng.integers(0, len(s_)))] |= 0x20
+        ragged.append(bytes(s_))
+    b = synth.ReadBatch.concat([b1, synth.ReadBatch.from_seqs([ragged]), synth.ReadBatch.from_seqs([[]]), small_cluster(283, n_fragments=40)])
+    ob, rec_o, blk_o, coff_o, st = oracle_full(b)
+    pk = api.pack2b(b)
+    assert len(pk[2]) > 0
+    with api.Context(0) as c:
+        c.set_option("digest", 1)
+        for it in range(2):
+            c.submit_packed(pk, b.cluster_off)
+            rec, aux, coff = c.wait()
+            assert np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o) and np.array_equal(aux["blocklen"], blk_o)
+        assert c.timing()["digest"] == api.records_digest(rec_o)
+        c.submit(b)  # and the ASCII form on the same ctx right after
+        rec, aux, coff = c.wait()
+        assert np.array_equal(rec, rec_o)
