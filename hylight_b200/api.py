@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhlovlp.so")
+# HLO_LIB: another build of the same library (the bounds-checking build `make -C hylight_b200/csrc debug`)
+LIB_PATH = os.environ.get("HLO_LIB") or os.path.join(_HERE, "libhlovlp.so")
 
 CAND_DT = np.dtype([("q", "<u4"), ("t", "<u4"), ("diag", "<i4"), ("strand_anchor", "<u4")])
 REC_DT = np.dtype([("idA", "<u4"), ("idB", "<u4"), ("OHA", "<i4"), ("OHB", "<i4"), ("OLA", "<u4"), ("OLB", "<u4"),
@@ -28,6 +29,7 @@ ABI_SYMBOLS = [
     "hlo_write_sfo", "hlo_write_overlaps", "hlo_format_overlap_line", "hlo_set_option", "hlo_stream", "hlo_score_records",
     "hlo_write_overlaps_scored", "hlo_write_overlaps16", "hlo_write_sfo16", "hlo_submit", "hlo_wait", "hlo_set_score_params",
     "hlo_write_overlaps8", "hlo_write_sfo8", "hlo_write_binary16", "hlo_pack2b",
+    "hlo_debug_check_reads",
 ]
 
 
@@ -314,6 +316,12 @@ class Context:
         r = self.wait_raw()
         self._inflight = None
         return self._recs(r)
+
+    def check_canaries(self, reads=None):
+        """hlo_debug_check_reads: raises when a kernel wrote into the padding around the packed rows"""
+        L = lib()
+        L.hlo_debug_check_reads.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(L.hlo_debug_check_reads(self.h, reads.handle if reads is not None else None))
 
     def set_score_params(self, mismatch_prob=0.0, min_read_len=0):
         self._check(lib().hlo_set_score_params(self.h, float(mismatch_prob), int(min_read_len)))

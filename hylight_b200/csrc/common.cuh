@@ -5,6 +5,16 @@
 
 #include "../../include/hlovlp.h"
 
+// -DHLO_DEBUG_BOUNDS (make debug -> libhlovlp_dbg.so): device-side asserts on the indices the kernels compute from device
+// data (counters, offsets, hash slots).  A failed assert traps the kernel and the next CUDA call reports it; the GPU
+// test-suite runs once under this build (HLO_LIB=.../libhlovlp_dbg.so), profiles/r2_debug_bounds.log.
+#ifdef HLO_DEBUG_BOUNDS
+#include <assert.h>
+#define HLO_DBG_ASSERT(c) assert(c)
+#else
+#define HLO_DBG_ASSERT(c) ((void)0)
+#endif
+
 namespace hlo {
 
 // ---------------------------------------------------------------------------------------------
@@ -39,6 +49,7 @@ struct DevReads {
     uint32_t *amb = nullptr;    // [2][n][stride_w]
 };
 #define HLO_PAD_WORDS 64
+#define HLO_PAD_CANARY 0xA5  // byte the padding is filled with; nothing may ever WRITE there (hlo_debug_check_reads)
 
 // One block of 64-bit device counters per context, zeroed once per batch and read back ONCE at its end: every stage
 // sizes its work from the counts its predecessor left here, so the host never waits between stages.

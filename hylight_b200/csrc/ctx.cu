@@ -559,6 +559,10 @@ static int pack_into(hlo_ctx *ctx, hlo_reads *R, const hlo_batch &B) {
     CK(cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long) * C_COUNT, s));
     CK(cudaMemsetAsync(ctr(ctx, C_MIDOCC_LO), 0xff, sizeof(unsigned long long), s));
     CK(cudaMemsetAsync(R->b_ambcount.p, 0, 16, s));
+    for (DevBuf *b : {&R->b_bases, &R->b_amb}) {  // canaries in the padding in front of and behind the rows (hlo_debug_check_reads)
+        CK(cudaMemsetAsync(b->p, HLO_PAD_CANARY, HLO_PAD_WORDS * 4, s));
+        CK(cudaMemsetAsync(b->as<uint32_t>() + HLO_PAD_WORDS + plane_words * 2, HLO_PAD_CANARY, HLO_PAD_WORDS * 4, s));
+    }
     CK(cudaEventRecord(ctx->ev[ST_H2D], s));
     if (packed && n_reads) {
         // words per read -> first word of every read (scan) -> rows of both strands; the listed ambiguous bases on top
@@ -1589,6 +1593,29 @@ int hlo_score_records(hlo_ctx *ctx, const hlo_reads *R, const char *quals, const
         ctx->tm.total_launches = ctx->lc.total;
     }
     *out = ctx->h_score.as<hlo_score>();
+    return HLO_OK;
+}
+
+int hlo_debug_check_reads(hlo_ctx *ctx, const hlo_reads *Rc) {
+    if (!ctx) return HLO_EINVAL;
+    const hlo_reads *R = Rc ? Rc : &ctx->scratch_reads;
+    if (!R->b_bases.p || !R->b_amb.p) return HLO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t plane_words = (size_t)R->d.n_reads * R->d.stride_w;
+    uint32_t h[4][HLO_PAD_WORDS];
+    const DevBuf *bufs[2] = {&R->b_bases, &R->b_amb};
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMemcpyAsync(h[2 * i], bufs[i]->p, HLO_PAD_WORDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h[2 * i + 1], bufs[i]->as<uint32_t>() + HLO_PAD_WORDS + plane_words * 2, HLO_PAD_WORDS * 4, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t want = 0x01010101u * HLO_PAD_CANARY;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < HLO_PAD_WORDS; ++j)
+            if (h[i][j] != want)
+                FAIL(HLO_ECUDA, "canary overwritten: %s padding of the %s plane, word %d = %08x", (i & 1) ? "trailing" : "leading",
+                     i < 2 ? "base" : "ambiguity", j, h[i][j]);
     return HLO_OK;
 }
 

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(IX_THREADS) bucket_index_kernel(const uint64_t
             const unsigned upto = bal[j] & (0xffffffffu >> (31 - lane));
             const int pb = upto ? (int)(r * 32) + 31 - __clz(upto) : last_before[r];
             const uint32_t st = pb < 0 ? tile_prev : (uint32_t)(base + (uint32_t)pb);
+            HLO_DBG_ASSERT(idx[j] < n && en <= n && st <= base + e && en > base + e);
             range[idx[j]] = (en - st) > midocc[clu[j]] ? make_uint2(0u, 0u) : make_uint2((uint32_t)(base + e) + 1u, en);
         } else if ((bal[j] >> lane) & 1u) {  // first entry of its bucket: one count for the bucket's size
             // sizes below IX_LO (nearly all: a bucket holds about one entry per read covering the minimizer) go to one of
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                     if (sidx + 1 < n_eff) e_n = stg[sidx + 1];
                 }
                 h_n = make_uint2(q, 0u);
+                HLO_DBG_ASSERT(end <= a.mz_off[a.reads.n_reads]);
                 if (i0 + l < end) h_n = __ldg(a.hits + i0 + l);
                 int newslot = -1;
                 if (in_range && h.x != q) {  // h.x == q: another minimizer of the query itself (-X: no self hits)
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                         slot = (slot + 1u) & smask;
                     }
                     if (done) {  // no other lane of the group holds this key in this chunk: plain read-modify-write
+                        HLO_DBG_ASSERT(slot < S && t < a.reads.n_reads && (uint32_t)(diag + (int)max_len) < (1u << a.dg_bits));
                         const uint32_t v = vals[slot];
                         const uint32_t mn = min(v & VMASK, qp), mx = max(v >> VSH, qp);
                         vals[slot] = (val_t)(mn | mx << VSH);
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
                 }
                 // remember the claimed slots (per-group list, positions from a ballot: no atomics)
                 const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & PG_GMASK;
+                HLO_DBG_ASSERT(list_n + __popc(gb) <= S);
                 if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
                 list_n += __popc(gb);
                 __syncwarp();  // orders the plain min/max updates of consecutive chunks (they may belong to different minimizers)

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(RT_THREADS) group_scatter_kernel(const Rec16 *
         const uint2 qt = *reinterpret_cast<const uint2 *>(&rec[i]);
         const uint32_t nq = r.plain_names ? qt.x : __ldg(r.nrank + qt.x), nt = r.plain_names ? qt.y : __ldg(r.nrank + qt.y);
         const uint32_t g = min(nq, nt), p = off[g] + slot[i];
+        HLO_DBG_ASSERT(g < r.n_reads && p < n && p < off[g + 1]);
         ent[p] = make_uint2(max(nq, nt), (uint32_t)i);
         entg[p] = g;
     }
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(RT_THREADS) group_expand_kernel(const Rec16 *_
             }
         }
         const uint32_t p = uoff[g] + rank;
+        HLO_DBG_ASSERT(p < uoff[g + 1] && p < n_cap && x.q < r.n_reads && x.t < r.n_reads);
         const uint4 mq = __ldg(r.meta + x.q), mt = __ldg(r.meta + x.t);  // (length, name, cluster, cluster base)
         const int ql = (int)mq.x, tl = (int)mt.x;
         const int diag = (int)(x.ds >> 1) - HLO_DIAG_BIAS;

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const uint64_
         if (e < tile_n) {
             const uint32_t d = (uint32_t)(key[j] >> shift) & (RS_BINS - 1);
             const uint32_t p = tile_start[d] + wcnt[wp][d] + rank[j];
+            HLO_DBG_ASSERT(p < tile_n);
             stage_k[p] = key[j];
             stage_v[p] = val[j];
         }
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const uint64_
         const uint64_t kx = stage_k[i];
         const uint32_t d = (uint32_t)(kx >> shift) & (RS_BINS - 1);
         const uint64_t dst = (uint64_t)gbase[d] + (i - tile_start[d]);
+        HLO_DBG_ASSERT(dst >= seg.seg_start[0] && dst < seg.seg_start[seg.n_seg]);
         keys_out[dst] = kx;
         vals_out[dst] = stage_v[i];
     }
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(CF_WARPS * 32) collision_fix_kernel(uint64_t *
                 const uint64_t kf = sk[wp][f];
                 r += (kf < ke || (kf == ke && f < e)) ? 1u : 0u;
             }
+            HLO_DBG_ASSERT(r < m && b0 + r < n);
             keys[b0 + r] = ke, vals[b0 + r] = sv[wp][e];
         }
         __syncwarp();

@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(256) sketch_compact_kernel(DevReads r, uint32_
     const uint64_t sb = (uint64_t)xi * cap;
     for (uint32_t j = l; j < n; j += 8) {
         const uint32_t dst = o + j;
+        HLO_DBG_ASSERT(dst < cap_mz && dst < off[r.n_reads]);
         const uint64_t x = sx[sb + j];
         if (mz_x) mz_x[dst] = x;
         mz_rr[dst] = make_uint2(read, srp[sb + j]);

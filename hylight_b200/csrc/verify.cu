@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
                     const int S = neg ? -Dn : Dn;
                     const uint4 *Xrow = neg ? Trow : Qrow;
                     const uint4 *Yrow = (neg ? Qrow : Trow) + (S >> 6);
+                    // a shifted row read may run past its row: into the next rows, or (last row of the plane) the padding
+                    HLO_DBG_ASSERT(q < a.reads.n_reads && t < a.reads.n_reads && (S >> 6) <= NV && NV <= HLO_PAD_WORDS / 4);
                     uint32_t x[NW], y[NW + 1];
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
         // stream compaction: accepted records are staged per warp in shared memory (positions from a ballot, no
         // atomics) and a full stage leaves with ONE global atomicAdd and coalesced 16-byte stores; no block barrier
         const unsigned acc_b = __ballot_sync(0xffffffffu, accept);
+        HLO_DBG_ASSERT(w_cnt + __popc(acc_b) <= VF_STAGE);
         if (accept) w_out[w_cnt + __popc(acc_b & lt_mask)] = rec;
         w_cnt += __popc(acc_b);
         const unsigned def_b = __ballot_sync(0xffffffffu, defer);
@@ -204,6 +207,7 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(a.def_counter, (unsigned long long)__popc(def_b));
             base = __shfl_sync(0xffffffffu, base, 0);
+            HLO_DBG_ASSERT(base + __popc(def_b) <= a.n_cap);
             if (defer) a.deferred[base + __popc(def_b & lt_mask)] = (uint32_t)c;  // (one slot per candidate: cannot overflow)
         }
         const bool last = c + n_threads >= n_round;
@@ -271,6 +275,8 @@ __device__ __forceinline__ void verify_exact_one(const VerifyArgs &a, uint64_t c
     const bool ambf = ((cd.w >> 29) & 1u) != 0;
     const int js = D < 0 ? -D : 0, je = min(ql, tl - D);
     if (je <= js) return;
+    HLO_DBG_ASSERT(q < a.reads.n_reads && t < a.reads.n_reads && (uint32_t)ql <= a.reads.stride_w * 16 && (uint32_t)tl <= a.reads.stride_w * 16 &&
+                   je + D <= tl && js + D >= 0);
     const uint64_t plane = (uint64_t)a.reads.n_reads * a.reads.stride_w;
     const uint32_t *Q = a.reads.bases + (uint64_t)strand * plane + (uint64_t)q * a.reads.stride_w;
     const uint32_t *T = a.reads.bases + (uint64_t)t * a.reads.stride_w;

@@ -314,6 +314,12 @@ int hlo_set_score_params(hlo_ctx *ctx, double mismatch_prob, uint32_t min_read_l
  * buffer estimates (tests use a small value to force the rerun path).  None of them changes a result. */
 int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value);
 
+/* Memory-safety check: the packed rows of a read set are padded on both sides because shifted vector loads may READ past
+ * a row; nothing may ever WRITE there.  The padding is filled with a canary byte when the reads are packed; this returns
+ * HLO_OK while it is intact (reads == NULL: the read set of the last hlo_submit on this ctx), HLO_ECUDA when a kernel wrote
+ * into it.  Waits for the ctx stream. */
+int hlo_debug_check_reads(hlo_ctx *ctx, const hlo_reads *reads);
+
 /* The CUDA stream (cudaStream_t) every call on this ctx enqueues its work on, so that a caller can
  * bracket calls with its own CUDA events. */
 void *hlo_stream(const hlo_ctx *ctx);

@@ -29,6 +29,7 @@ def test_submit_wait_equals_the_oracle_and_waits_twice():
             c.submit(b)
             rec, aux, coff = c.wait()
             tm = c.timing()
+            c.check_canaries()
             assert np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o) and np.array_equal(aux["blocklen"], blk_o)
             assert tm["n_candidates"] == st["candidates"] and tm["n_accepted"] == st["accepted"]
             if it > 0:  # buffer estimates are settled: one wait for the counters, one for the download

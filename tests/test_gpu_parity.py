@@ -321,6 +321,7 @@ def check_full(ctx, b, ids=None, **pkw):
         R = c.pack(ob)
         rec, aux, coff = c.overlap_batch(R)
         tm = c.timing()
+        c.check_canaries(R)  # no kernel wrote into the padding around the packed rows
         R.free()
     finally:
         if pkw:
