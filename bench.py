@@ -8,7 +8,7 @@ Workload = BASELINE.json configs[2]: ONE JOB of 1000 synthetic config-2 clusters
 5 strains, 0.5 % errors each), sharded DYNAMICALLY over the GPUs.  One step = one pass of the whole hot path (2-bit pack
 -> minimizer sketch -> radix sort -> seed buckets -> pair/diagonal generation -> verify -> per-pair dedup -> sorted
 records) over that job.  The work list holds 1000 entries drawn cyclically from 64 distinct generated clusters (seeds
-1000..1063); it is cut into batches of 16 clusters, and every rank (one per GPU) pulls the next batch index from an
+1000..1063); it is cut into batches of 32 clusters, and every rank (one per GPU) pulls the next batch index from an
 atomic counter on the rendezvous store (TCPStore.add) until the list is empty: no NCCL on the data path — clusters are
 independent — and total work is fixed, so the scaling is STRONG.  NCCL carries the barriers and the
 reductions of time / counts / digest only.
@@ -673,10 +673,14 @@ def files_leg(synth, distinct, args):
                 subprocess.run([exe, "--clusters", lst, "--rename", "--devices", "0", "--stats", stats] + flag, check=True, timeout=900)
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
-            n_rec = sum(json.loads(l)["records"] for l in open(stats))
+            rows = [json.loads(l) for l in open(stats)]
+            n_rec = sum(r["records"] for r in rows if not r.get("summary"))
+            summ = [r for r in rows if r.get("summary")]
             bytes_out = sum(os.path.getsize(os.path.join(d, "o_%s_%d_%d" % (mode, r, c))) for r in range(reps) for c in range(n_in))
             out[mode] = {"value": n_rec / best, "unit": UNIT, "wall_s": best, "clusters": n_in * reps, "records": n_rec,
-                         "bytes_written": bytes_out}
+                         "bytes_written": bytes_out, "in_process_wall_s": summ[0]["wall_ms"] / 1e3 if summ else None,
+                         "cuda_context_s": max((r["ms"]["ctx_create"] for r in rows if not r.get("summary")), default=0.0) / 1e3,
+                         "host_ms_sum": {k: sum(r["ms"][k] for r in rows if not r.get("summary")) for k in ("host_parse", "host_call", "host_write")}}
             for r in range(reps):
                 for c in range(n_in):
                     os.remove(os.path.join(d, "o_%s_%d_%d" % (mode, r, c)))
@@ -691,7 +695,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--job-clusters", type=int, default=JOB_CLUSTERS, help="clusters of the job (BASELINE configs[2]: 1000)")
-    ap.add_argument("--batch", type=int, default=16, help="clusters per device batch (the unit ranks pull)")
+    ap.add_argument("--batch", type=int, default=32, help="clusters per device batch (the unit ranks pull)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / concordance / files legs")
     ap.add_argument("--no-files", action="store_true", help="skip the host-binary leg")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to the CPUs closest to its GPU")

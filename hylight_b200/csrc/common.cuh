@@ -69,6 +69,7 @@ enum Ctr : int {
     C_DIGEST,       // order-independent sum of a 64-bit mix of every output record
     C_MIDOCC_LO,    // smallest / largest per-cluster occurrence cut-off of the batch
     C_MIDOCC_HI,
+    C_SK_TIE,       // reads in which the lean sketch automaton met equal keys: redone by the complete one
     C_COUNT = 32
 };
 #define HLO_PG_PASSES 5

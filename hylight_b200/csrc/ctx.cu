@@ -296,6 +296,10 @@ int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out) {
     }
     memset(&ctx->tm, 0, sizeof ctx->tm);
     ctx->scratch_reads.ctx = ctx;
+    if (const char *e = getenv("HLO_PAIRGEN_SLOTS_LOG2")) {  // tuning knob for processes that cannot call hlo_set_option (bench.py, the host binary)
+        const int v = atoi(e);
+        if (v >= 5 && v <= 10) ctx->pairgen_slots_log2 = v;
+    }
     *out = ctx;
     return HLO_OK;
 }
@@ -674,6 +678,7 @@ static int enqueue_sketch(hlo_ctx *ctx, const hlo_reads *R, bool want_x, bool *k
     CK(ctx->b_mzoff.ensure(((size_t)n + 2) * 4));
     CK(ctx->b_tmp.ensure(scan_tmp_words((uint64_t)n + 1) * 4));
     CK(ctx->b_ovf.ensure((size_t)n * 4 + 4));
+    CK(ctx->b_ovf2.ensure((size_t)n * 4 + 4));  // (the pair generator's second list: free until then)
     uint64_t *mz_x = nullptr;
     const bool fast = sketch_fast_supported(ctx->P.w, ctx->P.k) && !ctx->sketch_generic && n > 0;
     if (want_x || !fast) {
@@ -698,7 +703,8 @@ static int enqueue_sketch(hlo_ctx *ctx, const hlo_reads *R, bool want_x, bool *k
         CK(ctx->b_srp.ensure((size_t)n * scap * 4 + 4));
         CK(cudaMemsetAsync(ctx->b_cnt.as<uint32_t>() + n, 0, 4, s));
         launch_sketch_fast(d, ctx->P.w, ctx->P.k, scap, ctx->b_sx.as<uint64_t>(), ctx->b_srp.as<uint32_t>(), ctx->b_cnt.as<uint32_t>(),
-                           ctx->b_ovf.as<uint32_t>(), ctr(ctx, C_SK_OVF), R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
+                           ctx->b_ovf.as<uint32_t>(), ctr(ctx, C_SK_OVF), ctx->b_ovf2.as<uint32_t>(), ctr(ctx, C_SK_TIE),
+                           R->b_ambcount.as<uint32_t>(), s, &ctx->lc);
     } else {
         CK(cudaMemsetAsync(ctx->b_cnt.p, 0, ((size_t)n + 1) * 4, s));
         launch_sketch_count(d, ctx->P.w, ctx->P.k, ctx->b_cnt.as<uint32_t>(), s, &ctx->lc);

@@ -34,9 +34,10 @@ void launch_sketch_write(const DevReads &r, int w, int k, const uint32_t *off, u
                          LaunchCounter *lc);
 // single-pass fast path (static window, k odd): per-read strips of `cap` entries + counts, then a gather
 bool sketch_fast_supported(int w, int k);
+// tie_list / tie_cnt: reads in which equal window keys met; a second kernel reruns them with the complete automaton
 void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
-                        uint32_t *ovf_list, unsigned long long *ovf_cnt, const uint32_t *amb_count, cudaStream_t s,
-                        LaunchCounter *lc);
+                        uint32_t *ovf_list, unsigned long long *ovf_cnt, uint32_t *tie_list, unsigned long long *tie_cnt,
+                        const uint32_t *amb_count, cudaStream_t s, LaunchCounter *lc);
 void launch_sketch_compact(const DevReads &r, uint32_t cap, const uint64_t *sx, const uint32_t *srp, const uint32_t *count,
                            const uint32_t *off, uint64_t *mz_x, uint2 *mz_rr, uint64_t *keys, uint32_t *vals, int hash_bits,
                            uint32_t cap_mz, cudaStream_t s, LaunchCounter *lc);

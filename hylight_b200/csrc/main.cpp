@@ -551,6 +551,7 @@ uint64_t file_size(const std::string &p) {
 }  // namespace
 
 int main(int argc, char **argv) {
+    const auto t_main = std::chrono::steady_clock::now();
     Options o;
     std::string err;
     if (!parse_args(argc, argv, o, err)) {
@@ -592,6 +593,12 @@ int main(int argc, char **argv) {
     S.helpers = std::max<size_t>(1, std::thread::hardware_concurrency() / std::max<size_t>(1, n_workers));
     for (size_t i = 0; i < n_workers; ++i) th.emplace_back(worker, &S, o.devices[i % o.devices.size()]);
     for (auto &t : th) t.join();
+    if (S.stats) {  // one closing line: the whole run as the process saw it (CUDA start-up included, process teardown not)
+        uint64_t n_rec = 0;
+        for (const Cluster &c : o.clusters) n_rec += c.n_records;
+        fprintf(S.stats, "{\"summary\": true, \"clusters\": %zu, \"batches\": %zu, \"workers\": %zu, \"records\": %llu, \"wall_ms\": %.3f}\n",
+                o.clusters.size(), S.batches.size(), n_workers, (unsigned long long)n_rec, ms_since(t_main));
+    }
     if (S.stats && S.stats != stderr) fclose(S.stats);
     fflush(nullptr);
     _exit(S.failed ? 1 : 0);  // every output file is closed (and renamed into place) by now; skip the CUDA teardown

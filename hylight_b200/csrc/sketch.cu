@@ -17,6 +17,9 @@
 namespace hlo {
 
 #define HLO_MAX_W HLO_MAX_W_PUBLIC
+#ifndef HLO_SK_BLOCKS
+#define HLO_SK_BLOCKS 6  // resident blocks of sketch_fast_kernel<11> per SM the register budget is set for (6: 79 registers, no spill)
+#endif
 
 // minimap2's hash64 (Thomas Wang's 64-bit mix, every step masked to 2k bits).  The shift-add steps are
 // written as multiplications by constants (key + (key << 3) + (key << 8) = key * 265, ...): they run on
@@ -185,10 +188,10 @@ __device__ __forceinline__ void static_for(F &&f) {
 }
 
 // The complete automaton (ties included) for ONE read, same strip output: the rerun of a read in which the lean
-// automaton of sketch_fast_kernel met equal hashes.  Not inlined: it is the rare path and must not set the register
-// budget of the common one.
+// automaton of sketch_fast_kernel met equal keys.  It runs in a kernel of its own (sketch_exact_list_kernel) over the
+// list of such reads: it is the rare path and must not set the register budget of the common one.
 template <int WW>
-__device__ __noinline__ uint32_t sketch_strip_exact(const DevReads &r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+__device__ __forceinline__ uint32_t sketch_strip_exact(const DevReads &r, int k, uint32_t cap, uint64_t *__restrict__ sx,
                                                     uint32_t *__restrict__ srp, uint32_t xi) {
     const uint32_t read = __ldg(r.perm + xi);
     const uint32_t lenf = __ldg(r.len + read);
@@ -315,10 +318,17 @@ __device__ __noinline__ uint32_t sketch_strip_exact(const DevReads &r, int k, ui
 // positions after an N) get distinct markers ~i (bit 63 set, a newer one is smaller), so they never tie, never win
 // against a valid entry and keep mm_sketch's "rightmost" choice among themselves.
 
+// The window is ORDERED on 32-bit keys: hk = the top 31 bits of the hash (hash >> lo_bits, lo_bits = max(2k - 31, 0)); the
+// low bits ride along in the upper half of the position word (y = low << 16 | pos << 1 | strand; pos < 2^15).  hk_a < hk_b
+// implies hash_a < hash_b, and two entries with EQUAL hk are treated like equal hashes: the read goes to the complete
+// automaton, which compares the full values (a false alarm once in 2^31 comparisons).  Every compare and select of the
+// window logic is then one 32-bit operation instead of a 64-bit pair, and the ring and the suffix minima take 4 instead of
+// 6 registers per window slot.
 template <int WW, bool AMB>
 __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint32_t cap, uint64_t *__restrict__ sx,
                                                  uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
-                                                 uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt) {
+                                                 uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt,
+                                                 uint32_t *__restrict__ tie_list, unsigned long long *__restrict__ tie_cnt) {
     const uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x;
     if (xi >= r.n_reads) return;
     const uint32_t read = __ldg(r.perm + xi);
@@ -328,6 +338,8 @@ __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint3
     const uint32_t *row = r.bases + (uint64_t)read * r.stride_w;
     const uint32_t *arow = r.amb + (uint64_t)read * r.stride_w;
     const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
+    const int lo_bits = 2 * k > 31 ? 2 * k - 31 : 0;
+    const uint32_t lo_mask = (1u << lo_bits) - 1u;
     uint64_t kmer0 = 0, kmer1 = 0;
     // ring buffer of the last WW entries: slot = step mod WW, a compile-time constant in the unrolled body.
     // mm_sketch's `min` is at every step the RIGHTMOST SMALLEST entry of the window; it is kept by block
@@ -335,26 +347,26 @@ __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint3
     // of the previous block's slots j..WW-1, computed for all j at the block boundary (the same step for every
     // lane), and the minimum of the current block's slots 0..s runs along.  Window minimum after step s = the
     // smaller of the two, ties to the running one (it lies to the right).
-    uint64_t bx[WW], sufx[WW];
-    uint32_t by[WW], sufy[WW];
-    // (before the first block boundary the suffix minima are invalid entries that equal no marker ~i and no each other)
-    static_for<0, WW>([&](auto J) { bx[J] = ~(uint64_t)0, by[J] = 0xffffffffu, sufx[J] = (1ULL << 63) | (uint64_t)J, sufy[J] = 0xffffffffu; });
-    uint64_t px = ~(uint64_t)0, min_x = ~(uint64_t)0;  // running minimum of the current block; mm_sketch's `min`
+    // Invalid entries (first k-1 positions, positions after an N) get distinct markers 0xffffffff - i (bit 31 set, a newer
+    // one is smaller): they never tie, never win against a valid entry and keep mm_sketch's "rightmost" choice.
+    uint32_t bx[WW], sufx[WW], by[WW], sufy[WW];
+    // (before the first block boundary the suffix minima are invalid entries that equal no marker and not each other)
+    static_for<0, WW>([&](auto J) { bx[J] = 0xffffffffu, by[J] = 0xffffffffu, sufx[J] = 0x80000000u | (uint32_t)J, sufy[J] = 0xffffffffu; });
+    uint32_t px = 0xffffffffu, min_x = 0xffffffffu;  // running minimum of the current block; mm_sketch's `min`
     uint32_t py = 0xffffffffu, min_y = 0xffffffffu;
     bool tie = false;
     int l = 0;
     uint32_t n = 0;
     const uint64_t sbase = (uint64_t)xi * cap;
-    auto emit = [&](uint64_t X, uint32_t Y) {
-        if (n < cap) sx[sbase + n] = X, srp[sbase + n] = Y;
+    auto emit = [&](uint32_t X, uint32_t Y) {  // back to minimap2's words: x = hash << 8 | span, position word = pos << 1 | strand
+        if (n < cap) sx[sbase + n] = (((uint64_t)X << lo_bits) | (uint64_t)(Y >> 16)) << 8 | (uint64_t)k, srp[sbase + n] = Y & 0xffffu;
         ++n;
     };
-    auto valid = [](uint64_t X) { return (long long)X >= 0; };
+    auto valid = [](uint32_t X) { return (int)X >= 0; };
     uint32_t word = 0, aword = 0;
     for (int i0 = 0; i0 < len; i0 += WW) {
         if (i0 > 0) {  // block boundary: suffix minima of the block just finished (the ring holds exactly it)
-            uint64_t cx = bx[WW - 1];
-            uint32_t cy = by[WW - 1];
+            uint32_t cx = bx[WW - 1], cy = by[WW - 1];
             sufx[WW - 1] = cx, sufy[WW - 1] = cy;
             static_for<1, WW>([&](auto JJ) {
                 constexpr int j = WW - 1 - JJ;
@@ -375,7 +387,7 @@ __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint3
                 word >>= 2;
                 bool amb = false;
                 if (AMB) amb = aword & 1u, aword >>= 2;
-                uint64_t info_x = ~(uint64_t)(uint32_t)i;  // invalid marker
+                uint32_t info_x = 0xffffffffu - (uint32_t)i;  // invalid marker
                 uint32_t info_y = 0xffffffffu;
                 if (!amb) {
                     kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
@@ -383,8 +395,9 @@ __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint3
                     const uint32_t z = kmer0 < kmer1 ? 0u : 1u;  // k odd: kmer0 != kmer1 always
                     ++l;
                     if (l >= k) {
-                        info_x = mm_hash64(z ? kmer1 : kmer0, mask) << 8 | (uint64_t)k;
-                        info_y = (uint32_t)i << 1 | z;
+                        const uint64_t h = mm_hash64(z ? kmer1 : kmer0, mask);
+                        info_x = (uint32_t)(h >> lo_bits);
+                        info_y = ((uint32_t)h & lo_mask) << 16 | (uint32_t)i << 1 | z;
                     }
                 } else
                     l = 0;
@@ -396,8 +409,8 @@ __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint3
                     if (info_x <= px) px = info_x, py = info_y;
                 }
                 // the events of mm_sketch, decided against the OLD minimum
-                const bool ev_a = info_x <= min_x;                                  // a new minimum
-                const bool ev_b = !ev_a && (min_y >> 1) == (uint32_t)(i - WW);      // the old minimum left the window
+                const bool ev_a = info_x <= min_x;                                            // a new minimum
+                const bool ev_b = !ev_a && ((min_y & 0xffffu) >> 1) == (uint32_t)(i - WW);    // the old minimum left the window
                 if (((ev_a && l >= WW + k) || (ev_b && l >= WW + k - 1)) && valid(min_x)) emit(min_x, min_y);
                 // the new window minimum
                 if (s == WW - 1) min_x = px, min_y = py;
@@ -411,7 +424,11 @@ __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint3
         });
     }
     if (valid(min_x)) emit(min_x, min_y);
-    if (tie) n = sketch_strip_exact<WW>(r, k, cap, sx, srp, xi);  // equal hashes met: the complete automaton decides
+    if (tie) {  // equal keys met: the complete automaton decides (sketch_exact_list_kernel, right behind this kernel)
+        tie_list[atomicAdd(tie_cnt, 1ULL)] = xi;
+        count[xi] = 0;
+        return;
+    }
     count[xi] = n;
     if (n > cap) {  // more minimizers than the strip holds: the generic kernel writes this read
         const unsigned long long p = atomicAdd(ovf_cnt, 1ULL);
@@ -419,28 +436,58 @@ __device__ __forceinline__ void sketch_fast_body(const DevReads &r, int k, uint3
     }
 }
 
+template <int WW>
+__global__ void __launch_bounds__(128) sketch_exact_list_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+                                                                uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
+                                                                uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt,
+                                                                const uint32_t *__restrict__ tie_list,
+                                                                const unsigned long long *__restrict__ tie_cnt) {
+    const unsigned long long nl = *tie_cnt;
+    const uint32_t n_list = nl < (unsigned long long)r.n_reads ? (uint32_t)nl : r.n_reads;
+    for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < n_list; ti += gridDim.x * blockDim.x) {
+        const uint32_t xi = tie_list[ti];
+        const uint32_t n = sketch_strip_exact<WW>(r, k, cap, sx, srp, xi);
+        count[xi] = n;
+        if (n > cap) {
+            const unsigned long long p = atomicAdd(ovf_cnt, 1ULL);
+            ovf_list[p] = xi;
+        }
+    }
+}
+
 // A batch without ambiguous bases (the packer's device counter says so; the host never looks) runs the body that
 // does not touch the ambiguity plane.  The branch is uniform over the grid.
 template <int WW>
-__global__ void __launch_bounds__(128, WW <= 11 ? 5 : 2) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
+__global__ void __launch_bounds__(128, WW <= 11 ? HLO_SK_BLOCKS : 3) sketch_fast_kernel(DevReads r, int k, uint32_t cap, uint64_t *__restrict__ sx,
                                                              uint32_t *__restrict__ srp, uint32_t *__restrict__ count,
                                                              uint32_t *__restrict__ ovf_list, unsigned long long *__restrict__ ovf_cnt,
+                                                             uint32_t *__restrict__ tie_list, unsigned long long *__restrict__ tie_cnt,
                                                              const uint32_t *__restrict__ amb_count) {
-    if (*amb_count) sketch_fast_body<WW, true>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
-    else sketch_fast_body<WW, false>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt);
+    if (*amb_count) sketch_fast_body<WW, true>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, tie_list, tie_cnt);
+    else sketch_fast_body<WW, false>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, tie_list, tie_cnt);
 }
 
-bool sketch_fast_supported(int w, int k) { return (k & 1) && k >= 1 && k <= 28 && (w == 11 || w == 5 || w == 19); }
+// k <= 23: the hash bits below the 31-bit ordering key (2k - 31 <= 15) fit next to the 16-bit position word
+bool sketch_fast_supported(int w, int k) { return (k & 1) && k >= 1 && k <= 23 && (w == 11 || w == 5 || w == 19); }
+
+template <int WW>
+static void launch_sketch_fast_w(const DevReads &r, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count, uint32_t *ovf_list,
+                                 unsigned long long *ovf_cnt, uint32_t *tie_list, unsigned long long *tie_cnt, const uint32_t *amb_count,
+                                 cudaStream_t s) {
+    const unsigned grid = (r.n_reads + 127) / 128;
+    sketch_fast_kernel<WW><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, tie_list, tie_cnt, amb_count);
+    // the reads the lean automaton gave up on (usually none: a small grid that strides over the device-side list)
+    sketch_exact_list_kernel<WW><<<grid < 296u ? grid : 296u, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, tie_list, tie_cnt);
+}
 
 void launch_sketch_fast(const DevReads &r, int w, int k, uint32_t cap, uint64_t *sx, uint32_t *srp, uint32_t *count,
-                        uint32_t *ovf_list, unsigned long long *ovf_cnt, const uint32_t *amb_count, cudaStream_t s,
-                        LaunchCounter *lc) {
+                        uint32_t *ovf_list, unsigned long long *ovf_cnt, uint32_t *tie_list, unsigned long long *tie_cnt,
+                        const uint32_t *amb_count, cudaStream_t s, LaunchCounter *lc) {
     if (r.n_reads == 0) return;
-    const unsigned grid = (r.n_reads + 127) / 128;
-    if (w == 11) sketch_fast_kernel<11><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, amb_count);
-    else if (w == 5) sketch_fast_kernel<5><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, amb_count);
-    else sketch_fast_kernel<19><<<grid, 128, 0, s>>>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, amb_count);
-    if (lc) lc->total++;
+    if (w == 11) launch_sketch_fast_w<11>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, tie_list, tie_cnt, amb_count, s);
+    else if (w == 5) launch_sketch_fast_w<5>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, tie_list, tie_cnt, amb_count, s);
+    else launch_sketch_fast_w<19>(r, k, cap, sx, srp, count, ovf_list, ovf_cnt, tie_list, tie_cnt, amb_count, s);
+    if (lc) lc->total += 2;
 }
 
 // strips -> dense arrays in name order, plus the (cluster, hash | index) pairs the radix sort starts from.

@@ -75,7 +75,8 @@ constexpr int VF_STAGE = 128;  // records staged per WARP before one flush (one 
 
 // W = 32-bit data words per row actually compared (ceil(max_len / 16)); the row stride is NV = ceil(W/4)
 // 16-byte vectors.  FULLW = words that every overlap of at least min_len bases covers completely (no mask).
-template <int W, int FULLW>
+// PR = hlo_params.pair_rule (1: rows that fail only the overhang test are emitted, flagged)
+template <int W, int FULLW, bool PR>
 __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     constexpr int NV = (W + 3) / 4, NW = 4 * NV;
     __shared__ uint16_t s_tab[3 * 1024];
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     const unsigned long long n_dev = *a.n_ptr;
     const uint64_t a_n = n_dev < a.n_cap ? n_dev : a.n_cap;
     const uint64_t n_round = (a_n + 31) & ~31ull;  // whole warps iterate together
-    const int o = a.prm.max_overhang, min_len = a.prm.min_len;
+    const int o = a.prm.max_overhang, min_len = a.prm.min_len, defer_mm = a.prm.defer_mm;
+    const int o_reject = PR ? 33 : o;
     uint64_t c = (uint64_t)blockIdx.x * VF_THREADS + threadIdx.x;
     if (c >= n_round) return;  // (after the only block barrier)
     uint4 cv_next = make_uint4(0u, 0u, 0u, 0u);
@@ -164,10 +166,10 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
                     if (W & 1) mm += __popc(f[W - 1]);
                     // cheap exact reject: the block keeps at least mm - o mismatches (pair_rule 1: a flagged row may lose up
                     // to a window of them) and is at most OL long
-                    if (mm <= (int)t_max_k[OL] + (a.prm.pair_rule ? 33 : o)) {
+                    if (mm <= (int)t_max_k[OL] + o_reject) {
                         int cl = 0, cmm = 0;
                         bool ok = true;
-                        if (mm >= a.prm.defer_mm) {
+                        if (mm >= defer_mm) {
                             ok = false, defer = true;  // enough bad columns to cost a query-limited end its end bonus: the exact rule decides
                         } else if (mm > 0 && (left_t || right_t)) {
                             if (mm > a.prm.bad_limit) {
@@ -180,12 +182,12 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
                                 cl = r.clip, cmm = r.mm;
                             }
                         }
-                        if (ok && (cl <= o || a.prm.pair_rule)) {
+                        if (ok && (cl <= o || PR)) {
                             const int maplen = OL - cl;  // no ambiguous base on this path: blocklen = maplen
                             const int K = mm - cmm;
                             if (maplen >= min_len && maplen >= 1 && maplen - K >= (int)t_min_matches[maplen]) {
                                 const bool oh_ok = cl <= o && cl <= (int)t_max_clip[maplen];
-                                if (oh_ok || a.prm.pair_rule) {
+                                if (oh_ok || PR) {
                                     accept = true;
                                     rec = make_uint4(q, t, ((uint32_t)(D + HLO_DIAG_BIAS) << 1) | strand,
                                                      (uint32_t)K | (oh_ok ? 0u : HLO_KB_OVERHANG_FAIL) | ((uint32_t)maplen << 16));
@@ -228,13 +230,18 @@ bool verify_fast_supported(const DevReads &r, const VerifyTables &tab) {
     return r.max_len >= 1 && r.max_len <= 320 && tab.max_len + 1 <= 1024 && r.n_reads > 0;
 }
 
-template <int W, int F>
-static void launch_vf2(const VerifyArgs &a, int sms, cudaStream_t s) {
+template <int W, int F, bool PR>
+static void launch_vf3(const VerifyArgs &a, int sms, cudaStream_t s) {
     int per_sm = 8;  // persistent grid: as many blocks as are resident at once (each builds its tables once)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, verify_fast_kernel<W, F>, VF_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, verify_fast_kernel<W, F, PR>, VF_THREADS, 0);
     const uint64_t want = (a.n_cap + VF_THREADS - 1) / VF_THREADS;
     const uint64_t grid = std::min<uint64_t>(want, (uint64_t)sms * (per_sm > 0 ? per_sm : 1));
-    verify_fast_kernel<W, F><<<(unsigned)grid, VF_THREADS, 0, s>>>(a);
+    verify_fast_kernel<W, F, PR><<<(unsigned)grid, VF_THREADS, 0, s>>>(a);
+}
+template <int W, int F>
+static void launch_vf2(const VerifyArgs &a, int sms, cudaStream_t s) {
+    if (a.prm.pair_rule) launch_vf3<W, F, true>(a, sms, s);
+    else launch_vf3<W, F, false>(a, sms, s);
 }
 template <int W>
 static void launch_vf(const VerifyArgs &a, int sms, cudaStream_t s) {

@@ -36,6 +36,9 @@ def test_host_binary_shards_clusters_over_all_devices(tmp_path):
         orc.write_overlaps(rec, str(ref))
         assert open(tmp_path / ("c%d.txt" % c)).read() == open(ref).read()
     stats = [json.loads(l) for l in open(tmp_path / "stats.jsonl")]
+    summary = [s for s in stats if s.get("summary")]
+    stats = [s for s in stats if not s.get("summary")]
+    assert len(summary) == 1 and summary[0]["clusters"] == len(batches) and summary[0]["records"] == sum(s["records"] for s in stats)
     assert len(stats) == len(batches)
     assert len({s["device"] for s in stats}) >= 2  # the dynamic queue fed more than one GPU
 

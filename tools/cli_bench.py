@@ -22,6 +22,8 @@ for rep in range(2):
     print("rc", r.returncode, "clusters", n, "wall %.2f s" % dt, "lines", nl, "overlaps/s %.3g" % (nl / dt), r.stderr[-200:])
 import json
 st = [json.loads(l) for l in open(os.path.join(d, "stats.jsonl"))]
+print("summary", [x for x in st if x.get("summary")])
+st = [x for x in st if not x.get("summary")]
 for x in st[:3] + st[-3:]:
     print(x["batch"], x["device"], "wall %.0f ms" % x["ms"]["wall"], {k: round(v, 1) for k, v in x["ms"].items() if k != "wall"})
 print("sum over batches (ms): " + ", ".join("%s %.0f" % (k, sum(x["ms"].get(k, 0) for x in st)) for k in ("wall", "host_parse", "host_call", "host_write", "ctx_create", "device_total")))
