@@ -108,7 +108,7 @@ struct hlo_ctx {
     int pairgen_slots_log2 = 8;
     int pairgen_slots_auto = 0;  // raised by batches whose reads overflowed the tables
     int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0, sort_prefix = 1,
-        sort_hash_bits = 0, sort_segmented = 1, scores = 0, digest = 0, cap_scale_pct = 100, serialize_compute = 1;
+        sort_hash_bits = 0, sort_segmented = 1, scores = 0, digest = 0, cap_scale_pct = 100, serialize_compute = 1, pairgen_flat = 0;
     double score_mismatch_prob = 0.0;
     uint32_t score_min_read_len = 0;
     // what earlier batches needed, per unit of the quantity the estimate scales with (0 = nothing learned yet)
@@ -300,6 +300,7 @@ int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out) {
         const int v = atoi(e);
         if (v >= 5 && v <= 10) ctx->pairgen_slots_log2 = v;
     }
+    if (const char *e = getenv("HLO_PAIRGEN_FLAT")) ctx->pairgen_flat = atoi(e) != 0;
     *out = ctx;
     return HLO_OK;
 }
@@ -802,6 +803,7 @@ static PairgenArgs pairgen_args(hlo_ctx *ctx, const hlo_reads *R, int external) 
     a.k = ctx->P.k;
     a.gap_min = std::max(std::max(ctx->P.min_chain_score - ctx->P.k, ctx->P.min_seeds - 1), 0);
     a.external = external;
+    a.flat = ctx->pairgen_flat;
     a.cands = ctx->b_cands.p, a.cand_cap = ctx->cap_c;
     a.cand_counter = ctr(ctx, C_CAND), a.hit_counter = ctr(ctx, C_HITS);
     a.ovf_counter = ctr(ctx, C_PG_OVF), a.work_counter = ctr(ctx, C_PG_WORK);
@@ -954,7 +956,7 @@ static int enqueue_tail(hlo_ctx *ctx, const hlo_reads *R) {
     launch_exclusive_scan(g_cnt, g_off, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
     launch_group_scatter(rec, n_ptr, cap, d, g_off, g_slot, g_ent, g_entg, s, &ctx->lc);
     uint32_t *g_lt = g_slot;  // (the slots are consumed by the scatter)
-    launch_group_mark(rec, n_ptr, cap, g_off, g_entg, 1, g_ent, g_uniq, g_lt, s, &ctx->lc);
+    launch_group_mark(rec, n_ptr, cap, d, R->b_coff.as<uint32_t>(), g_off, g_entg, 1, g_ent, g_uniq, g_lt, s, &ctx->lc);
     launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), reinterpret_cast<uint32_t *>(ctr(ctx, C_NOUT)), s, &ctx->lc);
     ExpandOut eo;
     if (need_rec) eo.out = ctx->b_out.as<hlo_rec>();
@@ -1162,10 +1164,9 @@ static int complete_front(hlo_ctx *ctx, const hlo_reads *R, int external, bool w
             first_overflow = hc[C_PG_OVF];
             // a batch that overflowed a lot: the following ones start with larger tables
             const int slots0 = std::min(std::max(ctx->pairgen_slots_log2, ctx->pairgen_slots_auto), PAIRGEN_WIDE_SLOTS_LOG2);
-            // ... and so do batches whose tables run full: a table holds at least one key per candidate of its read, and
-            // probe chains grow quickly past ~1/3 load (BASELINE configs[3]: 152 chains per read, 256 slots: 13.4 ms; 512: 11.6)
-            const bool crowded = R->d.n_reads && (double)hc[C_CAND] / (double)R->d.n_reads > 0.3 * (double)(1u << slots0);
-            if ((first_overflow > R->d.n_reads / 16 || crowded) && ctx->pairgen_slots_auto < 10) ctx->pairgen_slots_auto = std::min(slots0 + 1, 10);
+            // (only overflow drives this: larger tables cost occupancy — config 2 runs 1.7x slower at 512 slots — and a
+            // crowded but not overflowing table measured the same at both sizes, BASELINE configs[3]: 13.4 ms)
+            if (first_overflow > R->d.n_reads / 16 && ctx->pairgen_slots_auto < 10) ctx->pairgen_slots_auto = std::min(slots0 + 1, 10);
         }
         ctx->tm.n_overflow_reads = ctx->fast_pairgen ? first_overflow : 0;
         if (n_list) {
@@ -1529,7 +1530,8 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
                         {"repack", &ctx->repack, 0, 1},                   {"compact", &ctx->compact, 0, 2},
                         {"aux", &ctx->aux_out, 0, 1},                     {"d2h", &ctx->d2h, 0, 1},
                         {"scores", &ctx->scores, 0, 1},                   {"digest", &ctx->digest, 0, 1},
-                        {"cap_scale_pct", &ctx->cap_scale_pct, 1, 100000}, {"serialize_compute", &ctx->serialize_compute, 0, 1}};
+                        {"cap_scale_pct", &ctx->cap_scale_pct, 1, 100000}, {"serialize_compute", &ctx->serialize_compute, 0, 1},
+                        {"pairgen_flat", &ctx->pairgen_flat, 0, 1}};
     for (const Opt &o : opts)
         if (!strcmp(name, o.name)) {
             if (value < o.lo || value > o.hi) FAIL(HLO_ERANGE, "%s=%lld outside [%lld,%lld]", name, (long long)value, (long long)o.lo, (long long)o.hi);

@@ -97,6 +97,8 @@ struct PairgenArgs {
     int k, gap_min;
     int dg_bits;             // bits of (diagonal + max_len) in the 32-bit table key
     int external;            // 1: emit hlo_cand (exact anchor span), 0: emit CandI
+    int flat = 0;            // 0: pairgen_group_kernel (one minimizer per chunk); 1: pairgen_flat_kernel (chunks drawn from the flat
+                             // hit sequence: measured 3x slower, kept as the record of that experiment — option "pairgen_flat")
     void *cands;             // output, 16 B per candidate
     uint64_t cand_cap;
     unsigned long long *cand_counter, *hit_counter;  // candidates (counted past cand_cap too), seed hits
@@ -151,8 +153,8 @@ void launch_group_count(const Rec16 *rec, const unsigned long long *n_ptr, uint6
                         cudaStream_t s, LaunchCounter *lc);
 void launch_group_scatter(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *off,
                           const uint32_t *slot, uint2 *ent, uint32_t *entg, cudaStream_t s, LaunchCounter *lc);
-void launch_group_mark(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, const uint32_t *off, const uint32_t *entg, int dedup,
-                       uint2 *ent, uint32_t *uniq, uint32_t *lt, cudaStream_t s, LaunchCounter *lc);
+void launch_group_mark(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *cluster_off, const uint32_t *off,
+                       const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq, uint32_t *lt, cudaStream_t s, LaunchCounter *lc);
 void launch_group_expand(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *off, const uint32_t *uoff,
                          const uint32_t *entg, const uint2 *ent, const uint32_t *lt, const ExpandOut &o, cudaStream_t s, LaunchCounter *lc);
 void launch_cluster_offsets(const uint32_t *uoff, const uint32_t *cluster_off, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,

@@ -513,6 +513,254 @@ __global__ void __launch_bounds__(PG_THREADS) pairgen_group_kernel(PairgenArgs a
     if (lane == 0 && nh_total) atomicAdd(a.hit_counter, nh_total);
 }
 
+// ------------------------------------------------------------------------------------------------
+// pairgen_flat_kernel: the same tables, the same lockstep of two reads per warp, but the lanes of a group walk the
+// read's seed hits as ONE FLAT SEQUENCE: lane l of a chunk takes hit number f0 + l of the concatenation of the staged
+// bucket suffixes (an exclusive prefix of their lengths maps a hit number to its suffix; a chunk spans at most
+// PF_SPAN suffixes).  pairgen_group_kernel gives every chunk to ONE minimizer, and a suffix holds ~12 hits for 16
+// lanes: 53 % of the lane slots carry a hit; here ~90 % do.  The price: hits of DIFFERENT minimizers of the query meet
+// in one chunk, and overlapping reads share most of their minimizers, so one chunk often holds the same (target,
+// strand, diagonal) two or three times.  MATCH.ANY on the key finds those lanes; the lowest lane of each peer set
+// takes the minimum and maximum anchor position of the set (REDUX over the peer mask) and is the only one to touch the
+// table — within a chunk every table key is still touched by exactly one lane, so min/max stay plain read-modify-writes.
+// MEASURED (B200, 32 config-2 clusters): 7.03 ms against 2.34 ms for pairgen_group_kernel — bit-identical candidates,
+// three times the time: MATCH.ANY over 32 mostly distinct values and the two REDUX over per-lane peer masks cost far more
+// than the idle lanes they remove.  Not the default (option "pairgen_flat" = 1 selects it; one parity test keeps it honest);
+// kept as the record of the experiment.
+constexpr int PF_SPAN = 5;  // bucket suffixes one chunk may draw from
+
+template <bool NARROW>
+__global__ void __launch_bounds__(PG_THREADS) pairgen_flat_kernel(PairgenArgs a, int slots_log2) {
+    extern __shared__ uint32_t pg_smem[];
+    typedef typename std::conditional<NARROW, uint16_t, uint32_t>::type val_t;
+    typedef typename std::conditional<NARROW, uint8_t, uint16_t>::type list_t;
+    constexpr int VSH = NARROW ? 8 : 16;
+    constexpr uint32_t VMASK = NARROW ? 0xffu : 0xffffu;
+    const uint32_t S = 1u << slots_log2, smask = S - 1u, ST = S + PG_PAD;
+    const uint32_t g = threadIdx.x / PG_G, l = threadIdx.x % PG_G;
+    uint32_t *keys = pg_smem + (size_t)g * ST;
+    val_t *vals = reinterpret_cast<val_t *>(pg_smem + (size_t)PG_GROUPS * ST) + (size_t)g * ST;
+    list_t *list = reinterpret_cast<list_t *>(reinterpret_cast<val_t *>(pg_smem + (size_t)PG_GROUPS * ST) + (size_t)PG_GROUPS * ST) +
+                   (size_t)g * ST;
+    // staging area of the group (PG_STAGE * 4 words): prefix of the suffix lengths | first hit | query pos<<1|strand
+    uint32_t *sP = pg_smem + pairgen_table_words(slots_log2, NARROW) + (size_t)g * PG_STAGE * 4;  // [PG_STAGE + PF_SPAN + 1]
+    uint32_t *sS = sP + PG_STAGE + PF_SPAN + 3;                                                    // [PG_STAGE]
+    uint32_t *sQ = sS + PG_STAGE;                                                                  // [PG_STAGE]
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned gshift = lane & ~(unsigned)(PG_G - 1);
+    const unsigned lt8 = (1u << l) - 1u;
+    const unsigned lt_lane = (1u << lane) - 1u;
+    const int kshift = a.dg_bits + 1;
+    const uint32_t max_len = a.reads.max_len;
+    uint32_t n_work = a.reads.n_reads;
+    if (a.work) {
+        const unsigned long long nw = *a.n_work_ptr;
+        n_work = nw < (unsigned long long)a.overflow_cap ? (uint32_t)nw : a.overflow_cap;
+    }
+    const int gap_min = a.gap_min;
+    unsigned long long nh_total = 0;
+    for (;;) {
+        unsigned long long qq = 0;
+        if (lane == 0) qq = atomicAdd(a.work_counter, (unsigned long long)PG_RPW);
+        qq = __shfl_sync(FULL, qq, 0);
+        if (qq >= n_work) break;
+        const uint32_t wi = (uint32_t)qq + lane / PG_G;
+        const bool have_read = wi < n_work;
+        const uint32_t xq = !have_read ? 0u : a.work ? __ldg(a.work + wi) : wi;
+        uint32_t m0 = 0, m1 = 0, q = 0, lq = 0, cb = 0;
+        if (have_read) {
+            m0 = __ldg(a.mz_off + xq), m1 = __ldg(a.mz_off + xq + 1);
+            q = __ldg(a.reads.perm + xq);
+            lq = __ldg(a.reads.len + q);
+            cb = __ldg(a.reads.cbase + q);
+        }
+        const uint32_t ql = lq & HLO_LEN_MASK;
+        const uint32_t nm = m1 - m0;
+        const uint32_t nm_max = __reduce_max_sync(FULL, nm);
+        if (nm_max == 0) continue;
+        {
+            uint4 *k4 = reinterpret_cast<uint4 *>(keys);
+            const uint4 e4 = make_uint4(HLO_EMPTY32, HLO_EMPTY32, HLO_EMPTY32, HLO_EMPTY32);
+            for (uint32_t i = l; i < S / 4; i += PG_G) k4[i] = e4;
+            const uint32_t f = NARROW ? VMASK * 0x10001u : VMASK;  // every value: min = VMASK, max = 0
+            uint4 *v4 = reinterpret_cast<uint4 *>(vals);
+            for (uint32_t i = l; i < S * (uint32_t)sizeof(val_t) / 16; i += PG_G) v4[i] = make_uint4(f, f, f, f);
+        }
+        __syncwarp();
+        uint32_t nh = 0, nq = 0, list_n = 0;
+        bool ovf = false;
+        for (uint32_t mb = 0; mb < nm_max; mb += PG_STAGE) {
+            // stage the non-empty bucket suffixes of minimizers mb .. mb + PG_STAGE - 1, with the prefix of their lengths
+            uint32_t T = 0;  // hits of this stage
+            {
+                static_assert(PG_STAGE == 2 * PG_G, "two staged entries per lane");
+                uint2 rg0 = make_uint2(0u, 0u), rg1 = make_uint2(0u, 0u);
+                uint32_t q0 = 0, q1 = 0;
+                const uint32_t i0 = mb + l, i1 = mb + PG_G + l;
+                if (i0 < nm) rg0 = __ldg(a.range + m0 + i0), q0 = __ldg(&a.mz_rr[m0 + i0].y);
+                if (i1 < nm) rg1 = __ldg(a.range + m0 + i1), q1 = __ldg(&a.mz_rr[m0 + i1].y);
+                const uint32_t z0 = rg0.y - rg0.x, z1 = rg1.y - rg1.x;
+                const unsigned b0 = (__ballot_sync(FULL, z0 != 0u) >> gshift) & PG_GMASK;
+                const unsigned b1 = (__ballot_sync(FULL, z1 != 0u) >> gshift) & PG_GMASK;
+                // exclusive prefix of the lengths in staged order: entries of the first half, then of the second
+                uint32_t inc0 = z0, inc1 = z1;
+#pragma unroll
+                for (int d = 1; d < PG_G; d <<= 1) {
+                    const uint32_t o0 = __shfl_up_sync(FULL, inc0, d), o1 = __shfl_up_sync(FULL, inc1, d);
+                    if ((int)l >= d) inc0 += o0, inc1 += o1;
+                }
+                const uint32_t tot0 = __shfl_sync(FULL, inc0, (int)(gshift + PG_G - 1));
+                const uint32_t tot1 = __shfl_sync(FULL, inc1, (int)(gshift + PG_G - 1));
+                const uint32_t n0 = __popc(b0), n_eff = n0 + __popc(b1);
+                T = tot0 + tot1;
+                if (z0) {
+                    const uint32_t p = __popc(b0 & lt8);
+                    sP[p] = inc0 - z0, sS[p] = rg0.x, sQ[p] = q0;
+                }
+                if (z1) {
+                    const uint32_t p = n0 + __popc(b1 & lt8);
+                    sP[p] = tot0 + inc1 - z1, sS[p] = rg1.x, sQ[p] = q1;
+                }
+                if (l < PF_SPAN + 1) sP[n_eff + l] = T;  // the walk below may look PF_SPAN entries past the last suffix
+            }
+            __syncwarp();
+            // chunk = hits [f0, f0 + PG_G) of the flat sequence, cut at the end of suffix r0 + PF_SPAN - 1
+            uint32_t f0 = 0, r0 = 0;
+            // this chunk's hit of the lane (loaded one chunk ahead)
+            uint2 h = make_uint2(0u, 0u);
+            uint32_t qrp = 0;
+            bool ok = false;
+            auto fetch = [&]() {  // maps f0 + l to its suffix, loads the hit, and moves (f0, r0) to the next chunk
+                const uint32_t f = f0 + l;
+                const uint32_t p1 = sP[r0 + 1], p2 = sP[r0 + 2], p3 = sP[r0 + 3], p4 = sP[r0 + 4], p5 = sP[r0 + 5];
+                const uint32_t r = r0 + (f >= p1) + (f >= p2) + (f >= p3) + (f >= p4);
+                ok = f < p5;
+                h = make_uint2(0u, 0u), qrp = 0u;
+                if (ok) {
+                    const uint32_t hi = sS[r] + (f - sP[r]);
+                    HLO_DBG_ASSERT(hi < a.mz_off[a.reads.n_reads]);
+                    h = __ldg(a.hits + hi), qrp = sQ[r];
+                }
+                const uint32_t nf = min(f0 + (uint32_t)PG_G, p5);
+                r0 += (nf >= p1) + (nf >= p2) + (nf >= p3) + (nf >= p4) + (nf >= p5);
+                f0 = nf;
+            };
+            static_assert(PF_SPAN == 5, "fetch() is written for five suffixes per chunk");
+            bool more = f0 < T;  // (T == 0: nothing staged for this read)
+            if (more) fetch();
+            else ok = false;
+            while (__any_sync(FULL, more)) {
+                const uint2 hc = h;
+                const uint32_t qrp_c = qrp;
+                const bool ok_c = more && ok;
+                more = more && f0 < T;
+                if (more) fetch();  // next chunk's hit, in flight while this one is folded in
+                // key and anchor position of this lane's hit
+                const bool live = ok_c && hc.x != q;  // hc.x == q: another minimizer of the query itself (-X: no self hits)
+                uint32_t key = 0xffffffffu - lane;     // (dead lanes: distinct values that equal no key — keys keep bit 31 clear... see below)
+                uint32_t qp = 0;
+                if (live) {
+                    const uint32_t t = hc.x;
+                    ++nh;
+                    const int qpos = (int)(qrp_c >> 1);
+                    const uint32_t strand = (hc.y ^ qrp_c) & 1u;
+                    const int tp = (int)((hc.y >> 1) & 0x7fffu);
+                    const int qpi = strand ? (int)ql - qpos + a.k - 2 : qpos;  // ql - (qpos + 1 - k) - 1
+                    const int diag = tp - qpi;
+                    qp = (uint32_t)qpi;
+                    key = (t - cb) << kshift | strand << a.dg_bits | (uint32_t)(diag + (int)max_len);
+                }
+                // lanes of the group that hold the same key: fold their anchor positions into the lowest one.  (The two
+                // groups of the warp work on different reads: bit 31, clear in every key, tells them apart.)
+                const unsigned peers = __match_any_sync(FULL, live ? (key | (gshift ? 0x80000000u : 0u)) : key);
+                const uint32_t mn_p = __reduce_min_sync(peers, qp), mx_p = __reduce_max_sync(peers, qp);
+                const bool leader = live && (peers & lt_lane) == 0u;
+                int newslot = -1;
+                if (leader) {
+                    uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
+                    bool done = false;
+                    uint32_t old = 0;
+                    for (uint32_t probe = 0; probe < S; ++probe) {
+                        old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
+                        if (old == HLO_EMPTY32 || old == key) {
+                            done = true;
+                            break;
+                        }
+                        slot = (slot + 1u) & smask;
+                    }
+                    if (done) {  // no other lane touches this key in this chunk: plain read-modify-write
+                        HLO_DBG_ASSERT(slot < S);
+                        const uint32_t v = vals[slot];
+                        const uint32_t mn = min(v & VMASK, mn_p), mx = max(v >> VSH, mx_p);
+                        vals[slot] = (val_t)(mn | mx << VSH);
+                        nq += ((int)((v >> VSH) - (v & VMASK)) < gap_min) && ((int)(mx - mn) >= gap_min);
+                        if (old == HLO_EMPTY32) newslot = (int)slot;
+                    }
+                    if (!done) ovf = true;
+                }
+                const unsigned gb = (__ballot_sync(FULL, newslot >= 0) >> gshift) & PG_GMASK;
+                HLO_DBG_ASSERT(list_n + __popc(gb) <= S);
+                if (newslot >= 0) list[list_n + __popc(gb & lt8)] = (list_t)newslot;
+                list_n += __popc(gb);
+                __syncwarp();  // orders the plain min/max updates of consecutive chunks
+            }
+            __syncwarp();  // the staging area is rewritten by the next stage
+        }
+        // per-read reductions inside the lane groups (uniform across the warp)
+        const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & PG_GMASK) != 0u;
+        // seed hits of the read = group sum
+        uint32_t nh_g = nh;
+#pragma unroll
+        for (int dd = PG_G / 2; dd > 0; dd >>= 1) nh_g += __shfl_xor_sync(FULL, nh_g, dd);
+        if (ovf_any) {  // redo this read with a larger table (its hits are counted there)
+            if (l == 0 && have_read) {
+                const unsigned long long p = atomicAdd(a.ovf_counter, 1ULL);
+                if (p < a.overflow_cap) a.overflow_reads[p] = xq;
+            }
+            nq = 0, list_n = 0;
+        } else if (l == 0) {
+            nh_total += nh_g;
+        }
+        uint32_t inc = nq;  // inclusive scan over the whole warp: groups are laid out consecutively
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if ((int)lane >= d) inc += o;
+        }
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
+        unsigned long long base = 0;
+        if (lane == 0 && total) base = atomicAdd(a.cand_counter, (unsigned long long)total);
+        base = __shfl_sync(FULL, base, 0);
+        const uint32_t gprev = __shfl_sync(FULL, inc, (gshift + 31u) & 31u);
+        unsigned long long p = base + (gshift ? gprev : 0u);
+        const uint32_t list_max = __reduce_max_sync(FULL, list_n);
+        for (uint32_t j0 = 0; j0 < list_max; j0 += PG_G) {
+            const uint32_t j = j0 + l;
+            bool okc = false;
+            uint32_t key = 0, v = 0;
+            if (j < list_n) {
+                const uint32_t e = list[j];
+                key = keys[e], v = vals[e];
+                okc = (int)((v >> VSH) - (v & VMASK)) >= gap_min;
+            }
+            const unsigned ob = (__ballot_sync(FULL, okc) >> gshift) & PG_GMASK;
+            if (okc) {
+                const uint32_t t = cb + (key >> kshift);
+                const uint32_t lt = __ldg(a.reads.len + t);
+                const uint32_t strand = (key >> a.dg_bits) & 1u;
+                const int diag = (int)(key & ((1u << a.dg_bits) - 1u)) - (int)max_len;
+                emit_cand(a, p + __popc(ob & lt8), q, t, strand, diag, v & VMASK, v >> VSH, ql, lt & 0x7fffu, (lt | lq) >> 31);
+            }
+            p += __popc(ob);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nh_total += __shfl_xor_sync(FULL, nh_total, d);
+    if (lane == 0 && nh_total) atomicAdd(a.hit_counter, nh_total);
+}
+
 static bool pairgen_narrow(const DevReads &r, int slots_log2) { return r.max_len <= 255 && slots_log2 <= 8; }
 size_t pairgen_smem_bytes(int slots_log2, bool narrow) {
     return pairgen_table_words(slots_log2, narrow) * 4 + (size_t)PG_GROUPS * PG_STAGE * sizeof(uint4);
@@ -532,7 +780,8 @@ void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, Launch
     if (n_work == 0) return;
     const bool narrow = pairgen_narrow(a.reads, slots_log2);
     const size_t smem = pairgen_smem_bytes(slots_log2, narrow);
-    void (*kern)(PairgenArgs, int) = narrow ? pairgen_group_kernel<true> : pairgen_group_kernel<false>;
+    void (*kern)(PairgenArgs, int) = a.flat ? (narrow ? pairgen_flat_kernel<true> : pairgen_flat_kernel<false>)
+                                            : (narrow ? pairgen_group_kernel<true> : pairgen_group_kernel<false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);

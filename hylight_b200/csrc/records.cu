@@ -32,6 +32,7 @@ __device__ __forceinline__ bool rec_better(const Rec16 &x, const Rec16 &y) {
 // Every pass takes the number of accepted records from the verify kernels' device counter (clamped to the buffer) and
 // runs on a resident grid that strides: the host sizes nothing from a count it would have to wait for.
 constexpr int RT_THREADS = 256;
+constexpr uint32_t GB_MIN = 48;  // groups (records per idA) above this size are ranked by group_rank_big_kernel
 static unsigned tail_grid(uint64_t n_cap) {
     const uint64_t want = (n_cap + RT_THREADS - 1) / RT_THREADS;
     return (unsigned)(want < 148ull * 8 ? (want ? want : 1) : 148ull * 8);
@@ -87,7 +88,7 @@ void launch_group_scatter(const Rec16 *rec, const unsigned long long *n_ptr, uin
 __global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__restrict__ rec, const unsigned long long *__restrict__ n_ptr,
                                                                 uint64_t n_cap, const uint32_t *__restrict__ off,
                                                                 const uint32_t *__restrict__ entg, int dedup, uint2 *ent,
-                                                                uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out) {
+                                                                uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out, int big_groups) {
     const uint64_t n = tail_n(n_ptr, n_cap);
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint2 me = ent[p];
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__r
         bool keep = true;
         uint32_t lt = 0;  // entries of the group with a smaller idB: my place in the group when it holds no duplicate pair
         const uint32_t b = off[g], e = off[g + 1];
+        if (big_groups && e - b > GB_MIN) continue;  // group_rank_big_kernel ranks the large groups (this loop is quadratic per group)
         for (uint32_t j = b; j < e; ++j) {
             const uint2 y = ent[j];
             lt += y.x < me.x;
@@ -111,11 +113,102 @@ __global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__r
         }
     }
 }
-void launch_group_mark(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, const uint32_t *off, const uint32_t *entg, int dedup,
-                       uint2 *ent, uint32_t *uniq, uint32_t *lt, cudaStream_t s, LaunchCounter *lc) {
+// Groups of more than GB_MIN entries (deep clusters: BASELINE configs[3] has 137 records per idA, and the pass above is
+// quadratic per group): one warp per group ranks the entries through a bitmap of the cluster's reads in shared memory —
+// bit = "some entry has this idB"; the number of set bits below an entry's idB is the entry's final place, distinct idB
+// counted once.  Linear in the group size.  A group that holds the same pair twice (the count of entries exceeds the set
+// bits) is rare: its warp runs the quadratic rule.  Clusters of more than GB_MAX_CLUSTER reads do not fit the bitmap
+// and stay with the pass above.
+constexpr uint32_t GB_WARPS = 4, GB_MAX_CLUSTER = 65536, GB_WORDS = GB_MAX_CLUSTER / 32;
+__global__ void __launch_bounds__(GB_WARPS * 32) group_rank_big_kernel(const Rec16 *__restrict__ rec, DevReads r, const uint32_t *__restrict__ off,
+                                                                       const uint32_t *__restrict__ cluster_off, int dedup, uint2 *ent,
+                                                                       uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out) {
+    __shared__ uint32_t bm[GB_WARPS][GB_WORDS];  // bitmap, then (in place) the exclusive prefix of its popcounts per 32 words
+    __shared__ uint32_t pre[GB_WARPS][GB_WORDS / 32 + 1];
+    const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5, FULL = 0xffffffffu;
+    const uint32_t n_groups = r.n_reads;
+    // a warp looks at 32 consecutive groups at a time (one per lane) and then takes the large ones among them one by one
+    for (uint32_t g0 = (blockIdx.x * GB_WARPS + wp) * 32; g0 < n_groups; g0 += gridDim.x * GB_WARPS * 32) {
+      const uint32_t gl = g0 + lane;
+      unsigned todo = __ballot_sync(FULL, gl < n_groups && off[gl + 1] - off[gl] > GB_MIN);
+      while (todo) {
+        const uint32_t g = g0 + (uint32_t)__ffs(todo) - 1u;
+        todo &= todo - 1u;
+        const uint32_t b = off[g], e = off[g + 1], sz = e - b;
+        const uint32_t cb = r.cbase[g], N = cluster_off[r.cidx[g] + 1] - cb;  // ranks of a cluster's names are cb .. cb + N - 1
+        const uint32_t nw = (N + 31) / 32;
+        uint32_t *m = bm[wp];
+        for (uint32_t i = lane; i < nw; i += 32) m[i] = 0u;
+        __syncwarp();
+        for (uint32_t j = b + lane; j < e; j += 32) {
+            const uint32_t x = ent[j].x - cb;
+            atomicOr(&m[x >> 5], 1u << (x & 31));
+        }
+        __syncwarp();
+        // pre[k] = set bits in words [0, 32k)
+        uint32_t run = 0;
+        for (uint32_t k0 = 0; k0 < nw; k0 += 32) {
+            const uint32_t c = k0 + lane < nw ? (uint32_t)__popc(m[k0 + lane]) : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, inc, d);
+                if ((int)lane >= d) inc += o;
+            }
+            if (lane == 0) pre[wp][k0 >> 5] = run;
+            run += __shfl_sync(FULL, inc, 31);
+        }
+        __syncwarp();
+        const uint32_t distinct = run;
+        if (!dedup || distinct == sz) {  // every pair once (or duplicates are wanted): the place of an entry = set bits below its idB
+            uint32_t kept = 0;  // (pair_rule 1 drops the rows that failed the overhang test)
+            for (uint32_t j = b + lane; j < e; j += 32) {
+                const uint2 me = ent[j];
+                const uint32_t x = me.x - cb, w = x >> 5;
+                uint32_t lt = pre[wp][w >> 5];
+                for (uint32_t k = w & ~31u; k < w; ++k) lt += __popc(m[k]);
+                lt += __popc(m[w] & ((1u << (x & 31)) - 1u));
+                lt_out[j] = lt;
+                if (!(rec[me.y & 0x7fffffffu].kb & HLO_KB_OVERHANG_FAIL)) ent[j].y = me.y | 0x80000000u, ++kept;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(FULL, kept, d);
+            if (lane == 0) uniq[g] = kept;
+        } else {  // the same pair twice in the group: the quadratic rule of group_mark_kernel, one lane per entry
+            uint32_t kept = 0;
+            for (uint32_t p = b + lane; p < e; p += 32) {
+                const uint2 me = ent[p];
+                bool keep = true;
+                uint32_t lt = 0;
+                for (uint32_t j = b; j < e; ++j) {
+                    const uint2 y = ent[j];
+                    lt += y.x < me.x;
+                    if (y.x == me.x && j != p && rec_better(rec[y.y & 0x7fffffffu], rec[me.y & 0x7fffffffu])) keep = false;
+                }
+                lt_out[p] = lt;
+                if (keep && (rec[me.y & 0x7fffffffu].kb & HLO_KB_OVERHANG_FAIL)) keep = false;
+                if (keep) ent[p].y = me.y | 0x80000000u, ++kept;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(FULL, kept, d);
+            if (lane == 0) uniq[g] = kept;
+        }
+        __syncwarp();
+      }
+    }
+}
+
+void launch_group_mark(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *cluster_off, const uint32_t *off,
+                       const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq, uint32_t *lt, cudaStream_t s, LaunchCounter *lc) {
     if (n_cap == 0) return;
-    group_mark_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, off, entg, dedup, ent, uniq, lt);
+    const int big = r.max_cluster <= GB_MAX_CLUSTER && r.n_reads > 0;
+    group_mark_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, off, entg, dedup, ent, uniq, lt, big);
     if (lc) lc->total++;
+    if (big) {
+        const uint32_t want = (r.n_reads + GB_WARPS * 32 - 1) / (GB_WARPS * 32);
+        group_rank_big_kernel<<<want < 148u * 6 ? want : 148u * 6, GB_WARPS * 32, 0, s>>>(rec, r, off, cluster_off, dedup, ent, uniq, lt);
+        if (lc) lc->total++;
+    }
 }
 
 // order-independent digest term of one output record (bench.py recomputes it on the host from the downloaded records)

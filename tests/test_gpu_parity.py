@@ -159,6 +159,21 @@ def test_candidates_table_overflow_path(ctx):
             ctx.set_option("pairgen_slots_log2", 8)
 
 
+def test_candidates_flat_kernel_variant(ctx):
+    """option pairgen_flat: chunks drawn from the flat hit sequence, duplicates inside a chunk folded with MATCH.ANY / REDUX
+    (the slower experiment of DESIGN.md §8) — same candidates"""
+    ctx.set_option("pairgen_flat", 1)
+    try:
+        check_candidates(ctx, small_cluster(27, n_fragments=250))
+        check_candidates(ctx, small_cluster(28, n_fragments=120, read_len=250, n_strains=1, strain_cov=30.0))
+        ctx.set_option("pairgen_slots_log2", 6)
+        _, tm = check_candidates(ctx, small_cluster(25, n_fragments=300, n_strains=1, strain_cov=40.0))
+        assert tm["n_overflow_reads"] > 0
+    finally:
+        ctx.set_option("pairgen_slots_log2", 8)
+        ctx.set_option("pairgen_flat", 0)
+
+
 def test_candidates_mid_occ_and_params(ctx):
     b = small_cluster(26, n_fragments=150, n_strains=1, strain_cov=30.0)
     check_candidates(ctx, b, mid_occ=20)
