@@ -65,7 +65,7 @@ class Timing(C.Structure):
                [(n, C.c_uint64) for n in ("n_reads", "n_bases", "n_minimizers", "n_seed_hits", "n_candidates",
                                           "n_accepted", "n_records", "n_deferred", "n_overflow_reads",
                                           "verify_launches", "total_launches", "digest", "n_reruns", "n_syncs")] + \
-               [("mid_occ_lo", C.c_uint32), ("mid_occ_hi", C.c_uint32), ("score_ms", C.c_float), ("reserved_", C.c_float)]
+               [("mid_occ_lo", C.c_uint32), ("mid_occ_hi", C.c_uint32), ("score_ms", C.c_float), ("n_sketch_reruns", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -1186,6 +1186,7 @@ static int complete_front(hlo_ctx *ctx, const hlo_reads *R, int external, bool w
             }
         }
         ctx->n_mz = (uint32_t)ctx->hc[C_MZ];
+        ctx->tm.n_sketch_reruns = (uint32_t)ctx->hc[C_SK_TIE];
         ctx->tm.n_seed_hits = ctx->hc[C_HITS];
         ctx->tm.n_candidates = ctx->hc[C_CAND];
         ctx->tm.mid_occ_lo = ctx->hc[C_MIDOCC_LO] > 0xffffffffull ? 0u : (uint32_t)ctx->hc[C_MIDOCC_LO];

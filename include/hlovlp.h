@@ -198,7 +198,7 @@ typedef struct hlo_timing {
     uint64_t n_syncs;        /* host waits on the device during the call */
     uint32_t mid_occ_lo, mid_occ_hi; /* smallest / largest per-cluster occurrence cut-off used */
     float score_ms;          /* the fused score kernel (option "scores") */
-    float reserved_;
+    uint32_t n_sketch_reruns; /* reads the lean sketch automaton handed to the complete one (equal window keys met) */
 } hlo_timing;
 
 typedef struct hlo_ctx hlo_ctx;
