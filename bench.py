@@ -294,6 +294,35 @@ def concordance_check(api, synth):
     return out
 
 
+def config1_standin(api, synth):
+    """BASELINE configs[0]: "example/short_reads.fq bundled MiSeq test set, one cluster, overlap stage on CPU".  The file is
+    not in the reference tree (.MISSING_LARGE_BLOBS:1) and no minimap2 exists here, so this is a DECLARED STAND-IN: one
+    seeded MiSeq-like cluster (6000 fragments, 2 x 250 bp, 3 strains at 20x, 0.5 % substitution errors), the chain once on
+    one CPU core (the reference runs `-t 1` per cluster: the oracle port, in memory) and once through hlo_submit / hlo_wait,
+    the two 13-column files compared byte for byte."""
+    from oracle import orc
+    kw = dict(n_fragments=6000, read_len=250, n_strains=3, strain_cov=20.0, snp_rate=0.01, err_rate=0.005)
+    b = synth.cluster_batch(1, seed0=31337, **kw)
+    ob = orc.Batch.from_arrays(b.bases, b.base_off, b.cluster_off)
+    t0 = time.perf_counter()
+    rec_o, _, _, st = orc.overlap_batch(ob)
+    cpu_s = time.perf_counter() - t0
+    with api.Context(0) as c:
+        c.submit(b)
+        c.wait()  # (first call on a new context: allocations)
+        t0 = time.perf_counter()
+        c.submit(b)
+        rec, aux, coff = c.wait()
+        gpu_s = time.perf_counter() - t0
+    with tempfile.TemporaryDirectory() as d:
+        api.write_overlaps(rec, os.path.join(d, "g.txt"))
+        orc.write_overlaps(rec_o, os.path.join(d, "c.txt"))
+        same = open(os.path.join(d, "g.txt"), "rb").read() == open(os.path.join(d, "c.txt"), "rb").read()
+    return {"stand_in_for": "example/short_reads.fq (missing from the reference tree)", "cluster": kw, "reads": int(b.n_reads),
+            "records": int(len(rec)), "cpu_port_1_core_s": cpu_s, "cpu_port_overlaps_per_s": len(rec_o) / cpu_s,
+            "gpu_call_s": gpu_s, "gpu_overlaps_per_s": len(rec) / gpu_s, "overlaps_files_byte_identical": bool(same)}
+
+
 def bind_to_gpu_cpus(local):
     """Run this rank (and the host workers it starts) on the CPUs NVML reports as closest to its GPU, so that the
     pinned buffers are first-touched on that NUMA node and the PCIe traffic does not cross sockets."""
@@ -627,6 +656,10 @@ def run_ours(args):
             line["digest"]["ERROR"] = "records of the job differ from the expected set"
         if world == 1 and not args.no_cpu:
             line["concordance"] = concordance_check(api, synth)
+            try:
+                line["config1_standin"] = config1_standin(api, synth)
+            except Exception as e:  # noqa: BLE001
+                line["config1_standin"] = {"error": str(e)[:300]}
             cores = os.cpu_count() or 1
             n_cl = max(1, min(cores, 32))
             cl = [distinct[c % nd] for c in range(n_cl)]

@@ -275,3 +275,26 @@ def test_packed_2bit_input_gives_the_same_records():
         c.submit(b)  # and the ASCII form on the same ctx right after
         rec, aux, coff = c.wait()
         assert np.array_equal(rec, rec_o)
+
+
+def test_submit_wait_degenerate_batches():
+    """no reads, empty clusters, a single read, reads shorter than k: nothing to report, nothing to crash on"""
+    with api.Context(0) as c:
+        c.set_option("compact", 2)
+        for seqs in ([[]], [[], [b"ACGT"], []], [[b"A" * 150]], [[b"ACGTACGTAC", b"ACGTACGTAC"]], [[b"N" * 200, b"N" * 200]]):
+            b = synth.ReadBatch.from_seqs(seqs)
+            c.submit(b)
+            rec, aux, coff = c.wait()
+            assert rec is None or len(rec) == 0
+            assert coff is None or list(coff) == [0] * (len(seqs) + 1)
+            pk = api.pack2b(b)
+            c.submit_packed(pk, b.cluster_off)
+            rec, aux, coff = c.wait()
+            assert rec is None or len(rec) == 0
+        # and a real batch right after on the same context
+        b = small_cluster(291, n_fragments=60)
+        ob, rec_o, blk_o, coff_o, st = oracle_full(b)
+        c.set_option("compact", 0)
+        c.submit(b)
+        rec, aux, coff = c.wait()
+        assert np.array_equal(rec, rec_o)
