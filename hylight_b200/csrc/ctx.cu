@@ -108,7 +108,8 @@ struct hlo_ctx {
     int pairgen_slots_log2 = 8;
     int pairgen_slots_auto = 0;  // raised by batches whose reads overflowed the tables
     int verify_exact = 0, repack = 0, d2h = 1, aux_out = 1, compact = 0, pairgen_generic = 0, sketch_generic = 0, sort_prefix = 1,
-        sort_hash_bits = 0, sort_segmented = 1, scores = 0, digest = 0, cap_scale_pct = 100, serialize_compute = 1, pairgen_flat = 0;
+        sort_hash_bits = 0, sort_segmented = 1, scores = 0, digest = 0, cap_scale_pct = 100, serialize_compute = 1;
+    int pg_dg_bits = 0;  // > 0: b_hits holds 32-bit hit words with this many diagonal bits (the shared-memory pair generator will run)
     double score_mismatch_prob = 0.0;
     uint32_t score_min_read_len = 0;
     // what earlier batches needed, per unit of the quantity the estimate scales with (0 = nothing learned yet)
@@ -300,7 +301,6 @@ int hlo_ctx_create(int device, const hlo_params *params, hlo_ctx **out) {
         const int v = atoi(e);
         if (v >= 5 && v <= 10) ctx->pairgen_slots_log2 = v;
     }
-    if (const char *e = getenv("HLO_PAIRGEN_FLAT")) ctx->pairgen_flat = atoi(e) != 0;
     *out = ctx;
     return HLO_OK;
 }
@@ -752,7 +752,9 @@ static int enqueue_index(hlo_ctx *ctx, const hlo_reads *R, bool keys_ready) {
     CK(ctx->b_midocc.ensure((size_t)d.n_clusters * 4 + 4));
     // occurrence histogram: a bucket can hold at most as many entries as its cluster has minimizers; sizes past the
     // clamp bin only matter when the cut-off quantile itself lands there (then the batch is refused)
-    const uint32_t bins = next_pow2_u32((uint32_t)std::min<uint64_t>(65536ull, (uint64_t)d.max_cluster * 4 + 64));
+    // (a tiny cluster of low-complexity reads can put every minimizer into one bucket: at least min(reads x length, 4096) bins)
+    const uint32_t bins = next_pow2_u32((uint32_t)std::min<uint64_t>(
+        65536ull, std::max<uint64_t>((uint64_t)d.max_cluster * 4 + 64, std::min<uint64_t>((uint64_t)d.max_cluster * d.max_len, 4096ull))));
     if (ctx->P.mid_occ <= 0) CK(ctx->b_hist.ensure(bucket_hist_words(d.n_clusters, bins) * 4));
     uint64_t *keys[2] = {ctx->b_keys[0].as<uint64_t>(), ctx->b_keys[1].as<uint64_t>()};
     uint32_t *vals[2] = {ctx->b_vals[0].as<uint32_t>(), ctx->b_vals[1].as<uint32_t>()};
@@ -784,9 +786,13 @@ static int enqueue_index(hlo_ctx *ctx, const hlo_reads *R, bool keys_ready) {
                              reinterpret_cast<uint32_t *>(ctr(ctx, C_COLL)), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_SORT], s));
+    // the hit array in the form its consumer wants: 32-bit words in the key layout of the shared-memory pair generator
+    // whenever that one can run, (read, pos<<1|strand) pairs for the HBM-table kernel otherwise
+    int dg_bits = 0;
+    ctx->pg_dg_bits = pairgen_fast_supported(d, &dg_bits) && !ctx->pairgen_generic ? dg_bits : 0;
     launch_bucket_index(keys[cur], vals[cur], ctx->b_mzrr.as<uint2>(), cap, n_ptr, hash_bits, ctx->P.mid_occ, d.n_clusters,
-                        ctx->b_midocc.as<uint32_t>(), ctx->b_hist.as<uint32_t>(), bins, ctr(ctx, 0), ctx->b_hits.as<uint2>(),
-                        ctx->b_range.as<uint2>(), s, &ctx->lc);
+                        ctx->b_midocc.as<uint32_t>(), ctx->b_hist.as<uint32_t>(), bins, ctr(ctx, 0), R->b_coff.as<uint32_t>(), ctx->pg_dg_bits,
+                        ctx->b_hits.p, ctx->b_range.as<uint2>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_INDEX], s));
     return HLO_OK;
@@ -803,12 +809,12 @@ static PairgenArgs pairgen_args(hlo_ctx *ctx, const hlo_reads *R, int external) 
     a.k = ctx->P.k;
     a.gap_min = std::max(std::max(ctx->P.min_chain_score - ctx->P.k, ctx->P.min_seeds - 1), 0);
     a.external = external;
-    a.flat = ctx->pairgen_flat;
+    a.hits32 = ctx->pg_dg_bits ? ctx->b_hits.as<uint32_t>() : nullptr;
     a.cands = ctx->b_cands.p, a.cand_cap = ctx->cap_c;
     a.cand_counter = ctr(ctx, C_CAND), a.hit_counter = ctr(ctx, C_HITS);
     a.ovf_counter = ctr(ctx, C_PG_OVF), a.work_counter = ctr(ctx, C_PG_WORK);
     a.overflow_reads = ctx->b_ovf.as<uint32_t>(), a.overflow_cap = d.n_reads;
-    a.dg_bits = 0;
+    a.dg_bits = ctx->pg_dg_bits;
     return a;
 }
 
@@ -824,7 +830,7 @@ static int enqueue_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external) {
     CK(ctx->b_ovf2.ensure((size_t)d.n_reads * 4 + 4));
     CK(ctx->b_cands.ensure(ctx->cap_c * 16 + 16));
     PairgenArgs a = pairgen_args(ctx, R, external);
-    ctx->fast_pairgen = pairgen_fast_supported(d, &a.dg_bits) && !ctx->pairgen_generic && d.n_reads > 0;
+    ctx->fast_pairgen = ctx->pg_dg_bits > 0 && d.n_reads > 0;
     ctx->n_pg_passes = 0;
     if (!ctx->fast_pairgen) return HLO_OK;
     const int slots0 = std::min(std::max(ctx->pairgen_slots_log2, ctx->pairgen_slots_auto), PAIRGEN_WIDE_SLOTS_LOG2);
@@ -1531,8 +1537,7 @@ int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value) {
                         {"repack", &ctx->repack, 0, 1},                   {"compact", &ctx->compact, 0, 2},
                         {"aux", &ctx->aux_out, 0, 1},                     {"d2h", &ctx->d2h, 0, 1},
                         {"scores", &ctx->scores, 0, 1},                   {"digest", &ctx->digest, 0, 1},
-                        {"cap_scale_pct", &ctx->cap_scale_pct, 1, 100000}, {"serialize_compute", &ctx->serialize_compute, 0, 1},
-                        {"pairgen_flat", &ctx->pairgen_flat, 0, 1}};
+                        {"cap_scale_pct", &ctx->cap_scale_pct, 1, 100000}, {"serialize_compute", &ctx->serialize_compute, 0, 1}};
     for (const Opt &o : opts)
         if (!strcmp(name, o.name)) {
             if (value < o.lo || value > o.hi) FAIL(HLO_ERANGE, "%s=%lld outside [%lld,%lld]", name, (long long)value, (long long)o.lo, (long long)o.hi);

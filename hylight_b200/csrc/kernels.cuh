@@ -79,26 +79,26 @@ void launch_copy_words(const uint32_t *src, uint32_t *dst, uint32_t n, cudaStrea
 // sort key = cluster index << hash_bits | minimizer hash (cluster-major: buckets of one cluster stay together)
 void launch_hash_keys(const uint64_t *mz_x, const uint2 *mz_rr, const uint32_t *cidx, int hash_bits, uint64_t n_cap, const uint32_t *n_ptr,
                       uint64_t *keys, uint32_t *vals, cudaStream_t s, LaunchCounter *lc);
-// hits[i] = (read, pos<<1|strand) of the i-th grouped entry; range[m] = (i + 1, bucket end) of minimizer m, or (0, 0)
+// hits[i] = the i-th grouped entry — (read, pos<<1|strand), 8 bytes, or with dg_bits > 0 the 32-bit word
+// (read - cluster_off[cluster]) << (dg_bits + 1) | strand << dg_bits | pos; range[m] = (i + 1, bucket end) of minimizer m, or (0, 0)
 // when its bucket holds more than the cluster's occurrence cut-off midocc[cluster] — fixed_mid_occ when > 0, else
 // minimap2's data-derived value from the occurrence histogram hist[n_clusters][bins] (both filled here).
 // skeys: equal keys adjacent (the grouped order; cluster = key >> hash_bits), svals: their m.
 size_t bucket_hist_words(uint32_t n_clusters, uint32_t bins);  // u32 words of `hist`
 void launch_bucket_index(const uint64_t *skeys, const uint32_t *svals, const uint2 *mz_rr, uint64_t n_cap, const uint32_t *n_ptr, int hash_bits,
                          int fixed_mid_occ, uint32_t n_clusters, uint32_t *midocc, uint32_t *hist, uint32_t bins, unsigned long long *counters,
-                         uint2 *hits, uint2 *range, cudaStream_t s, LaunchCounter *lc);
+                         const uint32_t *cluster_off, int dg_bits, void *hits, uint2 *range, cudaStream_t s, LaunchCounter *lc);
 
 struct PairgenArgs {
     DevReads reads;
     const uint32_t *mz_off;  // [n_reads+1] minimizers of the x-th read (name order)
     const uint2 *mz_rr;      // [n_mz] (read, pos<<1|strand), read order
     const uint2 *range;      // [n_mz] hits [s,e) minimizer m seeds (the part of its bucket behind its own entry)
-    const uint2 *hits;       // [n_mz] (read, pos<<1|strand) in hash order
+    const uint2 *hits;       // [n_mz] (read, pos<<1|strand) in hash order, or
+    const uint32_t *hits32 = nullptr;  // ... (read - cluster base) << (dg_bits + 1) | strand << dg_bits | pos (whenever the fast path is possible)
     int k, gap_min;
-    int dg_bits;             // bits of (diagonal + max_len) in the 32-bit table key
+    int dg_bits;             // bits of (diagonal + max_len) in the 32-bit table key (>= 5)
     int external;            // 1: emit hlo_cand (exact anchor span), 0: emit CandI
-    int flat = 0;            // 0: pairgen_group_kernel (one minimizer per chunk); 1: pairgen_flat_kernel (chunks drawn from the flat
-                             // hit sequence: measured 3x slower, kept as the record of that experiment — option "pairgen_flat")
     void *cands;             // output, 16 B per candidate
     uint64_t cand_cap;
     unsigned long long *cand_counter, *hit_counter;  // candidates (counted past cand_cap too), seed hits
@@ -111,7 +111,7 @@ struct PairgenArgs {
 };
 // fast path: 16 lanes per query read, seed table in shared memory (2^slots_log2 slots per read)
 bool pairgen_fast_supported(const DevReads &r, int *dg_bits_out);
-size_t pairgen_smem_bytes(int slots_log2, bool narrow);
+size_t pairgen_smem_bytes(int slots_log2);
 void launch_pairgen(const PairgenArgs &a, int slots_log2, cudaStream_t s, LaunchCounter *lc);
 // exact generic path: one block per listed read (list == nullptr: reads 0..n_list-1), 64-bit keys, table in HBM
 void launch_generic_hit_counts(const PairgenArgs &a, const uint32_t *list, uint32_t n_list, uint32_t *counts, cudaStream_t s,

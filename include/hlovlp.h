@@ -310,8 +310,7 @@ int hlo_set_score_params(hlo_ctx *ctx, double mismatch_prob, uint32_t min_read_l
  * generic (any w, k / 64-bit keyed) kernels instead of the specialised ones; "sort_segmented" (1|0): sort every
  * cluster's minimizers as its own segment (0: one segment with the cluster index in the key); "sort_prefix" (1|0):
  * sort only a prefix of the hash and repair the groups in which two hashes share it (0: all hash bits);
- * "sort_hash_bits" (0 = automatic): length of that prefix; "pairgen_flat" (0|1): the experimental pair generator that
- * packs hits of several minimizers into one chunk (slower); "cap_scale_pct" (default 100): scales the first-batch
+ * "sort_hash_bits" (0 = automatic): length of that prefix; "cap_scale_pct" (default 100): scales the first-batch
  * buffer estimates (tests use a small value to force the rerun path).  None of them changes a result. */
 int hlo_set_option(hlo_ctx *ctx, const char *name, int64_t value);
 

@@ -159,19 +159,13 @@ def test_candidates_table_overflow_path(ctx):
             ctx.set_option("pairgen_slots_log2", 8)
 
 
-def test_candidates_flat_kernel_variant(ctx):
-    """option pairgen_flat: chunks drawn from the flat hit sequence, duplicates inside a chunk folded with MATCH.ANY / REDUX
-    (the slower experiment of DESIGN.md §8) — same candidates"""
-    ctx.set_option("pairgen_flat", 1)
-    try:
-        check_candidates(ctx, small_cluster(27, n_fragments=250))
-        check_candidates(ctx, small_cluster(28, n_fragments=120, read_len=250, n_strains=1, strain_cov=30.0))
-        ctx.set_option("pairgen_slots_log2", 6)
-        _, tm = check_candidates(ctx, small_cluster(25, n_fragments=300, n_strains=1, strain_cov=40.0))
-        assert tm["n_overflow_reads"] > 0
-    finally:
-        ctx.set_option("pairgen_slots_log2", 8)
-        ctx.set_option("pairgen_flat", 0)
+def test_candidates_bucket_suffix_longer_than_one_stage(ctx):
+    """a pile of 2 600 reads on 320 bp with the occurrence cut-off out of the way: bucket suffixes of more than
+    PG_CAP * PG_G = 1024 hits are staged in pieces (pairgen.cu, `skip`), reads with more than 2048 chains go on to the
+    HBM-table kernel, which decodes the same 32-bit hit words"""
+    b = small_cluster(29, n_fragments=1300, n_strains=1, strain_cov=1e9, insert_mean=160.0, insert_sd=2.0)
+    _, tm = check_candidates(ctx, b, mid_occ=5000)
+    assert tm["n_seed_hits"] > 1024 * b.n_reads
 
 
 def test_candidates_mid_occ_and_params(ctx):
