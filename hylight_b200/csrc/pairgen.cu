@@ -343,7 +343,6 @@ __global__ void __launch_bounds__(PG_THREADS, HLO_PG_MINB) pairgen_group_kernel(
         const unsigned long long nw = *a.n_work_ptr;
         n_work = nw < (unsigned long long)a.overflow_cap ? (uint32_t)nw : a.overflow_cap;
     }
-    const uint32_t *hits_l = a.hits32 + l;
     unsigned long long nh_total = 0;
     for (;;) {
         unsigned long long qq = 0;
@@ -374,7 +373,7 @@ __global__ void __launch_bounds__(PG_THREADS, HLO_PG_MINB) pairgen_group_kernel(
         const uint32_t w_self = qrel << kshift;       // a hit word that names the query itself: skipped (-X), also stands for "no hit"
         const uint32_t KQ = ql + (uint32_t)a.k - 2u;  // reverse-strand anchor position = KQ - pos
         uint32_t nh = 0;
-        bool ovf = false;
+        uint32_t ovf = 0;
         uint32_t mb = 0, skip = 0;  // minimizers staged so far; hits already taken from the first unstaged suffix
         while (__any_sync(FULL, mb < nm)) {
             // ---- stage: PG_RPL consecutive suffixes per lane -> chunk entries, as many suffixes as fit PG_CAP chunks
@@ -436,10 +435,10 @@ __global__ void __launch_bounds__(PG_THREADS, HLO_PG_MINB) pairgen_group_kernel(
             const uint32_t trips = __reduce_max_sync(FULL, n_chunks);
             // ---- chunks: PG_G hits of one minimizer each, loaded one chunk ahead
             auto fetch = [&](uint32_t c, uint32_t &meta, uint32_t &W) {
-                const uint2 e = stg[c];
-                meta = e.y;
+                const unsigned long long e = reinterpret_cast<const unsigned long long *>(stg)[c];  // (one 8-byte broadcast load)
+                meta = (uint32_t)(e >> 32);
                 W = w_self;
-                if (l < (e.y & 31u)) W = __ldg(hits_l + e.x);
+                if (l < (meta & 31u)) W = __ldg(a.hits32 + ((uint32_t)e + l));
             };
             auto fold = [&](uint32_t meta, uint32_t W) {
                 if ((W >> kshift) != qrel) {  // == : another minimizer of the query itself (-X: no self hits), or no hit in this lane
@@ -450,18 +449,11 @@ __global__ void __launch_bounds__(PG_THREADS, HLO_PG_MINB) pairgen_group_kernel(
                     const uint32_t key = Wx + max_len - qp;                      // the position field becomes diagonal + max_len
                     const uint32_t upd = 0xffff0000u - qp * 0xffffu;             // qp | (0xffff - qp) << 16
                     uint32_t slot = (key * 0x9E3779B1u) >> (32 - slots_log2);
-                    bool done = false;
-                    for (uint32_t probe = 0; probe < S; ++probe) {
-                        const uint32_t old = atomicCAS(&keys[slot], HLO_EMPTY32, key);
-                        if (old == HLO_EMPTY32 || old == key) {
-                            done = true;
-                            break;
-                        }
-                        slot = (slot + 1u) & smask;
-                    }
+                    uint32_t left = S, old;  // claim-or-find, at most S probes (a full table: the read is redone with a larger one)
+                    while ((old = atomicCAS(&keys[slot], HLO_EMPTY32, key)) != HLO_EMPTY32 && old != key && --left) slot = (slot + 1u) & smask;
                     HLO_DBG_ASSERT(slot < S && (W >> kshift) + cb < a.reads.n_reads && (key & (sbit - 1u)) < 2u * max_len);
-                    if (done) vals[slot] = __vminu2(vals[slot], upd);  // no other lane holds this key in this chunk
-                    else ovf = true;
+                    if (left) vals[slot] = __vminu2(vals[slot], upd);  // no other lane holds this key in this chunk
+                    else ovf = 1u;
                 }
                 __syncwarp();  // orders the value updates of consecutive chunks (they may belong to different minimizers)
             };
@@ -476,7 +468,7 @@ __global__ void __launch_bounds__(PG_THREADS, HLO_PG_MINB) pairgen_group_kernel(
             __syncwarp();  // the chunk area is rewritten by the next stage
         }
         // ---- the read's chains: slots whose anchors span at least gap_min
-        const bool ovf_any = ((__ballot_sync(FULL, ovf) >> gshift) & PG_GMASK) != 0u;
+        const bool ovf_any = ((__ballot_sync(FULL, ovf != 0u) >> gshift) & PG_GMASK) != 0u;
         if (ovf_any) {  // redo this read with a larger table, or exactly in the generic kernel (its hits are counted there)
             if (l == 0 && have_read) {
                 const unsigned long long p = atomicAdd(a.ovf_counter, 1ULL);
