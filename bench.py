@@ -362,7 +362,7 @@ def kernel_rooflines(stage_ms, cnt, peak, params, launches_per_batch):
     ms = {"pack": stage_ms["pack_ms"], "sketch": stage_ms["sketch_ms"], "sort": stage_ms["sort_ms"], "index": stage_ms["index_ms"],
           "pairgen": stage_ms["pairgen_ms"], "verify": stage_ms["verify_fast_ms"], "records_tail": stage_ms["dedup_ms"]}
     bound = {"pack": "hbm", "sketch": "integer ALU pipe (per-read window automaton, 64-bit hash)", "sort": "hbm / MATCH.ANY ranking",
-             "index": "L2 gather/scatter", "pairgen": "instruction issue (shared-memory table inserts)",
+             "index": "L2 gather/scatter", "pairgen": "shared-memory (LSU) data pipe + instruction issue (hash-table inserts: ATOMS.CAS)",
              "verify": "integer ALU pipe; rows served from L2", "records_tail": "L2 gathers"}
     total = sum(ms.values()) or 1.0
     out = []
@@ -611,8 +611,8 @@ def run_ours(args):
                     "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": traffic,
                     "peak_source": peak_src, "ms_per_launch": dom["ms_per_batch"],
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_batch"],
-                    "note": "the dominant kernel is bound by instruction issue, not by HBM: its `frac` of the HBM roofline is low by "
-                            "construction (8 B per seed hit); warp instructions per seed hit and lane use are in profiles/ (ncu). "
+                    "note": "the dominant kernel is bound by the shared-memory (LSU) data pipe and by instruction issue (81 % / 76 % of "
+                            "peak, `ncu` below), not by HBM: its `frac` of the HBM roofline is low by construction (8 B per seed hit). "
                             "`verify` below is the north-star kernel with its >= 60 % target.",
                     "verify_kernel": {"achieved": vf["achieved_gbs"], "frac": vf["frac_of_hbm_peak"], "ms_per_launch": vf["ms_per_batch"]},
                     "kernels": kernels, "launch": "one batch of %d clusters" % args.batch}
@@ -625,7 +625,8 @@ def run_ours(args):
             t = json.load(open(pj))
             roofline["traffic"] = int((t["dram_bytes_read"] + t["dram_bytes_write"]) * counts["n_seed_hits"] / float(t["seed_hits_per_launch"]))
             roofline["ncu"] = {k: t[k] for k in ("warp_instructions_per_seed_hit", "active_threads_per_warp_instruction", "ipc_per_sm",
-                                                 "issue_slots_used_pct", "alu_pipe_pct", "dram_pct_of_peak", "source")}
+                                                 "issue_slots_used_pct", "lsu_data_pipe_wavefronts_pct_of_peak", "alu_pipe_pct",
+                                                 "dram_pct_of_peak", "source") if k in t}
         digest_ok = dev_digest == (expected_digest * K) & M64 and e_dig == (expected_digest * K) & M64
         line = {"metric": METRIC, "value": dev_records / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong",
@@ -723,6 +724,34 @@ def files_leg(synth, distinct, args):
             for r in range(reps):
                 for c in range(n_in):
                     os.remove(os.path.join(d, "o_%s_%d_%d" % (mode, r, c)))
+            # the same job three times over (384 clusters): what the second and third copy cost says what a long job pays
+            # per overlap once the process is up (CUDA start-up and first-batch allocations are in the 128-cluster number)
+            big = 3 * reps
+            try:
+                room = base is not None and shutil.disk_usage(base).free > (12 << 30)
+            except Exception:  # noqa: BLE001
+                room = False
+            if room:
+                lst3 = os.path.join(d, "list3_%s.tsv" % mode)
+                with open(lst3, "w") as f:
+                    for r in range(big):
+                        for c in range(n_in):
+                            f.write("%s,%s\t%s\n" % (os.path.join(d, "c%d.1.fq" % c), os.path.join(d, "c%d.2.fq" % c),
+                                                     os.path.join(d, "o3_%s_%d_%d" % (mode, r, c))))
+                dt3 = None
+                for rep in range(2):
+                    t0 = time.perf_counter()
+                    subprocess.run([exe, "--clusters", lst3, "--rename", "--devices", "0", "--stats", stats] + flag, check=True, timeout=900)
+                    dt = time.perf_counter() - t0
+                    dt3 = dt if dt3 is None else min(dt3, dt)
+                n3 = sum(r["records"] for r in (json.loads(l) for l in open(stats)) if not r.get("summary"))
+                out[mode]["x3"] = {"clusters": n_in * big, "records": n3, "wall_s": dt3, "value": n3 / dt3,
+                                   "marginal_value": (n3 - n_rec) / (dt3 - best) if dt3 > best * 1.05 else None,
+                                   "marginal": "records of the extra 256 clusters / extra wall time over the 128-cluster job (best of 2 "
+                                               "against best of 3; null when start-up noise swamps the difference)"}
+                for r in range(big):
+                    for c in range(n_in):
+                        os.remove(os.path.join(d, "o3_%s_%d_%d" % (mode, r, c)))
     out["note"] = "wall clock of the whole process incl. CUDA start-up (~0.5 s); inputs and outputs on %s" % (base or "the default temp dir")
     return out
 
