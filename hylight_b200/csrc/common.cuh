@@ -70,6 +70,7 @@ enum Ctr : int {
     C_MIDOCC_LO,    // smallest / largest per-cluster occurrence cut-off of the batch
     C_MIDOCC_HI,
     C_SK_TIE,       // reads in which the lean sketch automaton met equal keys: redone by the complete one
+    C_BIG_GROUPS,   // idA groups too large for the quadratic rule of the records tail (listed for group_rank_big_kernel)
     C_COUNT = 32
 };
 #define HLO_PG_PASSES 5

@@ -962,7 +962,9 @@ static int enqueue_tail(hlo_ctx *ctx, const hlo_reads *R) {
     launch_exclusive_scan(g_cnt, g_off, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), nullptr, s, &ctx->lc);
     launch_group_scatter(rec, n_ptr, cap, d, g_off, g_slot, g_ent, g_entg, s, &ctx->lc);
     uint32_t *g_lt = g_slot;  // (the slots are consumed by the scatter)
-    launch_group_mark(rec, n_ptr, cap, d, R->b_coff.as<uint32_t>(), g_off, g_entg, 1, g_ent, g_uniq, g_lt, s, &ctx->lc);
+    CK(cudaMemsetAsync(ctr(ctx, C_BIG_GROUPS), 0, sizeof(unsigned long long), s));  // (the tail may run twice per batch)
+    // (the per-group counts are consumed by the scan: their array takes the list of large groups)
+    launch_group_mark(rec, n_ptr, cap, d, R->b_coff.as<uint32_t>(), g_off, g_entg, 1, g_ent, g_uniq, g_lt, g_cnt, ctr(ctx, C_BIG_GROUPS), s, &ctx->lc);
     launch_exclusive_scan(g_uniq, g_uoff, (uint64_t)ng + 1, ctx->b_tmp.as<uint32_t>(), reinterpret_cast<uint32_t *>(ctr(ctx, C_NOUT)), s, &ctx->lc);
     ExpandOut eo;
     if (need_rec) eo.out = ctx->b_out.as<hlo_rec>();

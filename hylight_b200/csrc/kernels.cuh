@@ -154,7 +154,8 @@ void launch_group_count(const Rec16 *rec, const unsigned long long *n_ptr, uint6
 void launch_group_scatter(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *off,
                           const uint32_t *slot, uint2 *ent, uint32_t *entg, cudaStream_t s, LaunchCounter *lc);
 void launch_group_mark(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *cluster_off, const uint32_t *off,
-                       const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq, uint32_t *lt, cudaStream_t s, LaunchCounter *lc);
+                       const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq, uint32_t *lt, uint32_t *big_list, unsigned long long *big_cnt,
+                       cudaStream_t s, LaunchCounter *lc);  // big_list: n_reads words, *big_cnt zeroed by the caller
 void launch_group_expand(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *off, const uint32_t *uoff,
                          const uint32_t *entg, const uint2 *ent, const uint32_t *lt, const ExpandOut &o, cudaStream_t s, LaunchCounter *lc);
 void launch_cluster_offsets(const uint32_t *uoff, const uint32_t *cluster_off, uint32_t n_clusters, unsigned long long *coff, cudaStream_t s,

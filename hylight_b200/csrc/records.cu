@@ -88,7 +88,8 @@ void launch_group_scatter(const Rec16 *rec, const unsigned long long *n_ptr, uin
 __global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__restrict__ rec, const unsigned long long *__restrict__ n_ptr,
                                                                 uint64_t n_cap, const uint32_t *__restrict__ off,
                                                                 const uint32_t *__restrict__ entg, int dedup, uint2 *ent,
-                                                                uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out, int big_groups) {
+                                                                uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out, int big_groups,
+                                                                uint32_t *__restrict__ big_list, unsigned long long *__restrict__ big_cnt) {
     const uint64_t n = tail_n(n_ptr, n_cap);
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint2 me = ent[p];
@@ -96,7 +97,10 @@ __global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__r
         bool keep = true;
         uint32_t lt = 0;  // entries of the group with a smaller idB: my place in the group when it holds no duplicate pair
         const uint32_t b = off[g], e = off[g + 1];
-        if (big_groups && e - b > GB_MIN) continue;  // group_rank_big_kernel ranks the large groups (this loop is quadratic per group)
+        if (big_groups && e - b > GB_MIN) {  // group_rank_big_kernel ranks the large groups (this loop is quadratic per group):
+            if (p == b) big_list[atomicAdd(big_cnt, 1ULL)] = g;  // its first entry lists it
+            continue;
+        }
         for (uint32_t j = b; j < e; ++j) {
             const uint2 y = ent[j];
             lt += y.x < me.x;
@@ -118,22 +122,23 @@ __global__ void __launch_bounds__(RT_THREADS) group_mark_kernel(const Rec16 *__r
 // bit = "some entry has this idB"; the number of set bits below an entry's idB is the entry's final place, distinct idB
 // counted once.  Linear in the group size.  A group that holds the same pair twice (the count of entries exceeds the set
 // bits) is rare: its warp runs the quadratic rule.  Clusters of more than GB_MAX_CLUSTER reads do not fit the bitmap
-// and stay with the pass above.
+// and stay with the pass above.  The large groups come as a list (group_mark_kernel's), one warp per list entry: deep
+// clusters put their large groups next to each other (groups are in name order), and a warp that scanned a window of
+// consecutive groups had them all to itself.
 constexpr uint32_t GB_WARPS = 4, GB_MAX_CLUSTER = 65536, GB_WORDS = GB_MAX_CLUSTER / 32;
 __global__ void __launch_bounds__(GB_WARPS * 32) group_rank_big_kernel(const Rec16 *__restrict__ rec, DevReads r, const uint32_t *__restrict__ off,
                                                                        const uint32_t *__restrict__ cluster_off, int dedup, uint2 *ent,
-                                                                       uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out) {
+                                                                       uint32_t *__restrict__ uniq, uint32_t *__restrict__ lt_out,
+                                                                       const uint32_t *__restrict__ big_list,
+                                                                       const unsigned long long *__restrict__ big_cnt) {
     __shared__ uint32_t bm[GB_WARPS][GB_WORDS];  // bitmap, then (in place) the exclusive prefix of its popcounts per 32 words
     __shared__ uint32_t pre[GB_WARPS][GB_WORDS / 32 + 1];
     const unsigned lane = threadIdx.x & 31, wp = threadIdx.x >> 5, FULL = 0xffffffffu;
-    const uint32_t n_groups = r.n_reads;
-    // a warp looks at 32 consecutive groups at a time (one per lane) and then takes the large ones among them one by one
-    for (uint32_t g0 = (blockIdx.x * GB_WARPS + wp) * 32; g0 < n_groups; g0 += gridDim.x * GB_WARPS * 32) {
-      const uint32_t gl = g0 + lane;
-      unsigned todo = __ballot_sync(FULL, gl < n_groups && off[gl + 1] - off[gl] > GB_MIN);
-      while (todo) {
-        const uint32_t g = g0 + (uint32_t)__ffs(todo) - 1u;
-        todo &= todo - 1u;
+    const unsigned long long n_big = *big_cnt;
+    for (unsigned long long bi = (unsigned long long)blockIdx.x * GB_WARPS + wp; bi < n_big; bi += (unsigned long long)gridDim.x * GB_WARPS) {
+      {
+        const uint32_t g = big_list[bi];
+        HLO_DBG_ASSERT(g < r.n_reads && off[g + 1] - off[g] > GB_MIN);
         const uint32_t b = off[g], e = off[g + 1], sz = e - b;
         const uint32_t cb = r.cbase[g], N = cluster_off[r.cidx[g] + 1] - cb;  // ranks of a cluster's names are cb .. cb + N - 1
         const uint32_t nw = (N + 31) / 32;
@@ -199,14 +204,15 @@ __global__ void __launch_bounds__(GB_WARPS * 32) group_rank_big_kernel(const Rec
 }
 
 void launch_group_mark(const Rec16 *rec, const unsigned long long *n_ptr, uint64_t n_cap, DevReads r, const uint32_t *cluster_off, const uint32_t *off,
-                       const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq, uint32_t *lt, cudaStream_t s, LaunchCounter *lc) {
+                       const uint32_t *entg, int dedup, uint2 *ent, uint32_t *uniq, uint32_t *lt, uint32_t *big_list, unsigned long long *big_cnt,
+                       cudaStream_t s, LaunchCounter *lc) {
     if (n_cap == 0) return;
     const int big = r.max_cluster <= GB_MAX_CLUSTER && r.n_reads > 0;
-    group_mark_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, off, entg, dedup, ent, uniq, lt, big);
+    group_mark_kernel<<<tail_grid(n_cap), RT_THREADS, 0, s>>>(rec, n_ptr, n_cap, off, entg, dedup, ent, uniq, lt, big, big_list, big_cnt);
     if (lc) lc->total++;
     if (big) {
-        const uint32_t want = (r.n_reads + GB_WARPS * 32 - 1) / (GB_WARPS * 32);
-        group_rank_big_kernel<<<want < 148u * 6 ? want : 148u * 6, GB_WARPS * 32, 0, s>>>(rec, r, off, cluster_off, dedup, ent, uniq, lt);
+        const uint32_t want = (r.n_reads + GB_WARPS - 1) / GB_WARPS;  // (an upper bound of the list; usually it is short and the grid leaves at once)
+        group_rank_big_kernel<<<want < 148u * 6 ? want : 148u * 6, GB_WARPS * 32, 0, s>>>(rec, r, off, cluster_off, dedup, ent, uniq, lt, big_list, big_cnt);
         if (lc) lc->total++;
     }
 }
