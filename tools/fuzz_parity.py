@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Randomised parity sweep: hlo_submit / hlo_wait on the GPU against the CPU oracle, record for record, on batches the
+fixed tests do not enumerate — ragged read lengths (30 .. 600 bp in one batch), several clusters of very different
+depth, ambiguous and lower-case bases, low-complexity inserts, random (k, w), thresholds, pair rules, occurrence
+cut-offs and pair-generator table sizes.
+
+    python tools/fuzz_parity.py [--seconds 150] [--seed 1] > profiles/rN_fuzz.log
+
+Exit status 0 and a final "N batches, all identical" line, or the first differing batch with its seed.
+(oracle/ is the checker here, as in tests/: this is test infrastructure.)
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from hylight_b200 import api, synth  # noqa: E402
+from oracle import orc  # noqa: E402
+from util import to_orc_batch  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--seconds", type=float, default=150.0)
+ap.add_argument("--seed", type=int, default=1)
+args = ap.parse_args()
+
+
+def mutate(rng, b, n_rate, lower_rate, lowc_rate):
+    """ambiguous bases, lower case, and low-complexity stretches written over the reads of a batch"""
+    bases = np.array(b.bases, dtype=np.uint8, copy=True)
+    if n_rate:
+        bases[rng.random(len(bases)) < n_rate] = ord("N")
+    if lower_rate:
+        m = rng.random(len(bases)) < lower_rate
+        bases[m] |= 0x20
+    if lowc_rate:
+        off = np.asarray(b.base_off, dtype=np.int64)
+        for r in np.nonzero(rng.random(len(off) - 1) < lowc_rate)[0]:
+            L = int(off[r + 1] - off[r])
+            if L < 40:
+                continue
+            unit = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(rng.integers(1, 7)))]
+            n = int(rng.integers(20, L))
+            s = int(rng.integers(0, L - n + 1))
+            bases[off[r] + s: off[r] + s + n] = np.resize(unit, n)
+    return synth.ReadBatch(bases, b.base_off, b.cluster_off)
+
+
+def ragged(rng, b, lo):
+    """cut every read at a random length >= lo (a batch then mixes many lengths; offsets are rebuilt)"""
+    off = np.asarray(b.base_off, dtype=np.int64)
+    keep, new_off = [], [0]
+    for r in range(len(off) - 1):
+        L = int(off[r + 1] - off[r])
+        n = L if rng.random() < 0.5 else int(rng.integers(min(lo, L), L + 1))
+        keep.append(np.arange(off[r], off[r] + n))
+        new_off.append(new_off[-1] + n)
+    return synth.ReadBatch(np.asarray(b.bases, dtype=np.uint8)[np.concatenate(keep)], np.asarray(new_off, dtype=np.uint64), b.cluster_off)
+
+
+rng = np.random.default_rng(args.seed)
+t_end = time.time() + args.seconds
+n_batches = n_records = 0
+while time.time() < t_end:
+    seed = int(rng.integers(1, 1 << 30))
+    r = np.random.default_rng(seed)
+    k = int(r.choice([15, 17, 19, 21, 21, 21, 23]))
+    w = int(r.choice([5, 8, 11, 11, 11, 14]))
+    pkw = dict(k=k, w=w, min_ovlp_len=int(r.choice([30, 50, 60, 60, 90])), min_identity=float(r.choice([0.9, 0.95, 0.98, 0.98, 0.99])),
+               max_overhang=int(r.choice([0, 1, 1, 2, 4])), pair_rule=int(r.choice([0, 0, 1])),
+               mid_occ=int(r.choice([0, 0, 0, 10, 25, 1000])), min_seeds=int(r.choice([1, 2, 2, 3])),
+               min_chain_score=int(r.choice([k, 30, 30, 40])))
+    clusters = []
+    for c in range(int(r.integers(1, 5))):
+        read_len = int(r.choice([60, 100, 150, 150, 250, 400, 600]))
+        clusters.append(synth.cluster_batch(1, seed0=seed + c, n_fragments=int(r.integers(3, 260)), read_len=read_len,
+                                            n_strains=int(r.integers(1, 5)), strain_cov=float(r.choice([4.0, 8.0, 15.0, 40.0])),
+                                            snp_rate=float(r.choice([0.0, 0.005, 0.01, 0.03])), err_rate=float(r.choice([0.0, 0.002, 0.005, 0.02])),
+                                            insert_mean=float(max(read_len + 20, r.choice([200.0, 450.0, 900.0])))))
+    b = synth.ReadBatch.concat(clusters)
+    if r.random() < 0.5:
+        b = ragged(r, b, 30)
+    b = mutate(r, b, float(r.choice([0.0, 0.0, 0.002, 0.02])), float(r.choice([0.0, 0.0, 0.1])), float(r.choice([0.0, 0.0, 0.05, 0.3])))
+    slots = int(r.choice([8, 8, 8, 6, 5]))
+    try:
+        rec_o, blk_o, coff_o, st = orc.overlap_batch(to_orc_batch(b), orc.default_params(**pkw))
+        with api.Context(0, **pkw) as c:
+            c.set_option("pairgen_slots_log2", slots)
+            c.submit(b)
+            rec, aux, coff = c.wait()
+            tm = c.timing()
+            pk = api.pack2b(b)
+            c.submit_packed(pk, b.cluster_off)
+            rec_p, _, coff_p = c.wait()
+    except api.HloError as e:  # a refusal with a message is a result too — but then the oracle path must not have been asked
+        print("seed %d: refused: %s  %s" % (seed, e, pkw))
+        continue
+    same = (np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o) and np.array_equal(aux["blocklen"], blk_o) and
+            np.array_equal(rec_p, rec_o) and np.array_equal(coff_p, coff_o) and
+            tm["n_candidates"] == st["candidates"] and tm["n_accepted"] == st["accepted"] and tm["n_seed_hits"] == st["seed_hits"])
+    if not same:
+        print("DIFFERENT: seed %d params %s slots %d: %d vs %d records, candidates %d vs %d, hits %d vs %d"
+              % (seed, pkw, slots, len(rec), len(rec_o), tm["n_candidates"], st["candidates"], tm["n_seed_hits"], st["seed_hits"]))
+        sys.exit(1)
+    n_batches += 1
+    n_records += len(rec_o)
+    if n_batches % 20 == 0:
+        print("%d batches, %d records so far (last: %d reads, %d clusters, k=%d w=%d, %d overflow reads, %d deferred)"
+              % (n_batches, n_records, b.n_reads, b.n_clusters, k, w, tm["n_overflow_reads"], tm["n_deferred"]), flush=True)
+print("%d batches, %d records, all identical to the oracle (ASCII and packed input)" % (n_batches, n_records))
