@@ -99,20 +99,28 @@ struct CandI {
     uint32_t q, t, z, w;
 };
 #define HLO_REGION_CAP 127
+#define HLO_CAND_FAR (1u << 30)  // CandI.w: an end region is longer than HLO_REGION_CAP; the true lengths are in the side array
+// *far (when not null) receives el | er << 16, the uncapped distances from the overlap ends to the outermost anchors, for
+// a candidate flagged HLO_CAND_FAR: the exact verify kernel extends from the true anchors (an extension that starts 127
+// bases from the end instead of, say, 300 can stop elsewhere when mismatches lie in between); the fast kernel only ever
+// looks at whether a region covers its 32-base window.
 __host__ __device__ __forceinline__ CandI make_candi(uint32_t q, uint32_t t, int diag, uint32_t strand, uint32_t ql, uint32_t tl,
-                                                     int a_start, int a_end, uint32_t amb) {
+                                                     int a_start, int a_end, uint32_t amb, uint32_t *far = nullptr) {
     const int js = diag < 0 ? -diag : 0;
     const int je = (int)ql < (int)tl - diag ? (int)ql : (int)tl - diag;
     if (a_end == 0) a_start = je, a_end = js;  // no anchor information: each end region is the whole overlap
     if (a_start < js) a_start = js;
     if (a_end > je) a_end = je;
     int el = a_start - js, er = je - a_end;
-    el = el < 0 ? 0 : (el > HLO_REGION_CAP ? HLO_REGION_CAP : el);
-    er = er < 0 ? 0 : (er > HLO_REGION_CAP ? HLO_REGION_CAP : er);
+    el = el < 0 ? 0 : el, er = er < 0 ? 0 : er;
+    const bool is_far = el > HLO_REGION_CAP || er > HLO_REGION_CAP;
+    if (is_far && far) *far = (uint32_t)el | (uint32_t)er << 16;
+    el = el > HLO_REGION_CAP ? HLO_REGION_CAP : el;
+    er = er > HLO_REGION_CAP ? HLO_REGION_CAP : er;
     CandI c;
     c.q = q, c.t = t;
     c.z = (uint32_t)(diag + 32768) | ql << 16 | strand << 31;
-    c.w = tl | (uint32_t)el << 15 | (uint32_t)er << 22 | (amb & 1u) << 29;
+    c.w = tl | (uint32_t)el << 15 | (uint32_t)er << 22 | (amb & 1u) << 29 | (is_far && far ? HLO_CAND_FAR : 0u);
     return c;
 }
 

@@ -133,7 +133,7 @@ struct hlo_ctx {
     VerifyTables tab{};
     // workspaces
     DevBuf b_cnt, b_mzoff, b_mzx, b_mzrr, b_keys[2], b_vals[2], b_tmp, b_flags, b_bid, b_range, b_hits, b_midocc, b_hist, b_seg1;
-    DevBuf b_cands, b_counters, b_ovf, b_ovf2, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
+    DevBuf b_cands, b_candfar, b_counters, b_ovf, b_ovf2, b_ovfcnt, b_gkeys, b_gmn, b_gmx, b_goff;
     DevBuf b_rec16, b_deferred, b_best, b_pos, b_slot, b_ent, b_entg, b_out, b_outc, b_aux, b_coff, b_mz, b_candx, b_sx, b_srp;
     DevBuf b_qual, b_screc, b_scclu, b_scout, b_prob;
     PinBuf h_score;
@@ -315,7 +315,7 @@ void hlo_ctx_destroy(hlo_ctx *ctx) {
     }
     DevBuf *bufs[] = {&ctx->b_tab, &ctx->b_cnt, &ctx->b_mzoff, &ctx->b_mzx, &ctx->b_mzrr, &ctx->b_keys[0], &ctx->b_keys[1], &ctx->b_vals[0],
                       &ctx->b_vals[1], &ctx->b_tmp, &ctx->b_flags, &ctx->b_bid, &ctx->b_range, &ctx->b_hits, &ctx->b_midocc, &ctx->b_hist,
-                      &ctx->b_seg1, &ctx->b_cands, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovf2, &ctx->b_ovfcnt, &ctx->b_gkeys, &ctx->b_gmn,
+                      &ctx->b_seg1, &ctx->b_cands, &ctx->b_candfar, &ctx->b_counters, &ctx->b_ovf, &ctx->b_ovf2, &ctx->b_ovfcnt, &ctx->b_gkeys, &ctx->b_gmn,
                       &ctx->b_gmx, &ctx->b_goff, &ctx->b_rec16, &ctx->b_deferred, &ctx->b_best, &ctx->b_pos, &ctx->b_slot, &ctx->b_ent,
                       &ctx->b_entg, &ctx->b_out, &ctx->b_outc, &ctx->b_aux, &ctx->b_coff, &ctx->b_mz, &ctx->b_candx, &ctx->b_sx, &ctx->b_srp,
                       &ctx->b_qual, &ctx->b_screc, &ctx->b_scclu, &ctx->b_scout, &ctx->b_prob};
@@ -811,6 +811,7 @@ static PairgenArgs pairgen_args(hlo_ctx *ctx, const hlo_reads *R, int external) 
     a.external = external;
     a.hits32 = ctx->pg_dg_bits ? ctx->b_hits.as<uint32_t>() : nullptr;
     a.cands = ctx->b_cands.p, a.cand_cap = ctx->cap_c;
+    a.cand_far = ctx->b_candfar.as<uint32_t>();
     a.cand_counter = ctr(ctx, C_CAND), a.hit_counter = ctr(ctx, C_HITS);
     a.ovf_counter = ctr(ctx, C_PG_OVF), a.work_counter = ctr(ctx, C_PG_WORK);
     a.overflow_reads = ctx->b_ovf.as<uint32_t>(), a.overflow_cap = d.n_reads;
@@ -829,6 +830,7 @@ static int enqueue_pairgen(hlo_ctx *ctx, const hlo_reads *R, int external) {
     CK(ctx->b_ovf.ensure((size_t)d.n_reads * 4 + 4));
     CK(ctx->b_ovf2.ensure((size_t)d.n_reads * 4 + 4));
     CK(ctx->b_cands.ensure(ctx->cap_c * 16 + 16));
+    CK(ctx->b_candfar.ensure(ctx->cap_c * 4 + 16));
     PairgenArgs a = pairgen_args(ctx, R, external);
     ctx->fast_pairgen = ctx->pg_dg_bits > 0 && d.n_reads > 0;
     ctx->n_pg_passes = 0;
@@ -909,7 +911,7 @@ static int enqueue_verify(hlo_ctx *ctx, const hlo_reads *R, uint64_t n_cap) {
     CK(cudaMemsetAsync(ctr(ctx, C_ACC), 0, 2 * sizeof(unsigned long long), s));  // C_ACC, C_DEF (a second verify after the generic pair generator starts over)
     VerifyArgs a;
     a.reads = R->d, a.tab = ctx->tab, a.prm = verify_params(ctx);
-    a.cands = ctx->b_cands.as<CandI>();
+    a.cands = ctx->b_cands.as<CandI>(), a.cand_far = ctx->b_candfar.as<uint32_t>();
     a.n_ptr = ctr(ctx, C_CAND), a.n_cap = n_cap;
     a.out = ctx->b_rec16.as<Rec16>(), a.out_cap = ctx->cap_a;
     a.acc_counter = ctr(ctx, C_ACC), a.def_counter = ctr(ctx, C_DEF);
@@ -1385,12 +1387,13 @@ int hlo_verify(hlo_ctx *ctx, const hlo_reads *R, const hlo_cand *cands, uint64_t
     ctx->cap_c = n, ctx->cap_a = n;
     CK(ctx->b_candx.ensure(n * sizeof(hlo_cand) + 16));
     CK(ctx->b_cands.ensure(n * sizeof(CandI) + 16));
+    CK(ctx->b_candfar.ensure(n * 4 + 16));
     CK(ctx->h_small.ensure(64));
     CK(cudaMemsetAsync(ctr(ctx, 1), 0, sizeof(unsigned long long) * (C_COUNT - 1), s));
     *ctx->h_small.as<unsigned long long>() = n;
     CK(cudaMemcpyAsync(ctr(ctx, C_CAND), ctx->h_small.p, 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->b_candx.p, cands, n * sizeof(hlo_cand), cudaMemcpyHostToDevice, s));
-    launch_cands_to_internal(ctx->b_candx.as<hlo_cand>(), n, R->d, ctx->b_cands.as<CandI>(), s, &ctx->lc);
+    launch_cands_to_internal(ctx->b_candx.as<hlo_cand>(), n, R->d, ctx->b_cands.as<CandI>(), ctx->b_candfar.as<uint32_t>(), s, &ctx->lc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[ST_PAIRGEN], s));
     int rc = enqueue_verify(ctx, R, n);

@@ -100,6 +100,7 @@ struct PairgenArgs {
     int dg_bits;             // bits of (diagonal + max_len) in the 32-bit table key (>= 5)
     int external;            // 1: emit hlo_cand (exact anchor span), 0: emit CandI
     void *cands;             // output, 16 B per candidate
+    uint32_t *cand_far = nullptr;  // [cand_cap] true end-region lengths of the candidates flagged HLO_CAND_FAR (internal form only)
     uint64_t cand_cap;
     unsigned long long *cand_counter, *hit_counter;  // candidates (counted past cand_cap too), seed hits
     unsigned long long *ovf_counter;                 // reads whose table overflowed in this pass
@@ -126,6 +127,7 @@ struct VerifyArgs {
     VerifyTables tab;
     VerifyParams prm;
     const CandI *cands;
+    const uint32_t *cand_far = nullptr;  // side array of the candidates flagged HLO_CAND_FAR (same index)
     const unsigned long long *n_ptr;  // candidates: a device counter (the pair generator's), clamped to n_cap
     uint64_t n_cap;
     Rec16 *out;                    // accepted records (unordered)
@@ -137,7 +139,7 @@ bool verify_fast_supported(const DevReads &r, const VerifyTables &tab);
 void launch_verify_fast(const VerifyArgs &a, cudaStream_t s, LaunchCounter *lc);
 // exact per-candidate path: every candidate, or the candidates the fast kernel deferred
 void launch_verify_exact(const VerifyArgs &a, bool all_cands, cudaStream_t s, LaunchCounter *lc);
-void launch_cands_to_internal(const hlo_cand *in, uint64_t n, const DevReads &r, CandI *out, cudaStream_t s, LaunchCounter *lc);
+void launch_cands_to_internal(const hlo_cand *in, uint64_t n, const DevReads &r, CandI *out, uint32_t *far, cudaStream_t s, LaunchCounter *lc);
 
 // ---- records.cu -----------------------------------------------------------------------------
 // group the accepted records by idA, sort the small groups by idB, keep the best record of every pair.

@@ -273,8 +273,10 @@ __device__ __forceinline__ void emit_cand(const PairgenArgs &a, unsigned long lo
     if (a.external) {
         o = make_uint4(q, t, (uint32_t)diag, HLO_CAND_PACK(strand, a_start, a_end));
     } else {
-        const CandI c = make_candi(q, t, diag, strand, ql, tl, a_start, a_end, amb);
+        uint32_t far = 0;
+        const CandI c = make_candi(q, t, diag, strand, ql, tl, a_start, a_end, amb, &far);
         o = make_uint4(c.q, c.t, c.z, c.w);
+        if (c.w & HLO_CAND_FAR) a.cand_far[p] = far;  // (rare: an anchor more than 127 bases from its overlap end)
     }
     reinterpret_cast<uint4 *>(a.cands)[p] = o;
 }

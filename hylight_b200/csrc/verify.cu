@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
     const uint64_t a_n = n_dev < a.n_cap ? n_dev : a.n_cap;
     const uint64_t n_round = (a_n + 31) & ~31ull;  // whole warps iterate together
     const int o = a.prm.max_overhang, min_len = a.prm.min_len, defer_mm = a.prm.defer_mm;
-    const int o_reject = PR ? 33 : o;
     uint64_t c = (uint64_t)blockIdx.x * VF_THREADS + threadIdx.x;
     if (c >= n_round) return;  // (after the only block barrier)
     uint4 cv_next = make_uint4(0u, 0u, 0u, 0u);
@@ -164,12 +163,15 @@ __global__ void __launch_bounds__(VF_THREADS) verify_fast_kernel(VerifyArgs a) {
 #pragma unroll
                     for (int i = 0; i + 1 < W; i += 2) mm += __popc(f[i] | (f[i + 1] << 1));
                     if (W & 1) mm += __popc(f[W - 1]);
-                    // cheap exact reject: the block keeps at least mm - o mismatches (pair_rule 1: a flagged row may lose up
-                    // to a window of them) and is at most OL long
-                    if (mm <= (int)t_max_k[OL] + o_reject) {
+                    // cheap exact reject: the block is at most OL long and keeps at least mm - o mismatches.  pair_rule 1 also
+                    // wants the rows that fail the overhang test, and those may clip away any number of mismatches — but never
+                    // more than one per clipped base, and a block of min_len bases must remain: a row with more than
+                    // max_k + (OL - min_len) mismatches cannot pass; between a window's worth and that bound the exact kernel decides
+                    const int max_k = (int)t_max_k[OL];
+                    if (mm <= max_k + (PR ? OL - min_len : o)) {
                         int cl = 0, cmm = 0;
                         bool ok = true;
-                        if (mm >= defer_mm) {
+                        if (mm >= defer_mm || (PR && mm > max_k + 33)) {
                             ok = false, defer = true;  // enough bad columns to cost a query-limited end its end bonus: the exact rule decides
                         } else if (mm > 0 && (left_t || right_t)) {
                             if (mm > a.prm.bad_limit) {
@@ -278,7 +280,11 @@ __device__ __forceinline__ void verify_exact_one(const VerifyArgs &a, uint64_t c
     const int D = (int)(cd.z & 0xffffu) - 32768;
     const uint32_t strand = cd.z >> 31;
     const int ql = (int)((cd.z >> 16) & 0x7fffu), tl = (int)(cd.w & 0x7fffu);
-    const int EL = (int)((cd.w >> 15) & 0x7fu), ER = (int)((cd.w >> 22) & 0x7fu);
+    int EL = (int)((cd.w >> 15) & 0x7fu), ER = (int)((cd.w >> 22) & 0x7fu);
+    if (cd.w & HLO_CAND_FAR) {  // a region longer than the 7-bit fields hold: the true lengths
+        const uint32_t far = a.cand_far[c];
+        EL = (int)(far & 0xffffu), ER = (int)(far >> 16);
+    }
     const bool ambf = ((cd.w >> 29) & 1u) != 0;
     const int js = D < 0 ? -D : 0, je = min(ql, tl - D);
     if (je <= js) return;
@@ -289,7 +295,7 @@ __device__ __forceinline__ void verify_exact_one(const VerifyArgs &a, uint64_t c
     const uint32_t *T = a.reads.bases + (uint64_t)t * a.reads.stride_w;
     const uint32_t *QA = a.reads.amb + (uint64_t)strand * plane + (uint64_t)q * a.reads.stride_w;
     const uint32_t *TA = a.reads.amb + (uint64_t)t * a.reads.stride_w;
-    // the regions between the overlap ends and the outermost anchors, capped at HLO_REGION_CAP bases
+    // the regions between the overlap ends and the outermost anchors
     const int aS = min(js + EL, je), aE = max(je - ER, js);
     const int A = a.prm.a, B = a.prm.b, N = a.prm.n;
     int cl = 0, cr = 0;
@@ -372,17 +378,18 @@ void launch_verify_exact(const VerifyArgs &a, bool all_cands, cudaStream_t s, La
 }
 
 // hlo_cand (ABI) -> CandI, for caller-supplied candidate lists
-__global__ void cands_to_internal_kernel(const hlo_cand *__restrict__ in, uint64_t n, DevReads r, CandI *__restrict__ out) {
+__global__ void cands_to_internal_kernel(const hlo_cand *__restrict__ in, uint64_t n, DevReads r, CandI *__restrict__ out,
+                                         uint32_t *__restrict__ far) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const hlo_cand c = in[i];
     const uint32_t lq = r.len[c.q], lt = r.len[c.t];
     out[i] = make_candi(c.q, c.t, c.diag, c.strand_anchor & 1u, lq & 0x7fffu, lt & 0x7fffu, (int)((c.strand_anchor >> 1) & 0x7fffu),
-                        (int)(c.strand_anchor >> 16), (lq | lt) >> 31);
+                        (int)(c.strand_anchor >> 16), (lq | lt) >> 31, far + i);
 }
-void launch_cands_to_internal(const hlo_cand *in, uint64_t n, const DevReads &r, CandI *out, cudaStream_t s, LaunchCounter *lc) {
+void launch_cands_to_internal(const hlo_cand *in, uint64_t n, const DevReads &r, CandI *out, uint32_t *far, cudaStream_t s, LaunchCounter *lc) {
     if (n == 0) return;
-    cands_to_internal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, n, r, out);
+    cands_to_internal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, n, r, out, far);
     if (lc) lc->total++;
 }
 

@@ -23,12 +23,6 @@ from hylight_b200 import api, synth  # noqa: E402
 from oracle import orc  # noqa: E402
 from util import to_orc_batch  # noqa: E402
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--seconds", type=float, default=150.0)
-ap.add_argument("--seed", type=int, default=1)
-args = ap.parse_args()
-
-
 def mutate(rng, b, n_rate, lower_rate, lowc_rate):
     """ambiguous bases, lower case, and low-complexity stretches written over the reads of a batch"""
     bases = np.array(b.bases, dtype=np.uint8, copy=True)
@@ -62,11 +56,9 @@ def ragged(rng, b, lo):
     return synth.ReadBatch(np.asarray(b.bases, dtype=np.uint8)[np.concatenate(keep)], np.asarray(new_off, dtype=np.uint64), b.cluster_off)
 
 
-rng = np.random.default_rng(args.seed)
-t_end = time.time() + args.seconds
-n_batches = n_records = 0
-while time.time() < t_end:
-    seed = int(rng.integers(1, 1 << 30))
+def make_case(seed):
+    """the batch, the parameters and the pair-generator table size of one seed (tests/test_gpu_fuzz_cases.py replays the seeds
+    that once differed)"""
     r = np.random.default_rng(seed)
     k = int(r.choice([15, 17, 19, 21, 21, 21, 23]))
     w = int(r.choice([5, 8, 11, 11, 11, 14]))
@@ -86,29 +78,69 @@ while time.time() < t_end:
         b = ragged(r, b, 30)
     b = mutate(r, b, float(r.choice([0.0, 0.0, 0.002, 0.02])), float(r.choice([0.0, 0.0, 0.1])), float(r.choice([0.0, 0.0, 0.05, 0.3])))
     slots = int(r.choice([8, 8, 8, 6, 5]))
-    try:
-        rec_o, blk_o, coff_o, st = orc.overlap_batch(to_orc_batch(b), orc.default_params(**pkw))
-        with api.Context(0, **pkw) as c:
-            c.set_option("pairgen_slots_log2", slots)
-            c.submit(b)
-            rec, aux, coff = c.wait()
-            tm = c.timing()
-            pk = api.pack2b(b)
-            c.submit_packed(pk, b.cluster_off)
-            rec_p, _, coff_p = c.wait()
-    except api.HloError as e:  # a refusal with a message is a result too — but then the oracle path must not have been asked
-        print("seed %d: refused: %s  %s" % (seed, e, pkw))
-        continue
+    return b, pkw, slots
+
+
+def run_case(seed):
+    """(same?, text) for one seed; raises api.HloError when the library refuses the parameters"""
+    b, pkw, slots = make_case(seed)
+    rec_o, blk_o, coff_o, st = orc.overlap_batch(to_orc_batch(b), orc.default_params(**pkw))
+    with api.Context(0, **pkw) as c:
+        c.set_option("pairgen_slots_log2", slots)
+        c.submit(b)
+        rec, aux, coff = c.wait()
+        tm = c.timing()
+        pk = api.pack2b(b)
+        c.submit_packed(pk, b.cluster_off)
+        rec_p, _, coff_p = c.wait()
     same = (np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o) and np.array_equal(aux["blocklen"], blk_o) and
             np.array_equal(rec_p, rec_o) and np.array_equal(coff_p, coff_o) and
             tm["n_candidates"] == st["candidates"] and tm["n_accepted"] == st["accepted"] and tm["n_seed_hits"] == st["seed_hits"])
-    if not same:
-        print("DIFFERENT: seed %d params %s slots %d: %d vs %d records, candidates %d vs %d, hits %d vs %d"
-              % (seed, pkw, slots, len(rec), len(rec_o), tm["n_candidates"], st["candidates"], tm["n_seed_hits"], st["seed_hits"]))
-        sys.exit(1)
-    n_batches += 1
-    n_records += len(rec_o)
-    if n_batches % 20 == 0:
-        print("%d batches, %d records so far (last: %d reads, %d clusters, k=%d w=%d, %d overflow reads, %d deferred)"
-              % (n_batches, n_records, b.n_reads, b.n_clusters, k, w, tm["n_overflow_reads"], tm["n_deferred"]), flush=True)
-print("%d batches, %d records, all identical to the oracle (ASCII and packed input)" % (n_batches, n_records))
+    info = dict(b=b, pkw=pkw, slots=slots, rec=rec, rec_o=rec_o, rec_p=rec_p, tm=tm, st=st)
+    return same, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=150.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--replay", type=int, default=0, help="run the batch of this seed only and print what differs")
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    t_end = time.time() + args.seconds
+    n_batches = n_records = 0
+    while time.time() < t_end:
+        seed = args.replay or int(rng.integers(1, 1 << 30))
+        try:
+            same, x = run_case(seed)
+        except api.HloError as e:  # a refusal with a message is a result too
+            print("seed %d: refused: %s" % (seed, e))
+            if args.replay:
+                break
+            continue
+        b, pkw, slots, rec, rec_o, rec_p, tm, st = (x[k] for k in ("b", "pkw", "slots", "rec", "rec_o", "rec_p", "tm", "st"))
+        if not same:
+            print("DIFFERENT: seed %d params %s slots %d: %d vs %d records, candidates %d vs %d, hits %d vs %d, accepted %d vs %d, packed input %d records"
+                  % (seed, pkw, slots, len(rec), len(rec_o), tm["n_candidates"], st["candidates"], tm["n_seed_hits"], st["seed_hits"],
+                     tm["n_accepted"], st["accepted"], len(rec_p)))
+            got = {tuple(int(v) for v in r_) for r_ in rec.tolist()}
+            want = {tuple(int(v) for v in r_) for r_ in rec_o.tolist()}
+            print("fields:", rec_o.dtype.names)
+            for r_ in sorted(want - got)[:10]:
+                print("  only the oracle:", r_)
+            for r_ in sorted(got - want)[:10]:
+                print("  only the GPU:   ", r_)
+            sys.exit(1)
+        if args.replay:
+            print("seed %d: identical (%d records)" % (seed, len(rec_o)))
+            return
+        n_batches += 1
+        n_records += len(rec_o)
+        if n_batches % 20 == 0:
+            print("%d batches, %d records so far (last: %d reads, %d clusters, k=%d w=%d, %d overflow reads, %d deferred)"
+                  % (n_batches, n_records, b.n_reads, b.n_clusters, pkw["k"], pkw["w"], tm["n_overflow_reads"], tm["n_deferred"]), flush=True)
+    print("%d batches, %d records, all identical to the oracle (ASCII and packed input)" % (n_batches, n_records))
+
+
+if __name__ == "__main__":
+    main()
