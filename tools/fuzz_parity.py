@@ -56,9 +56,10 @@ def ragged(rng, b, lo):
     return synth.ReadBatch(np.asarray(b.bases, dtype=np.uint8)[np.concatenate(keep)], np.asarray(new_off, dtype=np.uint64), b.cluster_off)
 
 
-def make_case(seed):
+def make_case(seed, gen=1):
     """the batch, the parameters and the pair-generator table size of one seed (tests/test_gpu_fuzz_cases.py replays the seeds
-    that once differed)"""
+    that once differed).  gen 2 adds what generation 1 did not draw: reads of 1 and 3 kb, read names of the caller's own,
+    the 16- and 8-byte record forms — behind a switch, so that the seeds recorded under generation 1 keep their batches."""
     r = np.random.default_rng(seed)
     k = int(r.choice([15, 17, 19, 21, 21, 21, 23]))
     w = int(r.choice([5, 8, 11, 11, 11, 14]))
@@ -68,8 +69,8 @@ def make_case(seed):
                min_chain_score=int(r.choice([k, 30, 30, 40])))
     clusters = []
     for c in range(int(r.integers(1, 5))):
-        read_len = int(r.choice([60, 100, 150, 150, 250, 400, 600]))
-        clusters.append(synth.cluster_batch(1, seed0=seed + c, n_fragments=int(r.integers(3, 260)), read_len=read_len,
+        read_len = int(r.choice([60, 100, 150, 150, 250, 400, 600] + ([1000, 3000] if gen >= 2 else [])))
+        clusters.append(synth.cluster_batch(1, seed0=seed + c, n_fragments=int(r.integers(3, 260 if read_len < 1000 else 50)), read_len=read_len,
                                             n_strains=int(r.integers(1, 5)), strain_cov=float(r.choice([4.0, 8.0, 15.0, 40.0])),
                                             snp_rate=float(r.choice([0.0, 0.005, 0.01, 0.03])), err_rate=float(r.choice([0.0, 0.002, 0.005, 0.02])),
                                             insert_mean=float(max(read_len + 20, r.choice([200.0, 450.0, 900.0])))))
@@ -78,21 +79,52 @@ def make_case(seed):
         b = ragged(r, b, 30)
     b = mutate(r, b, float(r.choice([0.0, 0.0, 0.002, 0.02])), float(r.choice([0.0, 0.0, 0.1])), float(r.choice([0.0, 0.0, 0.05, 0.3])))
     slots = int(r.choice([8, 8, 8, 6, 5]))
-    return b, pkw, slots
+    if gen < 2:
+        return b, pkw, slots
+    ids = None
+    if r.random() < 0.3:  # names of the caller's own: any distinct integers below 65 536 per cluster
+        ids = np.concatenate([r.permutation(int(b.cluster_off[c + 1] - b.cluster_off[c])) * int(r.integers(1, 4)) + int(r.integers(0, 9))
+                              for c in range(b.n_clusters)]).astype(np.uint32)
+    return b, pkw, slots, ids, int(r.choice([0, 1, 2]))
 
 
-def run_case(seed):
-    """(same?, text) for one seed; raises api.HloError when the library refuses the parameters"""
-    b, pkw, slots = make_case(seed)
-    rec_o, blk_o, coff_o, st = orc.overlap_batch(to_orc_batch(b), orc.default_params(**pkw))
+def full_records(rec, coff, b, ids):
+    """the 32-byte form of whatever form came back (hlo_rec16_expand / hlo_rec8_expand of the header, cluster by cluster:
+    the 8-byte form needs the lengths of the cluster's reads by name)"""
+    if rec.dtype == api.REC_DT:
+        return rec
+    if rec.dtype == api.REC16_DT:
+        return api.expand_rec16(rec)
+    lens = (np.asarray(b.base_off[1:], dtype=np.int64) - np.asarray(b.base_off[:-1], dtype=np.int64))
+    out = []
+    for c in range(b.n_clusters):
+        r0, r1 = int(b.cluster_off[c]), int(b.cluster_off[c + 1])
+        names = np.arange(r1 - r0) if ids is None else np.asarray(ids[r0:r1], dtype=np.int64)
+        by_name = np.zeros(int(names.max()) + 1 if len(names) else 1, dtype=np.int64)
+        by_name[names] = lens[r0:r1]
+        out.append(api.expand_rec8(rec[int(coff[c]):int(coff[c + 1])], by_name))
+    return np.concatenate(out) if out else np.zeros(0, dtype=api.REC_DT)
+
+
+def run_case(seed, gen=1):
+    """(same?, details) for one seed; raises api.HloError when the library refuses the parameters"""
+    case = make_case(seed, gen)
+    b, pkw, slots = case[:3]
+    ids, form = (case[3], case[4]) if gen >= 2 else (None, 0)
+    rec_o, blk_o, coff_o, st = orc.overlap_batch(to_orc_batch(b, ids), orc.default_params(**pkw))
     with api.Context(0, **pkw) as c:
         c.set_option("pairgen_slots_log2", slots)
-        c.submit(b)
+        c.submit(b, ids=ids)
         rec, aux, coff = c.wait()
         tm = c.timing()
-        pk = api.pack2b(b)
-        c.submit_packed(pk, b.cluster_off)
+        c.set_option("compact", form)
+        if ids is None:
+            pk = api.pack2b(b)
+            c.submit_packed(pk, b.cluster_off)
+        else:
+            c.submit(b, ids=ids)
         rec_p, _, coff_p = c.wait()
+        rec_p = full_records(rec_p, coff_p, b, ids)
     same = (np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o) and np.array_equal(aux["blocklen"], blk_o) and
             np.array_equal(rec_p, rec_o) and np.array_equal(coff_p, coff_o) and
             tm["n_candidates"] == st["candidates"] and tm["n_accepted"] == st["accepted"] and tm["n_seed_hits"] == st["seed_hits"])
@@ -105,6 +137,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=150.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--replay", type=int, default=0, help="run the batch of this seed only and print what differs")
+    ap.add_argument("--gen", type=int, default=2, help="case generator: 1 = the first sweep's, 2 = + long reads, own names, compact record forms")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     t_end = time.time() + args.seconds
@@ -112,7 +145,7 @@ def main():
     while time.time() < t_end:
         seed = args.replay or int(rng.integers(1, 1 << 30))
         try:
-            same, x = run_case(seed)
+            same, x = run_case(seed, args.gen)
         except api.HloError as e:  # a refusal with a message is a result too
             print("seed %d: refused: %s" % (seed, e))
             if args.replay:
@@ -120,8 +153,8 @@ def main():
             continue
         b, pkw, slots, rec, rec_o, rec_p, tm, st = (x[k] for k in ("b", "pkw", "slots", "rec", "rec_o", "rec_p", "tm", "st"))
         if not same:
-            print("DIFFERENT: seed %d params %s slots %d: %d vs %d records, candidates %d vs %d, hits %d vs %d, accepted %d vs %d, packed input %d records"
-                  % (seed, pkw, slots, len(rec), len(rec_o), tm["n_candidates"], st["candidates"], tm["n_seed_hits"], st["seed_hits"],
+            print("DIFFERENT: gen %d seed %d params %s slots %d: %d vs %d records, candidates %d vs %d, hits %d vs %d, accepted %d vs %d, packed input %d records"
+                  % (args.gen, seed, pkw, slots, len(rec), len(rec_o), tm["n_candidates"], st["candidates"], tm["n_seed_hits"], st["seed_hits"],
                      tm["n_accepted"], st["accepted"], len(rec_p)))
             got = {tuple(int(v) for v in r_) for r_ in rec.tolist()}
             want = {tuple(int(v) for v in r_) for r_ in rec_o.tolist()}
@@ -139,7 +172,7 @@ def main():
         if n_batches % 20 == 0:
             print("%d batches, %d records so far (last: %d reads, %d clusters, k=%d w=%d, %d overflow reads, %d deferred)"
                   % (n_batches, n_records, b.n_reads, b.n_clusters, pkw["k"], pkw["w"], tm["n_overflow_reads"], tm["n_deferred"]), flush=True)
-    print("%d batches, %d records, all identical to the oracle (ASCII and packed input)" % (n_batches, n_records))
+    print("%d batches, %d records, all identical to the oracle (ASCII and packed input; generator %d)" % (n_batches, n_records, args.gen))
 
 
 if __name__ == "__main__":
