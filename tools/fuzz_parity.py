@@ -106,14 +106,20 @@ def full_records(rec, coff, b, ids):
     return np.concatenate(out) if out else np.zeros(0, dtype=api.REC_DT)
 
 
-def run_case(seed, gen=1):
-    """(same?, details) for one seed; raises api.HloError when the library refuses the parameters"""
+def run_case(seed, gen=1, ctx=None, pkw_fixed=None):
+    """(same?, details) for one seed; raises api.HloError when the library refuses the parameters.
+    ctx + pkw_fixed: run the case's batch on a context that lives across cases (its parameters replace the case's): buffer
+    estimates, table-size hints and counters then carry over from whatever batch came before"""
     case = make_case(seed, gen)
     b, pkw, slots = case[:3]
+    if pkw_fixed is not None:
+        pkw = pkw_fixed
     ids, form = (case[3], case[4]) if gen >= 2 else (None, 0)
     rec_o, blk_o, coff_o, st = orc.overlap_batch(to_orc_batch(b, ids), orc.default_params(**pkw))
-    with api.Context(0, **pkw) as c:
+    import contextlib
+    with (contextlib.nullcontext(ctx) if ctx is not None else api.Context(0, **pkw)) as c:
         c.set_option("pairgen_slots_log2", slots)
+        c.set_option("compact", 0)
         c.submit(b, ids=ids)
         rec, aux, coff = c.wait()
         tm = c.timing()
@@ -138,15 +144,28 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--replay", type=int, default=0, help="run the batch of this seed only and print what differs")
     ap.add_argument("--gen", type=int, default=2, help="case generator: 1 = the first sweep's, 2 = + long reads, own names, compact record forms")
+    ap.add_argument("--reuse", type=int, default=0, help="N > 0: one context (the parameters of its first case) serves N consecutive cases")
     args = ap.parse_args()
+    shared, shared_pkw, shared_left = None, None, 0
     rng = np.random.default_rng(args.seed)
     t_end = time.time() + args.seconds
     n_batches = n_records = 0
     while time.time() < t_end:
         seed = args.replay or int(rng.integers(1, 1 << 30))
         try:
-            same, x = run_case(seed, args.gen)
+            if args.reuse and not args.replay:
+                if shared_left == 0:
+                    if shared is not None:
+                        shared.close()
+                        shared = None
+                    shared_pkw = make_case(seed, args.gen)[1]
+                    shared, shared_left = api.Context(0, **shared_pkw), args.reuse
+                shared_left -= 1
+                same, x = run_case(seed, args.gen, shared, shared_pkw)
+            else:
+                same, x = run_case(seed, args.gen)
         except api.HloError as e:  # a refusal with a message is a result too
+            shared_left = 0
             print("seed %d: refused: %s" % (seed, e))
             if args.replay:
                 break
