@@ -68,8 +68,14 @@ def make_case(seed, gen=1):
                mid_occ=int(r.choice([0, 0, 0, 10, 25, 1000])), min_seeds=int(r.choice([1, 2, 2, 3])),
                min_chain_score=int(r.choice([k, 30, 30, 40])))
     clusters = []
+    deep = gen >= 3 and seed % 4 == 0  # gen 3, every fourth seed: one deep pile (hundreds of chains per read: the table-size cascade)
     for c in range(int(r.integers(1, 5))):
         read_len = int(r.choice([60, 100, 150, 150, 250, 400, 600] + ([1000, 3000] if gen >= 2 else [])))
+        if deep and c == 0:
+            clusters.append(synth.cluster_batch(1, seed0=seed, n_fragments=int(r.integers(300, 1500)), read_len=int(r.choice([100, 150, 250])),
+                                                n_strains=int(r.integers(1, 4)), strain_cov=float(r.choice([100.0, 300.0, 1e9])),
+                                                snp_rate=0.01, err_rate=0.005, insert_mean=float(r.choice([260.0, 450.0])), insert_sd=5.0))
+            continue
         clusters.append(synth.cluster_batch(1, seed0=seed + c, n_fragments=int(r.integers(3, 260 if read_len < 1000 else 50)), read_len=read_len,
                                             n_strains=int(r.integers(1, 5)), strain_cov=float(r.choice([4.0, 8.0, 15.0, 40.0])),
                                             snp_rate=float(r.choice([0.0, 0.005, 0.01, 0.03])), err_rate=float(r.choice([0.0, 0.002, 0.005, 0.02])),
@@ -85,7 +91,13 @@ def make_case(seed, gen=1):
     if r.random() < 0.3:  # names of the caller's own: any distinct integers below 65 536 per cluster
         ids = np.concatenate([r.permutation(int(b.cluster_off[c + 1] - b.cluster_off[c])) * int(r.integers(1, 4)) + int(r.integers(0, 9))
                               for c in range(b.n_clusters)]).astype(np.uint32)
-    return b, pkw, slots, ids, int(r.choice([0, 1, 2]))
+    form = int(r.choice([0, 1, 2]))
+    if gen < 3:
+        return b, pkw, slots, ids, form
+    quals = (r.integers(2, 42, size=int(b.base_off[-1])) + 33).astype(np.uint8) if r.random() < 0.4 else None  # gen 3: fused scores
+    if ids is not None:
+        quals = None  # (the consumer indexes its reads by name: scores exist for names 0..N-1 only, as rename_fas.py leaves them)
+    return b, pkw, slots, ids, form, quals, (float(r.choice([0.0, 1e-3])), int(r.choice([0, 0, 120])))
 
 
 def full_records(rec, coff, b, ids):
@@ -115,7 +127,9 @@ def run_case(seed, gen=1, ctx=None, pkw_fixed=None):
     if pkw_fixed is not None:
         pkw = pkw_fixed
     ids, form = (case[3], case[4]) if gen >= 2 else (None, 0)
-    rec_o, blk_o, coff_o, st = orc.overlap_batch(to_orc_batch(b, ids), orc.default_params(**pkw))
+    quals, score_prm = (case[5], case[6]) if gen >= 3 else (None, None)
+    ob = to_orc_batch(b, ids)
+    rec_o, blk_o, coff_o, st = orc.overlap_batch(ob, orc.default_params(**pkw))
     import contextlib
     with (contextlib.nullcontext(ctx) if ctx is not None else api.Context(0, **pkw)) as c:
         c.set_option("pairgen_slots_log2", slots)
@@ -131,7 +145,20 @@ def run_case(seed, gen=1, ctx=None, pkw_fixed=None):
             c.submit(b, ids=ids)
         rec_p, _, coff_p = c.wait()
         rec_p = full_records(rec_p, coff_p, b, ids)
-    same = (np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o) and np.array_equal(aux["blocklen"], blk_o) and
+        score_ok = True
+        if quals is not None:  # the consumer's overlap score, fused into the batch, against the CPU port of EdgeCalculator::overlap_score
+            c.set_option("scores", 1)
+            c.set_score_params(*score_prm)
+            c.submit(b, quals=quals, ids=ids)
+            rec_s, _, coff_s = c.wait()
+            got = c.last_score
+            c.set_option("scores", 0)
+            clu = np.repeat(np.arange(b.n_clusters, dtype=np.uint32), np.diff(coff_o).astype(np.int64))
+            want = orc.score_records(ob, quals, rec_o, clu, *score_prm)
+            score_ok = (got is not None and len(got) == len(rec_o) and np.array_equal(full_records(rec_s, coff_s, b, ids), rec_o) and
+                        np.array_equal(got["mismatch_rate"], want[:, 1]) and np.allclose(got["score"], want[:, 0], rtol=1e-12, atol=0.0) and
+                        np.array_equal(got["score"] == 0.0, want[:, 0] == 0.0))
+    same = score_ok and (np.array_equal(rec, rec_o) and np.array_equal(coff, coff_o) and np.array_equal(aux["blocklen"], blk_o) and
             np.array_equal(rec_p, rec_o) and np.array_equal(coff_p, coff_o) and
             tm["n_candidates"] == st["candidates"] and tm["n_accepted"] == st["accepted"] and tm["n_seed_hits"] == st["seed_hits"])
     info = dict(b=b, pkw=pkw, slots=slots, rec=rec, rec_o=rec_o, rec_p=rec_p, tm=tm, st=st)
