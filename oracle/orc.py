@@ -323,6 +323,10 @@ def score_records(b, quals, rec, rec_cluster=None, mismatch_prob=0.0, min_read_l
     rec = np.ascontiguousarray(rec, dtype=REC_DT)
     quals = np.ascontiguousarray(quals, dtype=np.uint8)
     rc = None if rec_cluster is None else np.ascontiguousarray(rec_cluster, dtype=np.uint32)
+    if b.ids is not None:  # the consumer (FastqStorage.cpp:109-117) indexes its reads by name: names must be 0..N-1 in file order
+        pos = np.arange(b.n_reads, dtype=np.int64) - np.repeat(np.asarray(b.cluster_off[:-1], dtype=np.int64), np.diff(b.cluster_off).astype(np.int64))
+        if not np.array_equal(np.asarray(b.ids, dtype=np.int64), pos):
+            raise ValueError("score_records: read names must be 0..N-1 in file order inside every cluster")
     out = np.zeros((max(len(rec), 1), 2), dtype=np.float64)
     lib().orc_score_records(_ptr(b.bases), _ptr(quals), _ptr(b.base_off), _ptr(b.cluster_off), _ptr(rec), _ptr(rc),
                             C.c_uint64(len(rec)), C.c_double(mismatch_prob), C.c_uint32(min_read_len), _ptr(out))
