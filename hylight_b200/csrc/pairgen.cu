@@ -285,8 +285,9 @@ __device__ __forceinline__ void emit_cand(const PairgenArgs &a, unsigned long lo
 // fast path: PG_G lanes per query read, PG_RPW reads per warp in LOCKSTEP (every loop bound is the maximum over
 // the warp's reads, so the warp never diverges into per-read paths), table in shared memory.
 //
-// What one seed hit costs is the whole story of this kernel (it is issue-bound: 77 % of the issue slots, 5 % of the
-// HBM bandwidth), so the inner loop is built to be short:
+// What one seed hit costs is the whole story of this kernel (round 1: issue-bound at 8.9 warp instructions per hit; now
+// 5.4, and the shared-memory data pipe, 81 % of its wavefront rate, is the first limit with issue at 76 % right behind;
+// HBM 7 %), so the inner loop is built to be short:
 //   * a hit is ONE 32-bit word W = (t - cluster base) << (dg_bits + 1) | strand(t) << dg_bits | pos(t), laid down by
 //     the bucket index in the field layout of the table key: key = (W ^ strand(q) << dg_bits) + max_len - qp, where
 //     qp (the query anchor position on the hit's strand) is one of two per-minimizer values — five instructions
@@ -297,7 +298,8 @@ __device__ __forceinline__ void emit_cand(const PairgenArgs &a, unsigned long lo
 //   * a slot's value is (min anchor position, 0xffff - max anchor position) in two 16-bit halves: one VIMNMX.U16x2
 //     between a load and a store updates both;
 //   * nothing is recorded while inserting: after the last chunk the lanes scan the value array once (a fresh slot's
-//     value fails the span test by itself), list the qualifying slots, and emit from the list.
+//     value fails the span test by itself), list the qualifying slots through a shared counter (positions from ballots
+//     were measured slower: more instructions for fewer wavefronts), and emit from the list.
 // Within one chunk all keys are distinct (one minimizer, one bucket), so only the key claim is an atomic (ATOMS.CAS);
 // the value update is a plain read-modify-write ordered by a __syncwarp per chunk.
 constexpr int PG_THREADS = 128;
@@ -305,7 +307,8 @@ constexpr int PG_THREADS = 128;
 #define HLO_PG_G 16
 #endif
 #ifndef HLO_PG_MINB
-#define HLO_PG_MINB 10  // 48 registers: 10 blocks per SM (measured: 9 blocks 1.59 ms, 10 blocks 1.54 ms, 40 registers 1.60 ms)
+#define HLO_PG_MINB 10  // 48 registers: 10 blocks per SM (measured: 9 blocks 1.59 ms, 10 blocks 1.54 ms, 40 registers 1.60 ms; left to
+                        // itself ptxas takes 86 registers and the kernel 2.34 ms)
 #endif
 constexpr int PG_G = HLO_PG_G;                 // lanes per read
 constexpr unsigned PG_GMASK = PG_G == 32 ? 0xffffffffu : ((1u << PG_G) - 1u);
