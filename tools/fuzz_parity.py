@@ -63,6 +63,8 @@ def make_case(seed, gen=1):
     r = np.random.default_rng(seed)
     k = int(r.choice([15, 17, 19, 21, 21, 21, 23]))
     w = int(r.choice([5, 8, 11, 11, 11, 14]))
+    if gen >= 4 and seed % 2 == 0:  # gen 4, every other seed: even k (palindromic k-mers are skipped), windows off the specialised set
+        k, w = int(np.random.default_rng(seed ^ 0x5bd1e995).choice([14, 16, 18, 20, 22])), int(np.random.default_rng(seed ^ 0x27d4eb2f).choice([3, 7, 19, 25, 32]))
     pkw = dict(k=k, w=w, min_ovlp_len=int(r.choice([30, 50, 60, 60, 90])), min_identity=float(r.choice([0.9, 0.95, 0.98, 0.98, 0.99])),
                max_overhang=int(r.choice([0, 1, 1, 2, 4])), pair_rule=int(r.choice([0, 0, 1])),
                mid_occ=int(r.choice([0, 0, 0, 10, 25, 1000])), min_seeds=int(r.choice([1, 2, 2, 3])),
@@ -170,7 +172,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=150.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--replay", type=int, default=0, help="run the batch of this seed only and print what differs")
-    ap.add_argument("--gen", type=int, default=2, help="case generator: 1 = the first sweep's, 2 = + long reads, own names, compact record forms")
+    ap.add_argument("--gen", type=int, default=2, help="case generator: 1 = the first sweep's, 2 = + long reads, own names, compact record forms, 3 = + fused scores, deep piles, 4 = + even k, other windows")
     ap.add_argument("--reuse", type=int, default=0, help="N > 0: one context (the parameters of its first case) serves N consecutive cases")
     args = ap.parse_args()
     shared, shared_pkw, shared_left = None, None, 0
