@@ -156,7 +156,9 @@ typedef struct hlo_recs {
     uint32_t n_clusters;
     const hlo_rec16 *rec16;     /* with option "compact" = 1 (or 2 when a name of the batch is >= 65536): the n records in 16-byte form, rec == NULL */
     const hlo_rec8 *rec8;       /* with option "compact" = 2: the n records in 8-byte form, rec == rec16 == NULL */
-    const struct hlo_score *score; /* with option "scores" = 1 and qualities in the batch: n entries parallel to the records, else NULL */
+    const struct hlo_score *score; /* with option "scores" = 1, qualities in the batch and read names 0..N-1 in file order (the
+                                      consumer indexes its reads by name, FastqStorage.cpp:109-117): n entries parallel to the
+                                      records; else NULL */
 } hlo_recs;
 
 /* One batch of clusters on the host, the input of hlo_submit (and of hlo_overlap_host through its arguments). */
